@@ -1,0 +1,134 @@
+/*
+ * ssq.h — C-ABI of libssq.so, the B200-native implementation of the `speedseq align` hot path.
+ *
+ * The reference's drop-in boundary for this path is a PROCESS boundary, not an FFI:
+ * bin/speedseq sources speedseq.config (/root/reference/bin/speedseq:15-24,361) and interpolates
+ * $BWA and $SAMBLASTER into the pipeline text at /root/reference/bin/speedseq:437-449 (interleaved)
+ * and :467-479 (two files); the index is made by `$BWA index` at :389.  libssq.so is what the two
+ * replacement executables (speedseq_b200/bin/bwa, speedseq_b200/bin/samblaster) link; its entry
+ * points are the batch forms of the functions those tools spend their time in.
+ * Each declaration cites the reference call site it serves and names the upstream routine it
+ * replaces (upstream sources are NOT vendored in the reference tree: .SUBMODULES.json:23-29,51-57).
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers unless a name ends in _dev,
+ * int return code (0 = ok, <0 = SSQ_E*), no global state other than the CUDA context, one CUDA
+ * stream per handle.  Every entry point fails with SSQ_ENOGPU when no sm_100 device is usable —
+ * there is no CPU fallback inside this library.
+ */
+#ifndef SSQ_H
+#define SSQ_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSQ_OK        0
+#define SSQ_ENOGPU   (-1)  /* no CUDA device / wrong architecture */
+#define SSQ_EIO      (-2)  /* index files missing or malformed */
+#define SSQ_ENOMEM   (-3)
+#define SSQ_EINVAL   (-4)
+#define SSQ_ECAP     (-5)  /* caller buffer too small; required size returned through *needed */
+#define SSQ_ECUDA    (-6)  /* a CUDA call failed; see ssq_last_error() */
+#define SSQ_ELEN     (-7)  /* a read is longer than SSQ_MAX_READ_LEN */
+
+#define SSQ_MAX_READ_LEN 255
+
+const char *ssq_last_error(void);
+int ssq_device_count(void);
+
+/* ---------------------------------------------------------------- options ----
+ * Scoring/heuristic parameters of `bwa mem`; speedseq passes none of them on the command line
+ * (/root/reference/bin/speedseq:438), so ssq_opts_default() is what the pipeline runs with.
+ * Replaces upstream mem_opt_init(). */
+typedef struct {
+	int32_t a, b, o_del, e_del, o_ins, e_ins;
+	int32_t pen_unpaired, pen_clip5, pen_clip3, w, zdrop, T;
+	int32_t min_seed_len, split_width, max_occ, max_chain_gap, max_mem_intv;
+	int32_t min_chain_weight, max_chain_extend, max_ins, max_matesw, max_XA_hits;
+	float split_factor, mask_level, drop_ratio, XA_drop_ratio, mask_level_redun;
+	int32_t mapQ_coef_len, mapQ_coef_fac;
+} ssq_opts_t;
+void ssq_opts_default(ssq_opts_t *o);
+
+/* ------------------------------------------------------------------ index ----
+ * Device-resident FM index + packed reference.  ssq_index_load replaces upstream bwa_idx_load()
+ * (start of `$BWA mem`, /root/reference/bin/speedseq:438): reads PREFIX.{bwt,sa,pac,ann,amb} in the
+ * on-disk format of the reference's goldens (/root/reference/example/data/ *.fasta.{amb,ann,pac,bwt,sa})
+ * and uploads them to `device`. */
+typedef struct ssq_index ssq_index_t;
+int ssq_index_load(const char *prefix, int device, ssq_index_t **out);
+void ssq_index_free(ssq_index_t *idx);
+/* what: 0 l_pac, 1 seq_len(=2*l_pac), 2 primary, 3 n_seqs, 4 bwt words, 5 n_sa, 6 device bytes */
+uint64_t ssq_index_info(const ssq_index_t *idx, int what);
+
+/* ----------------------------------------------------- kernel-level batches ----
+ * Reads are passed as one byte per base (0=A 1=C 2=G 3=T 4=N), concatenated, with read_off[n+1]. */
+
+/* SMEM seeding, all three passes, per read.  Replaces upstream mem_collect_intv() →
+ * bwt_smem1a / bwt_seed_strategy1 / bwt_extend / bwt_2occ4 (inside `$BWA mem`, speedseq:438).
+ * Output intervals of read i are out[out_off[i] .. out_off[i+1]) sorted by (qbeg<<32|qend). */
+typedef struct { uint64_t k, l, s; uint32_t qbeg, qend; } ssq_smem_t;
+int ssq_smem_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
+                   ssq_smem_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed);
+
+/* Suffix-array lookup of BWT rows.  Replaces upstream bwt_sa() / bwt_invPsi() (speedseq:438). */
+int ssq_sa_lookup_batch(const ssq_index_t *idx, uint64_t n, const uint64_t *rows, uint64_t *pos);
+
+/* Banded affine-gap seed extension.  Replaces upstream ksw_extend2() as called from
+ * mem_chain2aln() (speedseq:438).  Sequences are one byte per base in qbuf/tbuf. */
+typedef struct { uint64_t q_off, t_off; int32_t qlen, tlen, h0, w, end_bonus, zdrop; } ssq_sw_task_t;
+typedef struct { int32_t score, qle, tle, gtle, gscore, max_off; } ssq_sw_result_t;
+int ssq_sw_extend_batch(const ssq_opts_t *opt, int device, uint64_t n, const ssq_sw_task_t *tasks,
+                        const uint8_t *qbuf, uint64_t qbuf_len, const uint8_t *tbuf, uint64_t tbuf_len, ssq_sw_result_t *out);
+
+/* Chains after seeding + SA lookup + chaining + chain filter.  Replaces upstream mem_chain() +
+ * mem_chain_flt() (speedseq:438).  Flattened: read i owns chains [read_chain_off[i], read_chain_off[i+1]),
+ * chain c owns seeds [chain_seed_off[c], chain_seed_off[c+1]). */
+typedef struct { int64_t rbeg; int32_t qbeg, len; } ssq_seed_t;
+int ssq_chain_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
+                    ssq_seed_t *seeds, uint64_t seed_cap, uint64_t *chain_seed_off, uint64_t chain_cap, uint64_t *read_chain_off,
+                    uint64_t *n_chains, uint64_t *n_seeds);
+
+/* Duplicate marking over pair signatures, first occurrence in input order is kept.  Replaces the
+ * signature hash sets of samblaster's markDupsDiscordants() (`$SAMBLASTER`, speedseq:439).
+ * valid==0 entries (both ends unmapped) are never duplicates. */
+typedef struct { uint64_t pos1, pos2; uint8_t strand1, strand2, valid, pad[5]; } ssq_dupsig_t;
+int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig, uint8_t *is_dup);
+
+/* ------------------------------------------------- the alignment pipeline ----
+ * Seeding → SA lookup → chaining → chain filter → seed extension → alignment regions, all on the
+ * device (the single-end core of `$BWA mem`, upstream mem_align1_core() up to and including
+ * mem_chain2aln(); stage 1 adds mem_sort_dedup_patch()).  Regions of read i are
+ * out[out_off[i] .. out_off[i+1]) in the order the reference produces them. */
+typedef struct {
+	int64_t rb, re;
+	int32_t qb, qe, rid, score, truesc, w, seedcov, seedlen0;
+	float frac_rep;
+	int32_t read_id;
+} ssq_alnreg_t;
+
+/* one-shot, HOST buffers in and out (this is what the CLI shim calls per batch; `e2e` in bench.py) */
+int ssq_align_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
+                    int stage, ssq_alnreg_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed);
+
+/* staged form: upload once, run the kernels any number of times with everything resident in HBM
+ * (`value` in bench.py), fetch results when wanted */
+typedef struct ssq_batch ssq_batch_t;
+int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off, ssq_batch_t **out);
+int ssq_batch_run(ssq_batch_t *b);                 /* asynchronous on the batch's stream */
+int ssq_batch_sync(ssq_batch_t *b);
+int ssq_batch_fetch(ssq_batch_t *b, ssq_alnreg_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed);
+void *ssq_batch_stream(ssq_batch_t *b);            /* cudaStream_t, for event timing on the launching stream */
+/* per-run work counters measured on the device: what: 0 occ blocks read by seeding, 1 occ blocks read by SA walks,
+ * 2 SA samples read, 3 SW extension calls, 4 SW cells, 5 SW algorithmic bytes, 6 kernels launched per run, 7 seeds, 8 regions */
+uint64_t ssq_batch_counter(const ssq_batch_t *b, int what);
+/* milliseconds of the last run per stage (CUDA events on the batch stream): 0 smem, 1 sa, 2 chain, 3 extend, 4 finalize */
+float ssq_batch_stage_ms(const ssq_batch_t *b, int stage);
+void ssq_batch_free(ssq_batch_t *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,707 @@
+// ssq_dev.cuh — device-side data layout and the per-read / per-seed routines of the alignment path.
+//
+// Everything that is arithmetic lives here as SSQ_HD templates so that (a) the __global__ wrappers in
+// ssq_fm.cu / ssq_chain.cu / ssq_extend.cu stay thin and (b) tests/hostsim can compile the very same
+// routines for the host and compare them with the oracle on a box without a GPU (test-only harness,
+// never part of libssq.so: the shipped library has no CPU path).
+//
+// Reference behaviour being reproduced (upstream bwa, not vendored in /root/reference; call site
+// /root/reference/bin/speedseq:438): SURVEY.md §8a rows a4-a7 and Appendix A.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "../../include/ssq.h"
+
+#ifdef __CUDACC__
+#define SSQ_HD __host__ __device__ __forceinline__
+#define SSQ_D __device__ __forceinline__
+#else
+#define SSQ_HD inline
+#endif
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+typedef int32_t i32;
+
+// ---------------------------------------------------------------- HBM layout of the index ----
+// bwt  : the occ-interleaved BWT exactly as in PREFIX.bwt after its 40-byte header: one 64-byte block per
+//        128 symbols = u64 occ[4] (A,C,G,T before the block) + u32 w[8] (16 symbols/word, MSB first).
+//        64 B = two 32-B sectors = one L2 line half; cudaMalloc alignment keeps blocks line-aligned.
+// sa   : u64 SA[32k], k=0..n_sa-1 (sa[0] = -1 like the reference loader).
+// pac  : forward strand, 2 bit/base, base i at pac[i>>2] >> ((~i&3)<<1) & 3.
+// ann  : per-contig offset/len for rid look-ups.
+struct DevIndex {
+	const u32 *bwt;
+	const u64 *sa;
+	const uint8_t *pac;
+	const i64 *ann_off;
+	const i32 *ann_len;
+	u64 primary, L2[5], seq_len, n_sa;
+	i64 l_pac;
+	i32 n_seqs, sa_intv;
+};
+
+struct Counters { // device-measured work, feeds roofline.achieved (algorithmic bytes)
+	unsigned long long occ_smem, occ_sa, sa_reads, sw_calls, sw_cells, sw_bytes, n_seeds, n_regs;
+};
+
+struct Intv { u64 x0, x1, x2; u32 qb, qe; }; // bi-interval + query span [qb,qe)
+
+// ----------------------------------------------------------------------- occ / extension ----
+// counts of A,C,G,T in rows [0,k] given the 16 words of the block holding k ('$'-less coordinate kk)
+SSQ_HD void occ4_from_block(const u32 *blk, u64 kk, u64 cnt[4])
+{
+	const u64 *c64 = (const u64*)blk;
+	int r = (int)(kk & 127) + 1; // symbols to count
+	u32 acc[4] = {0, 0, 0, 0};
+	cnt[0] = c64[0]; cnt[1] = c64[1]; cnt[2] = c64[2]; cnt[3] = c64[3];
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		int n = r - 16 * j;
+		if (n > 0) {
+			u32 w = blk[8 + j];
+			u32 m = n >= 16 ? 0x55555555u : (0x55555555u & ~(0xffffffffu >> (2 * n)));
+			u32 lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+#ifdef __CUDA_ARCH__
+			acc[0] += __popc(~hi & ~lo & m); acc[1] += __popc(~hi & lo & m);
+			acc[2] += __popc(hi & ~lo & m);  acc[3] += __popc(hi & lo & m);
+#else
+			acc[0] += __builtin_popcount(~hi & ~lo & m); acc[1] += __builtin_popcount(~hi & lo & m);
+			acc[2] += __builtin_popcount(hi & ~lo & m);  acc[3] += __builtin_popcount(hi & lo & m);
+#endif
+		}
+	}
+	cnt[0] += acc[0]; cnt[1] += acc[1]; cnt[2] += acc[2]; cnt[3] += acc[3];
+}
+
+// scalar context: one thread does the whole look-up (used by the SA walk, by hostsim, and as the
+// thread-per-read variant of the seeding kernel)
+struct ScalarFm {
+	const DevIndex &ix;
+	unsigned long long n_blk;
+	SSQ_HD ScalarFm(const DevIndex &i) : ix(i), n_blk(0) {}
+	SSQ_HD void occ4(u64 k, u64 cnt[4])
+	{
+		if (k == (u64)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
+		u64 kk = k - (k >= ix.primary);
+		const u32 *p = ix.bwt + ((kk >> 7) << 4);
+		u32 blk[16];
+#ifdef __CUDA_ARCH__
+		const uint4 *p4 = (const uint4*)p;
+		uint4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2), d = __ldg(p4 + 3);
+		blk[0] = a.x; blk[1] = a.y; blk[2] = a.z; blk[3] = a.w; blk[4] = b.x; blk[5] = b.y; blk[6] = b.z; blk[7] = b.w;
+		blk[8] = c.x; blk[9] = c.y; blk[10] = c.z; blk[11] = c.w; blk[12] = d.x; blk[13] = d.y; blk[14] = d.z; blk[15] = d.w;
+#else
+		memcpy(blk, p, 64);
+#endif
+		++n_blk;
+		occ4_from_block(blk, kk, cnt);
+	}
+	// ok[c] of a forward (is_back=0) or backward (is_back=1) extension of ik by every base c
+	SSQ_HD void extend(const Intv &ik, Intv ok[4], int is_back)
+	{
+		u64 tk[4], tl[4];
+		u64 kf = is_back ? ik.x0 : ik.x1; // the component looked up in the BWT
+		u64 ko = is_back ? ik.x1 : ik.x0; // the component updated by accumulation
+		occ4(kf - 1, tk);
+		occ4(kf - 1 + ik.x2, tl);
+		u64 nf[4], ns[4], no[4];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) { nf[c] = ix.L2[c] + 1 + tk[c]; ns[c] = tl[c] - tk[c]; }
+		no[3] = ko + (kf <= ix.primary && kf + ik.x2 - 1 >= ix.primary);
+		no[2] = no[3] + ns[3]; no[1] = no[2] + ns[2]; no[0] = no[1] + ns[1];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			ok[c].x2 = ns[c];
+			if (is_back) { ok[c].x0 = nf[c]; ok[c].x1 = no[c]; } else { ok[c].x1 = nf[c]; ok[c].x0 = no[c]; }
+		}
+	}
+};
+
+SSQ_HD void set_intv(const DevIndex &ix, int c, Intv &ik)
+{
+	ik.x0 = ix.L2[c] + 1; ik.x2 = ix.L2[c + 1] - ix.L2[c]; ik.x1 = ix.L2[3 - c] + 1; ik.qb = ik.qe = 0;
+}
+
+// ------------------------------------------------------------------------ SMEM search ----
+// Per-read scratch: two ping-pong lists of at most len+1 intervals (shared memory on the device) and an
+// output list `mem` (global scratch).  Fm is ScalarFm or the warp-cooperative context of ssq_fm.cu; with the
+// latter every lane runs this code with identical values (warp-uniform control flow).
+template <class Fm>
+SSQ_HD int smem1(Fm &fm, const DevIndex &ix, int len, const uint8_t *q, int x, u64 min_intv,
+                 Intv *mem, int mem_cap, int &mem_n, Intv *prev, Intv *curr, int &err)
+{
+	int i, j, c, ret, n_curr = 0, n_prev, base = mem_n;
+	Intv ik, ok[4];
+	if (q[x] > 3) return x + 1;
+	if (min_intv < 1) min_intv = 1;
+	set_intv(ix, q[x], ik);
+	ik.qe = x + 1;
+	for (i = x + 1; i < len; ++i) { // forward, remembering every change of interval size
+		if (q[i] < 4) {
+			c = 3 - q[i];
+			fm.extend(ik, ok, 0);
+			if (ok[c].x2 != ik.x2) {
+				curr[n_curr++] = ik;
+				if (ok[c].x2 < min_intv) break;
+			}
+			ik = ok[c]; ik.qe = i + 1;
+		} else { curr[n_curr++] = ik; break; }
+	}
+	if (i == len) curr[n_curr++] = ik;
+	for (j = 0; j < n_curr >> 1; ++j) { Intv t = curr[j]; curr[j] = curr[n_curr - 1 - j]; curr[n_curr - 1 - j] = t; } // longest first
+	ret = (int)curr[0].qe;
+	{ Intv *t = curr; curr = prev; prev = t; n_prev = n_curr; }
+	for (i = x - 1; i >= -1; --i) { // backward, the whole set at once
+		c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
+		n_curr = 0;
+		for (j = 0; j < n_prev; ++j) {
+			Intv p = prev[j];
+			if (c >= 0) fm.extend(p, ok, 1);
+			if (c < 0 || ok[c].x2 < min_intv) {
+				if (n_curr == 0) { // nothing longer survives: p is left-maximal
+					if (mem_n == base || (u32)(i + 1) < mem[mem_n - 1].qb) {
+						if (mem_n >= mem_cap) { err = 1; return ret; }
+						p.qb = (u32)(i + 1);
+						mem[mem_n++] = p;
+					}
+				}
+			} else if (n_curr == 0 || ok[c].x2 != curr[n_curr - 1].x2) {
+				ok[c].qb = 0; ok[c].qe = p.qe;
+				curr[n_curr++] = ok[c];
+			}
+		}
+		if (n_curr == 0) break;
+		{ Intv *t = curr; curr = prev; prev = t; n_prev = n_curr; }
+	}
+	for (j = 0; j < (mem_n - base) >> 1; ++j) { Intv t = mem[base + j]; mem[base + j] = mem[mem_n - 1 - j]; mem[mem_n - 1 - j] = t; }
+	return ret;
+}
+
+template <class Fm>
+SSQ_HD int seed_strategy1(Fm &fm, const DevIndex &ix, int len, const uint8_t *q, int x, int min_len, u64 max_intv, Intv &m)
+{
+	int i, c;
+	Intv ik, ok[4];
+	m.x0 = m.x1 = m.x2 = 0; m.qb = m.qe = 0;
+	if (q[x] > 3) return x + 1;
+	set_intv(ix, q[x], ik);
+	for (i = x + 1; i < len; ++i) {
+		if (q[i] < 4) {
+			c = 3 - q[i];
+			fm.extend(ik, ok, 0);
+			if (ok[c].x2 < max_intv && i - x >= min_len) {
+				m = ok[c]; m.qb = (u32)x; m.qe = (u32)(i + 1);
+				return i + 1;
+			}
+			ik = ok[c];
+		} else return i + 1;
+	}
+	return len;
+}
+
+// the three seeding passes of one read; result in mem[0..return) sorted by (qb,qe)
+template <class Fm>
+SSQ_HD int collect_intv(Fm &fm, const DevIndex &ix, const ssq_opts_t &opt, int len, const uint8_t *q,
+                        Intv *mem, int mem_cap, Intv *bufA, Intv *bufB, int &err)
+{
+	int x = 0, n = 0, i, k, old_n, base;
+	int split_len = (int)(opt.min_seed_len * opt.split_factor + .499f);
+	if (len < opt.min_seed_len) return 0;
+	while (x < len) { // pass 1: SMEMs
+		if (q[x] < 4) {
+			base = n;
+			x = smem1(fm, ix, len, q, x, 1, mem, mem_cap, n, bufA, bufB, err);
+			if (err) return 0;
+			for (i = k = base; i < n; ++i) if ((int)(mem[i].qe - mem[i].qb) >= opt.min_seed_len) mem[k++] = mem[i];
+			n = k;
+		} else ++x;
+	}
+	old_n = n;
+	for (k = 0; k < old_n; ++k) { // pass 2: re-seed long, nearly unique SMEMs from their midpoint
+		Intv p = mem[k];
+		int start = (int)p.qb, end = (int)p.qe, kk;
+		if (end - start < split_len || p.x2 > (u64)opt.split_width) continue;
+		base = n;
+		smem1(fm, ix, len, q, (start + end) >> 1, p.x2 + 1, mem, mem_cap, n, bufA, bufB, err);
+		if (err) return 0;
+		for (i = kk = base; i < n; ++i) if ((int)(mem[i].qe - mem[i].qb) >= opt.min_seed_len) mem[kk++] = mem[i];
+		n = kk;
+	}
+	if (opt.max_mem_intv > 0) { // pass 3: greedy forward seeds
+		x = 0;
+		while (x < len) {
+			if (q[x] < 4) {
+				Intv m;
+				x = seed_strategy1(fm, ix, len, q, x, opt.min_seed_len, (u64)opt.max_mem_intv, m);
+				if (m.x2 > 0) { if (n >= mem_cap) { err = 1; return 0; } mem[n++] = m; }
+			} else ++x;
+		}
+	}
+	// order by (qb<<32|qe); equal keys are identical intervals, so any sort gives the reference order
+	for (i = 1; i < n; ++i) {
+		Intv t = mem[i];
+		u64 key = (u64)t.qb << 32 | t.qe;
+		for (k = i; k > 0 && ((u64)mem[k - 1].qb << 32 | mem[k - 1].qe) > key; --k) mem[k] = mem[k - 1];
+		mem[k] = t;
+	}
+	return n;
+}
+
+// number of SA look-ups an interval contributes (max_occ rows, evenly strided when it has more)
+SSQ_HD int intv_occ_count(u64 s, int max_occ, u64 &step)
+{
+	step = s > (u64)max_occ ? s / max_occ : 1;
+	u64 cnt = (s + step - 1) / step;
+	return (int)(cnt < (u64)max_occ ? cnt : (u64)max_occ);
+}
+
+// ------------------------------------------------------------------------- SA look-up ----
+SSQ_HD u64 sa_lookup(ScalarFm &fm, u64 k, unsigned long long &n_sa)
+{
+	const DevIndex &ix = fm.ix;
+	u64 sa = 0, mask = (u64)ix.sa_intv - 1;
+	while (k & mask) { // walk LF until a sampled row
+		++sa;
+		if (k == ix.primary) { k = 0; continue; }
+		u64 x = k - (k > ix.primary);
+		const u32 *p = ix.bwt + ((x >> 7) << 4) + 8;
+		int c = p[(x & 0x7f) >> 4] >> ((~x & 0xf) << 1) & 3;
+		u64 cnt[4];
+		fm.occ4(k, cnt);
+		k = ix.L2[c] + cnt[c];
+	}
+	++n_sa;
+	return sa + ix.sa[k / ix.sa_intv];
+}
+
+// ------------------------------------------------------------------- reference helpers ----
+SSQ_HD int pos2rid(const DevIndex &ix, i64 pos_f)
+{
+	int left = 0, mid = 0, right = ix.n_seqs;
+	if (pos_f >= ix.l_pac) return -1;
+	while (left < right) {
+		mid = (left + right) >> 1;
+		if (pos_f >= ix.ann_off[mid]) {
+			if (mid == ix.n_seqs - 1) break;
+			if (pos_f < ix.ann_off[mid + 1]) break;
+			left = mid + 1;
+		} else right = mid;
+	}
+	return mid;
+}
+SSQ_HD i64 depos(const DevIndex &ix, i64 pos, int &is_rev) { is_rev = pos >= ix.l_pac; return is_rev ? (ix.l_pac << 1) - 1 - pos : pos; }
+SSQ_HD int intv2rid(const DevIndex &ix, i64 rb, i64 re)
+{
+	int is_rev, rid_b, rid_e;
+	if (rb < ix.l_pac && re > ix.l_pac) return -2;
+	rid_b = pos2rid(ix, depos(ix, rb, is_rev));
+	rid_e = rb < re ? pos2rid(ix, depos(ix, re - 1, is_rev)) : rid_b;
+	return rid_b == rid_e ? rid_b : -1;
+}
+// base at coordinate p of the doubled (forward + reverse-complement) reference
+SSQ_HD int ref_base(const DevIndex &ix, i64 p)
+{
+	if (p >= ix.l_pac) { i64 f = (ix.l_pac << 1) - 1 - p; return 3 - (ix.pac[f >> 2] >> ((~f & 3) << 1) & 3); }
+	return ix.pac[p >> 2] >> ((~p & 3) << 1) & 3;
+}
+SSQ_HD int cal_max_gap(const ssq_opts_t &o, int qlen)
+{
+	int l_del = (int)((double)(qlen * o.a - o.o_del) / o.e_del + 1.);
+	int l_ins = (int)((double)(qlen * o.a - o.o_ins) / o.e_ins + 1.);
+	int l = l_del > l_ins ? l_del : l_ins;
+	l = l > 1 ? l : 1;
+	return l < o.w << 1 ? l : o.w << 1;
+}
+
+// ---------------------------------------------------------------------------- chaining ----
+struct Seed { i64 rbeg; i32 qbeg, len; };
+struct ChainRec { // chain under construction / after the filter
+	i64 pos, first_r, last_r;
+	i32 first_q, last_q, last_len, rid, n, w, first, kept, seed_start;
+	float frac_rep;
+};
+
+// klib-style introsort restated on (key, payload) pairs, comparisons on key only ("a before b" iff LT(a,b));
+// the order it leaves equal keys in is part of the reference's behaviour (see oracle/ssqo_sort.h)
+template <class T, class LT>
+SSQ_HD void ks_isort(T *a, long lo, long hi, LT lt)
+{
+	for (long i = lo + 1; i < hi; ++i)
+		for (long j = i; j > lo && lt(a[j], a[j - 1]); --j) { T t = a[j]; a[j] = a[j - 1]; a[j - 1] = t; }
+}
+template <class T, class LT>
+SSQ_HD void ks_combsort(T *a, long n, LT lt)
+{
+	const double shrink = 1.2473309501039786540366528676643;
+	int swapped;
+	long gap = n;
+	do {
+		if (gap > 2) { gap = (long)(gap / shrink); if (gap == 9 || gap == 10) gap = 11; }
+		swapped = 0;
+		for (long i = 0; i < n - gap; ++i)
+			if (lt(a[i + gap], a[i])) { T t = a[i]; a[i] = a[i + gap]; a[i + gap] = t; swapped = 1; }
+	} while (swapped || gap > 2);
+	if (gap != 1) ks_isort(a, 0, n, lt);
+}
+template <class T, class LT>
+SSQ_HD void ks_introsort(long n, T *a, LT lt)
+{
+	long s, t, i, j, k, top = 0;
+	int d;
+	long stl[64], str[64]; int std_[64];
+	if (n < 1) return;
+	if (n == 2) { if (lt(a[1], a[0])) { T x = a[0]; a[0] = a[1]; a[1] = x; } return; }
+	for (d = 2; (1L << d) < n; ++d);
+	s = 0; t = n - 1; d <<= 1;
+	for (;;) {
+		if (s < t) {
+			T rp, x;
+			if (--d == 0) { ks_combsort(a + s, t - s + 1, lt); t = s; continue; }
+			i = s; j = t; k = i + ((j - i) >> 1) + 1;
+			if (lt(a[k], a[i])) { if (lt(a[k], a[j])) k = j; }
+			else k = lt(a[j], a[i]) ? i : j;
+			rp = a[k];
+			if (k != t) { x = a[k]; a[k] = a[t]; a[t] = x; }
+			for (;;) {
+				do ++i; while (lt(a[i], rp));
+				do --j; while (i <= j && lt(rp, a[j]));
+				if (j <= i) break;
+				x = a[i]; a[i] = a[j]; a[j] = x;
+			}
+			x = a[i]; a[i] = a[t]; a[t] = x;
+			if (i - s > t - i) {
+				if (i - s > 16) { stl[top] = s; str[top] = i - 1; std_[top] = d; ++top; }
+				s = t - i > 16 ? i + 1 : t;
+			} else {
+				if (t - i > 16) { stl[top] = i + 1; str[top] = t; std_[top] = d; ++top; }
+				t = i - s > 16 ? i - 1 : s;
+			}
+		} else {
+			if (top == 0) { ks_isort(a, 0, n, lt); return; }
+			--top; s = stl[top]; t = str[top]; d = std_[top];
+		}
+	}
+}
+
+struct WIdx { i32 w, idx; };
+struct WIdxLt { SSQ_HD bool operator()(const WIdx &a, const WIdx &b) const { return a.w > b.w; } };
+
+// Build the chains of one read from its seeds (in look-up order) and filter them.
+//   seeds[0..n)      in : seeds of the read (rbeg from the SA look-up, qbeg/len from their interval)
+//   chain_of[0..n)   scratch: chain index of each seed, -1 = dropped/absorbed
+//   ch[0..n)         scratch: chain records (at most one chain per seed)
+//   ord[0..n)        scratch: chain indices ordered by pos
+//   sorted[0..n)     out: seeds regrouped chain by chain (chain order = filter order)
+//   outc[0..n)       out: kept chains (seed_start relative to `sorted`)
+// returns the number of kept chains.  l_rep/len gives frac_rep.
+SSQ_HD int chain_and_filter(const DevIndex &ix, const ssq_opts_t &opt, int len, int n, const Seed *seeds, int l_rep,
+                            i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc)
+{
+	int n_ch = 0, i, k;
+	const i64 l_pac = ix.l_pac;
+	for (i = 0; i < n; ++i) {
+		Seed s = seeds[i];
+		int rid = intv2rid(ix, s.rbeg, s.rbeg + s.len);
+		chain_of[i] = -1;
+		if (rid < 0) continue;
+		int lo = 0, hi = n_ch, slot, merged = 0;
+		while (lo < hi) { int mid = (lo + hi) >> 1; if (ch[ord[mid]].pos < s.rbeg) lo = mid + 1; else hi = mid; }
+		slot = (lo < n_ch && ch[ord[lo]].pos == s.rbeg) ? lo : lo - 1;
+		if (n_ch && slot >= 0) {
+			ChainRec &c = ch[ord[slot]];
+			i64 qend = c.last_q + c.last_len, rend = c.last_r + c.last_len;
+			if (rid == c.rid) {
+				if (s.qbeg >= c.first_q && s.qbeg + s.len <= qend && s.rbeg >= c.first_r && s.rbeg + s.len <= rend) merged = 1; // contained
+				else if (!((c.last_r < l_pac || c.first_r < l_pac) && s.rbeg >= l_pac)) {
+					i64 x = s.qbeg - c.last_q, y = s.rbeg - c.last_r;
+					if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - c.last_len < opt.max_chain_gap && y - c.last_len < opt.max_chain_gap) {
+						c.last_q = s.qbeg; c.last_r = s.rbeg; c.last_len = s.len; ++c.n;
+						chain_of[i] = ord[slot];
+						merged = 1;
+					}
+				}
+			}
+		}
+		if (!merged) {
+			ChainRec &c = ch[n_ch];
+			c.pos = s.rbeg; c.first_r = c.last_r = s.rbeg; c.first_q = c.last_q = s.qbeg; c.last_len = s.len;
+			c.rid = rid; c.n = 1; c.w = 0; c.first = -1; c.kept = 0; c.seed_start = 0; c.frac_rep = 0.f;
+			for (k = n_ch; k > slot + 1; --k) ord[k] = ord[k - 1];
+			ord[slot + 1] = n_ch;
+			chain_of[i] = n_ch;
+			++n_ch;
+		}
+	}
+	if (n_ch == 0) return 0;
+	// regroup seeds chain by chain, chains in pos order (= the order the reference's tree is traversed)
+	{
+		int off = 0;
+		for (k = 0; k < n_ch; ++k) { ChainRec &c = ch[ord[k]]; c.seed_start = off; off += c.n; c.n = 0; }
+		for (i = 0; i < n; ++i) if (chain_of[i] >= 0) { ChainRec &c = ch[chain_of[i]]; sorted[c.seed_start + c.n++] = seeds[i]; }
+	}
+	// weight = min(query coverage, reference coverage) of the seeds
+	for (k = 0; k < n_ch; ++k) {
+		ChainRec &c = ch[ord[k]];
+		const Seed *s = sorted + c.seed_start;
+		i64 end; int j, w = 0, tmp;
+		for (j = 0, end = 0; j < c.n; ++j) {
+			if (s[j].qbeg >= end) w += s[j].len; else if (s[j].qbeg + s[j].len > end) w += (int)(s[j].qbeg + s[j].len - end);
+			end = end > s[j].qbeg + s[j].len ? end : s[j].qbeg + s[j].len;
+		}
+		tmp = w; w = 0;
+		for (j = 0, end = 0; j < c.n; ++j) {
+			if (s[j].rbeg >= end) w += s[j].len; else if (s[j].rbeg + s[j].len > end) w += (int)(s[j].rbeg + s[j].len - end);
+			end = end > s[j].rbeg + s[j].len ? end : s[j].rbeg + s[j].len;
+		}
+		w = w < tmp ? w : tmp;
+		c.w = w < 1 << 30 ? w : (1 << 30) - 1;
+		c.first = -1; c.kept = 0;
+		c.frac_rep = (float)l_rep / len;
+		wi[k].w = c.w; wi[k].idx = ord[k];
+	}
+	ks_introsort((long)n_ch, wi, WIdxLt());
+	// pairwise overlap filter over chains in decreasing weight; ord[] is reused as the list of kept positions
+#define CH(i_) ch[wi[i_].idx]
+#define CBEG(c_) (sorted[(c_).seed_start].qbeg)
+#define CEND(c_) (sorted[(c_).seed_start + (c_).n - 1].qbeg + sorted[(c_).seed_start + (c_).n - 1].len)
+	int n_kept = 0;
+	CH(0).kept = 3; ord[n_kept++] = 0;
+	for (i = 1; i < n_ch; ++i) {
+		int large_ovlp = 0;
+		ChainRec &ci = CH(i);
+		for (k = 0; k < n_kept; ++k) {
+			int j = ord[k];
+			ChainRec &cj = CH(j);
+			int bi = CBEG(ci), ei = CEND(ci), bj = CBEG(cj), ej = CEND(cj);
+			int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
+			if (e_min > b_max) {
+				int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
+				if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+					large_ovlp = 1;
+					if (cj.first < 0) cj.first = i;
+					if (ci.w < cj.w * opt.drop_ratio && cj.w - ci.w >= opt.min_seed_len << 1) break;
+				}
+			}
+		}
+		if (k == n_kept) { ord[n_kept++] = i; ci.kept = large_ovlp ? 2 : 3; }
+	}
+	for (i = 0; i < n_kept; ++i) { ChainRec &c = CH(ord[i]); if (c.first >= 0) CH(c.first).kept = 1; }
+	for (i = k = 0; i < n_ch; ++i) {
+		if (CH(i).kept == 0 || CH(i).kept == 3) continue;
+		if (++k >= opt.max_chain_extend) break;
+	}
+	for (; i < n_ch; ++i) if (CH(i).kept < 3) CH(i).kept = 0;
+	for (i = k = 0; i < n_ch; ++i) if (CH(i).kept) outc[k++] = CH(i);
+#undef CH
+#undef CBEG
+#undef CEND
+	return k;
+}
+
+// ----------------------------------------------------------------- banded SW extension ----
+// ksw_extend2 semantics: row-sequential DP with per-row band trimming and z-drop (the trimming makes
+// the result differ from an untrimmed band, so the evaluation order is part of the contract).
+// Q(j) / T(i) fetch the j-th query and i-th target base of this extension (0..4).
+// eh is a strided array of packed cells: low 16 bits = H, high 16 bits = E (both 0..32767).
+struct EhAcc {
+	u32 *base; int stride;
+	SSQ_HD u32 get(int j) const { return base[(size_t)j * stride]; }
+	SSQ_HD void set(int j, u32 v) const { base[(size_t)j * stride] = v; }
+};
+
+template <class QF, class TF>
+SSQ_HD int sw_extend(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, int w, int end_bonus, int zdrop, int h0, const EhAcc &eh,
+                     int &qle, int &tle, int &gtle, int &gscore_, int &max_off_, unsigned long long &cells)
+{
+	const int o_del = o.o_del, e_del = o.e_del, o_ins = o.o_ins, e_ins = o.e_ins;
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	int i, j, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
+	// row -1
+	eh.set(0, (u32)h0);
+	{
+		int h = h0 > oe_ins ? h0 - oe_ins : 0;
+		if (qlen >= 1) eh.set(1, (u32)h);
+		for (j = 2; j <= qlen && h > e_ins; ++j) { h -= e_ins; eh.set(j, (u32)h); }
+		for (; j <= qlen; ++j) eh.set(j, 0);
+	}
+	max = o.a; // largest matrix entry is the match score
+	max_ins = (int)((double)(qlen * max + end_bonus - o_ins) / e_ins + 1.);
+	max_ins = max_ins > 1 ? max_ins : 1;
+	w = w < max_ins ? w : max_ins;
+	max_del = (int)((double)(qlen * max + end_bonus - o_del) / e_del + 1.);
+	max_del = max_del > 1 ? max_del : 1;
+	w = w < max_del ? w : max_del;
+	max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+	beg = 0; end = qlen;
+	for (i = 0; i < tlen; ++i) {
+		int f = 0, h1, m = 0, mj = -1, t;
+		const int tb = T(i);
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+		for (j = beg; j < end; ++j) {
+			u32 p = eh.get(j);
+			int M = (int)(p & 0xffffu), e = (int)(p >> 16), h;
+			const int qb = Q(j);
+			const int sc = (qb > 3 || tb > 3) ? -1 : (qb == tb ? o.a : -o.b);
+			M = M ? M + sc : 0;
+			h = M > e ? M : e;
+			h = h > f ? h : f;
+			mj = m > h ? mj : j;
+			m = m > h ? m : h;
+			t = M - oe_del; t = t > 0 ? t : 0;
+			e -= e_del; e = e > t ? e : t;
+			eh.set(j, (u32)h1 | (u32)e << 16); // H(i,j-1) for the next row, E(i+1,j)
+			h1 = h;
+			t = M - oe_ins; t = t > 0 ? t : 0;
+			f -= e_ins; f = f > t ? f : t;
+		}
+		cells += (unsigned long long)(end > beg ? end - beg : 0);
+		eh.set(end, (u32)h1);
+		if (j == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+		if (m == 0) break;
+		if (m > max) {
+			max = m; max_i = i; max_j = mj;
+			int d = mj - i; d = d < 0 ? -d : d;
+			max_off = max_off > d ? max_off : d;
+		} else if (zdrop > 0) {
+			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break; }
+			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
+		}
+		for (j = beg; j < end && eh.get(j) == 0; ++j);
+		beg = j;
+		for (j = end; j >= beg && eh.get(j) == 0; --j);
+		end = j + 2 < qlen ? j + 2 : qlen;
+	}
+	qle = max_j + 1; tle = max_i + 1; gtle = max_ie + 1; gscore_ = gscore; max_off_ = max_off;
+	return max;
+}
+
+// One alignment-region candidate per seed of a kept chain: left then right extension (h0 of the right one is
+// the left score), up to two band widths each — mem_chain2aln()'s body for a single seed.
+struct RegCand { // == ssq_alnreg_t minus read_id bookkeeping
+	i64 rb, re;
+	i32 qb, qe, rid, score, truesc, w, seedcov, seedlen0;
+	float frac_rep;
+};
+
+SSQ_HD void chain_window(const DevIndex &ix, const ssq_opts_t &opt, int l_query, const Seed *cs, int n, i64 &rmax0, i64 &rmax1)
+{
+	const i64 l_pac = ix.l_pac;
+	rmax0 = l_pac << 1; rmax1 = 0;
+	for (int i = 0; i < n; ++i) {
+		i64 b = cs[i].rbeg - (cs[i].qbeg + cal_max_gap(opt, cs[i].qbeg));
+		i64 e = cs[i].rbeg + cs[i].len + ((l_query - cs[i].qbeg - cs[i].len) + cal_max_gap(opt, l_query - cs[i].qbeg - cs[i].len));
+		rmax0 = rmax0 < b ? rmax0 : b;
+		rmax1 = rmax1 > e ? rmax1 : e;
+	}
+	rmax0 = rmax0 > 0 ? rmax0 : 0;
+	rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+	if (rmax0 < l_pac && l_pac < rmax1) { if (cs[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+	// clamp to the contig holding the chain (bns_fetch_seq)
+	int is_rev;
+	int rid = pos2rid(ix, depos(ix, cs[0].rbeg, is_rev));
+	i64 far_beg = ix.ann_off[rid], far_end = far_beg + ix.ann_len[rid];
+	if (is_rev) { i64 t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+	rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
+	rmax1 = rmax1 < far_end ? rmax1 : far_end;
+}
+
+SSQ_HD void extend_seed(const DevIndex &ix, const ssq_opts_t &opt, int l_query, const uint8_t *query, const ChainRec &c, const Seed *cs,
+                        int si, const EhAcc &eh, RegCand &a, Counters *cnt_sw_calls_cells_bytes /* may be null */)
+{
+	i64 rmax0, rmax1;
+	int aw0 = opt.w, aw1 = opt.w, i;
+	unsigned long long cells = 0, calls = 0, bytes = 0;
+	const Seed s = cs[si];
+	chain_window(ix, opt, l_query, cs, c.n, rmax0, rmax1);
+	a.rid = c.rid; a.score = a.truesc = -1; a.w = opt.w;
+	if (s.qbeg) { // left: reversed query prefix against the reversed reference prefix
+		int qle, tle, gtle, gscore, max_off, tlen = (int)(s.rbeg - rmax0);
+		const uint8_t *qp = query + s.qbeg - 1;
+		const i64 rp = s.rbeg - 1;
+		for (i = 0; i < 2; ++i) {
+			int prev = a.score;
+			aw0 = opt.w << i;
+			a.score = sw_extend(opt, s.qbeg, [&](int j) { return (int)qp[-j]; }, tlen, [&](int t) { return ref_base(ix, rp - t); },
+			                    aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, eh, qle, tle, gtle, gscore, max_off, cells);
+			++calls; bytes += (unsigned long long)s.qbeg + (tlen + 3) / 4 + 24;
+			if (a.score == prev || max_off < (aw0 >> 1) + (aw0 >> 2)) break;
+		}
+		if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) { a.qb = s.qbeg - qle; a.rb = s.rbeg - tle; a.truesc = a.score; }
+		else { a.qb = 0; a.rb = s.rbeg - gtle; a.truesc = gscore; }
+	} else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+	if (s.qbeg + s.len != l_query) { // right
+		int qle, tle, gtle, gscore, max_off, sc0 = a.score, qe = s.qbeg + s.len;
+		const i64 re = s.rbeg + s.len;
+		const int tlen = (int)(rmax1 - re);
+		const uint8_t *qp = query + qe;
+		for (i = 0; i < 2; ++i) {
+			int prev = a.score;
+			aw1 = opt.w << i;
+			a.score = sw_extend(opt, l_query - qe, [&](int j) { return (int)qp[j]; }, tlen, [&](int t) { return ref_base(ix, re + t); },
+			                    aw1, opt.pen_clip3, opt.zdrop, sc0, eh, qle, tle, gtle, gscore, max_off, cells);
+			++calls; bytes += (unsigned long long)(l_query - qe) + (tlen + 3) / 4 + 24;
+			if (a.score == prev || max_off < (aw1 >> 1) + (aw1 >> 2)) break;
+		}
+		if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) { a.qe = qe + qle; a.re = re + tle; a.truesc += a.score - sc0; }
+		else { a.qe = l_query; a.re = re + gtle; a.truesc += gscore - sc0; }
+	} else { a.qe = l_query; a.re = s.rbeg + s.len; }
+	a.seedcov = 0;
+	for (i = 0; i < c.n; ++i)
+		if (cs[i].qbeg >= a.qb && cs[i].qbeg + cs[i].len <= a.qe && cs[i].rbeg >= a.rb && cs[i].rbeg + cs[i].len <= a.re) a.seedcov += cs[i].len;
+	a.w = aw0 > aw1 ? aw0 : aw1;
+	a.seedlen0 = s.len;
+	a.frac_rep = c.frac_rep;
+	if (cnt_sw_calls_cells_bytes) {
+#ifdef __CUDA_ARCH__
+		atomicAdd(&cnt_sw_calls_cells_bytes->sw_calls, calls);
+		atomicAdd(&cnt_sw_calls_cells_bytes->sw_cells, cells);
+		atomicAdd(&cnt_sw_calls_cells_bytes->sw_bytes, bytes);
+#else
+		cnt_sw_calls_cells_bytes->sw_calls += calls; cnt_sw_calls_cells_bytes->sw_cells += cells; cnt_sw_calls_cells_bytes->sw_bytes += bytes;
+#endif
+	}
+}
+
+// Replay of mem_chain2aln()'s seed loop for ONE chain with every seed's candidate already computed:
+// walks the seeds from longest to shortest, skips those explained by an accepted region of this read
+// (regions of earlier chains included), appends the rest to out[0..n_out).
+SSQ_HD void select_regions(const ssq_opts_t &opt, int l_query, const ChainRec &c, const Seed *cs, const RegCand *cand,
+                           u64 *srt /* scratch c.n */, RegCand *out, int &n_out)
+{
+	int i, k;
+	for (i = 0; i < c.n; ++i) srt[i] = (u64)(u32)cs[i].len << 32 | (u32)i; // seed score == len
+	for (i = 1; i < c.n; ++i) { u64 t = srt[i]; for (k = i; k > 0 && srt[k - 1] > t; --k) srt[k] = srt[k - 1]; srt[k] = t; } // keys are unique
+	for (k = c.n - 1; k >= 0; --k) {
+		const Seed s = cs[(u32)srt[k]];
+		for (i = 0; i < n_out; ++i) {
+			const RegCand &p = out[i];
+			i64 rd; int qd, w, max_gap;
+			if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+			if (s.len - p.seedlen0 > .1 * l_query) continue;
+			qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
+			max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+			w = max_gap < p.w ? max_gap : p.w;
+			if (qd - rd < w && rd - qd < w) break;
+			qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+			max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+			w = max_gap < p.w ? max_gap : p.w;
+			if (qd - rd < w && rd - qd < w) break;
+		}
+		if (i < n_out) {
+			for (i = k + 1; i < c.n; ++i) {
+				if (srt[i] == 0) continue;
+				const Seed t = cs[(u32)srt[i]];
+				if (t.len < s.len * .95) continue;
+				if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+				if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+			}
+			if (i == c.n) { srt[k] = 0; continue; }
+		}
+		out[n_out++] = cand[(u32)srt[k]];
+	}
+}

@@ -1,0 +1,747 @@
+// ssq_kernels.cu — sm_100a kernels of the alignment path and their stream-ordered launch sequence.
+//
+// Stage map (reference: inside `$BWA mem`, /root/reference/bin/speedseq:438):
+//   k_smem     a4  warp-per-read SMEM seeding, three passes; the 64-B occ block of each rank query is fetched by one
+//                  half-warp (one coalesced 64-B request), popcounts are done by 8 lanes and merged with shuffles.
+//                  Bound: random 64-B reads (L2 when the BWT fits its 126 MB, else HBM).
+//   k_sa       a5  thread-per-occurrence LF walk to the next sampled SA row. Same bound.
+//   k_chain    a6  thread-per-read chaining + chain filter (small, branchy, integer).
+//   k_extend   a7  thread-per-seed banded affine-gap extension, DP row state in shared memory (int16 H|E pairs,
+//                  bank-conflict-free striding), target bases streamed from the 2-bit reference. Integer-ALU bound.
+//   k_select       thread-per-read replay of the seed-skipping rules over the pre-computed candidates.
+// Scans use CUB (plumbing).  No CPU fallback exists in this library.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "ssq_dev.cuh"
+#include "ssq_host.h"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------ warp-cooperative FM context ----
+struct WarpFm {
+	const DevIndex &ix;
+	int lane;
+	unsigned long long n_blk;
+	__device__ WarpFm(const DevIndex &i, int l) : ix(i), lane(l), n_blk(0) {}
+	__device__ __forceinline__ void extend(const Intv &ik, Intv ok[4], int is_back)
+	{
+		const u64 kf = is_back ? ik.x0 : ik.x1, ko = is_back ? ik.x1 : ik.x0;
+		const u64 k = (lane & 16) ? kf - 1 + ik.x2 : kf - 1; // lower half-warp: row before the interval, upper: its last row
+		const bool valid = k != (u64)-1;
+		const u64 kk = k - (k >= ix.primary);
+		const int l16 = lane & 15;
+		u32 wv = 0, packed = 0;
+		if (valid) wv = __ldg(ix.bwt + ((kk >> 7) << 4) + l16); // 16 lanes x 4 B = the 64-B block
+		if (valid && l16 >= 8) {
+			const int n = (int)(kk & 127) + 1 - 16 * (l16 - 8);
+			if (n > 0) {
+				const u32 m = n >= 16 ? 0x55555555u : (0x55555555u & ~(0xffffffffu >> (2 * n)));
+				const u32 lo = wv & 0x55555555u, hi = (wv >> 1) & 0x55555555u;
+				packed = __popc(~hi & ~lo & m) | __popc(~hi & lo & m) << 8 | __popc(hi & ~lo & m) << 16 | __popc(hi & lo & m) << 24;
+			}
+		}
+		packed += __shfl_xor_sync(FULL, packed, 1);
+		packed += __shfl_xor_sync(FULL, packed, 2);
+		packed += __shfl_xor_sync(FULL, packed, 4); // lanes 8..15 / 24..31 now hold the per-block symbol counts
+		const u32 pa = __shfl_sync(FULL, packed, 8), pb = __shfl_sync(FULL, packed, 24);
+		u64 tk[4], tl[4];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			u32 alo = __shfl_sync(FULL, wv, 2 * c), ahi = __shfl_sync(FULL, wv, 2 * c + 1);
+			u32 blo = __shfl_sync(FULL, wv, 16 + 2 * c), bhi = __shfl_sync(FULL, wv, 17 + 2 * c);
+			tk[c] = ((u64)ahi << 32 | alo) + ((pa >> (8 * c)) & 0xff);
+			tl[c] = ((u64)bhi << 32 | blo) + ((pb >> (8 * c)) & 0xff);
+		}
+		n_blk += 2;
+		u64 nf[4], ns[4], no[4];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) { nf[c] = ix.L2[c] + 1 + tk[c]; ns[c] = tl[c] - tk[c]; }
+		no[3] = ko + (kf <= ix.primary && kf + ik.x2 - 1 >= ix.primary);
+		no[2] = no[3] + ns[3]; no[1] = no[2] + ns[2]; no[0] = no[1] + ns[1];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			ok[c].x2 = ns[c];
+			if (is_back) { ok[c].x0 = nf[c]; ok[c].x1 = no[c]; } else { ok[c].x1 = nf[c]; ok[c].x0 = no[c]; }
+		}
+	}
+};
+
+// ----------------------------------------------------------------------------- k_smem ----
+// grid: persistent, blockDim = 32*warps; dynamic smem = warps * 2*(lcap+1) * sizeof(Intv)
+__global__ void __launch_bounds__(256) k_smem(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                              int lcap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
+                                              u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+	Intv *bufA = (Intv*)smem_raw + (size_t)wib * 2 * (lcap + 1), *bufB = bufA + (lcap + 1);
+	Intv *mem = scratch + (size_t)(blockIdx.x * wpb + wib) * scratch_cap;
+	WarpFm fm(ix, lane);
+	for (;;) {
+		int r = 0;
+		if (lane == 0) r = atomicAdd(work, 1);
+		r = __shfl_sync(FULL, r, 0);
+		if (r >= n_reads) break;
+		const u64 off = read_off[r];
+		const int len = (int)(read_off[r + 1] - off);
+		int e = 0, n = 0;
+		if (len > lcap) e = 3;
+		else n = collect_intv(fm, ix, opt, len, seq + off, mem, scratch_cap, bufA, bufB, e);
+		if (e) { if (lane == 0) atomicMax(err, e); n = 0; }
+		// query bases covered by over-frequent seeds (frac_rep numerator)
+		int b = 0, en = 0, l_rep = 0;
+		for (int i = 0; i < n; ++i) {
+			const Intv p = mem[i];
+			if (p.x2 <= (u64)opt.max_occ) continue;
+			if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
+		}
+		l_rep += en - b;
+		unsigned long long base = 0;
+		if (lane == 0) base = atomicAdd(pool_n, (unsigned long long)n);
+		base = __shfl_sync(FULL, base, 0);
+		if (base + n > pool_cap) { if (lane == 0) atomicMax(err, 2); n = 0; }
+		__syncwarp();
+		for (int i = lane; i < n; i += 32) pool[base + i] = mem[i];
+		if (lane == 0) { intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep; }
+		__syncwarp();
+	}
+	if (lane == 0 && fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
+// ------------------------------------------------------------------------------- k_sa ----
+__global__ void k_occ_count(const Intv *__restrict__ pool, u64 n, int max_occ, u32 *nocc)
+{
+	u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n) return;
+	u64 step;
+	nocc[g] = (u32)intv_occ_count(pool[g].x2, max_occ, step);
+}
+
+__global__ void __launch_bounds__(256) k_sa(DevIndex ix, ssq_opts_t opt, const Intv *__restrict__ pool, const u64 *__restrict__ seed_off, u64 n_intv,
+                                            u64 n_seeds, Seed *seeds, Counters *cnt)
+{
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long n_sa = 0, n_blk = 0;
+	if (t < n_seeds) {
+		u64 lo = 0, hi = n_intv; // last g with seed_off[g] <= t
+		while (hi - lo > 1) { u64 mid = (lo + hi) >> 1; if (seed_off[mid] <= t) lo = mid; else hi = mid; }
+		const Intv p = pool[lo];
+		u64 step;
+		intv_occ_count(p.x2, opt.max_occ, step);
+		ScalarFm fm(ix);
+		Seed s;
+		s.rbeg = (i64)sa_lookup(fm, p.x0 + (t - seed_off[lo]) * step, n_sa);
+		s.qbeg = (i32)p.qb; s.len = (i32)(p.qe - p.qb);
+		seeds[t] = s;
+		n_blk = fm.n_blk;
+	}
+	// one atomic per warp
+	for (int o = 16; o; o >>= 1) { n_sa += __shfl_xor_sync(FULL, n_sa, o); n_blk += __shfl_xor_sync(FULL, n_blk, o); }
+	if ((threadIdx.x & 31) == 0 && n_sa) { atomicAdd(&cnt->sa_reads, n_sa); atomicAdd(&cnt->occ_sa, n_blk); }
+}
+
+__global__ void k_sa_rows(DevIndex ix, u64 n, const u64 *__restrict__ rows, u64 *pos)
+{
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	ScalarFm fm(ix);
+	unsigned long long n_sa = 0;
+	pos[t] = sa_lookup(fm, rows[t], n_sa);
+}
+
+// ---------------------------------------------------------------------------- k_chain ----
+__global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
+                                               const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
+                                               const Seed *__restrict__ seeds, i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc,
+                                               i32 *n_kept, u32 *n_kseeds)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int len = (int)(read_off[r + 1] - read_off[r]);
+	const int ni = intv_cnt[r];
+	int nk = 0; u32 ns = 0;
+	if (ni > 0) {
+		const u64 s0 = seed_off[intv_off[r]], s1 = seed_off[intv_off[r] + ni];
+		const int n = (int)(s1 - s0);
+		if (n > 0) {
+			nk = chain_and_filter(ix, opt, len, n, seeds + s0, l_rep[r], chain_of + s0, ch + s0, ord + s0, wi + s0, sorted + s0, outc + s0);
+			for (int c = 0; c < nk; ++c) ns += (u32)outc[s0 + c].n;
+		}
+	}
+	n_kept[r] = nk; n_kseeds[r] = ns;
+}
+
+// --------------------------------------------------------------------------- k_extend ----
+struct Task { i32 read, chain, seed; };
+
+__global__ void k_tasks(int n_reads, const u64 *__restrict__ intv_off, const i32 *__restrict__ intv_cnt, const u64 *__restrict__ seed_off,
+                        const ChainRec *__restrict__ outc, const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, Task *tasks)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads || n_kept[r] == 0) return;
+	const u64 s0 = seed_off[intv_off[r]];
+	u64 t = task_off[r];
+	for (int c = 0; c < n_kept[r]; ++c)
+		for (int s = 0; s < outc[s0 + c].n; ++s) { Task k; k.read = r; k.chain = c; k.seed = s; tasks[t++] = k; }
+}
+
+// dynamic smem: blockDim.x * (qmax + 2) * 4 bytes, cell j of thread t at word j*blockDim.x + t
+__global__ void __launch_bounds__(64) k_extend(DevIndex ix, ssq_opts_t opt, u64 n_tasks, const Task *__restrict__ tasks, const uint8_t *__restrict__ seq,
+                                               const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off, const u64 *__restrict__ seed_off,
+                                               const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted, RegCand *cand, Counters *cnt)
+{
+	extern __shared__ u32 eh_smem[];
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tasks) return;
+	const Task k = tasks[t];
+	const u64 s0 = seed_off[intv_off[k.read]];
+	const ChainRec c = outc[s0 + k.chain];
+	EhAcc eh; eh.base = eh_smem + threadIdx.x; eh.stride = blockDim.x;
+	RegCand a;
+	extend_seed(ix, opt, (int)(read_off[k.read + 1] - read_off[k.read]), seq + read_off[k.read], c, sorted + s0 + c.seed_start, k.seed, eh, a, cnt);
+	cand[t] = a;
+}
+
+// batch form of ksw_extend2 on explicit byte sequences (C-ABI ssq_sw_extend_batch)
+__global__ void __launch_bounds__(64) k_sw_tasks(ssq_opts_t opt, u64 n, const ssq_sw_task_t *__restrict__ tk, const uint8_t *__restrict__ qbuf,
+                                                 const uint8_t *__restrict__ tbuf, ssq_sw_result_t *out)
+{
+	extern __shared__ u32 eh_smem[];
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const ssq_sw_task_t k = tk[t];
+	const uint8_t *q = qbuf + k.q_off, *tg = tbuf + k.t_off;
+	EhAcc eh; eh.base = eh_smem + threadIdx.x; eh.stride = blockDim.x;
+	ssq_sw_result_t r;
+	unsigned long long cells = 0;
+	r.score = sw_extend(opt, k.qlen, [&](int j) { return (int)q[j]; }, k.tlen, [&](int i) { return (int)tg[i]; }, k.w, k.end_bonus, k.zdrop, k.h0, eh,
+	                    r.qle, r.tle, r.gtle, r.gscore, r.max_off, cells);
+	out[t] = r;
+}
+
+// --------------------------------------------------------------------------- k_select ----
+__global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
+                                                const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
+                                                const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, const RegCand *__restrict__ cand, u64 *srt,
+                                                RegCand *regs, u32 *n_regs)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	int n_out = 0;
+	if (n_kept[r] > 0) {
+		const u64 s0 = seed_off[intv_off[r]];
+		const int len = (int)(read_off[r + 1] - read_off[r]);
+		u64 t = task_off[r];
+		RegCand *out = regs + task_off[r];
+		for (int c = 0; c < n_kept[r]; ++c) {
+			const ChainRec ch = outc[s0 + c];
+			select_regions(opt, len, ch, sorted + s0 + ch.seed_start, cand + t, srt + t, out, n_out);
+			t += ch.n;
+		}
+	}
+	n_regs[r] = (u32)n_out;
+}
+
+__global__ void k_gather_regs(int n_reads, const u64 *__restrict__ task_off, const u64 *__restrict__ reg_off, const u32 *__restrict__ n_regs,
+                              const RegCand *__restrict__ regs, ssq_alnreg_t *out)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	for (u32 i = 0; i < n_regs[r]; ++i) {
+		const RegCand a = regs[task_off[r] + i];
+		ssq_alnreg_t o;
+		o.rb = a.rb; o.re = a.re; o.qb = a.qb; o.qe = a.qe; o.rid = a.rid; o.score = a.score; o.truesc = a.truesc; o.w = a.w;
+		o.seedcov = a.seedcov; o.seedlen0 = a.seedlen0; o.frac_rep = a.frac_rep; o.read_id = r;
+		out[reg_off[r] + i] = o;
+	}
+}
+
+__global__ void k_gather_intv(int n_reads, const u64 *__restrict__ intv_off, const i32 *__restrict__ intv_cnt, const u64 *__restrict__ dst_off,
+                              const Intv *__restrict__ pool, ssq_smem_t *out)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	for (int i = 0; i < intv_cnt[r]; ++i) {
+		const Intv p = pool[intv_off[r] + i];
+		ssq_smem_t o; o.k = p.x0; o.l = p.x1; o.s = p.x2; o.qbeg = p.qb; o.qend = p.qe;
+		out[dst_off[r] + i] = o;
+	}
+}
+
+__global__ void k_gather_chains(int n_reads, const u64 *__restrict__ intv_off, const i32 *__restrict__ intv_cnt, const u64 *__restrict__ seed_off,
+                                const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted, const i32 *__restrict__ n_kept,
+                                const u64 *__restrict__ chain_dst, const u64 *__restrict__ seed_dst, ssq_seed_t *seeds_out, u64 *chain_seed_off)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads || n_kept[r] == 0) return;
+	const u64 s0 = seed_off[intv_off[r]];
+	u64 so = seed_dst[r];
+	for (int c = 0; c < n_kept[r]; ++c) {
+		const ChainRec ch = outc[s0 + c];
+		chain_seed_off[chain_dst[r] + c] = so;
+		for (int s = 0; s < ch.n; ++s) {
+			const Seed x = sorted[s0 + ch.seed_start + s];
+			ssq_seed_t o; o.rbeg = x.rbeg; o.qbeg = x.qbeg; o.len = x.len;
+			seeds_out[so++] = o;
+		}
+	}
+}
+
+__global__ void k_widen_i32(int n, const i32 *in, u64 *out) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (u64)in[i]; }
+__global__ void k_widen_u32(u64 n, const u32 *in, u64 *out) { u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (u64)in[i]; }
+
+// --------------------------------------------------------------------------- dup-mark ----
+__global__ void k_dup_keys(u64 n, const ssq_dupsig_t *__restrict__ sig, u64 *key1, u64 *key2, u32 *idx)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const ssq_dupsig_t s = sig[i];
+	key1[i] = s.valid ? (s.pos1 << 1 | (s.strand1 & 1)) : ~0ull;
+	key2[i] = s.valid ? (s.pos2 << 1 | (s.strand2 & 1)) : ~0ull;
+	idx[i] = (u32)i;
+}
+__global__ void k_dup_gather(u64 n, const u32 *__restrict__ idx, const u64 *__restrict__ key1, u64 *key1g)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) key1g[i] = key1[idx[i]];
+}
+// after the two stable passes elements are ordered by (key1, key2, input ordinal): every element equal to its
+// predecessor is a later occurrence of the same signature
+__global__ void k_dup_mark(u64 n, const u32 *__restrict__ idx, const u64 *__restrict__ key1s, const u64 *__restrict__ key2, const ssq_dupsig_t *__restrict__ sig, uint8_t *is_dup)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u32 me = idx[i];
+	uint8_t d = 0;
+	if (i > 0 && sig[me].valid) {
+		const u32 pv = idx[i - 1];
+		d = sig[pv].valid && key1s[i] == key1s[i - 1] && key2[me] == key2[pv];
+	}
+	is_dup[me] = d;
+}
+
+// ===================================================================== host-side launch code ====
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ssq_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return SSQ_ECUDA; } } while (0)
+
+struct DBuf { // growable device buffer
+	void *p; size_t cap;
+	DBuf() : p(0), cap(0) {}
+	~DBuf() { release(); }
+	int need(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		size_t want = bytes + bytes / 4 + 256;
+		if (cudaMalloc(&p, want) != cudaSuccess) { p = 0; cap = 0; ssq_set_error("cudaMalloc(%zu) failed", want); return SSQ_ENOMEM; }
+		cap = want; return 0;
+	}
+	void release() { if (p) cudaFree(p); p = 0; cap = 0; }
+	template <class T> T *as() { return (T*)p; }
+};
+
+struct ssq_batch {
+	const ssq_index *idx;
+	ssq_opts_t opt;
+	int n_reads, max_len, n_sm;
+	cudaStream_t st;
+	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
+	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
+	u64 n_intv, n_seeds, n_tasks, n_regs_total;
+	u64 pool_cap;
+	Counters h_cnt;
+	int launches;
+	cudaEvent_t ev[6];
+	float stage_ms[5];
+	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; pool_cap = 0; memset(stage_ms, 0, sizeof stage_ms); }
+};
+
+// misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
+struct Misc { unsigned long long pool_n; int work, err; Counters cnt; };
+
+static int scan_u64(ssq_batch *b, const u64 *in, u64 *out, size_t n) // exclusive sum, out has n+1 entries (out[n] = total)
+{
+	size_t tmp = 0;
+	cub::DeviceScan::ExclusiveSum(0, tmp, in, out, (int)n, b->st);
+	if (b->cubtmp.need(tmp)) return SSQ_ENOMEM;
+	CK(cub::DeviceScan::ExclusiveSum(b->cubtmp.p, tmp, in, out, (int)n, b->st));
+	return 0;
+}
+
+extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off, ssq_batch_t **out)
+{
+	if (!idx || !opt || n_reads < 0 || !read_off || !out) return SSQ_EINVAL;
+	int rc = ssq_use_device(idx->device);
+	if (rc) return rc;
+	ssq_batch *b = new ssq_batch();
+	b->idx = idx; b->opt = *opt; b->n_reads = n_reads;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, idx->device));
+	b->n_sm = prop.multiProcessorCount;
+	CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
+	b->max_len = 0;
+	for (int i = 0; i < n_reads; ++i) { int l = (int)(read_off[i + 1] - read_off[i]); if (l > b->max_len) b->max_len = l; }
+	if (b->max_len > SSQ_MAX_READ_LEN) { ssq_set_error("read longer than %d bases", SSQ_MAX_READ_LEN); delete b; return SSQ_ELEN; }
+	const u64 total = read_off[n_reads];
+	if (b->seq.need(total + 16) || b->read_off.need((size_t)(n_reads + 1) * 8)) { delete b; return SSQ_ENOMEM; }
+	CK(cudaMemcpyAsync(b->seq.p, seq, total, cudaMemcpyHostToDevice, b->st));
+	CK(cudaMemcpyAsync(b->read_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	*out = b;
+	return SSQ_OK;
+}
+
+extern "C" void ssq_batch_free(ssq_batch_t *b)
+{
+	if (!b) return;
+	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
+	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
+	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out};
+	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
+	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
+	cudaStreamDestroy(b->st);
+	delete b;
+}
+
+extern "C" void *ssq_batch_stream(ssq_batch_t *b) { return (void*)b->st; }
+extern "C" int ssq_batch_sync(ssq_batch_t *b) { CK(cudaStreamSynchronize(b->st)); return SSQ_OK; }
+
+// stage A: seeding (+ pool overflow retry). leaves intervals in pool, per-read (intv_off, intv_cnt, l_rep)
+static int run_smem(ssq_batch *b)
+{
+	const int n = b->n_reads, lcap = b->max_len > 0 ? b->max_len : 1;
+	const int warps_per_block = 4, threads = warps_per_block * 32;
+	const size_t smem = (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv);
+	int blocks_per_sm = (int)((200 * 1024) / (smem + 1024));
+	if (blocks_per_sm > 8) blocks_per_sm = 8;
+	if (blocks_per_sm < 1) blocks_per_sm = 1;
+	const int grid = b->n_sm * blocks_per_sm;
+	const int scratch_cap = 2048;
+	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
+	if (b->scratch.need((size_t)grid * warps_per_block * scratch_cap * sizeof(Intv))) return SSQ_ENOMEM;
+	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc))) return SSQ_ENOMEM;
+	CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	for (int attempt = 0; attempt < 6; ++attempt) {
+		if (b->pool.need(b->pool_cap * sizeof(Intv))) return SSQ_ENOMEM;
+		CK(cudaMemsetAsync(b->misc.p, 0, sizeof(Misc), b->st));
+		k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
+		                                      b->pool.as<Intv>(), b->pool_cap, &b->misc.as<Misc>()->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(),
+		                                      b->l_rep.as<i32>(), &b->misc.as<Misc>()->work, &b->misc.as<Misc>()->err, &b->misc.as<Misc>()->cnt);
+		++b->launches;
+		CK(cudaGetLastError());
+		Misc hm;
+		CK(cudaMemcpyAsync(&hm, b->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, b->st));
+		CK(cudaStreamSynchronize(b->st));
+		if (hm.err == 0) { b->n_intv = hm.pool_n; return SSQ_OK; }
+		if (hm.err == 2) { b->pool_cap = hm.pool_n + hm.pool_n / 8 + 4096; continue; } // pool too small: its true size is now known
+		ssq_set_error(hm.err == 3 ? "read longer than the kernel's length cap" : "a read produced more than %d seed intervals", scratch_cap);
+		return hm.err == 3 ? SSQ_ELEN : SSQ_ECAP;
+	}
+	ssq_set_error("interval pool kept overflowing");
+	return SSQ_ECAP;
+}
+
+// stage B: SA look-ups -> seeds (read-contiguous)
+static int run_sa(ssq_batch *b)
+{
+	const u64 ni = b->n_intv;
+	if (b->nocc.need((ni + 1) * 4) || b->seed_off.need((ni + 2) * 8) || b->tasks.need((ni + 1) * 8)) return SSQ_ENOMEM; // tasks reused as temp u64
+	b->n_seeds = 0;
+	if (ni == 0) { CK(cudaMemsetAsync(b->seed_off.p, 0, 16, b->st)); return SSQ_OK; }
+	k_occ_count<<<(unsigned)((ni + 255) / 256), 256, 0, b->st>>>(b->pool.as<Intv>(), ni, b->opt.max_occ, b->nocc.as<u32>());
+	k_widen_u32<<<(unsigned)((ni + 255) / 256), 256, 0, b->st>>>(ni, b->nocc.as<u32>(), b->tasks.as<u64>());
+	b->launches += 2;
+	int rc = scan_u64(b, b->tasks.as<u64>(), b->seed_off.as<u64>(), ni + 1); // ni+1 inputs so that out[ni] = total (input[ni] is ignored garbage)
+	if (rc) return rc;
+	++b->launches;
+	CK(cudaMemcpyAsync(&b->n_seeds, b->seed_off.as<u64>() + ni, 8, cudaMemcpyDeviceToHost, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	if (b->seeds.need((b->n_seeds + 1) * sizeof(Seed))) return SSQ_ENOMEM;
+	if (b->n_seeds) {
+		k_sa<<<(unsigned)((b->n_seeds + 255) / 256), 256, 0, b->st>>>(b->idx->dev, b->opt, b->pool.as<Intv>(), b->seed_off.as<u64>(), ni, b->n_seeds, b->seeds.as<Seed>(),
+		                                                               &b->misc.as<Misc>()->cnt);
+		++b->launches;
+		CK(cudaGetLastError());
+	}
+	return SSQ_OK;
+}
+
+// stage C: chaining + filter
+static int run_chain(ssq_batch *b)
+{
+	const int n = b->n_reads;
+	const u64 ns = b->n_seeds + 1;
+	if (b->chain_of.need(ns * 4) || b->ch.need(ns * sizeof(ChainRec)) || b->ord.need(ns * 4) || b->wi.need(ns * sizeof(WIdx)) || b->sorted.need(ns * sizeof(Seed)) ||
+	    b->outc.need(ns * sizeof(ChainRec)) || b->n_kept.need((size_t)(n + 1) * 4) || b->n_kseeds.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+	if (n) {
+		k_chain<<<(n + 127) / 128, 128, 0, b->st>>>(b->idx->dev, b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
+		                                           b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
+		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>());
+		++b->launches;
+		CK(cudaGetLastError());
+	}
+	return SSQ_OK;
+}
+
+// stage D: task list + extension ; stage E: selection
+static int run_extend(ssq_batch *b)
+{
+	const int n = b->n_reads;
+	if (b->task_off.need((size_t)(n + 2) * 8) || b->reg_off.need((size_t)(n + 2) * 8) || b->n_regs.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+	b->n_tasks = 0;
+	if (n == 0) return SSQ_OK;
+	// reg_off used as a temp for the widened counts
+	k_widen_u32<<<(n + 255) / 256, 256, 0, b->st>>>((u64)n, b->n_kseeds.as<u32>(), b->reg_off.as<u64>());
+	int rc = scan_u64(b, b->reg_off.as<u64>(), b->task_off.as<u64>(), (size_t)n + 1);
+	if (rc) return rc;
+	b->launches += 2;
+	CK(cudaMemcpyAsync(&b->n_tasks, b->task_off.as<u64>() + n, 8, cudaMemcpyDeviceToHost, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	const u64 nt = b->n_tasks;
+	if (b->tasks.need((nt + 1) * sizeof(Task)) || b->cand.need((nt + 1) * sizeof(RegCand)) || b->srt.need((nt + 1) * 8) || b->regs.need((nt + 1) * sizeof(RegCand))) return SSQ_ENOMEM;
+	CK(cudaEventRecord(b->ev[3], b->st));
+	if (nt) {
+		k_tasks<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(),
+		                                           b->task_off.as<u64>(), b->tasks.as<Task>());
+		const int threads = 64;
+		const size_t smem = (size_t)threads * (b->max_len + 2) * 4;
+		CK(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_extend<<<(unsigned)((nt + threads - 1) / threads), threads, smem, b->st>>>(b->idx->dev, b->opt, nt, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+		                                                                            b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+		                                                                            b->cand.as<RegCand>(), &b->misc.as<Misc>()->cnt);
+		b->launches += 2;
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(b->ev[4], b->st));
+	k_select<<<(n + 127) / 128, 128, 0, b->st>>>(b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+	                                            b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>());
+	++b->launches;
+	CK(cudaGetLastError());
+	return SSQ_OK;
+}
+
+static int run_upto(ssq_batch *b, int last_stage) // 0 smem, 1 sa, 2 chain, 3 extend+select
+{
+	int rc;
+	b->launches = 0;
+	CK(cudaEventRecord(b->ev[0], b->st));
+	if ((rc = run_smem(b))) return rc;
+	CK(cudaEventRecord(b->ev[1], b->st));
+	if (last_stage >= 1 && (rc = run_sa(b))) return rc;
+	CK(cudaEventRecord(b->ev[2], b->st));
+	if (last_stage >= 2 && (rc = run_chain(b))) return rc;
+	CK(cudaEventRecord(b->ev[3], b->st));
+	CK(cudaEventRecord(b->ev[4], b->st));
+	if (last_stage >= 3 && (rc = run_extend(b))) return rc;
+	CK(cudaEventRecord(b->ev[5], b->st));
+	return SSQ_OK;
+}
+
+extern "C" int ssq_batch_run(ssq_batch_t *b)
+{
+	int rc = ssq_use_device(b->idx->device);
+	if (rc) return rc;
+	return run_upto(b, 3);
+}
+
+static int finish_counters(ssq_batch *b)
+{
+	Misc hm;
+	CK(cudaMemcpyAsync(&hm, b->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	b->h_cnt = hm.cnt;
+	for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&b->stage_ms[i], b->ev[i], b->ev[i + 1]);
+	return SSQ_OK;
+}
+
+extern "C" uint64_t ssq_batch_counter(const ssq_batch_t *b_, int what)
+{
+	ssq_batch *b = (ssq_batch*)b_;
+	if (finish_counters(b)) return 0;
+	switch (what) {
+	case 0: return b->h_cnt.occ_smem; case 1: return b->h_cnt.occ_sa; case 2: return b->h_cnt.sa_reads; case 3: return b->h_cnt.sw_calls;
+	case 4: return b->h_cnt.sw_cells; case 5: return b->h_cnt.sw_bytes; case 6: return (uint64_t)b->launches; case 7: return b->n_seeds; case 8: return b->n_regs_total;
+	case 9: return b->n_intv; case 10: return b->n_tasks;
+	}
+	return 0;
+}
+
+extern "C" float ssq_batch_stage_ms(const ssq_batch_t *b_, int stage)
+{
+	ssq_batch *b = (ssq_batch*)b_;
+	if (stage < 0 || stage > 4 || finish_counters(b)) return -1.f;
+	return b->stage_ms[stage];
+}
+
+extern "C" int ssq_batch_fetch(ssq_batch_t *b, ssq_alnreg_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed)
+{
+	const int n = b->n_reads;
+	int rc = ssq_use_device(b->idx->device);
+	if (rc) return rc;
+	if (n == 0) { if (out_off) out_off[0] = 0; if (needed) *needed = 0; return SSQ_OK; }
+	if (b->srt.need((size_t)(n + 2) * 8)) return SSQ_ENOMEM; // temp for widened counts (selection is finished by now)
+	k_widen_u32<<<(n + 255) / 256, 256, 0, b->st>>>((u64)n, b->n_regs.as<u32>(), b->srt.as<u64>());
+	if ((rc = scan_u64(b, b->srt.as<u64>(), b->reg_off.as<u64>(), (size_t)n + 1))) return rc;
+	CK(cudaMemcpyAsync(&b->n_regs_total, b->reg_off.as<u64>() + n, 8, cudaMemcpyDeviceToHost, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	if (needed) *needed = b->n_regs_total;
+	if (out_off) CK(cudaMemcpyAsync(out_off, b->reg_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, b->st));
+	if (b->n_regs_total > out_cap || !out) { CK(cudaStreamSynchronize(b->st)); return b->n_regs_total > out_cap ? SSQ_ECAP : SSQ_OK; }
+	if (b->out.need((b->n_regs_total + 1) * sizeof(ssq_alnreg_t))) return SSQ_ENOMEM;
+	k_gather_regs<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->task_off.as<u64>(), b->reg_off.as<u64>(), b->n_regs.as<u32>(), b->regs.as<RegCand>(), b->out.as<ssq_alnreg_t>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, b->out.p, b->n_regs_total * sizeof(ssq_alnreg_t), cudaMemcpyDeviceToHost, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	return SSQ_OK;
+}
+
+extern "C" int ssq_align_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
+                               int stage, ssq_alnreg_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed)
+{
+	ssq_batch_t *b = 0;
+	if (stage != 0) { ssq_set_error("ssq_align_batch: only stage 0 (regions out of seed extension) is implemented"); return SSQ_EINVAL; }
+	int rc = ssq_batch_create(idx, opt, n_reads, seq, read_off, &b);
+	if (rc) return rc;
+	rc = ssq_batch_run(b);
+	if (!rc) rc = ssq_batch_fetch(b, out, out_cap, out_off, needed);
+	ssq_batch_free(b);
+	return rc;
+}
+
+// ------------------------------------------------------------ kernel-level C-ABI entry points ----
+extern "C" int ssq_smem_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
+                              ssq_smem_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed)
+{
+	ssq_batch_t *b = 0;
+	int rc = ssq_batch_create(idx, opt, n_reads, seq, read_off, &b);
+	if (rc) return rc;
+	rc = run_upto(b, 0);
+	if (!rc && n_reads > 0) {
+		const int n = n_reads;
+		do {
+			if (b->srt.need((size_t)(n + 2) * 8) || b->reg_off.need((size_t)(n + 2) * 8)) { rc = SSQ_ENOMEM; break; }
+			k_widen_i32<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_cnt.as<i32>(), b->srt.as<u64>());
+			if ((rc = scan_u64(b, b->srt.as<u64>(), b->reg_off.as<u64>(), (size_t)n + 1))) break;
+			if (needed) *needed = b->n_intv;
+			if (cudaMemcpyAsync(out_off, b->reg_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, b->st) != cudaSuccess) { rc = SSQ_ECUDA; break; }
+			if (b->n_intv > out_cap) { cudaStreamSynchronize(b->st); rc = SSQ_ECAP; break; }
+			if (b->out.need((b->n_intv + 1) * sizeof(ssq_smem_t))) { rc = SSQ_ENOMEM; break; }
+			k_gather_intv<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->reg_off.as<u64>(), b->pool.as<Intv>(), b->out.as<ssq_smem_t>());
+			if (cudaMemcpyAsync(out, b->out.p, b->n_intv * sizeof(ssq_smem_t), cudaMemcpyDeviceToHost, b->st) != cudaSuccess || cudaStreamSynchronize(b->st) != cudaSuccess) {
+				ssq_set_error("copy-back failed: %s", cudaGetErrorString(cudaGetLastError())); rc = SSQ_ECUDA;
+			}
+		} while (0);
+	} else if (!rc) { out_off[0] = 0; if (needed) *needed = 0; }
+	ssq_batch_free(b);
+	return rc;
+}
+
+extern "C" int ssq_chain_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
+                               ssq_seed_t *seeds, uint64_t seed_cap, uint64_t *chain_seed_off, uint64_t chain_cap, uint64_t *read_chain_off,
+                               uint64_t *n_chains, uint64_t *n_seeds)
+{
+	ssq_batch_t *b = 0;
+	int rc = ssq_batch_create(idx, opt, n_reads, seq, read_off, &b);
+	if (rc) return rc;
+	rc = run_upto(b, 2);
+	const int n = n_reads;
+	if (!rc && n > 0) {
+		do {
+			DBuf cdst, sdst, tmp, d_seeds, d_cso;
+			u64 nc = 0, ns = 0;
+			if (cdst.need((size_t)(n + 2) * 8) || sdst.need((size_t)(n + 2) * 8) || tmp.need((size_t)(n + 2) * 8)) { rc = SSQ_ENOMEM; break; }
+			k_widen_i32<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->n_kept.as<i32>(), tmp.as<u64>());
+			if ((rc = scan_u64(b, tmp.as<u64>(), cdst.as<u64>(), (size_t)n + 1))) break;
+			k_widen_u32<<<(n + 255) / 256, 256, 0, b->st>>>((u64)n, b->n_kseeds.as<u32>(), tmp.as<u64>());
+			if ((rc = scan_u64(b, tmp.as<u64>(), sdst.as<u64>(), (size_t)n + 1))) break;
+			cudaMemcpyAsync(&nc, cdst.as<u64>() + n, 8, cudaMemcpyDeviceToHost, b->st);
+			cudaMemcpyAsync(&ns, sdst.as<u64>() + n, 8, cudaMemcpyDeviceToHost, b->st);
+			cudaMemcpyAsync(read_chain_off, cdst.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, b->st);
+			if (cudaStreamSynchronize(b->st) != cudaSuccess) { rc = SSQ_ECUDA; break; }
+			if (n_chains) *n_chains = nc;
+			if (n_seeds) *n_seeds = ns;
+			if (nc > chain_cap || ns > seed_cap) { rc = SSQ_ECAP; cdst.release(); sdst.release(); tmp.release(); break; }
+			if (d_seeds.need((ns + 1) * sizeof(ssq_seed_t)) || d_cso.need((nc + 2) * 8)) { rc = SSQ_ENOMEM; break; }
+			k_gather_chains<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+			                                                   b->n_kept.as<i32>(), cdst.as<u64>(), sdst.as<u64>(), d_seeds.as<ssq_seed_t>(), d_cso.as<u64>());
+			cudaMemcpyAsync(seeds, d_seeds.p, ns * sizeof(ssq_seed_t), cudaMemcpyDeviceToHost, b->st);
+			cudaMemcpyAsync(chain_seed_off, d_cso.p, nc * 8, cudaMemcpyDeviceToHost, b->st);
+			if (cudaStreamSynchronize(b->st) != cudaSuccess) { ssq_set_error("chain copy-back: %s", cudaGetErrorString(cudaGetLastError())); rc = SSQ_ECUDA; }
+			chain_seed_off[nc] = ns;
+			cdst.release(); sdst.release(); tmp.release(); d_seeds.release(); d_cso.release();
+		} while (0);
+	} else if (!rc) { read_chain_off[0] = 0; chain_seed_off[0] = 0; if (n_chains) *n_chains = 0; if (n_seeds) *n_seeds = 0; }
+	ssq_batch_free(b);
+	return rc;
+}
+
+extern "C" int ssq_sa_lookup_batch(const ssq_index_t *idx, uint64_t n, const uint64_t *rows, uint64_t *pos)
+{
+	int rc = ssq_use_device(idx->device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	DBuf in, out;
+	if (in.need(n * 8) || out.need(n * 8)) return SSQ_ENOMEM;
+	CK(cudaMemcpy(in.p, rows, n * 8, cudaMemcpyHostToDevice));
+	k_sa_rows<<<(unsigned)((n + 255) / 256), 256>>>(idx->dev, n, in.as<u64>(), out.as<u64>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(pos, out.p, n * 8, cudaMemcpyDeviceToHost));
+	in.release(); out.release();
+	return SSQ_OK;
+}
+
+extern "C" int ssq_sw_extend_batch(const ssq_opts_t *opt, int device, uint64_t n, const ssq_sw_task_t *tasks,
+                                   const uint8_t *qbuf, uint64_t qbuf_len, const uint8_t *tbuf, uint64_t tbuf_len, ssq_sw_result_t *out)
+{
+	int rc = ssq_use_device(device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	int qmax = 0;
+	for (u64 i = 0; i < n; ++i) {
+		if (tasks[i].qlen < 1 || tasks[i].qlen > SSQ_MAX_READ_LEN || tasks[i].h0 < 1 || tasks[i].q_off + tasks[i].qlen > qbuf_len || tasks[i].t_off + tasks[i].tlen > tbuf_len) {
+			ssq_set_error("ssq_sw_extend_batch: task %llu out of range", (unsigned long long)i); return SSQ_EINVAL;
+		}
+		if (tasks[i].qlen > qmax) qmax = tasks[i].qlen;
+	}
+	DBuf dt, dq, dtb, dout;
+	if (dt.need(n * sizeof(ssq_sw_task_t)) || dq.need(qbuf_len + 16) || dtb.need(tbuf_len + 16) || dout.need(n * sizeof(ssq_sw_result_t))) return SSQ_ENOMEM;
+	CK(cudaMemcpy(dt.p, tasks, n * sizeof(ssq_sw_task_t), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(dq.p, qbuf, qbuf_len, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(dtb.p, tbuf, tbuf_len, cudaMemcpyHostToDevice));
+	const int threads = 64;
+	const size_t smem = (size_t)threads * (qmax + 2) * 4;
+	CK(cudaFuncSetAttribute(k_sw_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_sw_tasks<<<(unsigned)((n + threads - 1) / threads), threads, smem>>>(*opt, n, dt.as<ssq_sw_task_t>(), dq.as<uint8_t>(), dtb.as<uint8_t>(), dout.as<ssq_sw_result_t>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(out, dout.p, n * sizeof(ssq_sw_result_t), cudaMemcpyDeviceToHost));
+	dt.release(); dq.release(); dtb.release(); dout.release();
+	return SSQ_OK;
+}
+
+extern "C" int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig, uint8_t *is_dup)
+{
+	int rc = ssq_use_device(device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	if (n >= 0xffffffffull) { ssq_set_error("ssq_dupmark_batch: more than 2^32-1 pairs in one call"); return SSQ_EINVAL; }
+	DBuf dsig, k1, k2, k1g, ka, idx_a, idx_b, tmp, dd;
+	if (dsig.need(n * sizeof(ssq_dupsig_t)) || k1.need(n * 8) || k2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dd.need(n)) return SSQ_ENOMEM;
+	CK(cudaMemcpy(dsig.p, sig, n * sizeof(ssq_dupsig_t), cudaMemcpyHostToDevice));
+	const unsigned g = (unsigned)((n + 255) / 256);
+	k_dup_keys<<<g, 256>>>(n, dsig.as<ssq_dupsig_t>(), k1.as<u64>(), k2.as<u64>(), idx_a.as<u32>());
+	size_t tb = 0;
+	cub::DeviceRadixSort::SortPairs(0, tb, k2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n);
+	if (tmp.need(tb)) return SSQ_ENOMEM;
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n)); // stable, by key2
+	k_dup_gather<<<g, 256>>>(n, idx_b.as<u32>(), k1.as<u64>(), k1g.as<u64>());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n)); // stable, by key1
+	k_dup_mark<<<g, 256>>>(n, idx_a.as<u32>(), ka.as<u64>(), k2.as<u64>(), dsig.as<ssq_dupsig_t>(), dd.as<uint8_t>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(is_dup, dd.p, n, cudaMemcpyDeviceToHost));
+	DBuf *all[] = {&dsig, &k1, &k2, &k1g, &ka, &idx_a, &idx_b, &tmp, &dd};
+	for (size_t i = 0; i < 9; ++i) all[i]->release();
+	return SSQ_OK;
+}

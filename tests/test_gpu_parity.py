@@ -1,0 +1,159 @@
+"""GPU parity: every C-ABI entry point of libssq.so against the oracle on the same seeded inputs (bit-exact), at sizes the
+oracle finishes in seconds, plus size-independent properties at larger sizes."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import ssq_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_ex(ssq, ex_index):
+    h = ssq.index_load(ex_index)
+    yield h
+    ssq.index_free(h)
+
+
+@pytest.fixture(scope="module")
+def gpu_syn(ssq, syn_index):
+    h = ssq.index_load(syn_index[0])
+    yield h
+    ssq.index_free(h)
+
+
+def test_index_upload_matches_files(ssq, oracle, ex_index, gpu_ex):
+    idx = oracle.load(ex_index)
+    for what in range(6):
+        assert int(ssq.lib.ssq_index_info(gpu_ex, what)) == oracle.info(idx, what), what
+
+
+def test_sa_lookup(ssq, oracle, ex_index, gpu_ex):
+    idx = oracle.load(ex_index)
+    n = oracle.info(idx, 1)
+    rows = np.concatenate([np.arange(0, 3000, dtype=np.uint64), np.random.default_rng(1).integers(0, n + 1, 50000).astype(np.uint64),
+                           np.array([oracle.info(idx, 2), n, n - 1], np.uint64)])
+    assert np.array_equal(ssq.sa_lookup_batch(gpu_ex, rows), oracle.sa_batch(idx, rows))
+
+
+def test_sa_lookup_is_a_permutation(ssq, oracle, ex_index, gpu_ex):
+    idx = oracle.load(ex_index)
+    n = oracle.info(idx, 1)
+    pos = ssq.sa_lookup_batch(gpu_ex, np.arange(1, n + 1, dtype=np.uint64))
+    assert np.array_equal(np.sort(pos), np.arange(0, n, dtype=np.uint64))
+
+
+def test_smem_example_reads(ssq, oracle, ex_index, ex_reads, gpu_ex):
+    idx = oracle.load(ex_index)
+    seq, off = T.encode_reads(ex_reads[1])
+    a, ao = oracle.smem_batch(idx, seq, off)
+    b, bo = ssq.smem_batch(gpu_ex, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+
+
+def test_smem_edge_cases(ssq, oracle, syn_index, gpu_syn):
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    acgt = "ACGT"
+    ref = "".join(acgt[x] for x in g[5000:5400])
+    seqs = ["", "A", "N" * 30, "ACGT" * 4, ref[:18], ref[:19], ref[:20], ref[:150], "N" + ref[1:150], ref[:75] + "N" + ref[76:150], "AC" * 60,
+            ref[:60] + ref[200:290], "".join(acgt[x] for x in g[int(bounds[1]) - 70:int(bounds[1]) + 80]), "T" * 100, ref[:255]]
+    seq, off = T.encode_reads(seqs)
+    a, ao = oracle.smem_batch(idx, seq, off)
+    b, bo = ssq.smem_batch(gpu_syn, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    # empty batch
+    b, bo = ssq.smem_batch(gpu_syn, np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(b) == 0
+
+
+def test_read_too_long_is_rejected(ssq, gpu_syn):
+    seq, off = T.encode_reads(["A" * 256])
+    with pytest.raises(RuntimeError, match="rc=-7"):
+        ssq.smem_batch(gpu_syn, seq, off)
+
+
+def test_sw_extend(ssq, oracle):
+    rng = np.random.default_rng(5)
+    tasks, q, t = T.extension_tasks(rng, 20000, qmax=255)
+    assert np.array_equal(ssq.sw_extend_batch(tasks, q, t), oracle.sw_extend_batch(tasks, q, t))
+    tasks, q, t = T.extension_tasks(rng, 3000, qmax=20)
+    assert np.array_equal(ssq.sw_extend_batch(tasks, q, t), oracle.sw_extend_batch(tasks, q, t))
+
+
+@pytest.mark.parametrize("rl,seed", [(75, 1), (101, 4), (150, 2), (250, 3)])
+def test_chain_and_regions_synthetic(ssq, oracle, syn_index, gpu_syn, rl, seed):
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = T.simulate_pairs(g, bounds, 1500, rl, seed, err=0.01, indel=0.002, n_frac=0.003)
+    seq, off = T.encode_reads(seqs)
+    a = oracle.chain_batch(idx, seq, off)
+    b = ssq.chain_batch(gpu_syn, seq, off)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    a, ao = oracle.align_batch(idx, seq, off)
+    b, bo = ssq.align_batch(gpu_syn, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+
+
+def test_regions_example_reads(ssq, oracle, ex_index, ex_reads, gpu_ex):
+    idx = oracle.load(ex_index)
+    seq, off = T.encode_reads(ex_reads[1])
+    a, ao = oracle.align_batch(idx, seq, off)
+    b, bo = ssq.align_batch(gpu_ex, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    assert len(a) >= 3900
+
+
+def test_regions_large_batch_properties(ssq, oracle, syn_index, gpu_syn):
+    """60k reads: too slow to compare everything with the scalar oracle in the CPU budget, so check a 2k sample exactly and
+    the whole batch through properties: simulated origin recovered, coordinates inside one contig/strand, batch-split invariance"""
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = T.simulate_pairs(g, bounds, 30000, 150, 9)
+    seq, off = T.encode_reads(seqs)
+    regs, roff = ssq.align_batch(gpu_syn, seq, off)
+    l_pac = len(g)
+    assert (regs["rb"] < regs["re"]).all() and (regs["qb"] < regs["qe"]).all()
+    assert ((regs["re"] <= l_pac) | (regs["rb"] >= l_pac)).all()
+    hit = 0
+    for i in range(0, len(seqs), 2):
+        c, p = int(names[i].split("_")[1]), int(names[i].split("_")[2])
+        r = regs[int(roff[i]):int(roff[i + 1])]
+        if len(r):
+            best = r[np.argmax(r["score"])]
+            f = best["rb"] if best["rb"] < l_pac else 2 * l_pac - best["re"]
+            hit += abs(int(f) - (int(bounds[c]) + p)) < 700
+    assert hit > 0.97 * (len(seqs) // 2)
+    # the same reads in two halves give the same regions (no cross-read state)
+    h = len(seqs) // 2
+    s1, o1 = T.encode_reads(seqs[:h]); s2, o2 = T.encode_reads(seqs[h:])
+    r1, _ = ssq.align_batch(gpu_syn, s1, o1); r2, _ = ssq.align_batch(gpu_syn, s2, o2)
+    r2 = r2.copy(); r2["read_id"] += h
+    assert np.array_equal(np.concatenate([r1, r2]), regs)
+    # exact comparison on a sample
+    sub = seqs[:2000]
+    s, o = T.encode_reads(sub)
+    a, ao = oracle.align_batch(idx, s, o)
+    assert np.array_equal(a, regs[: int(roff[2000])])
+
+
+def test_dupmark(ssq, oracle):
+    rng = np.random.default_rng(8)
+    n = 200000
+    sig = np.zeros(n, T.DUPSIG_DT)
+    sig["pos1"] = rng.integers(0, 5000, n); sig["pos2"] = rng.integers(0, 50, n) + sig["pos1"]
+    sig["strand1"] = rng.integers(0, 2, n); sig["strand2"] = rng.integers(0, 2, n)
+    sig["valid"] = rng.random(n) > 0.02
+    sig["pos1"][::1000] = (1 << 40) + 5  # large coordinates
+    d = ssq.dupmark_batch(sig)
+    assert np.array_equal(d, oracle.dupmark(sig))
+    assert d[sig["valid"] == 0].sum() == 0 and 0 < d.sum() < n
+    # order-independence of the SET of survivors: exactly one survivor per distinct valid signature
+    v = sig[sig["valid"] == 1]
+    keys = set(zip(v["pos1"].tolist(), v["pos2"].tolist(), v["strand1"].tolist(), v["strand2"].tolist()))
+    assert int((d == 0)[sig["valid"] == 1].sum()) == len(keys)
+    assert len(ssq.dupmark_batch(np.zeros(0, T.DUPSIG_DT))) == 0

@@ -1,0 +1,56 @@
+"""The kernels' device routines (speedseq_b200/csrc/ssq_dev.cuh) compiled for the HOST by the test-only harness
+tests/hostsim and compared with the oracle.  This validates the arithmetic the GPU executes on a box without a GPU; the
+GPU parity proper is tests/test_gpu_parity.py.  The harness is not part of the product."""
+import numpy as np
+
+import ssq_testlib as T
+
+
+def _cmp_all(oracle, hostsim, idx, seqs):
+    seq, off = T.encode_reads(seqs)
+    a, ao = oracle.smem_batch(idx, seq, off)
+    b, bo = hostsim.smem_batch(idx, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    a = oracle.chain_batch(idx, seq, off)
+    b = hostsim.chain_batch(idx, seq, off)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    a, ao = oracle.align_batch(idx, seq, off)
+    b, bo = hostsim.align_batch(idx, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    return len(a)
+
+
+def test_example_reads(oracle, hostsim, ex_index, ex_reads):
+    idx = oracle.load(ex_index)
+    assert _cmp_all(oracle, hostsim, idx, ex_reads[1][:1500]) > 1000
+
+
+def test_synthetic_reads_with_repeats_indels_and_Ns(oracle, hostsim, syn_index):
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    for rl, seed in ((75, 1), (150, 2), (250, 3)):
+        names, seqs, quals = T.simulate_pairs(g, bounds, 300, rl, seed, err=0.01, indel=0.002, n_frac=0.003)
+        _cmp_all(oracle, hostsim, idx, seqs)
+
+
+def test_edge_cases(oracle, hostsim, syn_index):
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    acgt = "ACGT"
+    ref = "".join(acgt[x] for x in g[5000:5400])
+    seqs = ["", "A", "N" * 30, "ACGT" * 4, ref[:18], ref[:19], ref[:20], ref[:150], "N" + ref[1:150], ref[:75] + "N" + ref[76:150],
+            "AC" * 60,  # microsatellite, highly repetitive
+            ref[:60] + ref[200:290],  # split read
+            "".join(acgt[x] for x in g[int(bounds[1]) - 70:int(bounds[1]) + 80]),  # spans a contig boundary
+            "T" * 100]
+    _cmp_all(oracle, hostsim, idx, seqs)
+
+
+def test_sw_extend_random_tasks(oracle, hostsim):
+    rng = np.random.default_rng(5)
+    tasks, q, t = T.extension_tasks(rng, 4000, qmax=255)
+    a = oracle.sw_extend_batch(tasks, q, t)
+    b = hostsim.sw_extend_batch(tasks, q, t)
+    assert np.array_equal(a, b)
+    assert (a["score"] >= tasks["h0"]).all()
