@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the `speedseq align` hot path on B200 (BASELINE.json config 2).
+
+Workload ("config.workload"): 10 M synthetic 2x150 bp paired-end reads (wgsim-like: 0.5 % substitution errors, 0.085 % SNPs,
+~2 % of reads with a 1-3 bp indel, insert 500+-50) against a seeded synthetic chr20-sized reference (63,025,520 bp, planted
+repeat families — no real genome exists on the box), FM-index seeding + SA look-up + chaining + banded-SW seed extension,
+no dup-marking.  One STEP = one pass of that path over all 10 M reads (5 batches of 2 M reads).
+
+  value : reads/s with the reads already resident in HBM when the timed region starts (CUDA events on the launching stream,
+          max over ranks; L2 note: the five 300 MB read batches + per-batch scratch exceed the 126 MB L2, nothing is reused
+          between steps except the index, which is the hot working set by design).
+  e2e   : the same metric through the C-ABI with HOST (pinned) buffers: every step copies every batch's reads host->device
+          and the alignment regions device->host inside the timed region.
+  roofline : dominant kernel (the one with the largest share of the step).  achieved = algorithmic bytes per launch / mean
+          launch duration, both measured live: bytes = 64 B x occ blocks counted on the device (k_smem, k_sa) or
+          qlen + ceil(tlen/4) + 24 per extension call (k_extend) — SURVEY.md §8d; duration = CUDA events around the stage.
+  cpu_baseline : the oracle (scalar C restatement of BWA-MEM's seed/chain/extend, oracle/) on all host cores over a bounded
+          sample of the same reads ("port": the reference's own bwa is not vendored in /root/reference).
+
+`--impl reference` runs ONLY that CPU arm (rank 0), K steps of a bounded sample each.
+Multi-GPU: reads are independent, the index is replicated, every rank runs the same amount of work on its own reads
+(weak scaling), no data-path collective; torch.distributed/NCCL is used only for the barrier and the max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ssq_testlib as T  # noqa: E402  (ctypes bindings + seeded generators; no compute)
+
+GENOME_LEN = 63025520
+READ_LEN = 150
+
+
+def fast_pairs(g, n_pairs, read_len, seed, ins_mean=500, ins_sd=50):
+    """vectorised wgsim-like simulator -> (codes[2*n_pairs*read_len] uint8, offsets)"""
+    rng = np.random.default_rng(seed)
+    comp = np.array([3, 2, 1, 0, 4], np.uint8)
+    n = len(g)
+    ins = np.clip(rng.normal(ins_mean, ins_sd, n_pairs).astype(np.int64), read_len + 10, None)
+    p = (rng.random(n_pairs) * (n - ins - 8)).astype(np.int64)
+    ar = np.arange(read_len, dtype=np.int64 if n >= 2**31 - 1024 else np.int32)
+    if n < 2**31 - 1024:
+        p = p.astype(np.int32); ins = ins.astype(np.int32)
+    r1 = g[p[:, None] + ar]
+    r2 = comp[g[(p + ins - 1)[:, None] - ar]]
+    for r in (r1, r2):
+        m = rng.random(r.shape) < 0.00585
+        r[m] = (r[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+        who = np.nonzero(rng.random(n_pairs) < 0.0225)[0]
+        for i in who:  # small indels
+            at, l = int(rng.integers(10, read_len - 10)), int(rng.integers(1, 4))
+            if rng.random() < 0.5:
+                r[i, at + l:] = r[i, at:read_len - l].copy()
+                r[i, at:at + l] = rng.integers(0, 4, l, dtype=np.uint8)
+            else:
+                r[i, at:read_len - l] = r[i, at + l:].copy()
+                r[i, read_len - l:] = rng.integers(0, 4, l, dtype=np.uint8)
+    sw = rng.random(n_pairs) < 0.5
+    a = np.where(sw[:, None], r2, r1)
+    b = np.where(sw[:, None], r1, r2)
+    out = np.empty((2 * n_pairs, read_len), np.uint8)
+    out[0::2] = a
+    out[1::2] = b
+    off = np.arange(2 * n_pairs + 1, dtype=np.uint64) * np.uint64(read_len)
+    return out.reshape(-1), off
+
+
+def ensure_reference(cache, genome_len, builder):
+    """seeded synthetic genome + index under `cache`; builder(fasta) makes the five index files"""
+    os.makedirs(cache, exist_ok=True)
+    fa = os.path.join(cache, "syn_%d.fa" % genome_len)
+    gnpy = fa + ".npy"
+    if not os.path.exists(gnpy):
+        g, bounds = T.synth_genome(genome_len, 20, 1)
+        T.write_fasta(fa, g, bounds, ["chr20s"])
+        np.save(gnpy, g)
+    if not all(os.path.exists(fa + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
+        builder(fa)
+    return fa, np.load(gnpy)
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(int(r[1]) for r in rows if len(r) > 8 and r[1].isdigit())
+        reasons = set()
+        for r in rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip() == "Active":
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(rows[0][2]) if rows and rows[0][2].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(oracle, oidx, seq, off, threads, target_s=12.0):
+    """oracle seed+chain+extend on a bounded sample sized for ~target_s seconds; returns (reads/s, sample description)"""
+    n_all = len(off) - 1
+    probe = min(20000, n_all)
+    t0 = time.time()
+    oracle.align_batch(oidx, seq[: int(off[probe])], off[: probe + 1], 0, threads)
+    rate = probe / max(time.time() - t0, 1e-6)
+    n = int(min(n_all, max(probe, rate * target_s))) & ~1
+    t0 = time.time()
+    oracle.align_batch(oidx, seq[: int(off[n])], off[: n + 1], 0, threads)
+    dt = time.time() - t0
+    return n / dt, "%d reads (first %d of batch 0), %d threads, %.1f s" % (n, n, threads, dt)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--batch", type=int, default=2_000_000)
+    ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
+    ap.add_argument("--cache", default=os.environ.get("SSQ_BENCH_CACHE", os.path.join(ROOT, "data_cache")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    workload = "%dM synthetic 2x%dbp PE reads vs synthetic chr20-sized reference (%d bp), seed+SA+chain+extend, no dup-mark" % (a.reads // 1_000_000, READ_LEN, a.genome_len)
+    metric = "150bp PE reads/sec through FM-index seeding + chaining + banded-SW extension (BASELINE config 2)"
+    nb = max(1, a.reads // a.batch)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        o = T.Oracle()
+        fa, g = ensure_reference(a.cache, a.genome_len, lambda f: o.index_build(f))
+        oidx = o.load(fa)
+        seq, off = fast_pairs(g, min(a.batch, a.reads) // 2, READ_LEN, 1000)
+        rates = []
+        desc = ""
+        for s in range(a.warmup + a.steps):
+            r, desc = cpu_arm(o, oidx, seq, off, ncores, target_s=6.0 if s >= a.warmup else 1.0)
+            if s >= a.warmup:
+                rates.append(r)
+        v = float(np.mean(rates))
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1000.0 * a.reads / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                          "config": {"workload": workload, "note": "CPU arm: oracle port of the reference path (bwa/samblaster sources are not vendored in the reference tree), each step = bounded sample"},
+                          "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": desc},
+                          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    s = T.SSQ()
+    L = s.lib
+    # reference + index (rank 0 builds, the others wait)
+    if rank == 0:
+        fa, g = ensure_reference(a.cache, a.genome_len, lambda f: s.index_build(f, None, local))
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        fa, g = ensure_reference(a.cache, a.genome_len, lambda f: s.index_build(f, None, local))
+    idx = s.index_load(fa, local)
+    # reads: pinned host copies, one batch object per batch, all sharing one stream
+    host_seq, host_off, batches = [], [], []
+    stream = None
+    for b in range(nb):
+        seq, off = fast_pairs(g, a.batch // 2, READ_LEN, 1000 + rank * 100 + b)
+        ts, to = torch.from_numpy(seq).pin_memory(), torch.from_numpy(off.view(np.int64)).pin_memory()
+        host_seq.append(ts); host_off.append(to)
+        h = C.c_void_p()
+        s.ck(L.ssq_batch_create(idx, s.opts, C.c_int(0), None, None, C.byref(h)), "ssq_batch_create")
+        if stream is None:
+            stream = L.ssq_batch_stream(h)
+        else:
+            s.ck(L.ssq_batch_set_stream(h, C.c_void_p(stream)), "ssq_batch_set_stream")
+        s.ck(L.ssq_batch_upload(h, C.c_int(a.batch), C.c_void_p(ts.data_ptr()), C.c_void_p(to.data_ptr())), "ssq_batch_upload")
+        batches.append(h)
+    ext = torch.cuda.ExternalStream(stream)
+    n_reads_step = nb * a.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_resident():
+        for h in batches:
+            s.ck(L.ssq_batch_run(h), "ssq_batch_run")
+
+    # ---- value: HBM-resident ----
+    for _ in range(a.warmup):
+        run_resident()
+    barrier()
+    clk = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    stage_ms = np.zeros(5)
+    counters = np.zeros(11)
+    for _ in range(a.steps):
+        run_resident()
+        for h in batches:
+            stage_ms += [L.ssq_batch_stage_ms(h, i) for i in range(5)]
+            counters += [L.ssq_batch_counter(h, i) for i in range(11)]
+    ev1.record(ext)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = clk.stop()
+    # ---- e2e: host buffers through the C-ABI ----
+    eb = batches[0]
+    cap = int(counters[8] / max(1, a.steps * nb) * 1.5) + 1024 if counters[8] else a.batch * 2
+    need = C.c_uint64(0)
+    # size the pinned output from a first fetch
+    s.ck(L.ssq_batch_run(eb), "run"); L.ssq_batch_fetch(eb, None, C.c_uint64(0), None, C.byref(need))
+    cap = int(need.value * 1.3) + 1024
+    out_regs = torch.empty(cap * T.REG_DT.itemsize, dtype=torch.uint8).pin_memory()
+    out_off = torch.empty(a.batch + 1, dtype=torch.int64).pin_memory()
+    def run_e2e():
+        d2h = 0
+        for b in range(nb):
+            s.ck(L.ssq_batch_upload(eb, C.c_int(a.batch), C.c_void_p(host_seq[b].data_ptr()), C.c_void_p(host_off[b].data_ptr())), "upload")
+            s.ck(L.ssq_batch_run(eb), "run")
+            s.ck(L.ssq_batch_fetch(eb, C.c_void_p(out_regs.data_ptr()), C.c_uint64(cap), C.c_void_p(out_off.data_ptr()), C.byref(need)), "fetch")
+            d2h += int(need.value) * T.REG_DT.itemsize + (a.batch + 1) * 8
+        return d2h
+    run_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    d2h = 0
+    for _ in range(a.steps):
+        d2h = run_e2e()
+    e1.record(ext)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    h2d = sum(int(t.numel()) for t in host_seq) + sum(int(t.numel()) * 8 for t in host_off)
+    # restore batch 0 for consistency
+    # ---- max over ranks ----
+    tmax = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(tmax[0]), float(tmax[1])
+    value = world * n_reads_step * a.steps / (ms_total / 1000.0)
+    e2e_v = world * n_reads_step * a.steps / (ms_e2e / 1000.0)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        n_launch = a.steps * nb
+        kern = {
+            "k_smem": {"bytes": 64.0 * counters[0] / n_launch, "ms": stage_ms[0] / n_launch},
+            "k_sa": {"bytes": (64.0 * counters[1] + 8.0 * counters[2]) / n_launch, "ms": stage_ms[1] / n_launch},
+            "k_chain": {"bytes": None, "ms": stage_ms[2] / n_launch},
+            "k_extend": {"bytes": counters[5] / n_launch, "ms": stage_ms[3] / n_launch, "gcups": counters[4] / n_launch / (stage_ms[3] / n_launch * 1e6) if stage_ms[3] else None},
+            "k_select": {"bytes": None, "ms": stage_ms[4] / n_launch},
+        }
+        dom = max(("k_smem", "k_sa", "k_extend"), key=lambda k: kern[k]["ms"])
+        ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] else 0.0
+        for k in kern.values():
+            k["share_of_step"] = k["ms"] * n_launch / ms_total if ms_total else None
+            k["achieved_GBps"] = (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["bytes"] and k["ms"] else None
+        res = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+               "config": {"workload": workload, "batch_reads": a.batch, "batches_per_step": nb, "l2": "inputs+scratch per step exceed L2 (5 x 300 MB reads); index (110 MB) is the resident working set",
+                          "index": "replicated per GPU", "parallelism": "reads sharded per rank, no collective on this path"},
+               "clocks": clocks, "gpu_launches": int(counters[6]),
+               "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
+               "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"],
+                            "note": "random 64-B occ-block reads; with a chr20-sized index (110 MB) they are served mostly by the 126 MB L2, so DRAM traffic is far below algorithmic bytes; see profiles/"},
+               "kernels": kern,
+               "work_per_step": {"occ_blocks_smem": counters[0] / a.steps, "occ_blocks_sa": counters[1] / a.steps, "sa_samples": counters[2] / a.steps, "sw_calls": counters[3] / a.steps,
+                                 "sw_cells": counters[4] / a.steps, "seeds": counters[7] / a.steps, "regions": counters[8] / a.steps, "intervals": counters[9] / a.steps}}
+        if world == 1 and not a.no_cpu_baseline:
+            o = T.Oracle()
+            oidx = o.load(fa)
+            v, desc = cpu_arm(o, oidx, host_seq[0].numpy(), host_off[0].numpy().view(np.uint64), ncores)
+            res["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": desc}
+        print(json.dumps(res))
+    for h in reversed(batches):  # batch 0 owns the shared stream
+        L.ssq_batch_free(h)
+    s.index_free(idx)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

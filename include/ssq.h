@@ -58,6 +58,10 @@ void ssq_opts_default(ssq_opts_t *o);
  * on-disk format of the reference's goldens (/root/reference/example/data/ *.fasta.{amb,ann,pac,bwt,sa})
  * and uploads them to `device`. */
 typedef struct ssq_index ssq_index_t;
+/* `$BWA index $REF` (/root/reference/bin/speedseq:389): FASTA (plain or gz) -> PREFIX.{amb,ann,pac,bwt,sa}, byte-identical
+ * to the reference's goldens for example/data; suffix sorting, BWT, occ checkpoints and SA sampling run on `device`.
+ * prefix == NULL means prefix = fasta.  Replaces upstream bwa_idx_build(). */
+int ssq_index_build(const char *fasta, const char *prefix, int device);
 int ssq_index_load(const char *prefix, int device, ssq_index_t **out);
 void ssq_index_free(ssq_index_t *idx);
 /* what: 0 l_pac, 1 seq_len(=2*l_pac), 2 primary, 3 n_seqs, 4 bwt words, 5 n_sa, 6 device bytes */
@@ -117,10 +121,14 @@ int ssq_align_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, 
  * (`value` in bench.py), fetch results when wanted */
 typedef struct ssq_batch ssq_batch_t;
 int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off, ssq_batch_t **out);
-int ssq_batch_run(ssq_batch_t *b);                 /* asynchronous on the batch's stream */
+/* (re)load a batch object with new reads; device buffers are kept and grown, so one object serves a stream of batches.
+ * ssq_batch_create(..., read_off == NULL) makes an empty object to be filled by ssq_batch_upload(). */
+int ssq_batch_upload(ssq_batch_t *b, int n_reads, const uint8_t *seq, const uint64_t *read_off);
+int ssq_batch_run(ssq_batch_t *b);                 /* all kernels of the path on the batch's stream; returns when the last is queued */
 int ssq_batch_sync(ssq_batch_t *b);
 int ssq_batch_fetch(ssq_batch_t *b, ssq_alnreg_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed);
 void *ssq_batch_stream(ssq_batch_t *b);            /* cudaStream_t, for event timing on the launching stream */
+int ssq_batch_set_stream(ssq_batch_t *b, void *stream); /* make several batch objects share one caller-owned stream */
 /* per-run work counters measured on the device: what: 0 occ blocks read by seeding, 1 occ blocks read by SA walks,
  * 2 SA samples read, 3 SW extension calls, 4 SW cells, 5 SW algorithmic bytes, 6 kernels launched per run, 7 seeds, 8 regions */
 uint64_t ssq_batch_counter(const ssq_batch_t *b, int what);

@@ -352,10 +352,10 @@ struct ssq_batch {
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
-	int launches;
+	int launches, own_stream;
 	cudaEvent_t ev[6];
 	float stage_ms[5];
-	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; pool_cap = 0; memset(stage_ms, 0, sizeof stage_ms); }
+	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; memset(stage_ms, 0, sizeof stage_ms); }
 };
 
 // misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
@@ -370,26 +370,37 @@ static int scan_u64(ssq_batch *b, const u64 *in, u64 *out, size_t n) // exclusiv
 	return 0;
 }
 
+extern "C" int ssq_batch_upload(ssq_batch_t *b, int n_reads, const uint8_t *seq, const uint64_t *read_off)
+{
+	if (!b || n_reads < 0 || !read_off || (n_reads > 0 && !seq)) return SSQ_EINVAL;
+	int rc = ssq_use_device(b->idx->device);
+	if (rc) return rc;
+	b->n_reads = n_reads;
+	b->max_len = 0;
+	for (int i = 0; i < n_reads; ++i) { int l = (int)(read_off[i + 1] - read_off[i]); if (l > b->max_len) b->max_len = l; }
+	if (b->max_len > SSQ_MAX_READ_LEN) { ssq_set_error("read longer than %d bases", SSQ_MAX_READ_LEN); return SSQ_ELEN; }
+	const u64 total = read_off[n_reads];
+	if (b->seq.need(total + 16) || b->read_off.need((size_t)(n_reads + 1) * 8)) return SSQ_ENOMEM;
+	if (total) CK(cudaMemcpyAsync(b->seq.p, seq, total, cudaMemcpyHostToDevice, b->st));
+	CK(cudaMemcpyAsync(b->read_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->st));
+	CK(cudaStreamSynchronize(b->st));
+	b->n_intv = b->n_seeds = b->n_tasks = b->n_regs_total = 0;
+	return SSQ_OK;
+}
+
 extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off, ssq_batch_t **out)
 {
-	if (!idx || !opt || n_reads < 0 || !read_off || !out) return SSQ_EINVAL;
+	if (!idx || !opt || n_reads < 0 || !out) return SSQ_EINVAL;
 	int rc = ssq_use_device(idx->device);
 	if (rc) return rc;
 	ssq_batch *b = new ssq_batch();
-	b->idx = idx; b->opt = *opt; b->n_reads = n_reads;
+	b->idx = idx; b->opt = *opt; b->n_reads = 0; b->max_len = 0;
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, idx->device));
 	b->n_sm = prop.multiProcessorCount;
 	CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
 	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
-	b->max_len = 0;
-	for (int i = 0; i < n_reads; ++i) { int l = (int)(read_off[i + 1] - read_off[i]); if (l > b->max_len) b->max_len = l; }
-	if (b->max_len > SSQ_MAX_READ_LEN) { ssq_set_error("read longer than %d bases", SSQ_MAX_READ_LEN); delete b; return SSQ_ELEN; }
-	const u64 total = read_off[n_reads];
-	if (b->seq.need(total + 16) || b->read_off.need((size_t)(n_reads + 1) * 8)) { delete b; return SSQ_ENOMEM; }
-	CK(cudaMemcpyAsync(b->seq.p, seq, total, cudaMemcpyHostToDevice, b->st));
-	CK(cudaMemcpyAsync(b->read_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->st));
-	CK(cudaStreamSynchronize(b->st));
+	if (read_off && (rc = ssq_batch_upload(b, n_reads, seq, read_off))) { ssq_batch_free(b); return rc; }
 	*out = b;
 	return SSQ_OK;
 }
@@ -402,11 +413,18 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
-	cudaStreamDestroy(b->st);
+	if (b->own_stream) cudaStreamDestroy(b->st);
 	delete b;
 }
 
 extern "C" void *ssq_batch_stream(ssq_batch_t *b) { return (void*)b->st; }
+extern "C" int ssq_batch_set_stream(ssq_batch_t *b, void *stream)
+{
+	if (!b || !stream) return SSQ_EINVAL;
+	if (b->own_stream) cudaStreamDestroy(b->st);
+	b->st = (cudaStream_t)stream; b->own_stream = 0;
+	return SSQ_OK;
+}
 extern "C" int ssq_batch_sync(ssq_batch_t *b) { CK(cudaStreamSynchronize(b->st)); return SSQ_OK; }
 
 // stage A: seeding (+ pool overflow retry). leaves intervals in pool, per-read (intv_off, intv_cnt, l_rep)

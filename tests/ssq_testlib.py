@@ -203,6 +203,9 @@ class SSQ:
         self.ck(self.lib.ssq_index_load(prefix.encode(), C.c_int(device), C.byref(h)), "ssq_index_load")
         return h
 
+    def index_build(self, fasta, prefix=None, device=0):
+        self.ck(self.lib.ssq_index_build(fasta.encode(), (prefix or fasta).encode(), C.c_int(device)), "ssq_index_build")
+
     def index_free(self, h):
         self.lib.ssq_index_free(h)
 
