@@ -88,6 +88,24 @@ def ensure_reference(cache, genome_len, builder):
     return fa, np.load(gnpy)
 
 
+def usable_cores():
+    """host cores this process may actually use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, q // p))
+        except Exception:
+            pass
+    return n
+
+
 class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -146,7 +164,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ncores = os.cpu_count() or 1
+    ncores = usable_cores()
     workload = "%dM synthetic 2x%dbp PE reads vs synthetic chr20-sized reference (%d bp), seed+SA+chain+extend, no dup-mark" % (a.reads // 1_000_000, READ_LEN, a.genome_len)
     metric = "150bp PE reads/sec through FM-index seeding + chaining + banded-SW extension (BASELINE config 2)"
     nb = max(1, a.reads // a.batch)

@@ -187,8 +187,9 @@ __global__ void k_ib_interleave(u32 n, u32 n_blk, const uint8_t *__restrict__ bs
 	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b > n_blk) return;
 	if (b == n_blk) { // final checkpoint: totals
-		u64 *o = (u64*)(out + total_words - 8);
-		o[0] = c0[n_blk]; o[1] = c1[n_blk]; o[2] = c2[n_blk]; o[3] = c3[n_blk];
+		u32 *o = out + total_words - 8; // only 4-byte aligned when the symbol-word count is odd
+		const u64 t[4] = {c0[n_blk], c1[n_blk], c2[n_blk], c3[n_blk]};
+		for (int c = 0; c < 4; ++c) { o[2 * c] = (u32)t[c]; o[2 * c + 1] = (u32)(t[c] >> 32); }
 		return;
 	}
 	u64 *o = (u64*)(out + (u64)b * 16);

@@ -112,6 +112,39 @@ __global__ void __launch_bounds__(256) k_smem(DevIndex ix, ssq_opts_t opt, int n
 	if (lane == 0 && fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
 
+// thread-per-read variant: every lane runs the whole search of its own read with the scalar rank query (8 x LDG.128 per
+// extension); ping-pong lists and the interval list live in per-thread global scratch (L1/L2 resident)
+__global__ void __launch_bounds__(128) k_smem_t(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                                int lcap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
+                                                u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
+{
+	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1);
+	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per, *bufA = mem + scratch_cap, *bufB = bufA + (lcap + 1);
+	ScalarFm fm(ix);
+	for (;;) {
+		const int r = atomicAdd(work, 1);
+		if (r >= n_reads) break;
+		const u64 off = read_off[r];
+		const int len = (int)(read_off[r + 1] - off);
+		int e = 0, n = 0;
+		if (len > lcap) e = 3;
+		else n = collect_intv(fm, ix, opt, len, seq + off, mem, scratch_cap, bufA, bufB, e);
+		if (e) { atomicMax(err, e); n = 0; }
+		int b = 0, en = 0, l_rep = 0;
+		for (int i = 0; i < n; ++i) {
+			const Intv p = mem[i];
+			if (p.x2 <= (u64)opt.max_occ) continue;
+			if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
+		}
+		l_rep += en - b;
+		unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
+		if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
+		for (int i = 0; i < n; ++i) pool[base + i] = mem[i];
+		intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep;
+	}
+	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
 // ------------------------------------------------------------------------------- k_sa ----
 __global__ void k_occ_count(const Intv *__restrict__ pool, u64 n, int max_occ, u32 *nocc)
 {
@@ -352,10 +385,10 @@ struct ssq_batch {
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
-	int launches, own_stream;
+	int launches, own_stream, smem_variant;
 	cudaEvent_t ev[6];
 	float stage_ms[5];
-	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; memset(stage_ms, 0, sizeof stage_ms); }
+	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 1; } memset(stage_ms, 0, sizeof stage_ms); }
 };
 
 // misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
@@ -431,23 +464,29 @@ extern "C" int ssq_batch_sync(ssq_batch_t *b) { CK(cudaStreamSynchronize(b->st))
 static int run_smem(ssq_batch *b)
 {
 	const int n = b->n_reads, lcap = b->max_len > 0 ? b->max_len : 1;
+	const int variant = b->smem_variant;
 	const int warps_per_block = 4, threads = warps_per_block * 32;
-	const size_t smem = (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv);
-	int blocks_per_sm = (int)((200 * 1024) / (smem + 1024));
+	const size_t smem = variant == 0 ? (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv) : 0;
+	int blocks_per_sm = variant == 0 ? (int)((200 * 1024) / (smem + 1024)) : 8;
 	if (blocks_per_sm > 8) blocks_per_sm = 8;
 	if (blocks_per_sm < 1) blocks_per_sm = 1;
 	const int grid = b->n_sm * blocks_per_sm;
-	const int scratch_cap = 2048;
+	const int scratch_cap = variant == 0 ? 2048 : 768;
+	const size_t scratch_entries = variant == 0 ? (size_t)grid * warps_per_block * scratch_cap : (size_t)grid * threads * ((size_t)scratch_cap + 2 * (size_t)(lcap + 1));
 	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
-	if (b->scratch.need((size_t)grid * warps_per_block * scratch_cap * sizeof(Intv))) return SSQ_ENOMEM;
+	if (b->scratch.need(scratch_entries * sizeof(Intv))) return SSQ_ENOMEM;
 	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc))) return SSQ_ENOMEM;
-	CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	if (variant == 0) CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	for (int attempt = 0; attempt < 6; ++attempt) {
 		if (b->pool.need(b->pool_cap * sizeof(Intv))) return SSQ_ENOMEM;
 		CK(cudaMemsetAsync(b->misc.p, 0, sizeof(Misc), b->st));
-		k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
-		                                      b->pool.as<Intv>(), b->pool_cap, &b->misc.as<Misc>()->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(),
-		                                      b->l_rep.as<i32>(), &b->misc.as<Misc>()->work, &b->misc.as<Misc>()->err, &b->misc.as<Misc>()->cnt);
+		Misc *dm = b->misc.as<Misc>();
+		if (variant == 0)
+			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
+			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
+		else
+			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
+			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		++b->launches;
 		CK(cudaGetLastError());
 		Misc hm;
