@@ -249,6 +249,153 @@ SSQ_HD int collect_intv(Fm &fm, const DevIndex &ix, const ssq_opts_t &opt, int l
 	return n;
 }
 
+// ------------------------------------------------------------- seeding as a state machine ----
+// Same three passes as collect_intv(), unrolled into a machine whose only expensive transition is one rank query
+// (Fm::extend).  A GPU lane owns one machine; all lanes of a warp meet at the query no matter which phase each
+// is in, which is what keeps the SIMT lanes busy (the straight-line version spends most issue slots with 4-5 of 32
+// lanes active).  advance() runs the cheap bookkeeping up to the next query (returns false when the read is done),
+// post() consumes the query's result.  Every list operation happens in the same order as in smem1()/seed_strategy1().
+struct SmemMachine {
+	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3 };
+	const uint8_t *q; Intv *mem, *prev, *curr;
+	int len, mem_cap, n, base, state, pass, x, i, j, c, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width;
+	u64 min_intv, max_mem_intv;
+	Intv ik;      // current interval (FWD/S3)
+	Intv in;      // query input
+	int is_back;
+
+	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, Intv *bufA, Intv *bufB)
+	{
+		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; prev = bufA; curr = bufB;
+		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1;
+		min_seed_len = opt.min_seed_len; split_len = (int)(opt.min_seed_len * opt.split_factor + .499f); split_width = opt.split_width;
+		max_mem_intv = (u64)opt.max_mem_intv;
+		if (len < opt.min_seed_len) { state = NEXT_P3; pass = 3; x = len; }
+	}
+	SSQ_HD void start_smem1(const DevIndex &ix, int x_, u64 min_intv_)
+	{
+		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; base = n;
+		set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
+		i = x + 1; n_curr = 0; state = FWD;
+	}
+	SSQ_HD void end_forward() // forward list complete: longest first, then walk backwards
+	{
+		for (int a = 0; a < n_curr >> 1; ++a) { Intv t = curr[a]; curr[a] = curr[n_curr - 1 - a]; curr[n_curr - 1 - a] = t; }
+		ret = (int)curr[0].qe;
+		{ Intv *t = curr; curr = prev; prev = t; n_prev = n_curr; }
+		i = x - 1; j = 0; n_curr = 0;
+		c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
+		state = BWD;
+	}
+	SSQ_HD void keep(const Intv &p_) // p is left-maximal at i+1 unless a longer match survived
+	{
+		if (n_curr == 0 && (n == base || (u32)(i + 1) < mem[n - 1].qb)) {
+			if (n >= mem_cap) { err = 1; return; }
+			Intv p = p_; p.qb = (u32)(i + 1);
+			mem[n++] = p;
+		}
+	}
+	SSQ_HD void end_smem1() // reverse this call's output, drop short ones, pick what comes next
+	{
+		for (int a = 0; a < (n - base) >> 1; ++a) { Intv t = mem[base + a]; mem[base + a] = mem[n - 1 - a]; mem[n - 1 - a] = t; }
+		int k = base;
+		for (int a = base; a < n; ++a) if ((int)(mem[a].qe - mem[a].qb) >= min_seed_len) mem[k++] = mem[a];
+		n = k;
+		if (pass == 1) { x = ret; state = NEXT_P1; } else state = NEXT_P2;
+	}
+	// returns true when `in`/`is_back` hold the next rank query; false when the read's interval list is complete
+	SSQ_HD bool advance(const DevIndex &ix)
+	{
+		for (;;) {
+			if (err) return false;
+			switch (state) {
+			case NEXT_P1:
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) { old_n = n; k2 = 0; pass = 2; state = NEXT_P2; break; }
+				start_smem1(ix, x, 1);
+				break;
+			case NEXT_P2: {
+				bool started = false;
+				while (k2 < old_n) {
+					const Intv p = mem[k2++];
+					const int start = (int)p.qb, end = (int)p.qe;
+					if (end - start < split_len || p.x2 > (u64)split_width) continue;
+					start_smem1(ix, (start + end) >> 1, p.x2 + 1);
+					started = true;
+					break;
+				}
+				if (!started) { pass = 3; x = 0; state = NEXT_P3; if (max_mem_intv == 0) x = len; }
+				break;
+			}
+			case NEXT_P3:
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) return false;
+				set_intv(ix, q[x], ik);
+				i = x + 1; state = S3;
+				break;
+			case FWD:
+				if (i >= len) { curr[n_curr++] = ik; end_forward(); break; }
+				if (q[i] > 3) { curr[n_curr++] = ik; end_forward(); break; }
+				in = ik; is_back = 0;
+				return true;
+			case BWD:
+				if (j >= n_prev) { // one backward step done for the whole set
+					if (n_curr == 0) { end_smem1(); break; }
+					{ Intv *t = curr; curr = prev; prev = t; n_prev = n_curr; }
+					--i; j = 0; n_curr = 0;
+					if (i < -1) { end_smem1(); break; }
+					c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
+					break;
+				}
+				if (c < 0) { keep(prev[j]); ++j; break; }
+				in = prev[j]; is_back = 1;
+				return true;
+			case S3:
+				if (i >= len) { x = len; state = NEXT_P3; break; }
+				if (q[i] > 3) { x = i + 1; state = NEXT_P3; break; }
+				in = ik; is_back = 0;
+				return true;
+			}
+		}
+	}
+	SSQ_HD void post(const Intv ok[4])
+	{
+		if (state == FWD) {
+			const int cc = 3 - q[i];
+			if (ok[cc].x2 != ik.x2) {
+				curr[n_curr++] = ik;
+				if (ok[cc].x2 < min_intv) { end_forward(); return; }
+			}
+			ik = ok[cc]; ik.qe = (u32)(i + 1);
+			++i;
+		} else if (state == BWD) {
+			const Intv p = prev[j];
+			if (ok[c].x2 < min_intv) keep(p);
+			else if (n_curr == 0 || ok[c].x2 != curr[n_curr - 1].x2) { Intv t = ok[c]; t.qb = 0; t.qe = p.qe; curr[n_curr++] = t; }
+			++j;
+		} else { // S3
+			const int cc = 3 - q[i];
+			if (ok[cc].x2 < max_mem_intv && i - x >= min_seed_len) {
+				Intv m = ok[cc]; m.qb = (u32)x; m.qe = (u32)(i + 1);
+				if (m.x2 > 0) { if (n >= mem_cap) { err = 1; return; } mem[n++] = m; }
+				x = i + 1; state = NEXT_P3;
+			} else { ik = ok[cc]; ++i; }
+		}
+	}
+	SSQ_HD int finish() // order by (qb,qe); returns the interval count
+	{
+		if (err) return 0;
+		for (int a = 1; a < n; ++a) {
+			Intv t = mem[a];
+			u64 key = (u64)t.qb << 32 | t.qe;
+			int k;
+			for (k = a; k > 0 && ((u64)mem[k - 1].qb << 32 | mem[k - 1].qe) > key; --k) mem[k] = mem[k - 1];
+			mem[k] = t;
+		}
+		return n;
+	}
+};
+
 // number of SA look-ups an interval contributes (max_occ rows, evenly strided when it has more)
 SSQ_HD int intv_occ_count(u64 s, int max_occ, u64 &step)
 {
@@ -610,59 +757,100 @@ SSQ_HD void chain_window(const DevIndex &ix, const ssq_opts_t &opt, int l_query,
 	rmax1 = rmax1 < far_end ? rmax1 : far_end;
 }
 
-SSQ_HD void extend_seed(const DevIndex &ix, const ssq_opts_t &opt, int l_query, const uint8_t *query, const ChainRec &c, const Seed *cs,
-                        int si, const EhAcc &eh, RegCand &a, Counters *cnt_sw_calls_cells_bytes /* may be null */)
+// ---- mem_chain2aln()'s per-seed body, cut into pieces so that the GPU can run all left extensions, then all right
+// ---- extensions, each as size-sorted passes; extend_seed() below is the straight composition of the same pieces
+struct ExtInfo { i64 rmax0, rmax1, rbeg; i32 qbeg, len, lq, rid; }; // geometry of one seed's extension problem
+struct ExtRes { i32 score, qle, tle, gtle, gscore, max_off; };
+
+SSQ_HD void ext_prep(const DevIndex &ix, const ssq_opts_t &opt, int l_query, const ChainRec &c, const Seed *cs, int si, ExtInfo &e)
 {
-	i64 rmax0, rmax1;
-	int aw0 = opt.w, aw1 = opt.w, i;
-	unsigned long long cells = 0, calls = 0, bytes = 0;
-	const Seed s = cs[si];
-	chain_window(ix, opt, l_query, cs, c.n, rmax0, rmax1);
-	a.rid = c.rid; a.score = a.truesc = -1; a.w = opt.w;
-	if (s.qbeg) { // left: reversed query prefix against the reversed reference prefix
-		int qle, tle, gtle, gscore, max_off, tlen = (int)(s.rbeg - rmax0);
-		const uint8_t *qp = query + s.qbeg - 1;
-		const i64 rp = s.rbeg - 1;
-		for (i = 0; i < 2; ++i) {
-			int prev = a.score;
-			aw0 = opt.w << i;
-			a.score = sw_extend(opt, s.qbeg, [&](int j) { return (int)qp[-j]; }, tlen, [&](int t) { return ref_base(ix, rp - t); },
-			                    aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, eh, qle, tle, gtle, gscore, max_off, cells);
-			++calls; bytes += (unsigned long long)s.qbeg + (tlen + 3) / 4 + 24;
-			if (a.score == prev || max_off < (aw0 >> 1) + (aw0 >> 2)) break;
-		}
-		if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) { a.qb = s.qbeg - qle; a.rb = s.rbeg - tle; a.truesc = a.score; }
-		else { a.qb = 0; a.rb = s.rbeg - gtle; a.truesc = gscore; }
-	} else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
-	if (s.qbeg + s.len != l_query) { // right
-		int qle, tle, gtle, gscore, max_off, sc0 = a.score, qe = s.qbeg + s.len;
-		const i64 re = s.rbeg + s.len;
-		const int tlen = (int)(rmax1 - re);
-		const uint8_t *qp = query + qe;
-		for (i = 0; i < 2; ++i) {
-			int prev = a.score;
-			aw1 = opt.w << i;
-			a.score = sw_extend(opt, l_query - qe, [&](int j) { return (int)qp[j]; }, tlen, [&](int t) { return ref_base(ix, re + t); },
-			                    aw1, opt.pen_clip3, opt.zdrop, sc0, eh, qle, tle, gtle, gscore, max_off, cells);
-			++calls; bytes += (unsigned long long)(l_query - qe) + (tlen + 3) / 4 + 24;
-			if (a.score == prev || max_off < (aw1 >> 1) + (aw1 >> 2)) break;
-		}
-		if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) { a.qe = qe + qle; a.re = re + tle; a.truesc += a.score - sc0; }
-		else { a.qe = l_query; a.re = re + gtle; a.truesc += gscore - sc0; }
-	} else { a.qe = l_query; a.re = s.rbeg + s.len; }
+	chain_window(ix, opt, l_query, cs, c.n, e.rmax0, e.rmax1);
+	e.rbeg = cs[si].rbeg; e.qbeg = cs[si].qbeg; e.len = cs[si].len; e.lq = l_query; e.rid = c.rid;
+}
+SSQ_HD int ext_left_qlen(const ExtInfo &e) { return e.qbeg; }
+SSQ_HD int ext_left_tlen(const ExtInfo &e) { return (int)(e.rbeg - e.rmax0); }
+SSQ_HD int ext_right_qlen(const ExtInfo &e) { return e.lq - (e.qbeg + e.len); }
+SSQ_HD int ext_right_tlen(const ExtInfo &e) { return (int)(e.rmax1 - (e.rbeg + e.len)); }
+SSQ_HD bool ext_needs_retry(const ssq_opts_t &opt, const ExtRes &r) { return r.max_off >= (opt.w >> 1) + (opt.w >> 2); } // implies the score moved
+
+SSQ_HD void ext_left_run(const DevIndex &ix, const ssq_opts_t &opt, const uint8_t *query, const ExtInfo &e, int w, const EhAcc &eh, ExtRes &r, unsigned long long &cells)
+{
+	const uint8_t *qp = query + e.qbeg - 1;
+	const i64 rp = e.rbeg - 1;
+	r.score = sw_extend(opt, e.qbeg, [&](int j) { return (int)qp[-j]; }, ext_left_tlen(e), [&](int t) { return ref_base(ix, rp - t); },
+	                    w, opt.pen_clip5, opt.zdrop, e.len * opt.a, eh, r.qle, r.tle, r.gtle, r.gscore, r.max_off, cells);
+}
+SSQ_HD void ext_right_run(const DevIndex &ix, const ssq_opts_t &opt, const uint8_t *query, const ExtInfo &e, int sc0, int w, const EhAcc &eh, ExtRes &r, unsigned long long &cells)
+{
+	const int qe = e.qbeg + e.len;
+	const i64 re = e.rbeg + e.len;
+	const uint8_t *qp = query + qe;
+	r.score = sw_extend(opt, e.lq - qe, [&](int j) { return (int)qp[j]; }, ext_right_tlen(e), [&](int t) { return ref_base(ix, re + t); },
+	                    w, opt.pen_clip3, opt.zdrop, sc0, eh, r.qle, r.tle, r.gtle, r.gscore, r.max_off, cells);
+}
+// after the left side: score / qb / rb / truesc (has_left == false: the seed starts the read)
+SSQ_HD void ext_left_fin(const ssq_opts_t &opt, const ExtInfo &e, bool has_left, const ExtRes &r, RegCand &a)
+{
+	a.rid = e.rid;
+	if (has_left) {
+		a.score = r.score;
+		if (r.gscore <= 0 || r.gscore <= r.score - opt.pen_clip5) { a.qb = e.qbeg - r.qle; a.rb = e.rbeg - r.tle; a.truesc = r.score; }
+		else { a.qb = 0; a.rb = e.rbeg - r.gtle; a.truesc = r.gscore; }
+	} else { a.score = a.truesc = e.len * opt.a; a.qb = 0; a.rb = e.rbeg; }
+}
+// after the right side: score / qe / re / truesc, then seed coverage and band bookkeeping
+SSQ_HD void ext_right_fin(const ssq_opts_t &opt, const ExtInfo &e, bool has_right, const ExtRes &r, int aw0, int aw1, const ChainRec &c, const Seed *cs, RegCand &a)
+{
+	if (has_right) {
+		const int sc0 = a.score, qe = e.qbeg + e.len;
+		const i64 re = e.rbeg + e.len;
+		a.score = r.score;
+		if (r.gscore <= 0 || r.gscore <= r.score - opt.pen_clip3) { a.qe = qe + r.qle; a.re = re + r.tle; a.truesc += r.score - sc0; }
+		else { a.qe = e.lq; a.re = re + r.gtle; a.truesc += r.gscore - sc0; }
+	} else { a.qe = e.lq; a.re = e.rbeg + e.len; }
 	a.seedcov = 0;
-	for (i = 0; i < c.n; ++i)
+	for (int i = 0; i < c.n; ++i)
 		if (cs[i].qbeg >= a.qb && cs[i].qbeg + cs[i].len <= a.qe && cs[i].rbeg >= a.rb && cs[i].rbeg + cs[i].len <= a.re) a.seedcov += cs[i].len;
 	a.w = aw0 > aw1 ? aw0 : aw1;
-	a.seedlen0 = s.len;
+	a.seedlen0 = e.len;
 	a.frac_rep = c.frac_rep;
-	if (cnt_sw_calls_cells_bytes) {
+}
+
+SSQ_HD void extend_seed(const DevIndex &ix, const ssq_opts_t &opt, int l_query, const uint8_t *query, const ChainRec &c, const Seed *cs,
+                        int si, const EhAcc &eh, RegCand &a, Counters *cnt /* may be null */)
+{
+	ExtInfo e;
+	ExtRes r;
+	int aw0 = opt.w, aw1 = opt.w;
+	unsigned long long cells = 0, calls = 0, bytes = 0;
+	ext_prep(ix, opt, l_query, c, cs, si, e);
+	const bool has_left = ext_left_qlen(e) > 0, has_right = ext_right_qlen(e) > 0;
+	if (has_left) {
+		ext_left_run(ix, opt, query, e, opt.w, eh, r, cells);
+		++calls; bytes += (unsigned long long)e.qbeg + (ext_left_tlen(e) + 3) / 4 + 24;
+		if (ext_needs_retry(opt, r)) { // second and last band width
+			aw0 = opt.w << 1;
+			ext_left_run(ix, opt, query, e, aw0, eh, r, cells);
+			++calls; bytes += (unsigned long long)e.qbeg + (ext_left_tlen(e) + 3) / 4 + 24;
+		}
+	}
+	ext_left_fin(opt, e, has_left, r, a);
+	if (has_right) {
+		const int sc0 = a.score;
+		ext_right_run(ix, opt, query, e, sc0, opt.w, eh, r, cells);
+		++calls; bytes += (unsigned long long)ext_right_qlen(e) + (ext_right_tlen(e) + 3) / 4 + 24;
+		if (ext_needs_retry(opt, r)) {
+			aw1 = opt.w << 1;
+			ext_right_run(ix, opt, query, e, sc0, aw1, eh, r, cells);
+			++calls; bytes += (unsigned long long)ext_right_qlen(e) + (ext_right_tlen(e) + 3) / 4 + 24;
+		}
+	}
+	ext_right_fin(opt, e, has_right, r, aw0, aw1, c, cs, a);
+	if (cnt) {
 #ifdef __CUDA_ARCH__
-		atomicAdd(&cnt_sw_calls_cells_bytes->sw_calls, calls);
-		atomicAdd(&cnt_sw_calls_cells_bytes->sw_cells, cells);
-		atomicAdd(&cnt_sw_calls_cells_bytes->sw_bytes, bytes);
+		atomicAdd(&cnt->sw_calls, calls); atomicAdd(&cnt->sw_cells, cells); atomicAdd(&cnt->sw_bytes, bytes);
 #else
-		cnt_sw_calls_cells_bytes->sw_calls += calls; cnt_sw_calls_cells_bytes->sw_cells += cells; cnt_sw_calls_cells_bytes->sw_bytes += bytes;
+		cnt->sw_calls += calls; cnt->sw_cells += cells; cnt->sw_bytes += bytes;
 #endif
 	}
 }

@@ -145,6 +145,56 @@ __global__ void __launch_bounds__(128) k_smem_t(DevIndex ix, ssq_opts_t opt, int
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
 
+// state-machine variant (default): a lane owns one SmemMachine and keeps pulling reads from the work counter; the only
+// step all lanes of a warp take together is the rank query, whatever phase (forward / backward / pass 3) each is in
+__global__ void __launch_bounds__(128) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                                int lcap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
+                                                u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
+{
+	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1);
+	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per, *bufA = mem + scratch_cap, *bufB = bufA + (lcap + 1);
+	ScalarFm fm(ix);
+	SmemMachine m;
+	bool have = false;
+	int r = -1;
+	for (;;) {
+		bool need = false, done = false;
+		while (!need) {
+			if (!have) {
+				r = atomicAdd(work, 1);
+				if (r >= n_reads) { done = true; break; }
+				const u64 off = read_off[r];
+				const int len = (int)(read_off[r + 1] - off);
+				if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
+				m.init(opt, len, seq + off, mem, scratch_cap, bufA, bufB);
+				have = true;
+			}
+			need = m.advance(ix);
+			if (!need) { // read finished: order its intervals, publish them
+				int n = m.finish();
+				if (m.err) { atomicMax(err, 1); n = 0; }
+				int b = 0, en = 0, l_rep = 0;
+				for (int i = 0; i < n; ++i) {
+					const Intv p = mem[i];
+					if (p.x2 <= (u64)opt.max_occ) continue;
+					if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
+				}
+				l_rep += en - b;
+				unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
+				if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
+				for (int i = 0; i < n; ++i) pool[base + i] = mem[i];
+				intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep;
+				have = false;
+			}
+		}
+		if (done) break;
+		Intv ok[4];
+		fm.extend(m.in, ok, m.is_back);
+		m.post(ok);
+	}
+	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
 // ------------------------------------------------------------------------------- k_sa ----
 __global__ void k_occ_count(const Intv *__restrict__ pool, u64 n, int max_occ, u32 *nocc)
 {
@@ -222,20 +272,116 @@ __global__ void k_tasks(int n_reads, const u64 *__restrict__ intv_off, const i32
 		for (int s = 0; s < outc[s0 + c].n; ++s) { Task k; k.read = r; k.chain = c; k.seed = s; tasks[t++] = k; }
 }
 
-// dynamic smem: blockDim.x * (qmax + 2) * 4 bytes, cell j of thread t at word j*blockDim.x + t
-__global__ void __launch_bounds__(64) k_extend(DevIndex ix, ssq_opts_t opt, u64 n_tasks, const Task *__restrict__ tasks, const uint8_t *__restrict__ seq,
-                                               const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off, const u64 *__restrict__ seed_off,
-                                               const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted, RegCand *cand, Counters *cnt)
+// ---- seed extension as size-sorted passes -------------------------------------------------------------------
+// per task: geometry (ExtInfo), left/right results, band flags.  Jobs of one direction are radix-sorted by
+// (qlen << 16 | tlen) and launched per query-length class, so the lanes of a warp run near-identical DP loops and the
+// shared-memory row (packed int16 H|E, word j*blockDim + lane) is sized for the class, not for the longest read.
+#define EXT_NO_JOB 0xffffffffu
+__device__ __forceinline__ u32 ext_key(int qlen, int tlen) { return qlen > 0 ? ((u32)qlen << 16 | (u32)(tlen < 65535 ? tlen : 65535)) : EXT_NO_JOB; }
+
+__global__ void __launch_bounds__(256) k_ext_prep(DevIndex ix, ssq_opts_t opt, u64 n_tasks, const Task *__restrict__ tasks, const u64 *__restrict__ read_off,
+                                                  const u64 *__restrict__ intv_off, const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc,
+                                                  const Seed *__restrict__ sorted, ExtInfo *info, u32 *key, u32 *idx)
 {
-	extern __shared__ u32 eh_smem[];
 	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_tasks) return;
 	const Task k = tasks[t];
 	const u64 s0 = seed_off[intv_off[k.read]];
 	const ChainRec c = outc[s0 + k.chain];
+	ExtInfo e;
+	ext_prep(ix, opt, (int)(read_off[k.read + 1] - read_off[k.read]), c, sorted + s0 + c.seed_start, k.seed, e);
+	info[t] = e;
+	key[t] = ext_key(ext_left_qlen(e), ext_left_tlen(e));
+	idx[t] = (u32)t;
+}
+
+// bounds[c] = first sorted job whose qlen exceeds caps[c-1]; bounds[0] = 0, bounds[6] = number of real jobs
+__global__ void k_ext_bounds(u64 n, const u32 *__restrict__ keys, u32 *bounds)
+{
+	const int caps[6] = {32, 64, 96, 128, 160, 255};
+	const int c = threadIdx.x;
+	if (c > 6) return;
+	if (c == 0) { bounds[0] = 0; return; }
+	const u32 lim = (u32)(caps[c - 1] + 1) << 16;
+	u64 lo = 0, hi = n;
+	while (lo < hi) { u64 mid = (lo + hi) >> 1; if (keys[mid] < lim) lo = mid + 1; else hi = mid; }
+	bounds[c] = (u32)lo;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(128) k_ext_run(DevIndex ix, ssq_opts_t opt, u32 job_lo, u32 job_hi, const u32 *__restrict__ order, const Task *__restrict__ tasks,
+                                                 const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off, const ExtInfo *__restrict__ info,
+                                                 const RegCand *__restrict__ cand, ExtRes *res, u32 *retry, unsigned int *n_retry, Counters *cnt)
+{
+	extern __shared__ u32 eh_smem[];
+	const u32 job = job_lo + blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long cells = 0, calls = 0, bytes = 0;
+	if (job < job_hi) {
+		const u32 t = order[job];
+		const ExtInfo e = info[t];
+		const uint8_t *query = seq + read_off[tasks[t].read];
+		EhAcc eh; eh.base = eh_smem + threadIdx.x; eh.stride = blockDim.x;
+		ExtRes r;
+		if (DIR == 0) { ext_left_run(ix, opt, query, e, opt.w, eh, r, cells); bytes = (unsigned long long)e.qbeg + (ext_left_tlen(e) + 3) / 4 + 24; }
+		else { ext_right_run(ix, opt, query, e, cand[t].score, opt.w, eh, r, cells); bytes = (unsigned long long)ext_right_qlen(e) + (ext_right_tlen(e) + 3) / 4 + 24; }
+		calls = 1;
+		res[t] = r;
+		if (ext_needs_retry(opt, r)) retry[atomicAdd(n_retry, 1u)] = t;
+	}
+	for (int o = 16; o; o >>= 1) { cells += __shfl_xor_sync(FULL, cells, o); calls += __shfl_xor_sync(FULL, calls, o); bytes += __shfl_xor_sync(FULL, bytes, o); }
+	if ((threadIdx.x & 31) == 0 && calls) { atomicAdd(&cnt->sw_calls, calls); atomicAdd(&cnt->sw_cells, cells); atomicAdd(&cnt->sw_bytes, bytes); }
+}
+
+// the rare second try with the doubled band; shared memory sized for the longest read
+template <int DIR>
+__global__ void __launch_bounds__(64) k_ext_retry(DevIndex ix, ssq_opts_t opt, const u32 *__restrict__ retry, const unsigned int *__restrict__ n_retry,
+                                                  const Task *__restrict__ tasks, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                                  const ExtInfo *__restrict__ info, const RegCand *__restrict__ cand, ExtRes *res, uint8_t *wide, Counters *cnt)
+{
+	extern __shared__ u32 eh_smem[];
+	const unsigned int n = *n_retry;
+	unsigned long long cells = 0, calls = 0, bytes = 0;
 	EhAcc eh; eh.base = eh_smem + threadIdx.x; eh.stride = blockDim.x;
+	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const u32 t = retry[i];
+		const ExtInfo e = info[t];
+		const uint8_t *query = seq + read_off[tasks[t].read];
+		ExtRes r;
+		if (DIR == 0) { ext_left_run(ix, opt, query, e, opt.w << 1, eh, r, cells); bytes += (unsigned long long)e.qbeg + (ext_left_tlen(e) + 3) / 4 + 24; }
+		else { ext_right_run(ix, opt, query, e, cand[t].score, opt.w << 1, eh, r, cells); bytes += (unsigned long long)ext_right_qlen(e) + (ext_right_tlen(e) + 3) / 4 + 24; }
+		++calls;
+		res[t] = r;
+		wide[t] = 1;
+	}
+	if (calls) { atomicAdd(&cnt->sw_calls, calls); atomicAdd(&cnt->sw_cells, cells); atomicAdd(&cnt->sw_bytes, bytes); }
+}
+
+__global__ void __launch_bounds__(256) k_ext_left_fin(ssq_opts_t opt, u64 n_tasks, const ExtInfo *__restrict__ info, const ExtRes *__restrict__ lres, RegCand *cand, u32 *key, u32 *idx)
+{
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tasks) return;
+	const ExtInfo e = info[t];
 	RegCand a;
-	extend_seed(ix, opt, (int)(read_off[k.read + 1] - read_off[k.read]), seq + read_off[k.read], c, sorted + s0 + c.seed_start, k.seed, eh, a, cnt);
+	a.qe = 0; a.re = 0; a.w = 0; a.seedcov = 0; a.seedlen0 = 0; a.frac_rep = 0.f;
+	ext_left_fin(opt, e, ext_left_qlen(e) > 0, lres[t], a);
+	cand[t] = a;
+	key[t] = ext_key(ext_right_qlen(e), ext_right_tlen(e));
+	idx[t] = (u32)t;
+}
+
+__global__ void __launch_bounds__(256) k_ext_right_fin(ssq_opts_t opt, u64 n_tasks, const Task *__restrict__ tasks, const u64 *__restrict__ intv_off,
+                                                       const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
+                                                       const ExtInfo *__restrict__ info, const ExtRes *__restrict__ rres, const uint8_t *__restrict__ wide_l,
+                                                       const uint8_t *__restrict__ wide_r, RegCand *cand)
+{
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tasks) return;
+	const Task k = tasks[t];
+	const u64 s0 = seed_off[intv_off[k.read]];
+	const ChainRec c = outc[s0 + k.chain];
+	const ExtInfo e = info[t];
+	RegCand a = cand[t];
+	ext_right_fin(opt, e, ext_right_qlen(e) > 0, rres[t], opt.w << wide_l[t], opt.w << wide_r[t], c, sorted + s0 + c.seed_start, a);
 	cand[t] = a;
 }
 
@@ -382,13 +528,14 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
 	cudaEvent_t ev[6];
 	float stage_ms[5];
-	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 1; } memset(stage_ms, 0, sizeof stage_ms); }
+	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
 };
 
 // misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
@@ -443,7 +590,8 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	if (!b) return;
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
-	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out};
+	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
@@ -484,6 +632,9 @@ static int run_smem(ssq_batch *b)
 		if (variant == 0)
 			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
+		else if (variant == 2)
+			k_smem_m<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
+			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else
 			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
@@ -559,17 +710,67 @@ static int run_extend(ssq_batch *b)
 	CK(cudaStreamSynchronize(b->st));
 	const u64 nt = b->n_tasks;
 	if (b->tasks.need((nt + 1) * sizeof(Task)) || b->cand.need((nt + 1) * sizeof(RegCand)) || b->srt.need((nt + 1) * 8) || b->regs.need((nt + 1) * sizeof(RegCand))) return SSQ_ENOMEM;
+	if (b->xinfo.need((nt + 1) * sizeof(ExtInfo)) || b->xres[0].need((nt + 1) * sizeof(ExtRes)) || b->xres[1].need((nt + 1) * sizeof(ExtRes)) || b->xwide.need(2 * (nt + 1)) ||
+	    b->xkey[0].need((nt + 1) * 4) || b->xkey[1].need((nt + 1) * 4) || b->xidx[0].need((nt + 1) * 4) || b->xidx[1].need((nt + 1) * 4) || b->xretry.need((nt + 1) * 4) ||
+	    b->xmisc.need(256)) return SSQ_ENOMEM;
 	CK(cudaEventRecord(b->ev[3], b->st));
 	if (nt) {
 		k_tasks<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(),
 		                                           b->task_off.as<u64>(), b->tasks.as<Task>());
-		const int threads = 64;
-		const size_t smem = (size_t)threads * (b->max_len + 2) * 4;
-		CK(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_extend<<<(unsigned)((nt + threads - 1) / threads), threads, smem, b->st>>>(b->idx->dev, b->opt, nt, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
-		                                                                            b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
-		                                                                            b->cand.as<RegCand>(), &b->misc.as<Misc>()->cnt);
+		const unsigned G = (unsigned)((nt + 255) / 256);
+		uint8_t *wide_l = b->xwide.as<uint8_t>(), *wide_r = wide_l + (nt + 1);
+		u32 *bounds = b->xmisc.as<u32>();                 // [0..6]
+		unsigned int *n_retry = b->xmisc.as<unsigned int>() + 16;
+		CK(cudaMemsetAsync(b->xwide.p, 0, 2 * (nt + 1), b->st));
+		k_ext_prep<<<G, 256, 0, b->st>>>(b->idx->dev, b->opt, nt, b->tasks.as<Task>(), b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(),
+		                                b->sorted.as<Seed>(), b->xinfo.as<ExtInfo>(), b->xkey[0].as<u32>(), b->xidx[0].as<u32>());
 		b->launches += 2;
+		static const int caps[6] = {32, 64, 96, 128, 160, 255};
+		for (int dir = 0; dir < 2; ++dir) {
+			size_t tb = 0;
+			cub::DeviceRadixSort::SortPairs(0, tb, b->xkey[0].as<u32>(), b->xkey[1].as<u32>(), b->xidx[0].as<u32>(), b->xidx[1].as<u32>(), (int)nt, 0, 32, b->st);
+			if (b->cubtmp.need(tb)) return SSQ_ENOMEM;
+			CK(cub::DeviceRadixSort::SortPairs(b->cubtmp.p, tb, b->xkey[0].as<u32>(), b->xkey[1].as<u32>(), b->xidx[0].as<u32>(), b->xidx[1].as<u32>(), (int)nt, 0, 32, b->st));
+			k_ext_bounds<<<1, 32, 0, b->st>>>(nt, b->xkey[1].as<u32>(), bounds);
+			CK(cudaMemsetAsync(n_retry, 0, 4, b->st));
+			u32 hb[8];
+			CK(cudaMemcpyAsync(hb, bounds, 7 * 4, cudaMemcpyDeviceToHost, b->st));
+			CK(cudaStreamSynchronize(b->st));
+			b->launches += 3;
+			for (int c = 5; c >= 0; --c) { // longest class first
+				const u32 lo = hb[c], hi = hb[c + 1];
+				if (hi <= lo) continue;
+				const int threads = caps[c] > 160 ? 64 : 128;
+				const size_t smem = (size_t)threads * (caps[c] + 2) * 4;
+				const unsigned grid = (hi - lo + threads - 1) / threads;
+				if (dir == 0) {
+					CK(cudaFuncSetAttribute(k_ext_run<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
+					k_ext_run<0><<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, lo, hi, b->xidx[1].as<u32>(), b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+					                                            b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[0].as<ExtRes>(), b->xretry.as<u32>(), n_retry, &b->misc.as<Misc>()->cnt);
+				} else {
+					CK(cudaFuncSetAttribute(k_ext_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
+					k_ext_run<1><<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, lo, hi, b->xidx[1].as<u32>(), b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+					                                            b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[1].as<ExtRes>(), b->xretry.as<u32>(), n_retry, &b->misc.as<Misc>()->cnt);
+				}
+				++b->launches;
+			}
+			{
+				const size_t smem = (size_t)64 * (b->max_len + 2) * 4;
+				if (dir == 0) {
+					CK(cudaFuncSetAttribute(k_ext_retry<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+					k_ext_retry<0><<<b->n_sm * 2, 64, smem, b->st>>>(b->idx->dev, b->opt, b->xretry.as<u32>(), n_retry, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+					                                                b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[0].as<ExtRes>(), wide_l, &b->misc.as<Misc>()->cnt);
+					k_ext_left_fin<<<G, 256, 0, b->st>>>(b->opt, nt, b->xinfo.as<ExtInfo>(), b->xres[0].as<ExtRes>(), b->cand.as<RegCand>(), b->xkey[0].as<u32>(), b->xidx[0].as<u32>());
+				} else {
+					CK(cudaFuncSetAttribute(k_ext_retry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+					k_ext_retry<1><<<b->n_sm * 2, 64, smem, b->st>>>(b->idx->dev, b->opt, b->xretry.as<u32>(), n_retry, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+					                                                b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[1].as<ExtRes>(), wide_r, &b->misc.as<Misc>()->cnt);
+					k_ext_right_fin<<<G, 256, 0, b->st>>>(b->opt, nt, b->tasks.as<Task>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+					                                     b->xinfo.as<ExtInfo>(), b->xres[1].as<ExtRes>(), wide_l, wide_r, b->cand.as<RegCand>());
+				}
+				b->launches += 2;
+			}
+		}
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(b->ev[4], b->st));

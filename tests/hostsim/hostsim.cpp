@@ -35,7 +35,13 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	std::vector<Intv> bufA(len + 2), bufB(len + 2);
 	w.mem.assign(2048, Intv());
 	int err = 0;
-	w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
+	if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
+	else { // the state-machine form the GPU kernel runs
+		SmemMachine m; Intv ok[4];
+		m.init(opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data());
+		while (m.advance(ix)) { fm.extend(m.in, ok, m.is_back); m.post(ok); }
+		err = m.err; w.n_intv = m.finish();
+	}
 	if (err) abort();
 	int b = 0, en = 0; w.l_rep = 0;
 	for (int i = 0; i < w.n_intv; ++i) {
