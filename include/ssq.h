@@ -101,6 +101,14 @@ int ssq_chain_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, 
 typedef struct { uint64_t pos1, pos2; uint8_t strand1, strand2, valid, pad[5]; } ssq_dupsig_t;
 int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig, uint8_t *is_dup);
 
+/* Streaming form for inputs that arrive in pieces (the `samblaster` shim): the set remembers every signature it has seen,
+ * so "first occurrence wins" holds across calls as if all batches had been one. */
+typedef struct ssq_dupset ssq_dupset_t;
+int ssq_dupset_create(int device, ssq_dupset_t **out);
+int ssq_dupset_mark(ssq_dupset_t *set, uint64_t n, const ssq_dupsig_t *sig, uint8_t *is_dup);
+uint64_t ssq_dupset_size(const ssq_dupset_t *set);
+void ssq_dupset_free(ssq_dupset_t *set);
+
 /* ------------------------------------------------- the alignment pipeline ----
  * Seeding → SA lookup → chaining → chain filter → seed extension → alignment regions, all on the
  * device (the single-end core of `$BWA mem`, upstream mem_align1_core() up to and including
@@ -135,6 +143,20 @@ uint64_t ssq_batch_counter(const ssq_batch_t *b, int what);
 /* milliseconds of the last run per stage (CUDA events on the batch stream): 0 smem, 1 sa, 2 chain, 3 extend, 4 finalize */
 float ssq_batch_stage_ms(const ssq_batch_t *b, int stage);
 void ssq_batch_free(ssq_batch_t *b);
+
+/* ------------------------------------------------------- `bwa mem` for one batch ----
+ * What the `bwa` shim calls per batch of reads (upstream mem_process_seqs(); `$BWA mem`, speedseq:438,468): reads as ASCII
+ * strings (names already stripped of /1 /2), paired = adjacent reads are mates.  n_processed = global ordinal of reads[0]
+ * (tie-breaking hashes use it).  pes0 != NULL overrides the per-batch insert-size statistics (`-I`).  Returns the SAM
+ * records of the batch in input order as one malloc'd string (free with ssq_free).  Seeding, chaining, all Smith-Waterman
+ * variants and CIGAR/NM/MD generation run on the device; pairing, MAPQ and text formatting on the host. */
+typedef struct { int32_t low, high, failed, pad; double avg, std; } ssq_pestat_t;
+int ssq_mem_batch_sam(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const char *const *names, const char *const *seqs, const char *const *quals,
+                      const char *const *comments, int64_t n_processed, int paired, const ssq_pestat_t *pes0, const char *rg_id, int verbose, char **sam_out, size_t *sam_len,
+                      size_t *read_sam_off /* optional [n_reads+1]: byte range of each read's lines */);
+void ssq_free(void *p);
+/* contig table for the SAM header: name/length of contig i (0 <= i < ssq_index_info(idx,3)) */
+const char *ssq_index_contig(const ssq_index_t *idx, int i, int64_t *len);
 
 #ifdef __cplusplus
 }

@@ -183,3 +183,10 @@ extern "C" uint64_t ssq_index_info(const ssq_index_t *idx, int what)
 	}
 	return 0;
 }
+
+extern "C" const char *ssq_index_contig(const ssq_index_t *idx, int i, int64_t *len)
+{
+	if (!idx || i < 0 || i >= idx->n_seqs) return 0;
+	if (len) *len = idx->ann_len[i];
+	return idx->names[i];
+}

@@ -18,6 +18,7 @@
 #include <vector>
 #include "ssq_dev.cuh"
 #include "ssq_host.h"
+#include "ssq_batch.h"
 
 #define FULL 0xffffffffu
 
@@ -598,6 +599,14 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	delete b;
 }
 
+BatchView ssq_batch_view(ssq_batch_t *b)
+{
+	BatchView v;
+	v.ix = b->idx->dev; v.n_reads = b->n_reads; v.n_sm = b->n_sm;
+	v.seq = b->seq.as<uint8_t>(); v.read_off = b->read_off.as<u64>();
+	v.task_off = b->task_off.as<u64>(); v.n_regs = b->n_regs.as<u32>(); v.regs = b->regs.as<RegCand>();
+	return v;
+}
 extern "C" void *ssq_batch_stream(ssq_batch_t *b) { return (void*)b->st; }
 extern "C" int ssq_batch_set_stream(ssq_batch_t *b, void *stream)
 {
@@ -1001,5 +1010,95 @@ extern "C" int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig
 	CK(cudaMemcpy(is_dup, dd.p, n, cudaMemcpyDeviceToHost));
 	DBuf *all[] = {&dsig, &k1, &k2, &k1g, &ka, &idx_a, &idx_b, &tmp, &dd};
 	for (size_t i = 0; i < 9; ++i) all[i]->release();
+	return SSQ_OK;
+}
+
+// --------------------------------------------------------------------------- streaming dup-set ----
+// First-seen-wins across a stream of batches (what `$SAMBLASTER` needs: its input does not fit one call).  The set of
+// signatures seen so far is kept on the device as two parallel arrays sorted by (key1, key2); a batch is (1) marked within
+// itself by the two-pass stable sort above, (2) its survivors are looked up in the set by binary search, (3) the new ones
+// are appended and the set is re-sorted (two stable LSD passes).
+struct ssq_dupset { int device; u64 n, cap; u64 *k1, *k2; };
+
+__global__ void k_dupset_lookup(u64 n, const ssq_dupsig_t *__restrict__ sig, const u64 *__restrict__ key1, const u64 *__restrict__ key2, uint8_t *is_dup,
+                                const u64 *__restrict__ s1, const u64 *__restrict__ s2, u64 sn, uint8_t *is_new)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint8_t nw = 0;
+	if (sig[i].valid && !is_dup[i]) {
+		const u64 a = key1[i], b = key2[i];
+		u64 lo = 0, hi = sn;
+		while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (s1[mid] < a || (s1[mid] == a && s2[mid] < b)) lo = mid + 1; else hi = mid; }
+		if (lo < sn && s1[lo] == a && s2[lo] == b) is_dup[i] = 1; else nw = 1;
+	}
+	is_new[i] = nw;
+}
+
+extern "C" int ssq_dupset_create(int device, ssq_dupset_t **out)
+{
+	int rc = ssq_use_device(device);
+	if (rc) return rc;
+	ssq_dupset *s = (ssq_dupset*)calloc(1, sizeof(ssq_dupset));
+	s->device = device;
+	*out = s;
+	return SSQ_OK;
+}
+extern "C" void ssq_dupset_free(ssq_dupset_t *s) { if (!s) return; cudaFree(s->k1); cudaFree(s->k2); free(s); }
+extern "C" uint64_t ssq_dupset_size(const ssq_dupset_t *s) { return s ? s->n : 0; }
+
+extern "C" int ssq_dupset_mark(ssq_dupset_t *set, uint64_t n, const ssq_dupsig_t *sig, uint8_t *is_dup)
+{
+	if (!set) return SSQ_EINVAL;
+	int rc = ssq_use_device(set->device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	if (n >= 0x7fffffffull) { ssq_set_error("ssq_dupset_mark: more than 2^31-1 pairs in one call"); return SSQ_EINVAL; }
+	DBuf dsig, k1, k2, k1g, ka, idx_a, idx_b, tmp, dd, dnew, nk1, nk2, cnt;
+	if (dsig.need(n * sizeof(ssq_dupsig_t)) || k1.need(n * 8) || k2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dd.need(n) || dnew.need(n) ||
+	    nk1.need(n * 8) || nk2.need(n * 8) || cnt.need(16)) return SSQ_ENOMEM;
+	CK(cudaMemcpy(dsig.p, sig, n * sizeof(ssq_dupsig_t), cudaMemcpyHostToDevice));
+	const unsigned g = (unsigned)((n + 255) / 256);
+	k_dup_keys<<<g, 256>>>(n, dsig.as<ssq_dupsig_t>(), k1.as<u64>(), k2.as<u64>(), idx_a.as<u32>());
+	size_t tb = 0, tb2 = 0;
+	cub::DeviceRadixSort::SortPairs(0, tb, k2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n);
+	cub::DeviceSelect::Flagged(0, tb2, k1.as<u64>(), dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n);
+	if (tb2 > tb) tb = tb2;
+	const u64 grown = set->n + n;
+	cub::DeviceRadixSort::SortPairs(0, tb2, (u64*)0, (u64*)0, (u64*)0, (u64*)0, (int)(grown < 0x7fffffffull ? grown : 0x7ffffffe));
+	if (tb2 > tb) tb = tb2;
+	if (grown >= 0x7fffffffull) { ssq_set_error("ssq_dupset: more than 2^31-1 distinct signatures"); return SSQ_ECAP; }
+	if (tmp.need(tb)) return SSQ_ENOMEM;
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n));
+	k_dup_gather<<<g, 256>>>(n, idx_b.as<u32>(), k1.as<u64>(), k1g.as<u64>());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n));
+	k_dup_mark<<<g, 256>>>(n, idx_a.as<u32>(), ka.as<u64>(), k2.as<u64>(), dsig.as<ssq_dupsig_t>(), dd.as<uint8_t>());
+	k_dupset_lookup<<<g, 256>>>(n, dsig.as<ssq_dupsig_t>(), k1.as<u64>(), k2.as<u64>(), dd.as<uint8_t>(), set->k1, set->k2, set->n, dnew.as<uint8_t>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(is_dup, dd.p, n, cudaMemcpyDeviceToHost));
+	// absorb the new signatures
+	u64 n_new = 0;
+	CK(cub::DeviceSelect::Flagged(tmp.p, tb, k1.as<u64>(), dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n));
+	CK(cub::DeviceSelect::Flagged(tmp.p, tb, k2.as<u64>(), dnew.as<uint8_t>(), nk2.as<u64>(), cnt.as<u64>(), (int)n));
+	CK(cudaMemcpy(&n_new, cnt.p, 8, cudaMemcpyDeviceToHost));
+	if (n_new) {
+		const u64 total = set->n + n_new;
+		if (total > set->cap) { // grow, keeping the content
+			const u64 ncap = total + total / 2 + 1024;
+			u64 *a = 0, *b = 0;
+			CK(cudaMalloc(&a, ncap * 8)); CK(cudaMalloc(&b, ncap * 8));
+			if (set->n) { CK(cudaMemcpy(a, set->k1, set->n * 8, cudaMemcpyDeviceToDevice)); CK(cudaMemcpy(b, set->k2, set->n * 8, cudaMemcpyDeviceToDevice)); }
+			cudaFree(set->k1); cudaFree(set->k2);
+			set->k1 = a; set->k2 = b; set->cap = ncap;
+		}
+		CK(cudaMemcpy(set->k1 + set->n, nk1.p, n_new * 8, cudaMemcpyDeviceToDevice));
+		CK(cudaMemcpy(set->k2 + set->n, nk2.p, n_new * 8, cudaMemcpyDeviceToDevice));
+		DBuf t1, t2;
+		if (t1.need(total * 8) || t2.need(total * 8)) return SSQ_ENOMEM;
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, set->k2, t2.as<u64>(), set->k1, t1.as<u64>(), (int)total)); // by key2, key1 rides along
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, t1.as<u64>(), set->k1, t2.as<u64>(), set->k2, (int)total)); // stable by key1
+		set->n = total;
+	}
+	CK(cudaDeviceSynchronize());
 	return SSQ_OK;
 }

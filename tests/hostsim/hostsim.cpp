@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "../../speedseq_b200/csrc/ssq_dev.cuh"
+#include "../../speedseq_b200/csrc/ssq_mem_host.h"
 extern "C" {
 #include "../../oracle/ssqo.h"
 }
@@ -81,6 +82,65 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	w.regs.assign(out.begin(), out.begin() + n_out);
 }
 
+// ---- backend for mem_batch_sam(): the three base-level stages executed by the SSQ_HD routines on the host ----
+struct HostBackend {
+	const DevIndex &ix; ssq_opts_t o;
+	std::vector<uint8_t> codes; std::vector<u64> off; int n_reads;
+	std::vector<u64> aoff; std::vector<u32> na; std::vector<AlnReg> areg;
+	// scratch
+	std::vector<uint8_t> qbuf, rbuf, z, seq, ref; std::vector<i32> h, e, H0, H1, E, Hmax; std::vector<u64> b;
+	AlnScratch A; MateScratch M;
+	HostBackend(const DevIndex &i, const ssq_opts_t &o_) : ix(i), o(o_), n_reads(0), qbuf(256), rbuf(2048), z(256 * 768), seq(256), ref(12288), h(272), e(272), H0(272), H1(272), E(272), Hmax(272), b(12288)
+	{
+		A.qbuf = qbuf.data(); A.rbuf = rbuf.data(); A.rcap = 2048; A.g.h = h.data(); A.g.e = e.data(); A.g.z = z.data(); A.g.zcap = 256 * 768;
+		M.seq = seq.data(); M.ref = ref.data(); M.ref_cap = 12288; M.L.H0 = H0.data(); M.L.H1 = H1.data(); M.L.E = E.data(); M.L.Hmax = Hmax.data(); M.L.b = b.data(); M.L.b_cap = 12288; M.A = A;
+	}
+	int align(int n, const uint8_t *codes_, const u64 *off_, int paired, int max_matesw)
+	{
+		n_reads = n; codes.assign(codes_, codes_ + off_[n] + 1); off.assign(off_, off_ + n + 1);
+		std::vector<std::vector<RegCand> > r0(n);
+		for (int r = 0; r < n; ++r) { ReadWork w; run_read(ix, o, (int)(off[r + 1] - off[r]), codes.data() + off[r], 2, w); r0[r] = w.regs; }
+		aoff.assign(n + 1, 0); na.assign(n + 1, 0);
+		for (int r = 0; r < n; ++r) {
+			u64 m = paired ? r0[r ^ 1].size() : 0;
+			if (m > (u64)max_matesw) m = max_matesw;
+			aoff[r + 1] = aoff[r] + r0[r].size() + 4 * m + (paired ? 4 : 0);
+		}
+		areg.assign(aoff[n] + 1, AlnReg());
+		for (int r = 0; r < n; ++r) {
+			AlnReg *a = areg.data() + aoff[r];
+			for (size_t i = 0; i < r0[r].size(); ++i) reg_from_cand(r0[r][i], a[i]);
+			na[r] = (u32)sort_dedup_patch(ix, o, codes.data() + off[r], (int)r0[r].size(), a, A);
+		}
+		return 0;
+	}
+	int rescue(const PeStat pes[4])
+	{
+		for (int p = 0; p < n_reads / 2; ++p) {
+			AlnReg bb[2][64]; int nb[2] = {0, 0}, n[2]; AlnReg *a[2];
+			for (int i = 0; i < 2; ++i) {
+				a[i] = areg.data() + aoff[2 * p + i]; n[i] = (int)na[2 * p + i];
+				for (int j = 0; j < n[i]; ++j) if (a[i][j].score >= a[i][0].score - o.pen_unpaired && nb[i] < 64) bb[i][nb[i]++] = a[i][j];
+			}
+			for (int i = 0; i < 2; ++i) {
+				const int cap = (int)(aoff[2 * p + !i + 1] - aoff[2 * p + !i]);
+				for (int j = 0; j < nb[i] && j < o.max_matesw; ++j)
+					mate_rescue(ix, o, pes, bb[i][j], (int)(off[2 * p + !i + 1] - off[2 * p + !i]), codes.data() + off[2 * p + !i], a[!i], &n[!i], cap, M);
+			}
+			na[2 * p] = (u32)n[0]; na[2 * p + 1] = (u32)n[1];
+		}
+		return 0;
+	}
+	int cigar(const std::vector<CigTask> &tasks, std::vector<AlnOut> &outs, std::vector<u32> &cigs, std::vector<char> &mds)
+	{
+		for (size_t t = 0; t < tasks.size(); ++t) {
+			const int r = tasks[t].read;
+			reg2aln(ix, o, (int)(off[r + 1] - off[r]), codes.data() + off[r], tasks[t].reg, A, outs[t], cigs.data() + t * CIG_CAP, CIG_CAP, mds.data() + t * MD_CAP, MD_CAP);
+		}
+		return 0;
+	}
+};
+
 extern "C" {
 
 typedef struct { uint64_t k, l, s; uint32_t qbeg, qend; } api_smem_t;
@@ -137,6 +197,47 @@ int64_t hostsim_align_batch(const ssqo_idx_t *idx, int n_reads, const uint8_t *s
 		for (size_t i = 0; i < w.regs.size(); ++i, ++n) {
 			if (n >= cap) return -1;
 			const RegCand &a = w.regs[i];
+			out[n].rb = a.rb; out[n].re = a.re; out[n].qb = a.qb; out[n].qe = a.qe; out[n].rid = a.rid; out[n].score = a.score; out[n].truesc = a.truesc;
+			out[n].w = a.w; out[n].seedcov = a.seedcov; out[n].seedlen0 = a.seedlen0; out[n].frac_rep = a.frac_rep; out[n].read_id = r;
+		}
+	}
+	out_off[n_reads] = n;
+	return (int64_t)n;
+}
+
+// `bwa mem` for a batch of pairs through the product's host orchestration + the host backend -> malloc'd SAM text
+char *hostsim_mem_pe(const ssqo_idx_t *idx, int n_reads, const char **names, const char **seqs, const char **quals, int64_t n_processed, const char *rg_id, int paired)
+{
+	std::vector<i64> aoff_; std::vector<i32> alen_; DevIndex ix = make_ix(idx, aoff_, alen_);
+	ssq_opts_t opt; ssq_opts_default(&opt);
+	std::vector<u64> off(n_reads + 1, 0);
+	for (int i = 0; i < n_reads; ++i) off[i + 1] = off[i] + strlen(seqs[i]);
+	std::vector<uint8_t> codes(off[n_reads] + 1);
+	for (int i = 0; i < n_reads; ++i) for (size_t k = 0; seqs[i][k]; ++k) { char c = seqs[i][k]; codes[off[i] + k] = c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2 : c == 'T' || c == 't' ? 3 : 4; }
+	std::vector<char*> nm(idx->bns.n_seqs);
+	for (int i = 0; i < idx->bns.n_seqs; ++i) nm[i] = idx->bns.anns[i].name;
+	HostIndexInfo hi; hi.l_pac = idx->bns.l_pac; hi.n_seqs = idx->bns.n_seqs; hi.names = nm.data(); hi.ann_off = aoff_.data();
+	HostBackend be(ix, opt);
+	std::string sam, err;
+	int rc = mem_batch_sam(be, opt, &hi, n_reads, names, codes.data(), off.data(), quals, (const char *const *)0, n_processed, paired, (const PeStat*)0, rg_id, (FILE*)0, sam, err);
+	if (rc) return 0;
+	char *out = (char*)malloc(sam.size() + 1);
+	memcpy(out, sam.c_str(), sam.size() + 1);
+	return out;
+}
+
+int64_t hostsim_align1_batch(const ssqo_idx_t *idx, int n_reads, const uint8_t *seq, const uint64_t *read_off, api_alnreg_t *out, uint64_t cap, uint64_t *out_off)
+{
+	std::vector<i64> aoff_; std::vector<i32> alen_; DevIndex ix = make_ix(idx, aoff_, alen_);
+	ssq_opts_t opt; ssq_opts_default(&opt);
+	HostBackend be(ix, opt);
+	be.align(n_reads, seq, read_off, 0, opt.max_matesw);
+	uint64_t n = 0;
+	for (int r = 0; r < n_reads; ++r) {
+		out_off[r] = n;
+		for (u32 i = 0; i < be.na[r]; ++i, ++n) {
+			if (n >= cap) return -1;
+			const AlnReg &a = be.areg[be.aoff[r] + i];
 			out[n].rb = a.rb; out[n].re = a.re; out[n].qb = a.qb; out[n].qe = a.qe; out[n].rid = a.rid; out[n].score = a.score; out[n].truesc = a.truesc;
 			out[n].w = a.w; out[n].seedcov = a.seedcov; out[n].seedlen0 = a.seedlen0; out[n].frac_rep = a.frac_rep; out[n].read_id = r;
 		}

@@ -34,8 +34,8 @@ def build_oracle():
 def build_hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     src, out = os.path.join(d, "hostsim.cpp"), HOSTSIM_SO
-    hdr = os.path.join(ROOT, "speedseq_b200", "csrc", "ssq_dev.cuh")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(ORACLE_SO)):
+    hdrs = [os.path.join(ROOT, "speedseq_b200", "csrc", f) for f in ("ssq_dev.cuh", "ssq_dev2.cuh", "ssq_mem_host.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max([os.path.getmtime(src), os.path.getmtime(ORACLE_SO)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", out, src, "-L" + os.path.join(ROOT, "oracle"), "-lssqo",
                                "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
 
@@ -156,6 +156,28 @@ class HostSim:
 
     def sw_extend_batch(self, tasks, qbuf, tbuf):
         return self.o.sw_extend_batch(tasks, qbuf, tbuf, lib=self.lib, fn="hostsim_sw_extend_batch")
+
+    def mem_pe(self, idx, names, seqs, quals, n_processed=0, rg_id=b"", paired=1):
+        n = len(names)
+        arr = lambda xs: (C.c_char_p * n)(*[x if isinstance(x, bytes) else x.encode() for x in xs])
+        self.lib.hostsim_mem_pe.restype = C.c_void_p
+        p = self.lib.hostsim_mem_pe(C.c_void_p(idx), C.c_int(n), arr(names), arr(seqs), arr(quals), C.c_int64(n_processed), rg_id, C.c_int(paired))
+        assert p, "hostsim_mem_pe failed"
+        s = C.string_at(p).decode()
+        self.o.lib.ssqo_api_free(C.c_void_p(p))
+        return s
+
+    def align1_batch(self, idx, seq, off):
+        n = len(off) - 1
+        cap = max(1024, 16 * n)
+        self.lib.hostsim_align1_batch.restype = C.c_int64
+        while True:
+            out = np.zeros(cap, REG_DT)
+            ooff = np.zeros(n + 1, np.uint64)
+            r = self.lib.hostsim_align1_batch(C.c_void_p(idx), C.c_int(n), _ptr(seq), _ptr(off), _ptr(out), C.c_uint64(cap), _ptr(ooff))
+            if r >= 0:
+                return out[:r], ooff
+            cap *= 4
 
     def align_batch(self, idx, seq, off):
         n = len(off) - 1
