@@ -109,6 +109,10 @@ int ssq_dupset_mark(ssq_dupset_t *set, uint64_t n, const ssq_dupsig_t *sig, uint
 uint64_t ssq_dupset_size(const ssq_dupset_t *set);
 void ssq_dupset_free(ssq_dupset_t *set);
 
+/* Device-pointer form used by the multi-GPU exchange (speedseq_b200/dist.py): keys already sit in HBM (received by an NCCL
+ * all-to-all), element order = first-seen order, key = (5' position << 1 | strand) of the canonically ordered ends. */
+int ssq_dupmark_keys_dev(int device, uint64_t n, const uint64_t *d_key1, const uint64_t *d_key2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);
+
 /* ------------------------------------------------- the alignment pipeline ----
  * Seeding → SA lookup → chaining → chain filter → seed extension → alignment regions, all on the
  * device (the single-end core of `$BWA mem`, upstream mem_align1_core() up to and including

@@ -1102,3 +1102,46 @@ extern "C" int ssq_dupset_mark(ssq_dupset_t *set, uint64_t n, const ssq_dupsig_t
 	CK(cudaDeviceSynchronize());
 	return SSQ_OK;
 }
+
+// ------------------------------------------------------------- device-resident dup-marking ----
+// keys already in HBM (e.g. received through an NCCL all-to-all): key1/key2 = (pos << 1 | strand) of the canonically
+// ordered ends, valid[i] = 0 for pairs that can never be duplicates; elements are taken in array order (= first-seen order).
+__global__ void k_dup_iota(u64 n, u32 *idx) { u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) idx[i] = (u32)i; }
+__global__ void k_dup_mask(u64 n, const uint8_t *__restrict__ valid, const u64 *__restrict__ k1, const u64 *__restrict__ k2, u64 *m1, u64 *m2)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { m1[i] = valid[i] ? k1[i] : ~0ull; m2[i] = valid[i] ? k2[i] : ~0ull; }
+}
+__global__ void k_dup_mark_keys(u64 n, const u32 *__restrict__ idx, const u64 *__restrict__ key1s, const u64 *__restrict__ key2, const uint8_t *__restrict__ valid, uint8_t *is_dup)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u32 me = idx[i];
+	uint8_t d = 0;
+	if (i > 0 && valid[me]) { const u32 pv = idx[i - 1]; d = valid[pv] && key1s[i] == key1s[i - 1] && key2[me] == key2[pv]; }
+	is_dup[me] = d;
+}
+
+extern "C" int ssq_dupmark_keys_dev(int device, uint64_t n, const uint64_t *d_key1, const uint64_t *d_key2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream_)
+{
+	int rc = ssq_use_device(device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	if (n >= 0xffffffffull) { ssq_set_error("ssq_dupmark_keys_dev: more than 2^32-1 pairs in one call"); return SSQ_EINVAL; }
+	cudaStream_t st = (cudaStream_t)stream_;
+	DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp;
+	if (m1.need(n * 8) || m2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4)) return SSQ_ENOMEM;
+	const unsigned g = (unsigned)((n + 255) / 256);
+	k_dup_mask<<<g, 256, 0, st>>>(n, d_valid, d_key1, d_key2, m1.as<u64>(), m2.as<u64>());
+	k_dup_iota<<<g, 256, 0, st>>>(n, idx_a.as<u32>());
+	size_t tb = 0;
+	cub::DeviceRadixSort::SortPairs(0, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st);
+	if (tmp.need(tb)) return SSQ_ENOMEM;
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st));
+	k_dup_gather<<<g, 256, 0, st>>>(n, idx_b.as<u32>(), m1.as<u64>(), k1g.as<u64>());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n, 0, 64, st));
+	k_dup_mark_keys<<<g, 256, 0, st>>>(n, idx_a.as<u32>(), ka.as<u64>(), m2.as<u64>(), d_valid, d_is_dup);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
+	return SSQ_OK;
+}
