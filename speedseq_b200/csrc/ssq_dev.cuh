@@ -31,8 +31,12 @@ typedef int32_t i32;
 // sa   : u64 SA[32k], k=0..n_sa-1 (sa[0] = -1 like the reference loader).
 // pac  : forward strand, 2 bit/base, base i at pac[i>>2] >> ((~i&3)<<1) & 3.
 // ann  : per-contig offset/len for rid look-ups.
+// bwt32: derived at load time when the index has fewer than 2^32 rows — the same BWT re-blocked for the GPU's 32-byte
+//        sector: one block per 64 symbols = u32 occ[4] + u32 w[4].  A rank query reads exactly one sector and counts at
+//        most four words.  (Larger indexes keep using the 64-byte on-disk blocks with u64 counts.)
 struct DevIndex {
 	const u32 *bwt;
+	const u32 *bwt32;
 	const u64 *sa;
 	const uint8_t *pac;
 	const i64 *ann_off;
@@ -85,6 +89,31 @@ struct ScalarFm {
 	{
 		if (k == (u64)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
 		u64 kk = k - (k >= ix.primary);
+		if (ix.bwt32) { // one 32-byte sector: u32 occ[4] + 64 symbols
+			const u32 *p = ix.bwt32 + ((kk >> 6) << 3);
+			u32 c0, c1, c2, c3, w0, w1, w2, w3;
+#ifdef __CUDA_ARCH__
+			const uint4 a = __ldg((const uint4*)p), b = __ldg((const uint4*)p + 1);
+			c0 = a.x; c1 = a.y; c2 = a.z; c3 = a.w; w0 = b.x; w1 = b.y; w2 = b.z; w3 = b.w;
+#else
+			c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; w0 = p[4]; w1 = p[5]; w2 = p[6]; w3 = p[7];
+#endif
+			++n_blk;
+			const int r = (int)(kk & 63) + 1; // symbols to count, 1..64
+			// two 64-bit lanes of 32 symbols each, MSB-first within each original 32-bit word
+			const u64 lo_w = (u64)w0 << 32 | w1, hi_w = (u64)w2 << 32 | w3;
+			const int n0 = r < 32 ? r : 32, n1 = r - 32 > 0 ? r - 32 : 0;
+			const u64 m0 = 0x5555555555555555ull & ~(n0 >= 32 ? 0ull : (~0ull >> (2 * n0)));
+			const u64 m1 = n1 <= 0 ? 0ull : (0x5555555555555555ull & ~(n1 >= 32 ? 0ull : (~0ull >> (2 * n1))));
+			const u64 l0 = lo_w & m0, h0 = (lo_w >> 1) & m0, l1 = hi_w & m1, h1 = (hi_w >> 1) & m1;
+#ifdef __CUDA_ARCH__
+			const int p3 = __popcll(h0 & l0) + __popcll(h1 & l1), ph = __popcll(h0) + __popcll(h1), pl = __popcll(l0) + __popcll(l1);
+#else
+			const int p3 = __builtin_popcountll(h0 & l0) + __builtin_popcountll(h1 & l1), ph = __builtin_popcountll(h0) + __builtin_popcountll(h1), pl = __builtin_popcountll(l0) + __builtin_popcountll(l1);
+#endif
+			cnt[3] = (u64)c3 + p3; cnt[2] = (u64)c2 + (ph - p3); cnt[1] = (u64)c1 + (pl - p3); cnt[0] = (u64)c0 + (r - ph - pl + p3);
+			return;
+		}
 		const u32 *p = ix.bwt + ((kk >> 7) << 4);
 		u32 blk[16];
 #ifdef __CUDA_ARCH__
@@ -118,6 +147,25 @@ struct ScalarFm {
 		}
 	}
 };
+
+#define SSQ_SEL4(v0, v1, v2, v3, c) ((c) == 0 ? (v0) : (c) == 1 ? (v1) : (c) == 2 ? (v2) : (v3))
+// only ok[c] of an extension, computed without runtime-indexed arrays (keeps everything in registers on the GPU)
+template <class Fm>
+SSQ_HD void extend1(Fm &fm, const Intv &ik, int c, int is_back, Intv &out)
+{
+	const DevIndex &ix = fm.ix;
+	u64 tk[4], tl[4];
+	const u64 kf = is_back ? ik.x0 : ik.x1, ko = is_back ? ik.x1 : ik.x0;
+	fm.occ4(kf - 1, tk);
+	fm.occ4(kf - 1 + ik.x2, tl);
+	const u64 n0 = tl[0] - tk[0], n1 = tl[1] - tk[1], n2 = tl[2] - tk[2], n3 = tl[3] - tk[3];
+	const u64 nf = SSQ_SEL4(ix.L2[0] + 1 + tk[0], ix.L2[1] + 1 + tk[1], ix.L2[2] + 1 + tk[2], ix.L2[3] + 1 + tk[3], c);
+	const u64 base = ko + (kf <= ix.primary && kf + ik.x2 - 1 >= ix.primary);
+	const u64 no = base + (c < 3 ? n3 : 0) + (c < 2 ? n2 : 0) + (c < 1 ? n1 : 0);
+	out.x2 = SSQ_SEL4(n0, n1, n2, n3, c);
+	if (is_back) { out.x0 = nf; out.x1 = no; } else { out.x1 = nf; out.x0 = no; }
+	out.qb = out.qe = 0;
+}
 
 SSQ_HD void set_intv(const DevIndex &ix, int c, Intv &ik)
 {
@@ -250,28 +298,39 @@ SSQ_HD int collect_intv(Fm &fm, const DevIndex &ix, const ssq_opts_t &opt, int l
 }
 
 // ------------------------------------------------------------- seeding as a state machine ----
-// Same three passes as collect_intv(), unrolled into a machine whose only expensive transition is one rank query
-// (Fm::extend).  A GPU lane owns one machine; all lanes of a warp meet at the query no matter which phase each
-// is in, which is what keeps the SIMT lanes busy (the straight-line version spends most issue slots with 4-5 of 32
-// lanes active).  advance() runs the cheap bookkeeping up to the next query (returns false when the read is done),
-// post() consumes the query's result.  Every list operation happens in the same order as in smem1()/seed_strategy1().
-struct SmemMachine {
+// Same three passes as collect_intv(), unrolled into a machine whose only expensive transition is one rank query.
+// A GPU lane owns one machine; all lanes of a warp meet at the query no matter which phase each is in.  advance() runs
+// the cheap bookkeeping up to the next query (false = read done), post() consumes the query's result.  Every list
+// operation happens in the same order as in smem1()/seed_strategy1().
+// Lists: the two ping-pong interval lists behind get/set (shared memory with global overflow on the GPU, plain arrays
+// in the host harness); their tails and the tail of the output list are mirrored in registers so that the backward
+// phase never waits on a dependent memory read other than the rank query itself.
+struct HostLists { // plain arrays (hostsim, thread-per-read fallbacks)
+	Intv *a[2];
+	SSQ_HD Intv get(int id, int j) const { return a[id][j]; }
+	SSQ_HD void set(int id, int j, const Intv &v) const { a[id][j] = v; }
+};
+
+template <class Lists>
+struct SmemMachineT {
 	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3 };
-	const uint8_t *q; Intv *mem, *prev, *curr;
-	int len, mem_cap, n, base, state, pass, x, i, j, c, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width;
+	const uint8_t *q; Intv *mem; Lists L;
+	int len, mem_cap, n, base, state, pass, x, i, j, c, qc, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width, prev_id;
+	u32 last_mem_qb;   // mem[n-1].qb of the current smem1 call
+	u64 curr_tail_x2;  // x2 of the entry last pushed to the current list
 	u64 min_intv, max_mem_intv;
-	Intv ik;      // current interval (FWD/S3)
-	Intv in;      // query input
+	Intv ik, in;
 	int is_back;
 
-	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, Intv *bufA, Intv *bufB)
+	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists)
 	{
-		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; prev = bufA; curr = bufB;
+		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0;
 		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1;
 		min_seed_len = opt.min_seed_len; split_len = (int)(opt.min_seed_len * opt.split_factor + .499f); split_width = opt.split_width;
 		max_mem_intv = (u64)opt.max_mem_intv;
 		if (len < opt.min_seed_len) { state = NEXT_P3; pass = 3; x = len; }
 	}
+	SSQ_HD void push_curr(const Intv &v) { L.set(prev_id ^ 1, n_curr++, v); curr_tail_x2 = v.x2; }
 	SSQ_HD void start_smem1(const DevIndex &ix, int x_, u64 min_intv_)
 	{
 		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; base = n;
@@ -280,19 +339,20 @@ struct SmemMachine {
 	}
 	SSQ_HD void end_forward() // forward list complete: longest first, then walk backwards
 	{
-		for (int a = 0; a < n_curr >> 1; ++a) { Intv t = curr[a]; curr[a] = curr[n_curr - 1 - a]; curr[n_curr - 1 - a] = t; }
-		ret = (int)curr[0].qe;
-		{ Intv *t = curr; curr = prev; prev = t; n_prev = n_curr; }
+		const int cid = prev_id ^ 1;
+		for (int a = 0; a < n_curr >> 1; ++a) { const Intv t = L.get(cid, a), u = L.get(cid, n_curr - 1 - a); L.set(cid, a, u); L.set(cid, n_curr - 1 - a, t); }
+		ret = (int)L.get(cid, 0).qe;
+		prev_id = cid; n_prev = n_curr;
 		i = x - 1; j = 0; n_curr = 0;
 		c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
 		state = BWD;
 	}
 	SSQ_HD void keep(const Intv &p_) // p is left-maximal at i+1 unless a longer match survived
 	{
-		if (n_curr == 0 && (n == base || (u32)(i + 1) < mem[n - 1].qb)) {
+		if (n_curr == 0 && (n == base || (u32)(i + 1) < last_mem_qb)) {
 			if (n >= mem_cap) { err = 1; return; }
 			Intv p = p_; p.qb = (u32)(i + 1);
-			mem[n++] = p;
+			mem[n++] = p; last_mem_qb = p.qb;
 		}
 	}
 	SSQ_HD void end_smem1() // reverse this call's output, drop short ones, pick what comes next
@@ -303,7 +363,7 @@ struct SmemMachine {
 		n = k;
 		if (pass == 1) { x = ret; state = NEXT_P1; } else state = NEXT_P2;
 	}
-	// returns true when `in`/`is_back` hold the next rank query; false when the read's interval list is complete
+	// true: `in` / `qc` / `is_back` describe the next rank query (only ok[qc] is needed); false: the read is complete
 	SSQ_HD bool advance(const DevIndex &ix)
 	{
 		for (;;) {
@@ -334,63 +394,61 @@ struct SmemMachine {
 				i = x + 1; state = S3;
 				break;
 			case FWD:
-				if (i >= len) { curr[n_curr++] = ik; end_forward(); break; }
-				if (q[i] > 3) { curr[n_curr++] = ik; end_forward(); break; }
-				in = ik; is_back = 0;
+				if (i >= len || q[i] > 3) { push_curr(ik); end_forward(); break; }
+				in = ik; is_back = 0; qc = 3 - q[i];
 				return true;
 			case BWD:
 				if (j >= n_prev) { // one backward step done for the whole set
 					if (n_curr == 0) { end_smem1(); break; }
-					{ Intv *t = curr; curr = prev; prev = t; n_prev = n_curr; }
+					prev_id ^= 1; n_prev = n_curr;
 					--i; j = 0; n_curr = 0;
 					if (i < -1) { end_smem1(); break; }
 					c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
 					break;
 				}
-				if (c < 0) { keep(prev[j]); ++j; break; }
-				in = prev[j]; is_back = 1;
+				in = L.get(prev_id, j);
+				if (c < 0) { keep(in); ++j; break; }
+				is_back = 1; qc = c;
 				return true;
 			case S3:
 				if (i >= len) { x = len; state = NEXT_P3; break; }
 				if (q[i] > 3) { x = i + 1; state = NEXT_P3; break; }
-				in = ik; is_back = 0;
+				in = ik; is_back = 0; qc = 3 - q[i];
 				return true;
 			}
 		}
 	}
-	SSQ_HD void post(const Intv ok[4])
+	SSQ_HD void post(const Intv &okc) // okc = ok[qc] of the query
 	{
 		if (state == FWD) {
-			const int cc = 3 - q[i];
-			if (ok[cc].x2 != ik.x2) {
-				curr[n_curr++] = ik;
-				if (ok[cc].x2 < min_intv) { end_forward(); return; }
+			if (okc.x2 != ik.x2) {
+				push_curr(ik);
+				if (okc.x2 < min_intv) { end_forward(); return; }
 			}
-			ik = ok[cc]; ik.qe = (u32)(i + 1);
+			ik = okc; ik.qe = (u32)(i + 1);
 			++i;
 		} else if (state == BWD) {
-			const Intv p = prev[j];
-			if (ok[c].x2 < min_intv) keep(p);
-			else if (n_curr == 0 || ok[c].x2 != curr[n_curr - 1].x2) { Intv t = ok[c]; t.qb = 0; t.qe = p.qe; curr[n_curr++] = t; }
+			if (okc.x2 < min_intv) keep(in);
+			else if (n_curr == 0 || okc.x2 != curr_tail_x2) { Intv t = okc; t.qb = 0; t.qe = in.qe; push_curr(t); }
 			++j;
 		} else { // S3
-			const int cc = 3 - q[i];
-			if (ok[cc].x2 < max_mem_intv && i - x >= min_seed_len) {
-				Intv m = ok[cc]; m.qb = (u32)x; m.qe = (u32)(i + 1);
+			if (okc.x2 < max_mem_intv && i - x >= min_seed_len) {
+				Intv m = okc; m.qb = (u32)x; m.qe = (u32)(i + 1);
 				if (m.x2 > 0) { if (n >= mem_cap) { err = 1; return; } mem[n++] = m; }
 				x = i + 1; state = NEXT_P3;
-			} else { ik = ok[cc]; ++i; }
+			} else { ik = okc; ++i; }
 		}
 	}
-	SSQ_HD int finish() // order by (qb,qe); returns the interval count
+	// order by (qb,qe): only 4-byte keys (qb | qe | slot) move, the 32-byte records are gathered once when the caller
+	// copies them out through key & 0x3ff.  keys[] needs n entries.  returns the interval count.
+	SSQ_HD int finish(u32 *keys)
 	{
 		if (err) return 0;
-		for (int a = 1; a < n; ++a) {
-			Intv t = mem[a];
-			u64 key = (u64)t.qb << 32 | t.qe;
+		for (int a = 0; a < n; ++a) {
+			const u32 key = mem[a].qb << 18 | mem[a].qe << 10 | (u32)a; // qb,qe <= 255, a < 1024
 			int k;
-			for (k = a; k > 0 && ((u64)mem[k - 1].qb << 32 | mem[k - 1].qe) > key; --k) mem[k] = mem[k - 1];
-			mem[k] = t;
+			for (k = a; k > 0 && (keys[k - 1] >> 10) > (key >> 10); --k) keys[k] = keys[k - 1];
+			keys[k] = key;
 		}
 		return n;
 	}
@@ -413,8 +471,9 @@ SSQ_HD u64 sa_lookup(ScalarFm &fm, u64 k, unsigned long long &n_sa)
 		++sa;
 		if (k == ix.primary) { k = 0; continue; }
 		u64 x = k - (k > ix.primary);
-		const u32 *p = ix.bwt + ((x >> 7) << 4) + 8;
-		int c = p[(x & 0x7f) >> 4] >> ((~x & 0xf) << 1) & 3;
+		int c;
+		if (ix.bwt32) { const u32 *p = ix.bwt32 + ((x >> 6) << 3) + 4; c = p[(x & 0x3f) >> 4] >> ((~x & 0xf) << 1) & 3; }
+		else { const u32 *p = ix.bwt + ((x >> 7) << 4) + 8; c = p[(x & 0x7f) >> 4] >> ((~x & 0xf) << 1) & 3; }
 		u64 cnt[4];
 		fm.occ4(k, cnt);
 		k = ix.L2[c] + cnt[c];

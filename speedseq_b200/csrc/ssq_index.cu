@@ -50,6 +50,29 @@ extern "C" void ssq_opts_default(ssq_opts_t *o)
 	o->mapQ_coef_len = 50; o->mapQ_coef_fac = (int)log(50.0);
 }
 
+// re-block the on-disk rank structure (64 B per 128 symbols, u64 counts) into 32 B per 64 symbols with u32 counts
+__global__ void k_reblock32(const u32 *__restrict__ bwt, u64 n_sym, u64 n_blk32, u32 *out)
+{
+	const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_blk32) return;
+	const u32 *src = bwt + ((b >> 1) << 4);
+	const u64 *c64 = (const u64*)src;
+	u32 add[4] = {0, 0, 0, 0};
+	if (b & 1) {
+#pragma unroll
+		for (int w = 0; w < 4; ++w) {
+			const u32 v = src[8 + w], lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+			add[0] += __popc(~hi & ~lo & 0x55555555u); add[1] += __popc(~hi & lo); add[2] += __popc(hi & ~lo); add[3] += __popc(hi & lo);
+		}
+	}
+	uint4 cnt, sym;
+	cnt.x = (u32)(c64[0] + add[0]); cnt.y = (u32)(c64[1] + add[1]); cnt.z = (u32)(c64[2] + add[2]); cnt.w = (u32)(c64[3] + add[3]);
+	const u64 first = ((b >> 1) << 7) + (b & 1) * 64; // first symbol of this block
+	sym.x = first < n_sym ? src[8 + (b & 1) * 4] : 0; sym.y = first + 16 < n_sym ? src[9 + (b & 1) * 4] : 0;
+	sym.z = first + 32 < n_sym ? src[10 + (b & 1) * 4] : 0; sym.w = first + 48 < n_sym ? src[11 + (b & 1) * 4] : 0;
+	((uint4*)out)[b * 2] = cnt; ((uint4*)out)[b * 2 + 1] = sym;
+}
+
 static void *read_file(const char *fn, size_t skip, size_t *len)
 {
 	FILE *fp = fopen(fn, "rb");
@@ -96,6 +119,16 @@ extern "C" int ssq_index_load(const char *prefix, int device, ssq_index_t **out)
 		CKI(cudaMemset(d, 0, padded));
 		CKI(cudaMemcpy(d, h + 40, bytes, cudaMemcpyHostToDevice));
 		idx->dev.bwt = (const u32*)d; idx->dev_bytes += padded;
+		if (idx->dev.seq_len < 0xffffffffull && !getenv("SSQ_NO_BWT32")) {
+			const u64 nb = (idx->dev.seq_len + 63) / 64 + 1;
+			void *d32 = 0;
+			CKI(cudaMalloc(&d32, nb * 32 + 64));
+			CKI(cudaMemset(d32, 0, nb * 32 + 64));
+			k_reblock32<<<(unsigned)((nb + 255) / 256), 256>>>((const u32*)d, idx->dev.seq_len, nb, (u32*)d32);
+			CKI(cudaGetLastError());
+			CKI(cudaDeviceSynchronize());
+			idx->dev.bwt32 = (const u32*)d32; idx->dev_bytes += nb * 32 + 64;
+		}
 	}
 	cudaFreeHost(h);
 	// .sa : u64 primary, L2[1..4], sa_intv, seq_len, then SA[32k] k>=1
@@ -163,7 +196,7 @@ extern "C" int ssq_index_load(const char *prefix, int device, ssq_index_t **out)
 extern "C" void ssq_index_free(ssq_index_t *idx)
 {
 	if (!idx) return;
-	cudaFree((void*)idx->dev.bwt); cudaFree((void*)idx->dev.sa); cudaFree((void*)idx->dev.pac);
+	cudaFree((void*)idx->dev.bwt); cudaFree((void*)idx->dev.bwt32); cudaFree((void*)idx->dev.sa); cudaFree((void*)idx->dev.pac);
 	cudaFree((void*)idx->dev.ann_off); cudaFree((void*)idx->dev.ann_len);
 	for (int i = 0; i < idx->n_seqs && idx->names; ++i) free(idx->names[i]);
 	free(idx->names); free(idx->ann_off); free(idx->ann_len);

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) k_smem_t(DevIndex ix, ssq_opts_t opt, int
                                                 int lcap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
                                                 u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
 {
-	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1);
+	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1) + (size_t)(scratch_cap + 7) / 8;
 	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per, *bufA = mem + scratch_cap, *bufB = bufA + (lcap + 1);
 	ScalarFm fm(ix);
 	for (;;) {
@@ -146,16 +146,36 @@ __global__ void __launch_bounds__(128) k_smem_t(DevIndex ix, ssq_opts_t opt, int
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
 
-// state-machine variant (default): a lane owns one SmemMachine and keeps pulling reads from the work counter; the only
-// step all lanes of a warp take together is the rank query, whatever phase (forward / backward / pass 3) each is in
+// state-machine variant (default): a lane owns one machine and keeps pulling reads from the work counter; the only step
+// all lanes of a warp take together is the rank query, whatever phase (forward / backward / pass 3) each is in.
+// The ping-pong lists live in shared memory as 16-byte entries (k, l, s as u32 + query end) when the index has fewer than
+// 2^32 rows, entries beyond `cap` (and every entry of larger indexes) go to the lane's global scratch lists.
+struct DevLists {
+	uint4 *sm; int cap, stride; Intv *g0, *g1;
+	__device__ __forceinline__ Intv get(int id, int j) const
+	{
+		if (j < cap) { const uint4 v = sm[(size_t)(id * cap + j) * stride]; Intv r; r.x0 = v.x; r.x1 = v.y; r.x2 = v.z; r.qb = 0; r.qe = v.w; return r; }
+		return (id ? g1 : g0)[j];
+	}
+	__device__ __forceinline__ void set(int id, int j, const Intv &v) const
+	{
+		if (j < cap) sm[(size_t)(id * cap + j) * stride] = make_uint4((u32)v.x0, (u32)v.x1, (u32)v.x2, v.qe);
+		else (id ? g1 : g0)[j] = v;
+	}
+};
+
 __global__ void __launch_bounds__(128) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
-                                                int lcap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
+                                                int lcap, int list_cap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
                                                 u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
 {
-	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1);
+	extern __shared__ uint4 list_smem[];
+	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1) + (size_t)(scratch_cap + 7) / 8; // + 4-byte sort keys
 	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per, *bufA = mem + scratch_cap, *bufB = bufA + (lcap + 1);
+	u32 *keys = (u32*)(bufB + (lcap + 1));
+	DevLists lists;
+	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = bufA; lists.g1 = bufB;
 	ScalarFm fm(ix);
-	SmemMachine m;
+	SmemMachineT<DevLists> m;
 	bool have = false;
 	int r = -1;
 	for (;;) {
@@ -167,31 +187,31 @@ __global__ void __launch_bounds__(128) k_smem_m(DevIndex ix, ssq_opts_t opt, int
 				const u64 off = read_off[r];
 				const int len = (int)(read_off[r + 1] - off);
 				if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
-				m.init(opt, len, seq + off, mem, scratch_cap, bufA, bufB);
+				m.init(opt, len, seq + off, mem, scratch_cap, lists);
 				have = true;
 			}
 			need = m.advance(ix);
 			if (!need) { // read finished: order its intervals, publish them
-				int n = m.finish();
+				int n = m.finish(keys);
 				if (m.err) { atomicMax(err, 1); n = 0; }
 				int b = 0, en = 0, l_rep = 0;
 				for (int i = 0; i < n; ++i) {
-					const Intv p = mem[i];
+					const Intv p = mem[keys[i] & 0x3ff];
 					if (p.x2 <= (u64)opt.max_occ) continue;
 					if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
 				}
 				l_rep += en - b;
 				unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
 				if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
-				for (int i = 0; i < n; ++i) pool[base + i] = mem[i];
+				for (int i = 0; i < n; ++i) pool[base + i] = mem[keys[i] & 0x3ff];
 				intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep;
 				have = false;
 			}
 		}
 		if (done) break;
-		Intv ok[4];
-		fm.extend(m.in, ok, m.is_back);
-		m.post(ok);
+		Intv okc;
+		extend1(fm, m.in, m.qc, m.is_back, okc);
+		m.post(okc);
 	}
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
@@ -241,9 +261,10 @@ __global__ void k_sa_rows(DevIndex ix, u64 n, const u64 *__restrict__ rows, u64 
 __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
                                                const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
                                                const Seed *__restrict__ seeds, i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc,
-                                               i32 *n_kept, u32 *n_kseeds)
+                                               i32 *n_kept, u32 *n_kseeds, int *work)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+  for (;;) { // persistent: a lane that finishes a cheap read pulls the next one instead of idling behind a repeat-rich neighbour
+	const int r = atomicAdd(work, 1);
 	if (r >= n_reads) return;
 	const int len = (int)(read_off[r + 1] - read_off[r]);
 	const int ni = intv_cnt[r];
@@ -257,6 +278,7 @@ __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int 
 		}
 	}
 	n_kept[r] = nk; n_kseeds[r] = ns;
+  }
 }
 
 // --------------------------------------------------------------------------- k_extend ----
@@ -407,9 +429,10 @@ __global__ void __launch_bounds__(64) k_sw_tasks(ssq_opts_t opt, u64 n, const ss
 __global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
                                                 const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
                                                 const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, const RegCand *__restrict__ cand, u64 *srt,
-                                                RegCand *regs, u32 *n_regs)
+                                                RegCand *regs, u32 *n_regs, int *work)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+  for (;;) {
+	const int r = atomicAdd(work, 1);
 	if (r >= n_reads) return;
 	int n_out = 0;
 	if (n_kept[r] > 0) {
@@ -424,6 +447,7 @@ __global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_reads, con
 		}
 	}
 	n_regs[r] = (u32)n_out;
+  }
 }
 
 __global__ void k_gather_regs(int n_reads, const u64 *__restrict__ task_off, const u64 *__restrict__ reg_off, const u32 *__restrict__ n_regs,
@@ -624,12 +648,15 @@ static int run_smem(ssq_batch *b)
 	const int variant = b->smem_variant;
 	const int warps_per_block = 4, threads = warps_per_block * 32;
 	const size_t smem = variant == 0 ? (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv) : 0;
+	const char *lc_env = getenv("SSQ_LIST_CAP");
+	const int list_cap = variant == 2 && b->idx->dev.seq_len < 0xffffffffull ? (lc_env ? atoi(lc_env) : 10) : 0; // shared-memory list entries per lane
+	if (variant == 2) CK(cudaFuncSetAttribute(k_smem_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)threads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
 	int blocks_per_sm = variant == 0 ? (int)((200 * 1024) / (smem + 1024)) : 8;
 	if (blocks_per_sm > 8) blocks_per_sm = 8;
 	if (blocks_per_sm < 1) blocks_per_sm = 1;
 	const int grid = b->n_sm * blocks_per_sm;
 	const int scratch_cap = variant == 0 ? 2048 : 768;
-	const size_t scratch_entries = variant == 0 ? (size_t)grid * warps_per_block * scratch_cap : (size_t)grid * threads * ((size_t)scratch_cap + 2 * (size_t)(lcap + 1));
+	const size_t scratch_entries = variant == 0 ? (size_t)grid * warps_per_block * scratch_cap : (size_t)grid * threads * ((size_t)scratch_cap + 2 * (size_t)(lcap + 1) + (size_t)(scratch_cap + 7) / 8);
 	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
 	if (b->scratch.need(scratch_entries * sizeof(Intv))) return SSQ_ENOMEM;
 	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc))) return SSQ_ENOMEM;
@@ -642,7 +669,7 @@ static int run_smem(ssq_batch *b)
 			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else if (variant == 2)
-			k_smem_m<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
+			k_smem_m<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else
 			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
@@ -694,9 +721,10 @@ static int run_chain(ssq_batch *b)
 	if (b->chain_of.need(ns * 4) || b->ch.need(ns * sizeof(ChainRec)) || b->ord.need(ns * 4) || b->wi.need(ns * sizeof(WIdx)) || b->sorted.need(ns * sizeof(Seed)) ||
 	    b->outc.need(ns * sizeof(ChainRec)) || b->n_kept.need((size_t)(n + 1) * 4) || b->n_kseeds.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
 	if (n) {
-		k_chain<<<(n + 127) / 128, 128, 0, b->st>>>(b->idx->dev, b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
+		CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+		k_chain<<<b->n_sm * 12, 128, 0, b->st>>>(b->idx->dev, b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
 		                                           b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
-		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>());
+		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work);
 		++b->launches;
 		CK(cudaGetLastError());
 	}
@@ -783,8 +811,9 @@ static int run_extend(ssq_batch *b)
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(b->ev[4], b->st));
-	k_select<<<(n + 127) / 128, 128, 0, b->st>>>(b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
-	                                            b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>());
+	CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+	k_select<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+	                                            b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(), &b->misc.as<Misc>()->work);
 	++b->launches;
 	CK(cudaGetLastError());
 	return SSQ_OK;

@@ -11,10 +11,25 @@ extern "C" {
 #include "../../oracle/ssqo.h"
 }
 
+static std::vector<u32> g_bwt32; // re-blocked copy, rebuilt per call (test-only)
 static DevIndex make_ix(const ssqo_idx_t *o, std::vector<i64> &off, std::vector<i32> &len)
 {
 	DevIndex ix;
 	memset(&ix, 0, sizeof ix);
+	if (!getenv("HOSTSIM_NO_BWT32")) { // same derivation as k_reblock32 in ssq_index.cu
+		const u64 n = o->bwt.seq_len, nb = (n + 63) / 64 + 1;
+		g_bwt32.assign(nb * 8, 0);
+		for (u64 b = 0; b < nb; ++b) {
+			const u32 *src = o->bwt.bwt + ((b >> 1) << 4);
+			const u64 *c64 = (const u64*)src;
+			u32 add[4] = {0, 0, 0, 0};
+			if (b & 1) for (int i = 0; i < 64; ++i) ++add[src[8 + (i >> 4)] >> ((~i & 15) << 1) & 3];
+			const bool have = ((b >> 1) << 7) < n + 128; // within the stored blocks (incl. the final count block)
+			for (int c = 0; c < 4; ++c) g_bwt32[b * 8 + c] = have ? (u32)(c64[c] + add[c]) : 0;
+			for (int w = 0; w < 4; ++w) g_bwt32[b * 8 + 4 + w] = (((b >> 1) << 7) + (b & 1) * 64 + w * 16 < n) ? src[8 + (b & 1) * 4 + w] : 0;
+		}
+		ix.bwt32 = g_bwt32.data();
+	}
 	ix.bwt = o->bwt.bwt; ix.sa = o->bwt.sa; ix.pac = o->pac;
 	ix.primary = o->bwt.primary; memcpy(ix.L2, o->bwt.L2, sizeof ix.L2); ix.seq_len = o->bwt.seq_len; ix.n_sa = o->bwt.n_sa;
 	ix.l_pac = o->bns.l_pac; ix.n_seqs = o->bns.n_seqs; ix.sa_intv = o->bwt.sa_intv;
@@ -38,10 +53,13 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	int err = 0;
 	if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
 	else { // the state-machine form the GPU kernel runs
-		SmemMachine m; Intv ok[4];
-		m.init(opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data());
-		while (m.advance(ix)) { fm.extend(m.in, ok, m.is_back); m.post(ok); }
-		err = m.err; w.n_intv = m.finish();
+		SmemMachineT<HostLists> m; Intv okc;
+		HostLists hl; hl.a[0] = bufA.data(); hl.a[1] = bufB.data();
+		m.init(opt, len, q, w.mem.data(), 2048, hl);
+		while (m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
+		std::vector<u32> keys(2048);
+		err = m.err; w.n_intv = m.finish(keys.data());
+		{ std::vector<Intv> tmp(w.n_intv); for (int i = 0; i < w.n_intv; ++i) tmp[i] = w.mem[keys[i] & 0x3ff]; for (int i = 0; i < w.n_intv; ++i) w.mem[i] = tmp[i]; }
 	}
 	if (err) abort();
 	int b = 0, en = 0; w.l_rep = 0;
