@@ -297,14 +297,17 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         n_launch = a.steps * nb
+        blk = float(L.ssq_index_info(idx, 7))  # bytes one rank query must fetch: 32 (re-blocked sector) or 64 (on-disk block)
         kern = {
-            "k_smem": {"bytes": 64.0 * counters[0] / n_launch, "ms": stage_ms[0] / n_launch},
-            "k_sa": {"bytes": (64.0 * counters[1] + 8.0 * counters[2]) / n_launch, "ms": stage_ms[1] / n_launch},
+            "k_smem": {"bytes": blk * counters[0] / n_launch, "ms": stage_ms[0] / n_launch},
+            "k_sa": {"bytes": (blk * counters[1] + 8.0 * counters[2]) / n_launch, "ms": stage_ms[1] / n_launch},
             "k_chain": {"bytes": None, "ms": stage_ms[2] / n_launch},
             "k_extend": {"bytes": counters[5] / n_launch, "ms": stage_ms[3] / n_launch, "gcups": counters[4] / n_launch / (stage_ms[3] / n_launch * 1e6) if stage_ms[3] else None},
             "k_select": {"bytes": None, "ms": stage_ms[4] / n_launch},
         }
-        dom = max(("k_smem", "k_sa", "k_extend"), key=lambda k: kern[k]["ms"])
+        dom = max(("k_smem", "k_sa", "k_chain", "k_extend"), key=lambda k: kern[k]["ms"])
+        if kern[dom]["bytes"] is None:
+            dom = "k_smem"
         ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] else 0.0
         for k in kern.values():
             k["share_of_step"] = k["ms"] * n_launch / ms_total if ms_total else None
@@ -317,7 +320,8 @@ def main():
                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
                "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"],
-                            "note": "random 64-B occ-block reads; with a chr20-sized index (110 MB) they are served mostly by the 126 MB L2, so DRAM traffic is far below algorithmic bytes; see profiles/"},
+                            "rank_block_bytes": blk,
+                            "note": "algorithmic bytes = rank-block bytes x blocks dereferenced (counted on the device); random sector reads — with a chr20-sized index the 63 MB rank structure is served mostly by the 126 MB L2, so DRAM traffic is below algorithmic bytes; see profiles/"},
                "kernels": kern,
                "work_per_step": {"occ_blocks_smem": counters[0] / a.steps, "occ_blocks_sa": counters[1] / a.steps, "sa_samples": counters[2] / a.steps, "sw_calls": counters[3] / a.steps,
                                  "sw_cells": counters[4] / a.steps, "seeds": counters[7] / a.steps, "regions": counters[8] / a.steps, "intervals": counters[9] / a.steps}}

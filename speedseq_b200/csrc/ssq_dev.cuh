@@ -916,9 +916,10 @@ SSQ_HD void extend_seed(const DevIndex &ix, const ssq_opts_t &opt, int l_query, 
 
 // Replay of mem_chain2aln()'s seed loop for ONE chain with every seed's candidate already computed:
 // walks the seeds from longest to shortest, skips those explained by an accepted region of this read
-// (regions of earlier chains included), appends the rest to out[0..n_out).
-SSQ_HD void select_regions(const ssq_opts_t &opt, int l_query, const ChainRec &c, const Seed *cs, const RegCand *cand,
-                           u64 *srt /* scratch c.n */, RegCand *out, int &n_out)
+// (regions of earlier chains included), appends the rest to out[0..n_out).  With `have` flags the replay stops at the first
+// seed it needs whose candidate is missing and returns its index (-1 = chain complete): the GPU extends seeds lazily, in rounds.
+SSQ_HD int select_regions(const ssq_opts_t &opt, int l_query, const ChainRec &c, const Seed *cs, const RegCand *cand,
+                          u64 *srt /* scratch c.n */, RegCand *out, int &n_out, const uint8_t *have = 0)
 {
 	int i, k;
 	for (i = 0; i < c.n; ++i) srt[i] = (u64)(u32)cs[i].len << 32 | (u32)i; // seed score == len
@@ -949,6 +950,8 @@ SSQ_HD void select_regions(const ssq_opts_t &opt, int l_query, const ChainRec &c
 			}
 			if (i == c.n) { srt[k] = 0; continue; }
 		}
+		if (have && !have[(u32)srt[k]]) return (int)(u32)srt[k]; // this seed's extension has not been computed yet: ask for it
 		out[n_out++] = cand[(u32)srt[k]];
 	}
+	return -1;
 }

@@ -213,6 +213,7 @@ extern "C" uint64_t ssq_index_info(const ssq_index_t *idx, int what)
 	case 4: return ((idx->dev.seq_len + 15) / 16) + ((idx->dev.seq_len + 127) / 128 + 1) * 8;
 	case 5: return idx->dev.n_sa;
 	case 6: return (uint64_t)idx->dev_bytes;
+	case 7: return idx->dev.bwt32 ? 32 : 64; // bytes fetched per rank query (one re-blocked sector, or one on-disk block)
 	}
 	return 0;
 }

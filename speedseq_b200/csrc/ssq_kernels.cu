@@ -304,7 +304,7 @@ __device__ __forceinline__ u32 ext_key(int qlen, int tlen) { return qlen > 0 ? (
 
 __global__ void __launch_bounds__(256) k_ext_prep(DevIndex ix, ssq_opts_t opt, u64 n_tasks, const Task *__restrict__ tasks, const u64 *__restrict__ read_off,
                                                   const u64 *__restrict__ intv_off, const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc,
-                                                  const Seed *__restrict__ sorted, ExtInfo *info, u32 *key, u32 *idx)
+                                                  const Seed *__restrict__ sorted, ExtInfo *info)
 {
 	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_tasks) return;
@@ -314,8 +314,34 @@ __global__ void __launch_bounds__(256) k_ext_prep(DevIndex ix, ssq_opts_t opt, u
 	ExtInfo e;
 	ext_prep(ix, opt, (int)(read_off[k.read + 1] - read_off[k.read]), c, sorted + s0 + c.seed_start, k.seed, e);
 	info[t] = e;
-	key[t] = ext_key(ext_left_qlen(e), ext_left_tlen(e));
-	idx[t] = (u32)t;
+}
+
+// jobs of this round: tasks requested (need) and not yet extended (have)
+__global__ void __launch_bounds__(256) k_ext_keys(int dir, u64 n_tasks, const ExtInfo *__restrict__ info, const uint8_t *__restrict__ need, const uint8_t *__restrict__ have, u32 *key, u32 *idx)
+{
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tasks) return;
+	u32 kk = EXT_NO_JOB;
+	if (need[t] && !have[t]) { const ExtInfo e = info[t]; kk = dir == 0 ? ext_key(ext_left_qlen(e), ext_left_tlen(e)) : ext_key(ext_right_qlen(e), ext_right_tlen(e)); }
+	key[t] = kk; idx[t] = (u32)t;
+}
+
+// round 0 asks for the longest seed of every kept chain (the first one mem_chain2aln() looks at)
+__global__ void k_need_first(int n_reads, const u64 *__restrict__ intv_off, const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
+                             const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, uint8_t *need)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads || n_kept[r] == 0) return;
+	const u64 s0 = seed_off[intv_off[r]];
+	u64 t = task_off[r];
+	for (int c = 0; c < n_kept[r]; ++c) {
+		const ChainRec ch = outc[s0 + c];
+		const Seed *cs = sorted + s0 + ch.seed_start;
+		int best = 0;
+		for (int i = 1; i < ch.n; ++i) if (cs[i].len >= cs[best].len) best = i; // largest (len, index)
+		need[t + best] = 1;
+		t += ch.n;
+	}
 }
 
 // bounds[c] = first sorted job whose qlen exceeds caps[c-1]; bounds[0] = 0, bounds[6] = number of real jobs
@@ -379,26 +405,25 @@ __global__ void __launch_bounds__(64) k_ext_retry(DevIndex ix, ssq_opts_t opt, c
 	if (calls) { atomicAdd(&cnt->sw_calls, calls); atomicAdd(&cnt->sw_cells, cells); atomicAdd(&cnt->sw_bytes, bytes); }
 }
 
-__global__ void __launch_bounds__(256) k_ext_left_fin(ssq_opts_t opt, u64 n_tasks, const ExtInfo *__restrict__ info, const ExtRes *__restrict__ lres, RegCand *cand, u32 *key, u32 *idx)
+__global__ void __launch_bounds__(256) k_ext_left_fin(ssq_opts_t opt, u64 n_tasks, const ExtInfo *__restrict__ info, const ExtRes *__restrict__ lres, RegCand *cand,
+                                                      const uint8_t *__restrict__ need, const uint8_t *__restrict__ have)
 {
 	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n_tasks) return;
+	if (t >= n_tasks || !need[t] || have[t]) return;
 	const ExtInfo e = info[t];
 	RegCand a;
 	a.qe = 0; a.re = 0; a.w = 0; a.seedcov = 0; a.seedlen0 = 0; a.frac_rep = 0.f;
 	ext_left_fin(opt, e, ext_left_qlen(e) > 0, lres[t], a);
 	cand[t] = a;
-	key[t] = ext_key(ext_right_qlen(e), ext_right_tlen(e));
-	idx[t] = (u32)t;
 }
 
 __global__ void __launch_bounds__(256) k_ext_right_fin(ssq_opts_t opt, u64 n_tasks, const Task *__restrict__ tasks, const u64 *__restrict__ intv_off,
                                                        const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
                                                        const ExtInfo *__restrict__ info, const ExtRes *__restrict__ rres, const uint8_t *__restrict__ wide_l,
-                                                       const uint8_t *__restrict__ wide_r, RegCand *cand)
+                                                       const uint8_t *__restrict__ wide_r, RegCand *cand, const uint8_t *__restrict__ need, uint8_t *have)
 {
 	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n_tasks) return;
+	if (t >= n_tasks || !need[t] || have[t]) return;
 	const Task k = tasks[t];
 	const u64 s0 = seed_off[intv_off[k.read]];
 	const ChainRec c = outc[s0 + k.chain];
@@ -406,6 +431,7 @@ __global__ void __launch_bounds__(256) k_ext_right_fin(ssq_opts_t opt, u64 n_tas
 	RegCand a = cand[t];
 	ext_right_fin(opt, e, ext_right_qlen(e) > 0, rres[t], opt.w << wide_l[t], opt.w << wide_r[t], c, sorted + s0 + c.seed_start, a);
 	cand[t] = a;
+	have[t] = 1;
 }
 
 // batch form of ksw_extend2 on explicit byte sequences (C-ABI ssq_sw_extend_batch)
@@ -426,15 +452,22 @@ __global__ void __launch_bounds__(64) k_sw_tasks(ssq_opts_t opt, u64 n, const ss
 }
 
 // --------------------------------------------------------------------------- k_select ----
+// Replays mem_chain2aln()'s seed loop per read over the candidates computed so far.  A read whose replay reaches a seed
+// that must be extended but has no candidate yet flags that seed (need) and stays unfinished; the host runs another
+// extension round for the flagged seeds and replays the unfinished reads again.  force_all: flag every remaining seed of an
+// unfinished read at once (bounds the number of rounds).
 __global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
                                                 const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
                                                 const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, const RegCand *__restrict__ cand, u64 *srt,
-                                                RegCand *regs, u32 *n_regs, int *work)
+                                                RegCand *regs, u32 *n_regs, const uint8_t *__restrict__ have, uint8_t *need, uint8_t *done, int force_all,
+                                                unsigned int *n_unfinished, int *work)
 {
   for (;;) {
 	const int r = atomicAdd(work, 1);
 	if (r >= n_reads) return;
+	if (done[r]) continue;
 	int n_out = 0;
+	bool complete = true;
 	if (n_kept[r] > 0) {
 		const u64 s0 = seed_off[intv_off[r]];
 		const int len = (int)(read_off[r + 1] - read_off[r]);
@@ -442,11 +475,18 @@ __global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_reads, con
 		RegCand *out = regs + task_off[r];
 		for (int c = 0; c < n_kept[r]; ++c) {
 			const ChainRec ch = outc[s0 + c];
-			select_regions(opt, len, ch, sorted + s0 + ch.seed_start, cand + t, srt + t, out, n_out);
+			const int miss = select_regions(opt, len, ch, sorted + s0 + ch.seed_start, cand + t, srt + t, out, n_out, have + t);
+			if (miss >= 0) {
+				complete = false;
+				if (force_all) { u64 e = t; for (int cc = c; cc < n_kept[r]; ++cc) e += outc[s0 + cc].n; for (u64 x = t; x < e; ++x) need[x] = 1; }
+				else need[t + miss] = 1;
+				break;
+			}
 			t += ch.n;
 		}
 	}
-	n_regs[r] = (u32)n_out;
+	if (complete) { n_regs[r] = (u32)n_out; done[r] = 1; }
+	else atomicAdd(n_unfinished, 1u);
   }
 }
 
@@ -553,14 +593,15 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xdone;
+	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
 	cudaEvent_t ev[6];
 	float stage_ms[5];
-	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
+	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
 };
 
 // misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
@@ -616,7 +657,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xdone};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
@@ -750,72 +791,95 @@ static int run_extend(ssq_batch *b)
 	if (b->xinfo.need((nt + 1) * sizeof(ExtInfo)) || b->xres[0].need((nt + 1) * sizeof(ExtRes)) || b->xres[1].need((nt + 1) * sizeof(ExtRes)) || b->xwide.need(2 * (nt + 1)) ||
 	    b->xkey[0].need((nt + 1) * 4) || b->xkey[1].need((nt + 1) * 4) || b->xidx[0].need((nt + 1) * 4) || b->xidx[1].need((nt + 1) * 4) || b->xretry.need((nt + 1) * 4) ||
 	    b->xmisc.need(256)) return SSQ_ENOMEM;
+	if (b->xneed.need(nt + 1) || b->xhave.need(nt + 1) || b->xdone.need((size_t)n + 1)) return SSQ_ENOMEM;
 	CK(cudaEventRecord(b->ev[3], b->st));
+	float ms_sel = 0.f;
 	if (nt) {
 		k_tasks<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(),
 		                                           b->task_off.as<u64>(), b->tasks.as<Task>());
 		const unsigned G = (unsigned)((nt + 255) / 256);
-		uint8_t *wide_l = b->xwide.as<uint8_t>(), *wide_r = wide_l + (nt + 1);
+		uint8_t *wide_l = b->xwide.as<uint8_t>(), *wide_r = wide_l + (nt + 1), *need = b->xneed.as<uint8_t>(), *have = b->xhave.as<uint8_t>(), *done = b->xdone.as<uint8_t>();
 		u32 *bounds = b->xmisc.as<u32>();                 // [0..6]
-		unsigned int *n_retry = b->xmisc.as<unsigned int>() + 16;
+		unsigned int *n_retry = b->xmisc.as<unsigned int>() + 16, *n_unf = b->xmisc.as<unsigned int>() + 17;
 		CK(cudaMemsetAsync(b->xwide.p, 0, 2 * (nt + 1), b->st));
+		CK(cudaMemsetAsync(need, 0, nt + 1, b->st)); CK(cudaMemsetAsync(have, 0, nt + 1, b->st)); CK(cudaMemsetAsync(done, 0, (size_t)n + 1, b->st));
 		k_ext_prep<<<G, 256, 0, b->st>>>(b->idx->dev, b->opt, nt, b->tasks.as<Task>(), b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(),
-		                                b->sorted.as<Seed>(), b->xinfo.as<ExtInfo>(), b->xkey[0].as<u32>(), b->xidx[0].as<u32>());
-		b->launches += 2;
+		                                b->sorted.as<Seed>(), b->xinfo.as<ExtInfo>());
+		const int lazy = getenv("SSQ_EXT_ALL") ? 0 : 1;
+		if (lazy) k_need_first<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(), b->n_kept.as<i32>(), b->task_off.as<u64>(), need);
+		else CK(cudaMemsetAsync(need, 1, nt, b->st));
+		b->launches += 3;
 		static const int caps[6] = {32, 64, 96, 128, 160, 255};
-		for (int dir = 0; dir < 2; ++dir) {
-			size_t tb = 0;
-			cub::DeviceRadixSort::SortPairs(0, tb, b->xkey[0].as<u32>(), b->xkey[1].as<u32>(), b->xidx[0].as<u32>(), b->xidx[1].as<u32>(), (int)nt, 0, 32, b->st);
-			if (b->cubtmp.need(tb)) return SSQ_ENOMEM;
-			CK(cub::DeviceRadixSort::SortPairs(b->cubtmp.p, tb, b->xkey[0].as<u32>(), b->xkey[1].as<u32>(), b->xidx[0].as<u32>(), b->xidx[1].as<u32>(), (int)nt, 0, 32, b->st));
-			k_ext_bounds<<<1, 32, 0, b->st>>>(nt, b->xkey[1].as<u32>(), bounds);
-			CK(cudaMemsetAsync(n_retry, 0, 4, b->st));
-			u32 hb[8];
-			CK(cudaMemcpyAsync(hb, bounds, 7 * 4, cudaMemcpyDeviceToHost, b->st));
-			CK(cudaStreamSynchronize(b->st));
-			b->launches += 3;
-			for (int c = 5; c >= 0; --c) { // longest class first
-				const u32 lo = hb[c], hi = hb[c + 1];
-				if (hi <= lo) continue;
-				const int threads = caps[c] > 160 ? 64 : 128;
-				const size_t smem = (size_t)threads * (caps[c] + 2) * 4;
-				const unsigned grid = (hi - lo + threads - 1) / threads;
-				if (dir == 0) {
-					CK(cudaFuncSetAttribute(k_ext_run<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
-					k_ext_run<0><<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, lo, hi, b->xidx[1].as<u32>(), b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
-					                                            b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[0].as<ExtRes>(), b->xretry.as<u32>(), n_retry, &b->misc.as<Misc>()->cnt);
-				} else {
-					CK(cudaFuncSetAttribute(k_ext_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
-					k_ext_run<1><<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, lo, hi, b->xidx[1].as<u32>(), b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
-					                                            b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[1].as<ExtRes>(), b->xretry.as<u32>(), n_retry, &b->misc.as<Misc>()->cnt);
+		CK(cudaFuncSetAttribute(k_ext_run<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
+		CK(cudaFuncSetAttribute(k_ext_run<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
+		const size_t rsmem = (size_t)64 * (b->max_len + 2) * 4;
+		CK(cudaFuncSetAttribute(k_ext_retry<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+		CK(cudaFuncSetAttribute(k_ext_retry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+		cudaEvent_t es0, es1;
+		CK(cudaEventCreate(&es0)); CK(cudaEventCreate(&es1));
+		for (int round = 0;; ++round) {
+			for (int dir = 0; dir < 2; ++dir) {
+				size_t tb = 0;
+				k_ext_keys<<<G, 256, 0, b->st>>>(dir, nt, b->xinfo.as<ExtInfo>(), need, have, b->xkey[0].as<u32>(), b->xidx[0].as<u32>());
+				cub::DeviceRadixSort::SortPairs(0, tb, b->xkey[0].as<u32>(), b->xkey[1].as<u32>(), b->xidx[0].as<u32>(), b->xidx[1].as<u32>(), (int)nt, 0, 32, b->st);
+				if (b->cubtmp.need(tb)) return SSQ_ENOMEM;
+				CK(cub::DeviceRadixSort::SortPairs(b->cubtmp.p, tb, b->xkey[0].as<u32>(), b->xkey[1].as<u32>(), b->xidx[0].as<u32>(), b->xidx[1].as<u32>(), (int)nt, 0, 32, b->st));
+				k_ext_bounds<<<1, 32, 0, b->st>>>(nt, b->xkey[1].as<u32>(), bounds);
+				CK(cudaMemsetAsync(n_retry, 0, 4, b->st));
+				u32 hb[8];
+				CK(cudaMemcpyAsync(hb, bounds, 7 * 4, cudaMemcpyDeviceToHost, b->st));
+				CK(cudaStreamSynchronize(b->st));
+				b->launches += 4;
+				for (int c = 5; c >= 0; --c) { // longest class first
+					const u32 lo = hb[c], hi = hb[c + 1];
+					if (hi <= lo) continue;
+					const int threads = caps[c] > 160 ? 64 : 128;
+					const size_t smem = (size_t)threads * (caps[c] + 2) * 4;
+					const unsigned grid = (hi - lo + threads - 1) / threads;
+					if (dir == 0)
+						k_ext_run<0><<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, lo, hi, b->xidx[1].as<u32>(), b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+						                                            b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[0].as<ExtRes>(), b->xretry.as<u32>(), n_retry, &b->misc.as<Misc>()->cnt);
+					else
+						k_ext_run<1><<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, lo, hi, b->xidx[1].as<u32>(), b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+						                                            b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[1].as<ExtRes>(), b->xretry.as<u32>(), n_retry, &b->misc.as<Misc>()->cnt);
+					++b->launches;
 				}
-				++b->launches;
-			}
-			{
-				const size_t smem = (size_t)64 * (b->max_len + 2) * 4;
 				if (dir == 0) {
-					CK(cudaFuncSetAttribute(k_ext_retry<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-					k_ext_retry<0><<<b->n_sm * 2, 64, smem, b->st>>>(b->idx->dev, b->opt, b->xretry.as<u32>(), n_retry, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
-					                                                b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[0].as<ExtRes>(), wide_l, &b->misc.as<Misc>()->cnt);
-					k_ext_left_fin<<<G, 256, 0, b->st>>>(b->opt, nt, b->xinfo.as<ExtInfo>(), b->xres[0].as<ExtRes>(), b->cand.as<RegCand>(), b->xkey[0].as<u32>(), b->xidx[0].as<u32>());
+					k_ext_retry<0><<<b->n_sm * 2, 64, rsmem, b->st>>>(b->idx->dev, b->opt, b->xretry.as<u32>(), n_retry, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+					                                                 b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[0].as<ExtRes>(), wide_l, &b->misc.as<Misc>()->cnt);
+					k_ext_left_fin<<<G, 256, 0, b->st>>>(b->opt, nt, b->xinfo.as<ExtInfo>(), b->xres[0].as<ExtRes>(), b->cand.as<RegCand>(), need, have);
 				} else {
-					CK(cudaFuncSetAttribute(k_ext_retry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-					k_ext_retry<1><<<b->n_sm * 2, 64, smem, b->st>>>(b->idx->dev, b->opt, b->xretry.as<u32>(), n_retry, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
-					                                                b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[1].as<ExtRes>(), wide_r, &b->misc.as<Misc>()->cnt);
+					k_ext_retry<1><<<b->n_sm * 2, 64, rsmem, b->st>>>(b->idx->dev, b->opt, b->xretry.as<u32>(), n_retry, b->tasks.as<Task>(), b->seq.as<uint8_t>(), b->read_off.as<u64>(),
+					                                                 b->xinfo.as<ExtInfo>(), b->cand.as<RegCand>(), b->xres[1].as<ExtRes>(), wide_r, &b->misc.as<Misc>()->cnt);
 					k_ext_right_fin<<<G, 256, 0, b->st>>>(b->opt, nt, b->tasks.as<Task>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
-					                                     b->xinfo.as<ExtInfo>(), b->xres[1].as<ExtRes>(), wide_l, wide_r, b->cand.as<RegCand>());
+					                                     b->xinfo.as<ExtInfo>(), b->xres[1].as<ExtRes>(), wide_l, wide_r, b->cand.as<RegCand>(), need, have);
 				}
 				b->launches += 2;
 			}
+			// replay the selection for the reads that are not finished yet
+			unsigned int h_unf = 0;
+			CK(cudaMemsetAsync(n_unf, 0, 4, b->st));
+			CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+			CK(cudaEventRecord(es0, b->st));
+			k_select<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+			                                        b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(),
+			                                        have, need, done, round >= 2, n_unf, &b->misc.as<Misc>()->work);
+			CK(cudaEventRecord(es1, b->st));
+			++b->launches;
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(&h_unf, n_unf, 4, cudaMemcpyDeviceToHost, b->st));
+			CK(cudaStreamSynchronize(b->st));
+			{ float ms = 0.f; cudaEventElapsedTime(&ms, es0, es1); ms_sel += ms; }
+			b->ext_rounds = round + 1;
+			if (h_unf == 0) break;
+			if (round > 8) { ssq_set_error("seed-extension rounds did not converge"); return SSQ_ECUDA; }
 		}
-		CK(cudaGetLastError());
+		cudaEventDestroy(es0); cudaEventDestroy(es1);
+	} else {
+		CK(cudaMemsetAsync(b->n_regs.p, 0, (size_t)(n + 1) * 4, b->st));
 	}
+	b->select_ms = ms_sel;
 	CK(cudaEventRecord(b->ev[4], b->st));
-	CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
-	k_select<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
-	                                            b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(), &b->misc.as<Misc>()->work);
-	++b->launches;
-	CK(cudaGetLastError());
 	return SSQ_OK;
 }
 
@@ -850,6 +914,7 @@ static int finish_counters(ssq_batch *b)
 	CK(cudaStreamSynchronize(b->st));
 	b->h_cnt = hm.cnt;
 	for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&b->stage_ms[i], b->ev[i], b->ev[i + 1]);
+	b->stage_ms[3] -= b->select_ms; b->stage_ms[4] += b->select_ms; // the selection replays run inside the extension rounds
 	return SSQ_OK;
 }
 
@@ -860,7 +925,7 @@ extern "C" uint64_t ssq_batch_counter(const ssq_batch_t *b_, int what)
 	switch (what) {
 	case 0: return b->h_cnt.occ_smem; case 1: return b->h_cnt.occ_sa; case 2: return b->h_cnt.sa_reads; case 3: return b->h_cnt.sw_calls;
 	case 4: return b->h_cnt.sw_cells; case 5: return b->h_cnt.sw_bytes; case 6: return (uint64_t)b->launches; case 7: return b->n_seeds; case 8: return b->n_regs_total;
-	case 9: return b->n_intv; case 10: return b->n_tasks;
+	case 9: return b->n_intv; case 10: return b->n_tasks; case 11: return (uint64_t)b->ext_rounds;
 	}
 	return 0;
 }

@@ -91,11 +91,39 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	size_t total = 0;
 	for (int c = 0; c < w.n_kept; ++c) total += w.outc[c].n;
 	out.resize(total + 1);
-	for (int c = 0; c < w.n_kept; ++c) {
-		const ChainRec &cr = w.outc[c];
-		std::vector<RegCand> cand(cr.n); std::vector<u64> srt(cr.n);
-		for (int s = 0; s < cr.n; ++s) extend_seed(ix, opt, len, q, cr, w.sorted.data() + cr.seed_start, s, eh, cand[s], 0);
-		select_regions(opt, len, cr, w.sorted.data() + cr.seed_start, cand.data(), srt.data(), out.data(), n_out);
+	if (getenv("HOSTSIM_EAGER")) { // extend every seed, then replay
+		for (int c = 0; c < w.n_kept; ++c) {
+			const ChainRec &cr = w.outc[c];
+			std::vector<RegCand> cand(cr.n); std::vector<u64> srt(cr.n);
+			for (int s = 0; s < cr.n; ++s) extend_seed(ix, opt, len, q, cr, w.sorted.data() + cr.seed_start, s, eh, cand[s], 0);
+			select_regions(opt, len, cr, w.sorted.data() + cr.seed_start, cand.data(), srt.data(), out.data(), n_out);
+		}
+	} else { // the GPU's lazy rounds: longest seed of every chain first, then only what the replay asks for
+		std::vector<RegCand> cand(total + 1); std::vector<uint8_t> have(total + 1, 0), need(total + 1, 0); std::vector<u64> srt(total + 1);
+		size_t t = 0;
+		for (int c = 0; c < w.n_kept; ++c) {
+			const ChainRec &cr = w.outc[c]; const Seed *cs = w.sorted.data() + cr.seed_start;
+			int best = 0;
+			for (int i = 1; i < cr.n; ++i) if (cs[i].len >= cs[best].len) best = i;
+			need[t + best] = 1; t += cr.n;
+		}
+		for (int round = 0;; ++round) {
+			t = 0;
+			for (int c = 0; c < w.n_kept; ++c) {
+				const ChainRec &cr = w.outc[c];
+				for (int s = 0; s < cr.n; ++s) if (need[t + s] && !have[t + s]) { extend_seed(ix, opt, len, q, cr, w.sorted.data() + cr.seed_start, s, eh, cand[t + s], 0); have[t + s] = 1; }
+				t += cr.n;
+			}
+			n_out = 0; t = 0;
+			bool complete = true;
+			for (int c = 0; c < w.n_kept; ++c) {
+				const ChainRec &cr = w.outc[c];
+				const int miss = select_regions(opt, len, cr, w.sorted.data() + cr.seed_start, cand.data() + t, srt.data() + t, out.data(), n_out, have.data() + t);
+				if (miss >= 0) { complete = false; if (round >= 2) { for (size_t x = t; x < total; ++x) need[x] = 1; } else need[t + miss] = 1; break; }
+				t += cr.n;
+			}
+			if (complete) break;
+		}
 	}
 	w.regs.assign(out.begin(), out.begin() + n_out);
 }
