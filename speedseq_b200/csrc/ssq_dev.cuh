@@ -316,12 +316,16 @@ struct SmemMachineT {
 	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3 };
 	const uint8_t *q; Intv *mem; Lists L;
 	int len, mem_cap, n, base, state, pass, x, i, j, c, qc, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width, prev_id;
+	int qi, qnext;     // base at position i (forward phases) and the prefetched base at i+1: the load is issued before the rank
+	                   // query of step i and consumed after it, so the bookkeeping never waits on a query byte
+	int cnext;         // backward phase: prefetched base at i-1
 	u32 last_mem_qb;   // mem[n-1].qb of the current smem1 call
 	u64 curr_tail_x2;  // x2 of the entry last pushed to the current list
 	u64 min_intv, max_mem_intv;
 	Intv ik, in;
 	int is_back;
 
+	SSQ_HD int base_at(int p) const { return p >= 0 && p < len ? (int)q[p] : 4; }
 	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists)
 	{
 		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0;
@@ -335,7 +339,7 @@ struct SmemMachineT {
 	{
 		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; base = n;
 		set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
-		i = x + 1; n_curr = 0; state = FWD;
+		i = x + 1; qi = base_at(i); n_curr = 0; state = FWD;
 	}
 	SSQ_HD void end_forward() // forward list complete: longest first, then walk backwards
 	{
@@ -344,7 +348,8 @@ struct SmemMachineT {
 		ret = (int)L.get(cid, 0).qe;
 		prev_id = cid; n_prev = n_curr;
 		i = x - 1; j = 0; n_curr = 0;
-		c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
+		{ const int b0 = base_at(i); c = b0 < 4 ? b0 : -1; }
+		{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
 		state = BWD;
 	}
 	SSQ_HD void keep(const Intv &p_) // p is left-maximal at i+1 unless a longer match survived
@@ -391,11 +396,12 @@ struct SmemMachineT {
 				while (x < len && q[x] > 3) ++x;
 				if (x >= len) return false;
 				set_intv(ix, q[x], ik);
-				i = x + 1; state = S3;
+				i = x + 1; qi = base_at(i); state = S3;
 				break;
 			case FWD:
-				if (i >= len || q[i] > 3) { push_curr(ik); end_forward(); break; }
-				in = ik; is_back = 0; qc = 3 - q[i];
+				if (i >= len || qi > 3) { push_curr(ik); end_forward(); break; }
+				in = ik; is_back = 0; qc = 3 - qi;
+				qnext = base_at(i + 1);
 				return true;
 			case BWD:
 				if (j >= n_prev) { // one backward step done for the whole set
@@ -403,7 +409,8 @@ struct SmemMachineT {
 					prev_id ^= 1; n_prev = n_curr;
 					--i; j = 0; n_curr = 0;
 					if (i < -1) { end_smem1(); break; }
-					c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
+					c = cnext;
+					{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
 					break;
 				}
 				in = L.get(prev_id, j);
@@ -412,11 +419,31 @@ struct SmemMachineT {
 				return true;
 			case S3:
 				if (i >= len) { x = len; state = NEXT_P3; break; }
-				if (q[i] > 3) { x = i + 1; state = NEXT_P3; break; }
-				in = ik; is_back = 0; qc = 3 - q[i];
+				if (qi > 3) { x = i + 1; state = NEXT_P3; break; }
+				in = ik; is_back = 0; qc = 3 - qi;
+				qnext = base_at(i + 1);
 				return true;
 			}
 		}
+	}
+	// the common, transition-free way to the next query: returns true and sets in/qc/is_back, or returns false WITHOUT
+	// touching anything when the generic advance() (list reversal, filtering, pass changes, end of read) is needed
+	SSQ_HD bool try_fast_advance()
+	{
+		if (err) return false;
+		if (state == FWD || state == S3) {
+			if (i >= len || qi > 3) return false;
+			in = ik; is_back = 0; qc = 3 - qi;
+			qnext = base_at(i + 1);
+			return true;
+		}
+		if (state == BWD) {
+			if (j >= n_prev || c < 0) return false;
+			in = L.get(prev_id, j);
+			is_back = 1; qc = c;
+			return true;
+		}
+		return false;
 	}
 	SSQ_HD void post(const Intv &okc) // okc = ok[qc] of the query
 	{
@@ -426,7 +453,7 @@ struct SmemMachineT {
 				if (okc.x2 < min_intv) { end_forward(); return; }
 			}
 			ik = okc; ik.qe = (u32)(i + 1);
-			++i;
+			++i; qi = qnext;
 		} else if (state == BWD) {
 			if (okc.x2 < min_intv) keep(in);
 			else if (n_curr == 0 || okc.x2 != curr_tail_x2) { Intv t = okc; t.qb = 0; t.qe = in.qe; push_curr(t); }
@@ -436,7 +463,7 @@ struct SmemMachineT {
 				Intv m = okc; m.qb = (u32)x; m.qe = (u32)(i + 1);
 				if (m.x2 > 0) { if (n >= mem_cap) { err = 1; return; } mem[n++] = m; }
 				x = i + 1; state = NEXT_P3;
-			} else { ik = okc; ++i; }
+			} else { ik = okc; ++i; qi = qnext; }
 		}
 	}
 	// order by (qb,qe): only 4-byte keys (qb | qe | slot) move, the 32-byte records are gathered once when the caller
@@ -592,6 +619,7 @@ SSQ_HD void ks_introsort(long n, T *a, LT lt)
 }
 
 struct WIdx { i32 w, idx; };
+struct KeptChain { i32 b, e, w, i; }; // query span, weight and sorted rank of a chain that survived the overlap filter so far
 struct WIdxLt { SSQ_HD bool operator()(const WIdx &a, const WIdx &b) const { return a.w > b.w; } };
 
 // Build the chains of one read from its seeds (in look-up order) and filter them.
@@ -601,18 +629,25 @@ struct WIdxLt { SSQ_HD bool operator()(const WIdx &a, const WIdx &b) const { ret
 //   ord[0..n)        scratch: chain indices ordered by pos
 //   sorted[0..n)     out: seeds regrouped chain by chain (chain order = filter order)
 //   outc[0..n)       out: kept chains (seed_start relative to `sorted`)
-// returns the number of kept chains.  l_rep/len gives frac_rep.
-SSQ_HD int chain_and_filter(const DevIndex &ix, const ssq_opts_t &opt, int len, int n, const Seed *seeds, int l_rep,
-                            i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc)
-{
-	int n_ch = 0, i, k;
-	const i64 l_pac = ix.l_pac;
-	for (i = 0; i < n; ++i) {
-		Seed s = seeds[i];
-		int rid = intv2rid(ix, s.rbeg, s.rbeg + s.len);
+// add_seed() is the per-seed step of mem_chain()'s loop (one call per seed, in order); finish() does the regrouping, the
+// weights, the sort and the overlap filter and returns the number of kept chains.  On the GPU a lane keeps one ChainBuilder
+// and all lanes of a warp meet at add_seed(), so a read with hundreds of seeds does not idle its 31 neighbours.
+struct ChainBuilder {
+	const Seed *seeds; i32 *chain_of; ChainRec *ch; i32 *ord; WIdx *wi; Seed *sorted; ChainRec *outc; KeptChain *kp;
+	int n, n_ch, len, l_rep;
+
+	SSQ_HD void init(int len_, int n_, const Seed *seeds_, int l_rep_, i32 *chain_of_, ChainRec *ch_, i32 *ord_, WIdx *wi_, Seed *sorted_, ChainRec *outc_, KeptChain *kp_)
+	{
+		len = len_; n = n_; seeds = seeds_; l_rep = l_rep_; chain_of = chain_of_; ch = ch_; ord = ord_; wi = wi_; sorted = sorted_; outc = outc_; kp = kp_; n_ch = 0;
+	}
+	SSQ_HD void add_seed(const DevIndex &ix, const ssq_opts_t &opt, int i)
+	{
+		const i64 l_pac = ix.l_pac;
+		const Seed s = seeds[i];
+		const int rid = intv2rid(ix, s.rbeg, s.rbeg + s.len);
 		chain_of[i] = -1;
-		if (rid < 0) continue;
-		int lo = 0, hi = n_ch, slot, merged = 0;
+		if (rid < 0) return;
+		int lo = 0, hi = n_ch, slot, merged = 0, k;
 		while (lo < hi) { int mid = (lo + hi) >> 1; if (ch[ord[mid]].pos < s.rbeg) lo = mid + 1; else hi = mid; }
 		slot = (lo < n_ch && ch[ord[lo]].pos == s.rbeg) ? lo : lo - 1;
 		if (n_ch && slot >= 0) {
@@ -640,70 +675,85 @@ SSQ_HD int chain_and_filter(const DevIndex &ix, const ssq_opts_t &opt, int len, 
 			++n_ch;
 		}
 	}
-	if (n_ch == 0) return 0;
-	// regroup seeds chain by chain, chains in pos order (= the order the reference's tree is traversed)
+	SSQ_HD int finish(const ssq_opts_t &opt)
 	{
-		int off = 0;
-		for (k = 0; k < n_ch; ++k) { ChainRec &c = ch[ord[k]]; c.seed_start = off; off += c.n; c.n = 0; }
-		for (i = 0; i < n; ++i) if (chain_of[i] >= 0) { ChainRec &c = ch[chain_of[i]]; sorted[c.seed_start + c.n++] = seeds[i]; }
-	}
-	// weight = min(query coverage, reference coverage) of the seeds
-	for (k = 0; k < n_ch; ++k) {
-		ChainRec &c = ch[ord[k]];
-		const Seed *s = sorted + c.seed_start;
-		i64 end; int j, w = 0, tmp;
-		for (j = 0, end = 0; j < c.n; ++j) {
-			if (s[j].qbeg >= end) w += s[j].len; else if (s[j].qbeg + s[j].len > end) w += (int)(s[j].qbeg + s[j].len - end);
-			end = end > s[j].qbeg + s[j].len ? end : s[j].qbeg + s[j].len;
+		int i, k;
+		if (n_ch == 0) return 0;
+		// regroup seeds chain by chain, chains in pos order (= the order the reference's tree is traversed)
+		{
+			int off = 0;
+			for (k = 0; k < n_ch; ++k) { ChainRec &c = ch[ord[k]]; c.seed_start = off; off += c.n; c.n = 0; }
+			for (i = 0; i < n; ++i) if (chain_of[i] >= 0) { ChainRec &c = ch[chain_of[i]]; sorted[c.seed_start + c.n++] = seeds[i]; }
 		}
-		tmp = w; w = 0;
-		for (j = 0, end = 0; j < c.n; ++j) {
-			if (s[j].rbeg >= end) w += s[j].len; else if (s[j].rbeg + s[j].len > end) w += (int)(s[j].rbeg + s[j].len - end);
-			end = end > s[j].rbeg + s[j].len ? end : s[j].rbeg + s[j].len;
+		// weight = min(query coverage, reference coverage) of the seeds
+		for (k = 0; k < n_ch; ++k) {
+			ChainRec &c = ch[ord[k]];
+			const Seed *s = sorted + c.seed_start;
+			i64 end; int j, w = 0, tmp;
+			for (j = 0, end = 0; j < c.n; ++j) {
+				if (s[j].qbeg >= end) w += s[j].len; else if (s[j].qbeg + s[j].len > end) w += (int)(s[j].qbeg + s[j].len - end);
+				end = end > s[j].qbeg + s[j].len ? end : s[j].qbeg + s[j].len;
+			}
+			tmp = w; w = 0;
+			for (j = 0, end = 0; j < c.n; ++j) {
+				if (s[j].rbeg >= end) w += s[j].len; else if (s[j].rbeg + s[j].len > end) w += (int)(s[j].rbeg + s[j].len - end);
+				end = end > s[j].rbeg + s[j].len ? end : s[j].rbeg + s[j].len;
+			}
+			w = w < tmp ? w : tmp;
+			c.w = w < 1 << 30 ? w : (1 << 30) - 1;
+			c.first = -1; c.kept = 0;
+			c.frac_rep = (float)l_rep / len;
+			wi[k].w = c.w; wi[k].idx = ord[k];
 		}
-		w = w < tmp ? w : tmp;
-		c.w = w < 1 << 30 ? w : (1 << 30) - 1;
-		c.first = -1; c.kept = 0;
-		c.frac_rep = (float)l_rep / len;
-		wi[k].w = c.w; wi[k].idx = ord[k];
-	}
-	ks_introsort((long)n_ch, wi, WIdxLt());
-	// pairwise overlap filter over chains in decreasing weight; ord[] is reused as the list of kept positions
+		ks_introsort((long)n_ch, wi, WIdxLt());
+		// pairwise overlap filter over chains in decreasing weight.  The inner loop runs over the kept chains only through the
+		// compact list kp[] (begin, end, weight, rank) — one sequential 16-byte load per pair instead of a chain of dependent
+		// look-ups; a chain's query span comes from the fields kept while it was built (first seed's qbeg, last seed's end).
 #define CH(i_) ch[wi[i_].idx]
-#define CBEG(c_) (sorted[(c_).seed_start].qbeg)
-#define CEND(c_) (sorted[(c_).seed_start + (c_).n - 1].qbeg + sorted[(c_).seed_start + (c_).n - 1].len)
-	int n_kept = 0;
-	CH(0).kept = 3; ord[n_kept++] = 0;
-	for (i = 1; i < n_ch; ++i) {
-		int large_ovlp = 0;
-		ChainRec &ci = CH(i);
-		for (k = 0; k < n_kept; ++k) {
-			int j = ord[k];
-			ChainRec &cj = CH(j);
-			int bi = CBEG(ci), ei = CEND(ci), bj = CBEG(cj), ej = CEND(cj);
-			int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
-			if (e_min > b_max) {
-				int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
-				if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
-					large_ovlp = 1;
-					if (cj.first < 0) cj.first = i;
-					if (ci.w < cj.w * opt.drop_ratio && cj.w - ci.w >= opt.min_seed_len << 1) break;
+		int n_kept = 0;
+		{
+			ChainRec &c0 = CH(0);
+			c0.kept = 3;
+			kp[0].b = c0.first_q; kp[0].e = c0.last_q + c0.last_len; kp[0].w = c0.w; kp[0].i = 0; n_kept = 1;
+		}
+		for (i = 1; i < n_ch; ++i) {
+			int large_ovlp = 0;
+			ChainRec &ci = CH(i);
+			const int bi = ci.first_q, ei = ci.last_q + ci.last_len, wi_ = ci.w;
+			for (k = 0; k < n_kept; ++k) {
+				const KeptChain kj = kp[k];
+				const int b_max = kj.b > bi ? kj.b : bi, e_min = kj.e < ei ? kj.e : ei;
+				if (e_min > b_max) {
+					const int li = ei - bi, lj = kj.e - kj.b, min_l = li < lj ? li : lj;
+					if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+						large_ovlp = 1;
+						ChainRec &cj = CH(kj.i);
+						if (cj.first < 0) cj.first = i;
+						if (wi_ < kj.w * opt.drop_ratio && kj.w - wi_ >= opt.min_seed_len << 1) break;
+					}
 				}
 			}
+			if (k == n_kept) { kp[n_kept].b = bi; kp[n_kept].e = ei; kp[n_kept].w = wi_; kp[n_kept].i = i; ++n_kept; ci.kept = large_ovlp ? 2 : 3; }
 		}
-		if (k == n_kept) { ord[n_kept++] = i; ci.kept = large_ovlp ? 2 : 3; }
-	}
-	for (i = 0; i < n_kept; ++i) { ChainRec &c = CH(ord[i]); if (c.first >= 0) CH(c.first).kept = 1; }
-	for (i = k = 0; i < n_ch; ++i) {
-		if (CH(i).kept == 0 || CH(i).kept == 3) continue;
-		if (++k >= opt.max_chain_extend) break;
-	}
-	for (; i < n_ch; ++i) if (CH(i).kept < 3) CH(i).kept = 0;
-	for (i = k = 0; i < n_ch; ++i) if (CH(i).kept) outc[k++] = CH(i);
+		for (i = 0; i < n_kept; ++i) { ChainRec &c = CH(kp[i].i); if (c.first >= 0) CH(c.first).kept = 1; }
+		for (i = k = 0; i < n_ch; ++i) {
+			if (CH(i).kept == 0 || CH(i).kept == 3) continue;
+			if (++k >= opt.max_chain_extend) break;
+		}
+		for (; i < n_ch; ++i) if (CH(i).kept < 3) CH(i).kept = 0;
+		for (i = k = 0; i < n_ch; ++i) if (CH(i).kept) outc[k++] = CH(i);
 #undef CH
-#undef CBEG
-#undef CEND
-	return k;
+		return k;
+	}
+};
+
+SSQ_HD int chain_and_filter(const DevIndex &ix, const ssq_opts_t &opt, int len, int n, const Seed *seeds, int l_rep,
+                            i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc, KeptChain *kp)
+{
+	ChainBuilder b;
+	b.init(len, n, seeds, l_rep, chain_of, ch, ord, wi, sorted, outc, kp);
+	for (int i = 0; i < n; ++i) b.add_seed(ix, opt, i);
+	return b.finish(opt);
 }
 
 // ----------------------------------------------------------------- banded SW extension ----

@@ -164,8 +164,8 @@ struct DevLists {
 	}
 };
 
-__global__ void __launch_bounds__(128) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
-                                                int lcap, int list_cap, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
+__global__ void __launch_bounds__(128, 5) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                                int lcap, int list_cap, int slow_batch, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
                                                 u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
 {
 	extern __shared__ uint4 list_smem[];
@@ -176,42 +176,54 @@ __global__ void __launch_bounds__(128) k_smem_m(DevIndex ix, ssq_opts_t opt, int
 	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = bufA; lists.g1 = bufB;
 	ScalarFm fm(ix);
 	SmemMachineT<DevLists> m;
-	bool have = false;
+	bool have = false, ready = false, alive = true;
 	int r = -1;
+	const int batch = slow_batch > 0 ? slow_batch : 1;
 	for (;;) {
-		bool need = false, done = false;
-		while (!need) {
-			if (!have) {
-				r = atomicAdd(work, 1);
-				if (r >= n_reads) { done = true; break; }
-				const u64 off = read_off[r];
-				const int len = (int)(read_off[r + 1] - off);
-				if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
-				m.init(opt, len, seq + off, mem, scratch_cap, lists);
-				have = true;
-			}
-			need = m.advance(ix);
-			if (!need) { // read finished: order its intervals, publish them
-				int n = m.finish(keys);
-				if (m.err) { atomicMax(err, 1); n = 0; }
-				int b = 0, en = 0, l_rep = 0;
-				for (int i = 0; i < n; ++i) {
-					const Intv p = mem[keys[i] & 0x3ff];
-					if (p.x2 <= (u64)opt.max_occ) continue;
-					if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
+		// cheap, transition-free advance for lanes in the middle of a forward / backward / greedy run
+		if (alive && have && !ready) ready = m.try_fast_advance();
+		const bool need_slow = alive && !ready;
+		const unsigned slow_mask = __ballot_sync(FULL, need_slow), alive_mask = __ballot_sync(FULL, alive);
+		if (alive_mask == 0) break;
+		// slow transitions (list reversal, interval filtering, pass changes, publishing a read, fetching the next one) are
+		// batched: a lane that needs one idles until `batch` lanes need one (or nobody can issue a query), then they run together
+		const int n_slow = __popc(slow_mask), n_alive = __popc(alive_mask);
+		if (need_slow && (n_slow >= batch || n_slow == n_alive || 4 * n_slow >= n_alive)) {
+			while (alive && !ready) {
+				if (!have) {
+					r = atomicAdd(work, 1);
+					if (r >= n_reads) { alive = false; break; }
+					const u64 off = read_off[r];
+					const int len = (int)(read_off[r + 1] - off);
+					if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
+					m.init(opt, len, seq + off, mem, scratch_cap, lists);
+					have = true;
 				}
-				l_rep += en - b;
-				unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
-				if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
-				for (int i = 0; i < n; ++i) pool[base + i] = mem[keys[i] & 0x3ff];
-				intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep;
-				have = false;
+				ready = m.advance(ix);
+				if (!ready) { // read finished: order its intervals, publish them
+					int n = m.finish(keys);
+					if (m.err) { atomicMax(err, 1); n = 0; }
+					int b = 0, en = 0, l_rep = 0;
+					for (int i = 0; i < n; ++i) {
+						const Intv p = mem[keys[i] & 0x3ff];
+						if (p.x2 <= (u64)opt.max_occ) continue;
+						if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
+					}
+					l_rep += en - b;
+					unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
+					if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
+					for (int i = 0; i < n; ++i) pool[base + i] = mem[keys[i] & 0x3ff];
+					intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep;
+					have = false;
+				}
 			}
 		}
-		if (done) break;
-		Intv okc;
-		extend1(fm, m.in, m.qc, m.is_back, okc);
-		m.post(okc);
+		if (ready) { // the step all lanes that have a query take together
+			Intv okc;
+			extend1(fm, m.in, m.qc, m.is_back, okc);
+			m.post(okc);
+			ready = false;
+		}
 	}
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
@@ -260,25 +272,36 @@ __global__ void k_sa_rows(DevIndex ix, u64 n, const u64 *__restrict__ rows, u64 
 // ---------------------------------------------------------------------------- k_chain ----
 __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
                                                const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
-                                               const Seed *__restrict__ seeds, i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc,
+                                               const Seed *__restrict__ seeds, i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc, KeptChain *kp,
                                                i32 *n_kept, u32 *n_kseeds, int *work)
 {
-  for (;;) { // persistent: a lane that finishes a cheap read pulls the next one instead of idling behind a repeat-rich neighbour
-	const int r = atomicAdd(work, 1);
-	if (r >= n_reads) return;
-	const int len = (int)(read_off[r + 1] - read_off[r]);
-	const int ni = intv_cnt[r];
-	int nk = 0; u32 ns = 0;
-	if (ni > 0) {
-		const u64 s0 = seed_off[intv_off[r]], s1 = seed_off[intv_off[r] + ni];
-		const int n = (int)(s1 - s0);
-		if (n > 0) {
-			nk = chain_and_filter(ix, opt, len, n, seeds + s0, l_rep[r], chain_of + s0, ch + s0, ord + s0, wi + s0, sorted + s0, outc + s0);
-			for (int c = 0; c < nk; ++c) ns += (u32)outc[s0 + c].n;
+	// persistent per-lane machine: the step every lane of the warp takes together is "add my read's next seed to its chains"
+	ChainBuilder b;
+	int r = -1, i = 0;
+	u64 s0 = 0;
+	bool have = false;
+	for (;;) {
+		bool done = false;
+		while (!have || i >= b.n) {
+			if (have) { // read finished: regroup, weigh, sort, filter, publish
+				const int nk = b.finish(opt);
+				u32 ns = 0;
+				for (int c = 0; c < nk; ++c) ns += (u32)outc[s0 + c].n;
+				n_kept[r] = nk; n_kseeds[r] = ns;
+				have = false;
+			}
+			r = atomicAdd(work, 1);
+			if (r >= n_reads) { done = true; break; }
+			const int ni = intv_cnt[r];
+			int n = 0;
+			if (ni > 0) { s0 = seed_off[intv_off[r]]; n = (int)(seed_off[intv_off[r] + ni] - s0); }
+			if (n == 0) { n_kept[r] = 0; n_kseeds[r] = 0; continue; }
+			b.init((int)(read_off[r + 1] - read_off[r]), n, seeds + s0, l_rep[r], chain_of + s0, ch + s0, ord + s0, wi + s0, sorted + s0, outc + s0, kp + s0);
+			i = 0; have = true;
 		}
+		if (done) break;
+		b.add_seed(ix, opt, i++);
 	}
-	n_kept[r] = nk; n_kseeds[r] = ns;
-  }
 }
 
 // --------------------------------------------------------------------------- k_extend ----
@@ -593,7 +616,7 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xdone;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xdone, xkp;
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
@@ -657,7 +680,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xdone};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xdone, &b->xkp};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
@@ -710,7 +733,7 @@ static int run_smem(ssq_batch *b)
 			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else if (variant == 2)
-			k_smem_m<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+			k_smem_m<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, getenv("SSQ_SLOW_BATCH") ? atoi(getenv("SSQ_SLOW_BATCH")) : 8, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else
 			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
@@ -760,12 +783,12 @@ static int run_chain(ssq_batch *b)
 	const int n = b->n_reads;
 	const u64 ns = b->n_seeds + 1;
 	if (b->chain_of.need(ns * 4) || b->ch.need(ns * sizeof(ChainRec)) || b->ord.need(ns * 4) || b->wi.need(ns * sizeof(WIdx)) || b->sorted.need(ns * sizeof(Seed)) ||
-	    b->outc.need(ns * sizeof(ChainRec)) || b->n_kept.need((size_t)(n + 1) * 4) || b->n_kseeds.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+	    b->outc.need(ns * sizeof(ChainRec)) || b->xkp.need(ns * sizeof(KeptChain)) || b->n_kept.need((size_t)(n + 1) * 4) || b->n_kseeds.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
 	if (n) {
 		CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
 		k_chain<<<b->n_sm * 12, 128, 0, b->st>>>(b->idx->dev, b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
 		                                           b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
-		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work);
+		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work);
 		++b->launches;
 		CK(cudaGetLastError());
 	}

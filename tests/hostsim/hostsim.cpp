@@ -56,7 +56,7 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 		SmemMachineT<HostLists> m; Intv okc;
 		HostLists hl; hl.a[0] = bufA.data(); hl.a[1] = bufB.data();
 		m.init(opt, len, q, w.mem.data(), 2048, hl);
-		while (m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
+		for (bool go = m.advance(ix); go; go = m.try_fast_advance() || m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
 		std::vector<u32> keys(2048);
 		err = m.err; w.n_intv = m.finish(keys.data());
 		{ std::vector<Intv> tmp(w.n_intv); for (int i = 0; i < w.n_intv; ++i) tmp[i] = w.mem[keys[i] & 0x3ff]; for (int i = 0; i < w.n_intv; ++i) w.mem[i] = tmp[i]; }
@@ -81,9 +81,9 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	}
 	int n = (int)w.seeds.size();
 	if (n == 0) return;
-	std::vector<i32> chain_of(n), ord(n); std::vector<ChainRec> ch(n); std::vector<WIdx> wi(n);
+	std::vector<i32> chain_of(n), ord(n); std::vector<ChainRec> ch(n); std::vector<WIdx> wi(n); std::vector<KeptChain> kp(n);
 	w.sorted.assign(n, Seed()); w.outc.assign(n, ChainRec());
-	w.n_kept = chain_and_filter(ix, opt, len, n, w.seeds.data(), w.l_rep, chain_of.data(), ch.data(), ord.data(), wi.data(), w.sorted.data(), w.outc.data());
+	w.n_kept = chain_and_filter(ix, opt, len, n, w.seeds.data(), w.l_rep, chain_of.data(), ch.data(), ord.data(), wi.data(), w.sorted.data(), w.outc.data(), kp.data());
 	if (upto < 2) return;
 	std::vector<u32> ehbuf(len + 4);
 	EhAcc eh; eh.base = ehbuf.data(); eh.stride = 1;
