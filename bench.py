@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
     ap.add_argument("--cache", default=os.environ.get("SSQ_BENCH_CACHE", os.path.join(ROOT, "data_cache")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("SSQ_BENCH_STREAMS", "2")), help="host threads / CUDA streams that drive batches concurrently")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,21 +210,33 @@ def main():
     idx = s.index_load(fa, local)
     # reads: pinned host copies, one batch object per batch, all sharing one stream
     host_seq, host_off, batches = [], [], []
-    stream = None
+    nstreams = max(1, min(a.streams, nb))
+    streams = [None] * nstreams
     for b in range(nb):
         seq, off = fast_pairs(g, a.batch // 2, READ_LEN, 1000 + rank * 100 + b)
         ts, to = torch.from_numpy(seq).pin_memory(), torch.from_numpy(off.view(np.int64)).pin_memory()
         host_seq.append(ts); host_off.append(to)
         h = C.c_void_p()
         s.ck(L.ssq_batch_create(idx, s.opts, C.c_int(0), None, None, C.byref(h)), "ssq_batch_create")
-        if stream is None:
-            stream = L.ssq_batch_stream(h)
+        if streams[b % nstreams] is None:
+            streams[b % nstreams] = L.ssq_batch_stream(h)  # the first batch of a lane owns the stream, the others share it
         else:
-            s.ck(L.ssq_batch_set_stream(h, C.c_void_p(stream)), "ssq_batch_set_stream")
+            s.ck(L.ssq_batch_set_stream(h, C.c_void_p(streams[b % nstreams])), "ssq_batch_set_stream")
         s.ck(L.ssq_batch_upload(h, C.c_int(a.batch), C.c_void_p(ts.data_ptr()), C.c_void_p(to.data_ptr())), "ssq_batch_upload")
         batches.append(h)
-    ext = torch.cuda.ExternalStream(stream)
+    exts = [torch.cuda.ExternalStream(x) for x in streams]
     n_reads_step = nb * a.batch
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(nstreams)
+
+    def lanes(fn):
+        """run fn(lane) on every stream lane concurrently (ctypes calls release the GIL); re-raises worker errors"""
+        for f in [pool.submit(fn, k) for k in range(nstreams)]:
+            f.result()
+
+    def span_ms(ev_pairs):
+        """elapsed time from the earliest start event to the latest end event over all lanes"""
+        return max(ev_pairs[i][0].elapsed_time(ev_pairs[j][1]) for i in range(nstreams) for j in range(nstreams))
 
     def barrier():
         if world > 1:
@@ -231,54 +244,69 @@ def main():
         torch.cuda.synchronize()
 
     def run_resident():
-        for h in batches:
-            s.ck(L.ssq_batch_run(h), "ssq_batch_run")
+        def one(k):
+            torch.cuda.set_device(local)
+            for h in batches[k::nstreams]:
+                s.ck(L.ssq_batch_run(h), "ssq_batch_run")
+        lanes(one)
 
     # ---- value: HBM-resident ----
     for _ in range(a.warmup):
         run_resident()
     barrier()
     clk = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(ext)
-    stage_ms = np.zeros(5)
-    counters = np.zeros(11)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nstreams)]
+    for k in range(nstreams):
+        evs[k][0].record(exts[k])
     for _ in range(a.steps):
         run_resident()
-        for h in batches:
-            stage_ms += [L.ssq_batch_stage_ms(h, i) for i in range(5)]
-            counters += [L.ssq_batch_counter(h, i) for i in range(11)]
-    ev1.record(ext)
+    for k in range(nstreams):
+        evs[k][1].record(exts[k])
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = span_ms(evs)
     clocks = clk.stop()
+    # per-kernel stage times and device work counters: one extra step with the batches run one after the other, so that a
+    # kernel's CUDA-event duration is not stretched by kernels of the other stream lane
+    stage_ms = np.zeros(5)
+    counters = np.zeros(12)
+    for h in batches:
+        s.ck(L.ssq_batch_run(h), "ssq_batch_run")
+        stage_ms += [L.ssq_batch_stage_ms(h, i) for i in range(5)]
+        counters += [L.ssq_batch_counter(h, i) for i in range(12)]
+    stats_steps = 1
     # ---- e2e: host buffers through the C-ABI ----
-    eb = batches[0]
-    cap = int(counters[8] / max(1, a.steps * nb) * 1.5) + 1024 if counters[8] else a.batch * 2
+    ebs = batches[:nstreams]  # one reusable batch object per lane
     need = C.c_uint64(0)
-    # size the pinned output from a first fetch
-    s.ck(L.ssq_batch_run(eb), "run"); L.ssq_batch_fetch(eb, None, C.c_uint64(0), None, C.byref(need))
+    s.ck(L.ssq_batch_run(ebs[0]), "run"); L.ssq_batch_fetch(ebs[0], None, C.c_uint64(0), None, C.byref(need))  # sizes the pinned output
     cap = int(need.value * 1.3) + 1024
-    out_regs = torch.empty(cap * T.REG_DT.itemsize, dtype=torch.uint8).pin_memory()
-    out_off = torch.empty(a.batch + 1, dtype=torch.int64).pin_memory()
+    out_regs = [torch.empty(cap * T.REG_DT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(nstreams)]
+    out_off = [torch.empty(a.batch + 1, dtype=torch.int64).pin_memory() for _ in range(nstreams)]
+    d2h_lane = [0] * nstreams
+
     def run_e2e():
-        d2h = 0
-        for b in range(nb):
-            s.ck(L.ssq_batch_upload(eb, C.c_int(a.batch), C.c_void_p(host_seq[b].data_ptr()), C.c_void_p(host_off[b].data_ptr())), "upload")
-            s.ck(L.ssq_batch_run(eb), "run")
-            s.ck(L.ssq_batch_fetch(eb, C.c_void_p(out_regs.data_ptr()), C.c_uint64(cap), C.c_void_p(out_off.data_ptr()), C.byref(need)), "fetch")
-            d2h += int(need.value) * T.REG_DT.itemsize + (a.batch + 1) * 8
-        return d2h
+        def one(k):
+            torch.cuda.set_device(local)
+            nd = C.c_uint64(0)
+            d2h_lane[k] = 0
+            for b in range(k, nb, nstreams):
+                s.ck(L.ssq_batch_upload(ebs[k], C.c_int(a.batch), C.c_void_p(host_seq[b].data_ptr()), C.c_void_p(host_off[b].data_ptr())), "upload")
+                s.ck(L.ssq_batch_run(ebs[k]), "run")
+                s.ck(L.ssq_batch_fetch(ebs[k], C.c_void_p(out_regs[k].data_ptr()), C.c_uint64(cap), C.c_void_p(out_off[k].data_ptr()), C.byref(nd)), "fetch")
+                d2h_lane[k] += int(nd.value) * T.REG_DT.itemsize + (a.batch + 1) * 8
+        lanes(one)
+        return sum(d2h_lane)
     run_e2e()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
+    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nstreams)]
+    for k in range(nstreams):
+        ee[k][0].record(exts[k])
     d2h = 0
     for _ in range(a.steps):
         d2h = run_e2e()
-    e1.record(ext)
+    for k in range(nstreams):
+        ee[k][1].record(exts[k])
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = span_ms(ee)
     h2d = sum(int(t.numel()) for t in host_seq) + sum(int(t.numel()) * 8 for t in host_off)
     # restore batch 0 for consistency
     # ---- max over ranks ----
@@ -296,7 +324,7 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        n_launch = a.steps * nb
+        n_launch = stats_steps * nb
         blk = float(L.ssq_index_info(idx, 7))  # bytes one rank query must fetch: 32 (re-blocked sector) or 64 (on-disk block)
         kern = {
             "k_smem": {"bytes": blk * counters[0] / n_launch, "ms": stage_ms[0] / n_launch},
@@ -310,21 +338,22 @@ def main():
             dom = "k_smem"
         ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] else 0.0
         for k in kern.values():
-            k["share_of_step"] = k["ms"] * n_launch / ms_total if ms_total else None
+            k["share_of_step"] = k["ms"] / (sum(stage_ms) / n_launch) if stage_ms.sum() else None
             k["achieved_GBps"] = (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["bytes"] and k["ms"] else None
         res = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-               "config": {"workload": workload, "batch_reads": a.batch, "batches_per_step": nb, "l2": "inputs+scratch per step exceed L2 (5 x 300 MB reads); index (110 MB) is the resident working set",
+               "config": {"workload": workload, "batch_reads": a.batch, "batches_per_step": nb, "streams": nstreams, "l2": "inputs+scratch per step exceed L2 (5 x 300 MB reads); index (110 MB) is the resident working set",
                           "index": "replicated per GPU", "parallelism": "reads sharded per rank, no collective on this path"},
-               "clocks": clocks, "gpu_launches": int(counters[6]),
+               "clocks": clocks, "gpu_launches": int(counters[6]) * a.steps,
                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
                "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"],
                             "rank_block_bytes": blk,
                             "note": "algorithmic bytes = rank-block bytes x blocks dereferenced (counted on the device); random sector reads — with a chr20-sized index the 63 MB rank structure is served mostly by the 126 MB L2, so DRAM traffic is below algorithmic bytes; see profiles/"},
                "kernels": kern,
-               "work_per_step": {"occ_blocks_smem": counters[0] / a.steps, "occ_blocks_sa": counters[1] / a.steps, "sa_samples": counters[2] / a.steps, "sw_calls": counters[3] / a.steps,
-                                 "sw_cells": counters[4] / a.steps, "seeds": counters[7] / a.steps, "regions": counters[8] / a.steps, "intervals": counters[9] / a.steps}}
+               "work_per_step": {"occ_blocks_smem": counters[0], "occ_blocks_sa": counters[1], "sa_samples": counters[2], "sw_calls": counters[3], "sw_cells": counters[4], "seeds": counters[7],
+                                 "intervals": counters[9], "extension_tasks": counters[10], "extension_rounds_max": counters[11] / nb},
+               "kernel_stats_note": "kernels{} and work_per_step come from one extra non-overlapped step after the timed region"}
         if world == 1 and not a.no_cpu_baseline:
             o = T.Oracle()
             oidx = o.load(fa)
