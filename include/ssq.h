@@ -49,6 +49,7 @@ typedef struct {
 	int32_t min_chain_weight, max_chain_extend, max_ins, max_matesw, max_XA_hits;
 	float split_factor, mask_level, drop_ratio, XA_drop_ratio, mask_level_redun;
 	int32_t mapQ_coef_len, mapQ_coef_fac;
+	int32_t n_threads; /* host threads for the per-pair bookkeeping and SAM formatting (`bwa mem -t`); does not change any result */
 } ssq_opts_t;
 void ssq_opts_default(ssq_opts_t *o);
 

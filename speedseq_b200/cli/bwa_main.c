@@ -187,6 +187,7 @@ static int main_mem(int argc, char **argv, const char *prog)
 			if (*p && ispunct((unsigned char)*p) && isdigit((unsigned char)p[1])) pes[1].low = (int)(strtod(p + 1, &p) + .499);
 		} else return 1;
 	}
+	opt.n_threads = n_threads;
 	if (optind + 1 >= argc || optind + 3 < argc) { fprintf(stderr, "Usage: bwa mem [-t INT] [-p] [-C] [-I FLOAT[,FLOAT[,INT[,INT]]]] [-R STR] <idxbase> <in1.fq> [in2.fq]\n"); return 1; }
 	if ((rc = ssq_index_load(argv[optind], device, &idx))) die("ssq_index_load", rc);
 	if (!(f1 = fq_open(argv[optind + 1]))) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 1]); return 1; }

@@ -48,6 +48,7 @@ extern "C" void ssq_opts_default(ssq_opts_t *o)
 	o->min_chain_weight = 0; o->max_chain_extend = 1 << 30; o->max_ins = 10000; o->max_matesw = 50; o->max_XA_hits = 5;
 	o->split_factor = 1.5f; o->mask_level = 0.50f; o->drop_ratio = 0.50f; o->XA_drop_ratio = 0.80f; o->mask_level_redun = 0.95f;
 	o->mapQ_coef_len = 50; o->mapQ_coef_fac = (int)log(50.0);
+	o->n_threads = 1;
 }
 
 // re-block the on-disk rank structure (64 B per 128 symbols, u64 counts) into 32 B per 64 symbols with u32 counts

@@ -19,6 +19,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <chrono>
 #include "ssq_mem_host.h"
 #include "ssq_host.h"
 #include "ssq_batch.h"
@@ -28,24 +29,37 @@
 // ================================================================================ kernels ====
 #define REF_CAP 12288    // longest reference window a thread materialises (mate rescue: max_ins + 2 reads)
 
-struct ThreadScratch { // carved from one big per-thread slab
+struct ThreadScratch { // carved from a per-thread slab
 	uint8_t *qbuf, *rbuf, *z, *seq, *ref; i32 *h, *e, *H0, *H1, *E, *Hmax; u64 *b;
 };
 #define QMAX 256
 #define Z_BYTES (QMAX * 768)
-#define SLAB_BYTES (QMAX + 2048 + Z_BYTES + QMAX + REF_CAP + 6 * (QMAX + 16) * 4 + REF_CAP * 8 + 64)
+// big slab (mate rescue, CIGAR): the traceback matrix (k_cigar) and the rescue window + sub-optimal row list (k_matesw) are
+// never live together, so they share one area; small slab (k_dedup): score-only global DP needs two DP rows and two sequences
+#define BIG_AREA (Z_BYTES > REF_CAP * 9 ? Z_BYTES : REF_CAP * 9)
+#define SLAB_FIXED (6 * (QMAX + 16) * 4 + QMAX + 2048 + QMAX + 64)
+#define SLAB_BYTES (SLAB_FIXED + BIG_AREA)
+#define SLAB_SMALL_BYTES (2 * (QMAX + 16) * 4 + QMAX + 2048 + 64)
 
 __device__ __forceinline__ void carve(uint8_t *slab, ThreadScratch &t)
 {
 	uint8_t *p = slab;
-	t.b = (u64*)p; p += (size_t)REF_CAP * 8;
 	t.h = (i32*)p; p += (QMAX + 16) * 4; t.e = (i32*)p; p += (QMAX + 16) * 4;
 	t.H0 = (i32*)p; p += (QMAX + 16) * 4; t.H1 = (i32*)p; p += (QMAX + 16) * 4; t.E = (i32*)p; p += (QMAX + 16) * 4; t.Hmax = (i32*)p; p += (QMAX + 16) * 4;
-	t.qbuf = p; p += QMAX; t.rbuf = p; p += 2048; t.seq = p; p += QMAX; t.ref = p; p += REF_CAP; t.z = p;
+	t.qbuf = p; p += QMAX; t.rbuf = p; p += 2048; t.seq = p; p += QMAX + 64;
+	t.z = p;                                   // k_cigar's view of the shared area
+	t.b = (u64*)p; t.ref = p + (size_t)REF_CAP * 8; // k_matesw's view
+}
+__device__ __forceinline__ void carve_small(uint8_t *slab, ThreadScratch &t)
+{
+	uint8_t *p = slab;
+	t.h = (i32*)p; p += (QMAX + 16) * 4; t.e = (i32*)p; p += (QMAX + 16) * 4;
+	t.qbuf = p; p += QMAX; t.rbuf = p;
+	t.H0 = t.H1 = t.E = t.Hmax = 0; t.seq = t.ref = t.z = 0; t.b = 0;
 }
 __device__ __forceinline__ void scratch_views(const ThreadScratch &t, AlnScratch &A, MateScratch &M)
 {
-	A.qbuf = t.qbuf; A.rbuf = t.rbuf; A.rcap = 2048; A.g.h = t.h; A.g.e = t.e; A.g.z = t.z; A.g.zcap = Z_BYTES;
+	A.qbuf = t.qbuf; A.rbuf = t.rbuf; A.rcap = 2048; A.g.h = t.h; A.g.e = t.e; A.g.z = t.z; A.g.zcap = t.z ? Z_BYTES : 0;
 	M.seq = t.seq; M.ref = t.ref; M.ref_cap = REF_CAP; M.L.H0 = t.H0; M.L.H1 = t.H1; M.L.E = t.E; M.L.Hmax = t.Hmax; M.L.b = t.b; M.L.b_cap = REF_CAP; M.A = A;
 }
 
@@ -55,7 +69,7 @@ __global__ void __launch_bounds__(128) k_dedup(DevIndex ix, ssq_opts_t opt, int 
                                                const u64 *__restrict__ areg_off, AlnReg *areg, u32 *n_areg, uint8_t *slabs, int *work)
 {
 	ThreadScratch ts; AlnScratch A; MateScratch M;
-	carve(slabs + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * SLAB_BYTES, ts);
+	carve_small(slabs + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * SLAB_SMALL_BYTES, ts);
 	scratch_views(ts, A, M);
 	for (;;) {
 		const int r = atomicAdd(work, 1);
@@ -128,13 +142,15 @@ __global__ void k_areg_cap(int n, int paired, int max_matesw, const u32 *__restr
 }
 
 // =========================================================================== CUDA backend ====
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct CudaBackend {
+	double t_align, t_dedup, t_rescue, t_cigar, t_alloc;
 	const ssq_index *idx; ssq_opts_t o;
 	ssq_batch_t *b; cudaStream_t st; BatchView bv;
 	std::vector<void*> dev;
-	uint8_t *d_slabs; u64 *d_cap, *d_aoff; u32 *d_na; AlnReg *d_areg; int *d_work; int n_reads, slab_threads; u64 total_cap;
+	uint8_t *d_slabs, *d_slabs_small; u64 *d_cap, *d_aoff; u32 *d_na; AlnReg *d_areg; int *d_work; int n_reads, slab_threads; u64 total_cap;
 	std::vector<u64> aoff; std::vector<u32> na; std::vector<AlnReg> areg;
-	CudaBackend(const ssq_index *i, const ssq_opts_t &o_) : idx(i), o(o_), b(0), d_slabs(0), d_cap(0), d_aoff(0), d_na(0), d_areg(0), d_work(0), n_reads(0), slab_threads(0), total_cap(0) {}
+	CudaBackend(const ssq_index *i, const ssq_opts_t &o_) : idx(i), o(o_), b(0), d_slabs(0), d_slabs_small(0), d_cap(0), d_aoff(0), d_na(0), d_areg(0), d_work(0), n_reads(0), slab_threads(0), total_cap(0) { t_align = t_dedup = t_rescue = t_cigar = t_alloc = 0; }
 	~CudaBackend() { for (size_t i = 0; i < dev.size(); ++i) cudaFree(dev[i]); if (b) ssq_batch_free(b); }
 #define DMALLOC(p, bytes) do { CK(cudaMalloc((void**)&(p), (bytes))); dev.push_back((void*)(p)); } while (0)
 	int fetch()
@@ -149,13 +165,18 @@ struct CudaBackend {
 	{
 		int rc;
 		n_reads = n;
+		double t0 = now_s();
 		if ((rc = ssq_batch_create(idx, &o, n, codes, off, &b))) return rc;
 		if ((rc = ssq_batch_run(b))) return rc;
+		ssq_batch_sync(b); t_align = now_s() - t0; t0 = now_s();
 		st = (cudaStream_t)ssq_batch_stream(b);
 		bv = ssq_batch_view(b);
-		slab_threads = bv.n_sm * 2 * 128;
+		slab_threads = bv.n_sm * 128;            // big slabs: one block per SM
+		const int small_threads = bv.n_sm * 8 * 128; // small slabs: the dedup kernel runs wide
 		void *d_tmp = 0; size_t tmp_bytes = 0;
 		DMALLOC(d_slabs, (size_t)slab_threads * SLAB_BYTES);
+		DMALLOC(d_slabs_small, (size_t)small_threads * SLAB_SMALL_BYTES);
+		t_alloc = now_s() - t0; t0 = now_s();
 		DMALLOC(d_cap, (size_t)(n + 2) * 8); DMALLOC(d_aoff, (size_t)(n + 2) * 8); DMALLOC(d_na, (size_t)(n + 1) * 4); DMALLOC(d_work, 64);
 		CK(cudaMemsetAsync(d_aoff, 0, (size_t)(n + 2) * 8, st));
 		if (n) {
@@ -168,37 +189,42 @@ struct CudaBackend {
 		}
 		DMALLOC(d_areg, (total_cap + 1) * sizeof(AlnReg));
 		CK(cudaMemsetAsync(d_work, 0, 64, st));
-		if (n) k_dedup<<<bv.n_sm * 2, 128, 0, st>>>(bv.ix, o, n, bv.seq, bv.read_off, bv.task_off, bv.n_regs, bv.regs, d_aoff, d_areg, d_na, d_slabs, d_work);
+		if (n) k_dedup<<<bv.n_sm * 8, 128, 0, st>>>(bv.ix, o, n, bv.seq, bv.read_off, bv.task_off, bv.n_regs, bv.regs, d_aoff, d_areg, d_na, d_slabs_small, d_work);
 		CK(cudaGetLastError());
 		aoff.assign(n + 1, 0); na.assign(n + 1, 0); areg.resize(total_cap + 1);
-		return fetch();
+		rc = fetch(); t_dedup = now_s() - t0;
+		return rc;
 	}
 	int rescue(const PeStat pes[4])
 	{
+		double t0 = now_s();
 		PeStat *d_pes = 0; AlnReg *d_bbuf = 0; int *d_err = d_work + 8, h_err = 0;
 		DMALLOC(d_pes, 4 * sizeof(PeStat)); DMALLOC(d_bbuf, (size_t)slab_threads * 128 * sizeof(AlnReg));
 		CK(cudaMemcpyAsync(d_pes, pes, 4 * sizeof(PeStat), cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(d_work, 0, 64, st));
-		k_matesw<<<bv.n_sm * 2, 128, 0, st>>>(bv.ix, o, n_reads / 2, bv.seq, bv.read_off, d_aoff, d_areg, d_na, d_pes, d_slabs, d_bbuf, d_work, d_err);
+		k_matesw<<<bv.n_sm, 128, 0, st>>>(bv.ix, o, n_reads / 2, bv.seq, bv.read_off, d_aoff, d_areg, d_na, d_pes, d_slabs, d_bbuf, d_work, d_err);
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		if (h_err) { ssq_set_error("mate rescue overflowed a region list (internal capacity rule violated)"); return SSQ_ECAP; }
-		return fetch();
+		int rc = fetch(); t_rescue = now_s() - t0;
+		return rc;
 	}
 	int cigar(const std::vector<CigTask> &tasks, std::vector<AlnOut> &outs, std::vector<u32> &cigs, std::vector<char> &mds)
 	{
 		const int nt = (int)tasks.size();
+		double t0 = now_s();
 		CigTask *d_tasks = 0; AlnOut *d_out = 0; u32 *d_cig = 0; char *d_md = 0;
 		DMALLOC(d_tasks, (size_t)nt * sizeof(CigTask)); DMALLOC(d_out, (size_t)nt * sizeof(AlnOut)); DMALLOC(d_cig, (size_t)nt * CIG_CAP * 4); DMALLOC(d_md, (size_t)nt * MD_CAP);
 		CK(cudaMemcpyAsync(d_tasks, tasks.data(), (size_t)nt * sizeof(CigTask), cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(d_work, 0, 64, st));
-		k_cigar<<<bv.n_sm * 2, 128, 0, st>>>(bv.ix, o, nt, d_tasks, bv.seq, bv.read_off, d_out, d_cig, d_md, d_slabs, d_work);
+		k_cigar<<<bv.n_sm, 128, 0, st>>>(bv.ix, o, nt, d_tasks, bv.seq, bv.read_off, d_out, d_cig, d_md, d_slabs, d_work);
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(outs.data(), d_out, (size_t)nt * sizeof(AlnOut), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(cigs.data(), d_cig, (size_t)nt * CIG_CAP * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(mds.data(), d_md, (size_t)nt * MD_CAP, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		t_cigar = now_s() - t0;
 		return 0;
 	}
 };
@@ -224,7 +250,9 @@ extern "C" int ssq_mem_batch_sam(const ssq_index_t *idx, const ssq_opts_t *opt_,
 	CudaBackend be(idx, *opt_);
 	std::string sam, err;
 	std::vector<size_t> loff;
+	const double t_all0 = now_s();
 	rc = mem_batch_sam(be, *opt_, &hi, n_reads, names, codes.data(), off.data(), quals, comments, n_processed, paired, pes0 ? pes : 0, rg_id, verbose ? stderr : 0, sam, err, read_sam_off ? &loff : 0);
+	if (getenv("SSQ_MEM_TIMING")) fprintf(stderr, "[ssq_mem] %d reads: total %.3f s | seed..extend %.3f | slab alloc %.3f | dedup+fetch %.3f | rescue+fetch %.3f | cigar %.3f | host rest %.3f\n", n_reads, now_s() - t_all0, be.t_align, be.t_alloc, be.t_dedup, be.t_rescue, be.t_cigar, now_s() - t_all0 - be.t_align - be.t_alloc - be.t_dedup - be.t_rescue - be.t_cigar);
 	if (rc) { if (!err.empty()) ssq_set_error("%s", err.c_str()); return rc; }
 	*sam_out = (char*)malloc(sam.size() + 1);
 	if (!*sam_out) return SSQ_ENOMEM;

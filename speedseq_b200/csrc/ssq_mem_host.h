@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <thread>
 #include <vector>
 #include "ssq_dev2.cuh"
 
@@ -328,13 +329,15 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 	std::vector<u64> &aoff = be.aoff; std::vector<u32> &na = be.na; std::vector<AlnReg> &areg = be.areg;
 	// 5. host: primary marking, pairing, MAPQ; collect the alignments that need a CIGAR
 	std::vector<CigReq> reqs;
+	const int n_thr = o.n_threads > 1 ? (o.n_threads < 64 ? o.n_threads : 64) : 1;
+	std::vector<std::vector<CigReq> > reqs_t(n_thr);
 	std::vector<ReadPlan> plan(n_reads);
 	std::vector<std::vector<Aln> > mate_hdr(n_reads); // h[] of the pair (mate info), index 0 only
 	std::vector<int> z0(n_reads, -1);
 	struct PairInfo { int mode; /* 0 = paired output, 1 = no_pairing */ int z[2], q_se[2], extra_flag; };
 	std::vector<PairInfo> pinfo(paired ? n_reads / 2 : 0);
-	auto add_req = [&](int read, int reg_idx, int kind, int line, int xa_owner) { CigReq r; r.read = read; r.reg_idx = reg_idx; r.reg = areg[aoff[read] + reg_idx]; r.kind = kind; r.line = line; r.xa_owner = xa_owner; reqs.push_back(r); };
-	auto plan_xa = [&](int read) { // mem_gen_alt: secondary hits within 0.8x of their primary, at most max_XA_hits per primary
+	auto add_req = [&](std::vector<CigReq> &reqs, int read, int reg_idx, int kind, int line, int xa_owner) { CigReq r; r.read = read; r.reg_idx = reg_idx; r.reg = areg[aoff[read] + reg_idx]; r.kind = kind; r.line = line; r.xa_owner = xa_owner; reqs.push_back(r); };
+	auto plan_xa = [&](std::vector<CigReq> &reqs, int read) { // mem_gen_alt: secondary hits within 0.8x of their primary, at most max_XA_hits per primary
 		AlnReg *a = areg.data() + aoff[read];
 		const int n = (int)na[read];
 		std::vector<int> cnt(n, 0);
@@ -343,13 +346,13 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 			const int k = a[i].secondary_all;
 			if (!(k >= 0 && a[i].score >= a[k].score * (double)o.XA_drop_ratio)) continue;
 			if (cnt[k] > o.max_XA_hits) continue;
-			add_req(read, i, 1, -1, k);
+			add_req(reqs, read, i, 1, -1, k);
 		}
 	};
-	auto plan_reg2sam = [&](int read, int extra_flag) { // mem_reg2sam without -a: every non-secondary hit above T, first = primary, rest supplementary
+	auto plan_reg2sam = [&](std::vector<CigReq> &reqs, int read, int extra_flag) { // mem_reg2sam without -a: every non-secondary hit above T, first = primary, rest supplementary
 		AlnReg *a = areg.data() + aoff[read];
 		const int n = (int)na[read];
-		plan_xa(read);
+		plan_xa(reqs, read);
 		plan[read].extra_flag = extra_flag;
 		int l = 0;
 		for (int k = 0; k < n; ++k) {
@@ -359,14 +362,16 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 			q.has = true; q.flag = extra_flag | (l ? 0x800 : 0);
 			q.mapq = approx_mapq_se(o, a[k]);
 			if (l && q.mapq > plan[read].lines[0].mapq) q.mapq = plan[read].lines[0].mapq;
-			add_req(read, k, 0, l, k);
+			add_req(reqs, read, k, 0, l, k);
 			++l;
 		}
 	};
+	auto plan_range = [&](int tid, int lo, int hi) { // units: reads (single-end) or pairs (paired); every unit only touches its own reads
+	std::vector<CigReq> &reqs = reqs_t[tid];
 	if (!paired) {
-		for (int r = 0; r < n_reads; ++r) { mark_primary(o, (int)na[r], areg.data() + aoff[r], n_processed + r); plan_reg2sam(r, 0); }
+		for (int r = lo; r < hi; ++r) { mark_primary(o, (int)na[r], areg.data() + aoff[r], n_processed + r); plan_reg2sam(reqs, r, 0); }
 	} else {
-		for (int p = 0; p < n_reads / 2; ++p) {
+		for (int p = lo; p < hi; ++p) {
 			AlnReg *a[2] = {areg.data() + aoff[2 * p], areg.data() + aoff[2 * p + 1]};
 			int n[2] = {(int)na[2 * p], (int)na[2 * p + 1]}, z[2] = {0, 0}, osc = 0, subo = 0, n_sub = 0, extra_flag = 1;
 			const i64 id = (n_processed >> 1) + p;
@@ -409,12 +414,12 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 					pi.mode = 0; pi.z[0] = z[0]; pi.z[1] = z[1]; pi.q_se[0] = q_se[0]; pi.q_se[1] = q_se[1]; pi.extra_flag = extra_flag;
 					for (int i = 0; i < 2; ++i) {
 						const int read = 2 * p + i;
-						plan_xa(read);
+						plan_xa(reqs, read);
 						plan[read].lines.push_back(Aln());
 						Aln &h = plan[read].lines.back();
 						h.has = true; h.mapq = q_se[i]; h.flag = 0x40 << i | extra_flag;
 						// reg2aln sets the secondary flag from the region: requests carry the (possibly updated) region
-						add_req(read, z[i], 0, 0, z[i]);
+						add_req(reqs, read, z[i], 0, 0, z[i]);
 					}
 				}
 			}
@@ -423,7 +428,7 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 				for (int i = 0; i < 2; ++i) { // mate header h[i]: the best hit if above T, else unmapped
 					const int read = 2 * p + i;
 					mate_hdr[read].push_back(Aln());
-					if (n[i] && a[i][0].score >= o.T) { mate_hdr[read][0].has = true; add_req(read, 0, 2, 0, 0); }
+					if (n[i] && a[i][0].score >= o.T) { mate_hdr[read][0].has = true; add_req(reqs, read, 0, 2, 0, 0); }
 				}
 				int ef = 1;
 				if (n[0] && n[1] && a[0][0].score >= o.T && a[1][0].score >= o.T && a[0][0].rid == a[1][0].rid) {
@@ -432,10 +437,21 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 					if (!pes[d].failed && dist >= pes[d].low && dist <= pes[d].high) ef |= 2;
 				}
 				pi.extra_flag = ef;
-				plan_reg2sam(2 * p, 0x41 | ef);
-				plan_reg2sam(2 * p + 1, 0x81 | ef);
+				plan_reg2sam(reqs, 2 * p, 0x41 | ef);
+				plan_reg2sam(reqs, 2 * p + 1, 0x81 | ef);
 			}
 		}
+	}
+	};
+	{
+		const int units = paired ? n_reads / 2 : n_reads;
+		std::vector<std::thread> th;
+		for (int t = 0; t < n_thr; ++t) {
+			const int lo = (int)((long long)units * t / n_thr), hi = (int)((long long)units * (t + 1) / n_thr);
+			if (n_thr == 1) plan_range(0, lo, hi); else th.emplace_back(plan_range, t, lo, hi);
+		}
+		for (size_t t = 0; t < th.size(); ++t) th[t].join();
+		for (int t = 0; t < n_thr; ++t) reqs.insert(reqs.end(), reqs_t[t].begin(), reqs_t[t].end()); // thread order = read order
 	}
 	const int nt = (int)reqs.size();
 	std::vector<AlnOut> outs(nt);
@@ -471,27 +487,45 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 	for (int t = 0; t < nt; ++t) if (reqs[t].kind == 0) plan[reqs[t].read].lines[reqs[t].line].xa = xa[reqs[t].read][reqs[t].reg_idx];
 	// 8. SAM text in input order
 	sam.clear();
-	sam.reserve((size_t)n_reads * 400);
-	if (line_off) line_off->assign(n_reads + 1, 0);
-	for (int r = 0; r < n_reads; ++r) {
-		if (line_off) (*line_off)[r] = sam.size();
-		const char *sq = (const char*)codes.data() + off[r];
-		const int l_seq = (int)(off[r + 1] - off[r]);
-		const char *cm = comments ? comments[r] : 0;
-		const Aln *mate = 0;
-		Aln unm_mate;
-		if (paired) {
-			const int m = r ^ 1;
-			const PairInfo &pi = pinfo[r >> 1];
-			if (pi.mode == 0) mate = &plan[m].lines[0];
-			else mate = &mate_hdr[m][0]; // has==false -> unmapped header (rid -1)
+	std::vector<std::string> part(n_thr);
+	std::vector<size_t> rel_off(line_off ? n_reads + 1 : 0, 0);
+	auto fmt_range = [&](int tid, int lo, int hi) {
+		std::string &sam = part[tid];
+		sam.reserve((size_t)(hi - lo) * 400);
+		for (int r = lo; r < hi; ++r) {
+			if (line_off) rel_off[r] = sam.size();
+			const char *sq = (const char*)codes.data() + off[r];
+			const int l_seq = (int)(off[r + 1] - off[r]);
+			const char *cm = comments ? comments[r] : 0;
+			const Aln *mate = 0;
+			if (paired) {
+				const int m = r ^ 1;
+				const PairInfo &pi = pinfo[r >> 1];
+				if (pi.mode == 0) mate = &plan[m].lines[0];
+				else mate = &mate_hdr[m][0]; // has==false -> unmapped header (rid -1)
+			}
+			if (plan[r].lines.empty()) { // unaligned record
+				std::vector<Aln> one(1);
+				one[0].flag = 0x4 | plan[r].extra_flag;
+				aln2sam(idx, sam, names[r], sq, l_seq, quals ? quals[r] : 0, one, 0, mate, rg_id, cm);
+			} else {
+				for (size_t k = 0; k < plan[r].lines.size(); ++k) aln2sam(idx, sam, names[r], sq, l_seq, quals ? quals[r] : 0, plan[r].lines, (int)k, mate, rg_id, cm);
+			}
 		}
-		if (plan[r].lines.empty()) { // unaligned record
-			std::vector<Aln> one(1);
-			one[0].flag = 0x4 | plan[r].extra_flag;
-			aln2sam(idx, sam, names[r], sq, l_seq, quals ? quals[r] : 0, one, 0, mate, rg_id, cm);
-		} else {
-			for (size_t k = 0; k < plan[r].lines.size(); ++k) aln2sam(idx, sam, names[r], sq, l_seq, quals ? quals[r] : 0, plan[r].lines, (int)k, mate, rg_id, cm);
+	};
+	{
+		std::vector<std::thread> th;
+		std::vector<int> lo_of(n_thr + 1, 0);
+		for (int t = 0; t <= n_thr; ++t) lo_of[t] = (int)((long long)n_reads * t / n_thr);
+		for (int t = 0; t < n_thr; ++t) { if (n_thr == 1) fmt_range(0, lo_of[t], lo_of[t + 1]); else th.emplace_back(fmt_range, t, lo_of[t], lo_of[t + 1]); }
+		for (size_t t = 0; t < th.size(); ++t) th[t].join();
+		size_t total = 0;
+		for (int t = 0; t < n_thr; ++t) total += part[t].size();
+		sam.reserve(total + 1);
+		if (line_off) line_off->assign(n_reads + 1, 0);
+		for (int t = 0; t < n_thr; ++t) {
+			if (line_off) for (int r = lo_of[t]; r < lo_of[t + 1]; ++r) (*line_off)[r] = sam.size() + rel_off[r];
+			sam += part[t];
 		}
 	}
 	if (line_off) (*line_off)[n_reads] = sam.size();

@@ -256,6 +256,7 @@ char *hostsim_mem_pe(const ssqo_idx_t *idx, int n_reads, const char **names, con
 {
 	std::vector<i64> aoff_; std::vector<i32> alen_; DevIndex ix = make_ix(idx, aoff_, alen_);
 	ssq_opts_t opt; ssq_opts_default(&opt);
+	if (getenv("HOSTSIM_THREADS")) opt.n_threads = atoi(getenv("HOSTSIM_THREADS"));
 	std::vector<u64> off(n_reads + 1, 0);
 	for (int i = 0; i < n_reads; ++i) off[i + 1] = off[i] + strlen(seqs[i]);
 	std::vector<uint8_t> codes(off[n_reads] + 1);
@@ -314,6 +315,6 @@ void ssq_opts_default(ssq_opts_t *o) // same values as speedseq_b200/csrc/ssq_in
 	o->min_seed_len = 19; o->split_width = 10; o->max_occ = 500; o->max_chain_gap = 10000; o->max_mem_intv = 20;
 	o->min_chain_weight = 0; o->max_chain_extend = 1 << 30; o->max_ins = 10000; o->max_matesw = 50; o->max_XA_hits = 5;
 	o->split_factor = 1.5f; o->mask_level = 0.50f; o->drop_ratio = 0.50f; o->XA_drop_ratio = 0.80f; o->mask_level_redun = 0.95f;
-	o->mapQ_coef_len = 50; o->mapQ_coef_fac = 3;
+	o->mapQ_coef_len = 50; o->mapQ_coef_fac = 3; o->n_threads = 1;
 }
 }

@@ -36,7 +36,7 @@ def build_hostsim():
     src, out = os.path.join(d, "hostsim.cpp"), HOSTSIM_SO
     hdrs = [os.path.join(ROOT, "speedseq_b200", "csrc", f) for f in ("ssq_dev.cuh", "ssq_dev2.cuh", "ssq_mem_host.h")]
     if not os.path.exists(out) or os.path.getmtime(out) < max([os.path.getmtime(src), os.path.getmtime(ORACLE_SO)] + [os.path.getmtime(h) for h in hdrs]):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", out, src, "-L" + os.path.join(ROOT, "oracle"), "-lssqo",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread", "-o", out, src, "-L" + os.path.join(ROOT, "oracle"), "-lssqo",
                                "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
 
 
@@ -194,7 +194,7 @@ class HostSim:
 
 class SSQ:
     """the product's C-ABI (include/ssq.h); raises when libssq.so is missing — there is no fallback"""
-    OPTS_WORDS = 29
+    OPTS_WORDS = 30
 
     def __init__(self):
         if not os.path.exists(SSQ_SO):

@@ -33,8 +33,8 @@ def test_default_options_match_oracle(oracle):
     assert o[:17].tolist() == [1, 4, 6, 1, 6, 1, 17, 5, 5, 100, 100, 30, 19, 10, 500, 10000, 20]
     assert o[17:22].tolist() == [0, 1 << 30, 10000, 50, 5]
     assert np.allclose(f[22:27], [1.5, 0.5, 0.5, 0.8, 0.95])
-    assert o[27:29].tolist() == [50, 3]
-    assert C.sizeof(s.opts) == 29 * 4
+    assert o[27:30].tolist() == [50, 3, 1]
+    assert C.sizeof(s.opts) == 30 * 4
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="box has a GPU")
