@@ -48,6 +48,7 @@ struct DevIndex {
 
 struct Counters { // device-measured work, feeds roofline.achieved (algorithmic bytes)
 	unsigned long long occ_smem, occ_sa, sa_reads, sw_calls, sw_cells, sw_bytes, n_seeds, n_regs;
+	unsigned long long dbg[8]; // kernel-internal cycle counters (diagnostics)
 };
 
 struct Intv { u64 x0, x1, x2; u32 qb, qe; }; // bi-interval + query span [qb,qe)
@@ -81,6 +82,38 @@ SSQ_HD void occ4_from_block(const u32 *blk, u64 kk, u64 cnt[4])
 
 // scalar context: one thread does the whole look-up (used by the SA walk, by hostsim, and as the
 // thread-per-read variant of the seeding kernel)
+// one 32-byte rank block (u32 occ[4] + 4 words of 16 symbols) in ONE load instruction: sm_100 has 256-bit global loads, and with
+// every lane on a different line the L1 pipeline charges a wavefront per lane PER INSTRUCTION, so two 128-bit loads cost twice
+struct Blk32 { u32 c0, c1, c2, c3, w0, w1, w2, w3; };
+SSQ_HD Blk32 load_blk32(const u32 *p)
+{
+	Blk32 b;
+#ifdef __CUDA_ARCH__
+	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(b.w0), "=r"(b.w1), "=r"(b.w2), "=r"(b.w3) : "l"(p));
+#else
+	b.c0 = p[0]; b.c1 = p[1]; b.c2 = p[2]; b.c3 = p[3]; b.w0 = p[4]; b.w1 = p[5]; b.w2 = p[6]; b.w3 = p[7];
+#endif
+	return b;
+}
+// occurrences of each base in rows [block start, kk] of a 64-symbol rank block
+SSQ_HD void blk32_count(const Blk32 &b, u64 kk, u64 cnt[4])
+{
+	const int r = (int)(kk & 63) + 1; // symbols to count, 1..64
+	// two 64-bit lanes of 32 symbols each, MSB-first within each original 32-bit word
+	const u64 lo_w = (u64)b.w0 << 32 | b.w1, hi_w = (u64)b.w2 << 32 | b.w3;
+	const int n0 = r < 32 ? r : 32, n1 = r - 32 > 0 ? r - 32 : 0;
+	const u64 m0 = 0x5555555555555555ull & ~(n0 >= 32 ? 0ull : (~0ull >> (2 * n0)));
+	const u64 m1 = n1 <= 0 ? 0ull : (0x5555555555555555ull & ~(n1 >= 32 ? 0ull : (~0ull >> (2 * n1))));
+	const u64 l0 = lo_w & m0, h0 = (lo_w >> 1) & m0, l1 = hi_w & m1, h1 = (hi_w >> 1) & m1;
+#ifdef __CUDA_ARCH__
+	const int p3 = __popcll(h0 & l0) + __popcll(h1 & l1), ph = __popcll(h0) + __popcll(h1), pl = __popcll(l0) + __popcll(l1);
+#else
+	const int p3 = __builtin_popcountll(h0 & l0) + __builtin_popcountll(h1 & l1), ph = __builtin_popcountll(h0) + __builtin_popcountll(h1), pl = __builtin_popcountll(l0) + __builtin_popcountll(l1);
+#endif
+	cnt[3] = (u64)b.c3 + p3; cnt[2] = (u64)b.c2 + (ph - p3); cnt[1] = (u64)b.c1 + (pl - p3); cnt[0] = (u64)b.c0 + (r - ph - pl + p3);
+}
+
 struct ScalarFm {
 	const DevIndex &ix;
 	unsigned long long n_blk;
@@ -90,28 +123,9 @@ struct ScalarFm {
 		if (k == (u64)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
 		u64 kk = k - (k >= ix.primary);
 		if (ix.bwt32) { // one 32-byte sector: u32 occ[4] + 64 symbols
-			const u32 *p = ix.bwt32 + ((kk >> 6) << 3);
-			u32 c0, c1, c2, c3, w0, w1, w2, w3;
-#ifdef __CUDA_ARCH__
-			const uint4 a = __ldg((const uint4*)p), b = __ldg((const uint4*)p + 1);
-			c0 = a.x; c1 = a.y; c2 = a.z; c3 = a.w; w0 = b.x; w1 = b.y; w2 = b.z; w3 = b.w;
-#else
-			c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; w0 = p[4]; w1 = p[5]; w2 = p[6]; w3 = p[7];
-#endif
+			const Blk32 b = load_blk32(ix.bwt32 + ((kk >> 6) << 3));
 			++n_blk;
-			const int r = (int)(kk & 63) + 1; // symbols to count, 1..64
-			// two 64-bit lanes of 32 symbols each, MSB-first within each original 32-bit word
-			const u64 lo_w = (u64)w0 << 32 | w1, hi_w = (u64)w2 << 32 | w3;
-			const int n0 = r < 32 ? r : 32, n1 = r - 32 > 0 ? r - 32 : 0;
-			const u64 m0 = 0x5555555555555555ull & ~(n0 >= 32 ? 0ull : (~0ull >> (2 * n0)));
-			const u64 m1 = n1 <= 0 ? 0ull : (0x5555555555555555ull & ~(n1 >= 32 ? 0ull : (~0ull >> (2 * n1))));
-			const u64 l0 = lo_w & m0, h0 = (lo_w >> 1) & m0, l1 = hi_w & m1, h1 = (hi_w >> 1) & m1;
-#ifdef __CUDA_ARCH__
-			const int p3 = __popcll(h0 & l0) + __popcll(h1 & l1), ph = __popcll(h0) + __popcll(h1), pl = __popcll(l0) + __popcll(l1);
-#else
-			const int p3 = __builtin_popcountll(h0 & l0) + __builtin_popcountll(h1 & l1), ph = __builtin_popcountll(h0) + __builtin_popcountll(h1), pl = __builtin_popcountll(l0) + __builtin_popcountll(l1);
-#endif
-			cnt[3] = (u64)c3 + p3; cnt[2] = (u64)c2 + (ph - p3); cnt[1] = (u64)c1 + (pl - p3); cnt[0] = (u64)c0 + (r - ph - pl + p3);
+			blk32_count(b, kk, cnt);
 			return;
 		}
 		const u32 *p = ix.bwt + ((kk >> 7) << 4);
@@ -499,9 +513,18 @@ SSQ_HD u64 sa_lookup(ScalarFm &fm, u64 k, unsigned long long &n_sa)
 		if (k == ix.primary) { k = 0; continue; }
 		u64 x = k - (k > ix.primary);
 		int c;
-		if (ix.bwt32) { const u32 *p = ix.bwt32 + ((x >> 6) << 3) + 4; c = p[(x & 0x3f) >> 4] >> ((~x & 0xf) << 1) & 3; }
-		else { const u32 *p = ix.bwt + ((x >> 7) << 4) + 8; c = p[(x & 0x7f) >> 4] >> ((~x & 0xf) << 1) & 3; }
 		u64 cnt[4];
+		if (ix.bwt32) { // symbol of row x and the counts up to row k come from the same 32-byte block (x == k - (k >= primary) here): one load
+			const Blk32 b = load_blk32(ix.bwt32 + ((x >> 6) << 3));
+			const int wsel = (int)(x & 0x3f) >> 4;
+			const u32 wv = wsel == 0 ? b.w0 : wsel == 1 ? b.w1 : wsel == 2 ? b.w2 : b.w3;
+			c = wv >> ((~x & 0xf) << 1) & 3;
+			++fm.n_blk;
+			blk32_count(b, x, cnt);
+			k = ix.L2[c] + SSQ_SEL4(cnt[0], cnt[1], cnt[2], cnt[3], c);
+			continue;
+		}
+		{ const u32 *p = ix.bwt + ((x >> 7) << 4) + 8; c = p[(x & 0x7f) >> 4] >> ((~x & 0xf) << 1) & 3; }
 		fm.occ4(k, cnt);
 		k = ix.L2[c] + cnt[c];
 	}
@@ -638,8 +661,15 @@ struct ChainBuilder {
 
 	SSQ_HD void init(int len_, int n_, const Seed *seeds_, int l_rep_, i32 *chain_of_, ChainRec *ch_, i32 *ord_, WIdx *wi_, Seed *sorted_, ChainRec *outc_, KeptChain *kp_)
 	{
-		len = len_; n = n_; seeds = seeds_; l_rep = l_rep_; chain_of = chain_of_; ch = ch_; ord = ord_; wi = wi_; sorted = sorted_; outc = outc_; kp = kp_; n_ch = 0;
+		len = len_; n = n_; seeds = seeds_; l_rep = l_rep_; chain_of = chain_of_; ch = ch_; ord = ord_; wi = wi_; sorted = sorted_; outc = outc_; kp = kp_; n_ch = 0; root = -1;
 	}
+	// Chains are kept in the order of `pos` (rbeg of their first seed).  The reference does it with a B-tree; the oracle restates
+	// its look-up / insert on one ordered sequence: look-up = the first chain whose key equals pos, else the last chain with a
+	// smaller key; a new chain goes directly after the slot the look-up returned.  Here the same order is kept by an index-based
+	// binary search tree (left/right children in wi[].w / wi[].idx, which are free until finish()) on the composite key
+	// (pos, tie) with tie = INT_MIN for the first chain of a pos and -index for later ones — exactly the order "first, then the
+	// others newest first" that repeated insert-after-the-first produces.  Expected O(log n) per seed instead of O(n) shifts.
+	int root;
 	SSQ_HD void add_seed(const DevIndex &ix, const ssq_opts_t &opt, int i)
 	{
 		const i64 l_pac = ix.l_pac;
@@ -647,11 +677,16 @@ struct ChainBuilder {
 		const int rid = intv2rid(ix, s.rbeg, s.rbeg + s.len);
 		chain_of[i] = -1;
 		if (rid < 0) return;
-		int lo = 0, hi = n_ch, slot, merged = 0, k;
-		while (lo < hi) { int mid = (lo + hi) >> 1; if (ch[ord[mid]].pos < s.rbeg) lo = mid + 1; else hi = mid; }
-		slot = (lo < n_ch && ch[ord[lo]].pos == s.rbeg) ? lo : lo - 1;
-		if (n_ch && slot >= 0) {
-			ChainRec &c = ch[ord[slot]];
+		int slot = -1, exact = 0, merged = 0;
+		for (int cur = n_ch ? root : -1; cur >= 0;) { // look-up
+			const i64 p = ch[cur].pos;
+			if (p < s.rbeg) { slot = cur; cur = wi[cur].idx; }
+			else if (p > s.rbeg) cur = wi[cur].w;
+			else if (ch[cur].w == (i32)0x80000000) { slot = cur; exact = 1; break; } // the first chain with this pos
+			else cur = wi[cur].w;
+		}
+		if (slot >= 0) {
+			ChainRec &c = ch[slot];
 			i64 qend = c.last_q + c.last_len, rend = c.last_r + c.last_len;
 			if (rid == c.rid) {
 				if (s.qbeg >= c.first_q && s.qbeg + s.len <= qend && s.rbeg >= c.first_r && s.rbeg + s.len <= rend) merged = 1; // contained
@@ -659,26 +694,52 @@ struct ChainBuilder {
 					i64 x = s.qbeg - c.last_q, y = s.rbeg - c.last_r;
 					if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - c.last_len < opt.max_chain_gap && y - c.last_len < opt.max_chain_gap) {
 						c.last_q = s.qbeg; c.last_r = s.rbeg; c.last_len = s.len; ++c.n;
-						chain_of[i] = ord[slot];
+						chain_of[i] = slot;
 						merged = 1;
 					}
 				}
 			}
 		}
 		if (!merged) {
-			ChainRec &c = ch[n_ch];
+			const int nn = n_ch;
+			ChainRec &c = ch[nn];
 			c.pos = s.rbeg; c.first_r = c.last_r = s.rbeg; c.first_q = c.last_q = s.qbeg; c.last_len = s.len;
-			c.rid = rid; c.n = 1; c.w = 0; c.first = -1; c.kept = 0; c.seed_start = 0; c.frac_rep = 0.f;
-			for (k = n_ch; k > slot + 1; --k) ord[k] = ord[k - 1];
-			ord[slot + 1] = n_ch;
-			chain_of[i] = n_ch;
+			c.rid = rid; c.n = 1; c.first = -1; c.kept = 0; c.seed_start = 0; c.frac_rep = 0.f;
+			c.w = exact ? -nn : (i32)0x80000000; // tie component of the key
+			wi[nn].w = wi[nn].idx = -1;
+			if (nn == 0) root = 0;
+			else {
+				for (int cur = root;;) {
+					const i64 p = ch[cur].pos;
+					const bool go_left = s.rbeg < p || (s.rbeg == p && c.w < ch[cur].w);
+					i32 &child = go_left ? wi[cur].w : wi[cur].idx;
+					if (child < 0) { child = nn; break; }
+					cur = child;
+				}
+			}
+			chain_of[i] = nn;
 			++n_ch;
+		}
+	}
+	// in-order traversal without a stack (threads the tree through the right links and restores them): ord[] = chains by key
+	SSQ_HD void inorder()
+	{
+		int k = 0, cur = n_ch ? root : -1;
+		while (cur >= 0) {
+			if (wi[cur].w < 0) { ord[k++] = cur; cur = wi[cur].idx; }
+			else {
+				int pre = wi[cur].w;
+				while (wi[pre].idx >= 0 && wi[pre].idx != cur) pre = wi[pre].idx;
+				if (wi[pre].idx < 0) { wi[pre].idx = cur; cur = wi[cur].w; }
+				else { wi[pre].idx = -1; ord[k++] = cur; cur = wi[cur].idx; }
+			}
 		}
 	}
 	SSQ_HD int finish(const ssq_opts_t &opt)
 	{
 		int i, k;
 		if (n_ch == 0) return 0;
+		inorder();
 		// regroup seeds chain by chain, chains in pos order (= the order the reference's tree is traversed)
 		{
 			int off = 0;
@@ -968,13 +1029,29 @@ SSQ_HD void extend_seed(const DevIndex &ix, const ssq_opts_t &opt, int l_query, 
 // walks the seeds from longest to shortest, skips those explained by an accepted region of this read
 // (regions of earlier chains included), appends the rest to out[0..n_out).  With `have` flags the replay stops at the first
 // seed it needs whose candidate is missing and returns its index (-1 = chain complete): the GPU extends seeds lazily, in rounds.
+// The walk can also be RESUMED: srt[] (with the entries the walk zeroed) and out[] persist between rounds, so a later call with
+// resume_k = the position it stopped at goes straight to accepting that seed, whose skip test it had already failed.
 SSQ_HD int select_regions(const ssq_opts_t &opt, int l_query, const ChainRec &c, const Seed *cs, const RegCand *cand,
-                          u64 *srt /* scratch c.n */, RegCand *out, int &n_out, const uint8_t *have = 0)
+                          u64 *srt /* scratch c.n */, RegCand *out, int &n_out, const uint8_t *have = 0, int resume_k = -1, int *stop_k = 0)
 {
 	int i, k;
+	if (resume_k >= 0) {
+		k = resume_k;
+		if (have && !have[(u32)srt[k]]) { if (stop_k) *stop_k = k; return (int)(u32)srt[k]; }
+		out[n_out++] = cand[(u32)srt[k]];
+		--k;
+		goto walk;
+	}
 	for (i = 0; i < c.n; ++i) srt[i] = (u64)(u32)cs[i].len << 32 | (u32)i; // seed score == len
-	for (i = 1; i < c.n; ++i) { u64 t = srt[i]; for (k = i; k > 0 && srt[k - 1] > t; --k) srt[k] = srt[k - 1]; srt[k] = t; } // keys are unique
-	for (k = c.n - 1; k >= 0; --k) {
+	if (c.n <= 24) { for (i = 1; i < c.n; ++i) { u64 t = srt[i]; for (k = i; k > 0 && srt[k - 1] > t; --k) srt[k] = srt[k - 1]; srt[k] = t; } } // keys are unique: any sort gives the reference order
+	else { // heap sort, O(n log n) for the chains of repeat-rich reads
+		const int n = c.n;
+		for (int st = n / 2 - 1; st >= 0; --st) { int r = st; for (;;) { int ch_ = 2 * r + 1; if (ch_ >= n) break; if (ch_ + 1 < n && srt[ch_ + 1] > srt[ch_]) ++ch_; if (srt[r] >= srt[ch_]) break; u64 t = srt[r]; srt[r] = srt[ch_]; srt[ch_] = t; r = ch_; } }
+		for (int e = n - 1; e > 0; --e) { u64 t = srt[0]; srt[0] = srt[e]; srt[e] = t; int r = 0; for (;;) { int ch_ = 2 * r + 1; if (ch_ >= e) break; if (ch_ + 1 < e && srt[ch_ + 1] > srt[ch_]) ++ch_; if (srt[r] >= srt[ch_]) break; u64 t2 = srt[r]; srt[r] = srt[ch_]; srt[ch_] = t2; r = ch_; } }
+	}
+	k = c.n - 1;
+walk:
+	for (; k >= 0; --k) {
 		const Seed s = cs[(u32)srt[k]];
 		for (i = 0; i < n_out; ++i) {
 			const RegCand &p = out[i];
@@ -1000,8 +1077,34 @@ SSQ_HD int select_regions(const ssq_opts_t &opt, int l_query, const ChainRec &c,
 			}
 			if (i == c.n) { srt[k] = 0; continue; }
 		}
-		if (have && !have[(u32)srt[k]]) return (int)(u32)srt[k]; // this seed's extension has not been computed yet: ask for it
+		if (have && !have[(u32)srt[k]]) { if (stop_k) *stop_k = k; return (int)(u32)srt[k]; } // this seed's extension has not been computed yet: ask for it
 		out[n_out++] = cand[(u32)srt[k]];
 	}
 	return -1;
+}
+
+// Resume point of one read's region selection between extension rounds (all zero = nothing done yet).
+struct SelState { i32 c, n_out, kp1; u32 t_rel; }; // chain in progress, regions accepted so far, walk position + 1 (0 = chain not started), its first task
+// One round of one read: continue the selection from `st` until it completes (true) or needs an extension that has not been
+// computed (false; the seed is flagged in need[], or with force_all every remaining seed of the read).  Pointers are the read's
+// own slices: outc[0..n_kept), sorted (seeds of all its chains), cand/srt/out/have/need at its first task.
+SSQ_HD bool select_read(const ssq_opts_t &opt, int l_query, int n_kept, const ChainRec *outc, const Seed *sorted, const RegCand *cand, u64 *srt,
+                        RegCand *out, const uint8_t *have, uint8_t *need, int force_all, SelState &st)
+{
+	int c = st.c, n_out = st.n_out, k = st.kp1 - 1;
+	u32 t = st.t_rel;
+	for (; c < n_kept; ++c, k = -1) {
+		const ChainRec ch = outc[c];
+		int stop_k = -1;
+		const int miss = select_regions(opt, l_query, ch, sorted + ch.seed_start, cand + t, srt + t, out, n_out, have + t, k, &stop_k);
+		if (miss >= 0) {
+			if (force_all) { u32 e = t; for (int cc = c; cc < n_kept; ++cc) e += (u32)outc[cc].n; for (u32 x = t; x < e; ++x) need[x] = 1; }
+			else need[t + miss] = 1;
+			st.c = c; st.n_out = n_out; st.kp1 = stop_k + 1; st.t_rel = t;
+			return false;
+		}
+		t += (u32)ch.n;
+	}
+	st.c = c; st.n_out = n_out; st.kp1 = 0; st.t_rel = t;
+	return true;
 }

@@ -273,8 +273,10 @@ __global__ void k_sa_rows(DevIndex ix, u64 n, const u64 *__restrict__ rows, u64 
 __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
                                                const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
                                                const Seed *__restrict__ seeds, i32 *chain_of, ChainRec *ch, i32 *ord, WIdx *wi, Seed *sorted, ChainRec *outc, KeptChain *kp,
-                                               i32 *n_kept, u32 *n_kseeds, int *work)
+                                               i32 *n_kept, u32 *n_kseeds, int *work, Counters *cnt, const int *__restrict__ heavy_thresh_p, u32 *heavy_list, unsigned int *n_heavy)
 {
+	const int heavy_thresh = *heavy_thresh_p;
+	unsigned long long cyc_add = 0, cyc_fin = 0, cyc_fetch = 0, max_read = 0, max_n = 0, t_read0 = 0;
 	// persistent per-lane machine: the step every lane of the warp takes together is "add my read's next seed to its chains"
 	ChainBuilder b;
 	int r = -1, i = 0;
@@ -284,23 +286,216 @@ __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int 
 		bool done = false;
 		while (!have || i >= b.n) {
 			if (have) { // read finished: regroup, weigh, sort, filter, publish
+				const long long tf0 = clock64();
 				const int nk = b.finish(opt);
+				cyc_fin += clock64() - tf0;
+				{ const unsigned long long tr = clock64() - t_read0; if (tr > max_read) { max_read = tr; max_n = (unsigned long long)b.n << 32 | (unsigned)b.n_ch; } }
 				u32 ns = 0;
 				for (int c = 0; c < nk; ++c) ns += (u32)outc[s0 + c].n;
 				n_kept[r] = nk; n_kseeds[r] = ns;
 				have = false;
 			}
+			const long long tq0 = clock64();
 			r = atomicAdd(work, 1);
 			if (r >= n_reads) { done = true; break; }
 			const int ni = intv_cnt[r];
 			int n = 0;
+			t_read0 = tq0;
 			if (ni > 0) { s0 = seed_off[intv_off[r]]; n = (int)(seed_off[intv_off[r] + ni] - s0); }
 			if (n == 0) { n_kept[r] = 0; n_kseeds[r] = 0; continue; }
+			if (n > heavy_thresh) { heavy_list[atomicAdd(n_heavy, 1u)] = (u32)r; continue; } // gets a warp of its own in k_chain_heavy
 			b.init((int)(read_off[r + 1] - read_off[r]), n, seeds + s0, l_rep[r], chain_of + s0, ch + s0, ord + s0, wi + s0, sorted + s0, outc + s0, kp + s0);
 			i = 0; have = true;
+			cyc_fetch += clock64() - tq0;
 		}
 		if (done) break;
-		b.add_seed(ix, opt, i++);
+		{ const long long ta0 = clock64(); b.add_seed(ix, opt, i++); cyc_add += clock64() - ta0; }
+	}
+	atomicAdd(&cnt->dbg[0], cyc_add); atomicAdd(&cnt->dbg[1], cyc_fin); atomicAdd(&cnt->dbg[2], cyc_fetch);
+	atomicMax(&cnt->dbg[3], max_read);
+	if (max_read && max_read == cnt->dbg[3]) cnt->dbg[4] = max_n;
+}
+
+// Reads with many seeds (repeat families): one WARP per read.  In the thread-per-read kernel such a read's lane shares its warp with
+// 31 lanes doing unrelated work and gets a fraction of the issue slots, which stretched its sequential critical path ~30x and made one
+// read the duration of the whole kernel.  Here the warp cooperates: the chains' keys live in shared memory as ONE ORDERED ARRAY (the
+// oracle's formulation: look-up = first chain with an equal pos, else the predecessor; insert right after that slot), searched 32
+// keys at a time with ballots and shifted 32 entries at a time on insert; the O(n^2) overlap filter tests 32 kept chains per step and
+// takes the first "drop" position from a ballot.  Everything else (merge test, regrouping, weights, sort) is lane 0's.
+#define HEAVY_CAP 1024 // chains per read held in shared memory; reads beyond that fall back to the tree-based builder on lane 0
+
+__device__ __forceinline__ int warp_lower_bound(const i64 *pos, int n, i64 key, int lane) // first index with pos[idx] >= key (n <= 1024)
+{
+	const int stride = (n + 31) >> 5; // <= 32
+	const int p = (lane + 1) * stride - 1; // last element of this lane's segment
+	const int seg = __popc(__ballot_sync(FULL, p < n && pos[p] < key)); // segments entirely below the key (the predicate is monotone)
+	const int lo = seg * stride;
+	const int k = lo + lane;
+	return lo + __popc(__ballot_sync(FULL, lane < stride && k < n && pos[k] < key));
+}
+
+__global__ void __launch_bounds__(128) k_chain_heavy(DevIndex ix, ssq_opts_t opt, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
+                                                     const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
+                                                     const Seed *__restrict__ seeds_, i32 *chain_of_, ChainRec *ch_, i32 *ord_, WIdx *wi_, Seed *sorted_, ChainRec *outc_, KeptChain *kp_,
+                                                     i32 *n_kept, u32 *n_kseeds, int *work, const u32 *__restrict__ heavy_list, const unsigned int *__restrict__ n_heavy)
+{
+	__shared__ i64 s_pos[4][HEAVY_CAP];
+	__shared__ i32 s_idx[4][HEAVY_CAP];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	i64 *pos = s_pos[wib]; i32 *sidx = s_idx[wib];
+	const unsigned int nh = *n_heavy;
+	for (;;) {
+		int w = 0;
+		if (lane == 0) w = atomicAdd(work, 1);
+		w = __shfl_sync(FULL, w, 0);
+		if ((unsigned)w >= nh) break;
+		const int r = (int)heavy_list[w];
+		const u64 s0 = seed_off[intv_off[r]];
+		const int n = (int)(seed_off[intv_off[r] + intv_cnt[r]] - s0), len = (int)(read_off[r + 1] - read_off[r]);
+		const Seed *seeds = seeds_ + s0; i32 *chain_of = chain_of_ + s0; ChainRec *ch = ch_ + s0; i32 *ord = ord_ + s0; WIdx *wi = wi_ + s0;
+		Seed *sorted = sorted_ + s0; ChainRec *outc = outc_ + s0; KeptChain *kp = kp_ + s0;
+		const i64 l_pac = ix.l_pac;
+		int n_ch = 0, nk = 0;
+		bool overflow = false;
+		// ---- build: one seed at a time, warp-wide search / shift ----
+		for (int i = 0; i < n && !overflow; ++i) {
+			const Seed s = seeds[i];
+			const int rid = intv2rid(ix, s.rbeg, s.rbeg + s.len);
+			if (rid < 0) { if (lane == 0) chain_of[i] = -1; continue; }
+			const int lo = warp_lower_bound(pos, n_ch, s.rbeg, lane);
+			const int slot = (lo < n_ch && pos[lo] == s.rbeg) ? lo : lo - 1;
+			int merged = 0, cid = -1;
+			if (lane == 0 && slot >= 0) { // merge test on the chain record (global)
+				ChainRec &c = ch[sidx[slot]];
+				const i64 qend = c.last_q + c.last_len, rend = c.last_r + c.last_len;
+				if (rid == c.rid) {
+					if (s.qbeg >= c.first_q && s.qbeg + s.len <= qend && s.rbeg >= c.first_r && s.rbeg + s.len <= rend) merged = 1;
+					else if (!((c.last_r < l_pac || c.first_r < l_pac) && s.rbeg >= l_pac)) {
+						const i64 x = s.qbeg - c.last_q, y = s.rbeg - c.last_r;
+						if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - c.last_len < opt.max_chain_gap && y - c.last_len < opt.max_chain_gap) {
+							c.last_q = s.qbeg; c.last_r = s.rbeg; c.last_len = s.len; ++c.n;
+							cid = sidx[slot]; merged = 1;
+						}
+					}
+				}
+			}
+			merged = __shfl_sync(FULL, merged, 0);
+			if (!merged) {
+				if (n_ch >= HEAVY_CAP) { overflow = true; break; }
+				// shift [slot+1, n_ch) up by one, 32 entries at a time from the top
+				for (int hi = n_ch - 1; hi > slot; hi -= 32) {
+					const int kk = hi - lane;
+					i64 pv = 0; i32 iv = 0;
+					if (kk > slot) { pv = pos[kk]; iv = sidx[kk]; }
+					__syncwarp();
+					if (kk > slot) { pos[kk + 1] = pv; sidx[kk + 1] = iv; }
+					__syncwarp();
+				}
+				if (lane == 0) {
+					ChainRec &c = ch[n_ch];
+					c.pos = s.rbeg; c.first_r = c.last_r = s.rbeg; c.first_q = c.last_q = s.qbeg; c.last_len = s.len;
+					c.rid = rid; c.n = 1; c.w = 0; c.first = -1; c.kept = 0; c.seed_start = 0; c.frac_rep = 0.f;
+					pos[slot + 1] = s.rbeg; sidx[slot + 1] = n_ch;
+					cid = n_ch;
+				}
+				++n_ch;
+				__syncwarp();
+			}
+			if (lane == 0) chain_of[i] = cid;
+		}
+		if (overflow) { // more chains than the shared array holds: the generic builder, lane 0, from scratch
+			if (lane == 0) {
+				ChainBuilder b;
+				b.init(len, n, seeds, l_rep[r], chain_of, ch, ord, wi, sorted, outc, kp);
+				for (int i = 0; i < n; ++i) b.add_seed(ix, opt, i);
+				nk = b.finish(opt);
+			}
+		} else if (n_ch > 0) {
+			// ---- finish: lane 0 regroups / weighs / sorts, the warp runs the overlap filter ----
+			for (int k = lane; k < n_ch; k += 32) ord[k] = sidx[k];
+			__syncwarp();
+			if (lane == 0) {
+				int off = 0;
+				for (int k = 0; k < n_ch; ++k) { ChainRec &c = ch[ord[k]]; c.seed_start = off; off += c.n; c.n = 0; }
+				for (int i = 0; i < n; ++i) if (chain_of[i] >= 0) { ChainRec &c = ch[chain_of[i]]; sorted[c.seed_start + c.n++] = seeds[i]; }
+				for (int k = 0; k < n_ch; ++k) {
+					ChainRec &c = ch[ord[k]];
+					const Seed *sd = sorted + c.seed_start;
+					i64 end; int j, w2 = 0, tmp;
+					for (j = 0, end = 0; j < c.n; ++j) {
+						if (sd[j].qbeg >= end) w2 += sd[j].len; else if (sd[j].qbeg + sd[j].len > end) w2 += (int)(sd[j].qbeg + sd[j].len - end);
+						end = end > sd[j].qbeg + sd[j].len ? end : sd[j].qbeg + sd[j].len;
+					}
+					tmp = w2; w2 = 0;
+					for (j = 0, end = 0; j < c.n; ++j) {
+						if (sd[j].rbeg >= end) w2 += sd[j].len; else if (sd[j].rbeg + sd[j].len > end) w2 += (int)(sd[j].rbeg + sd[j].len - end);
+						end = end > sd[j].rbeg + sd[j].len ? end : sd[j].rbeg + sd[j].len;
+					}
+					w2 = w2 < tmp ? w2 : tmp;
+					c.w = w2 < 1 << 30 ? w2 : (1 << 30) - 1;
+					c.first = -1; c.kept = 0;
+					c.frac_rep = (float)l_rep[r] / len;
+					wi[k].w = c.w; wi[k].idx = ord[k];
+				}
+				ks_introsort((long)n_ch, wi, WIdxLt());
+				ChainRec &c0 = ch[wi[0].idx];
+				c0.kept = 3;
+				kp[0].b = c0.first_q; kp[0].e = c0.last_q + c0.last_len; kp[0].w = c0.w; kp[0].i = 0;
+			}
+			__syncwarp();
+			int n_keptc = 1;
+			for (int i = 1; i < n_ch; ++i) {
+				int bi = 0, ei = 0, wv = 0;
+				if (lane == 0) { const ChainRec &ci = ch[wi[i].idx]; bi = ci.first_q; ei = ci.last_q + ci.last_len; wv = ci.w; }
+				bi = __shfl_sync(FULL, bi, 0); ei = __shfl_sync(FULL, ei, 0); wv = __shfl_sync(FULL, wv, 0);
+				int large = 0; bool dropped = false;
+				for (int base = 0; base < n_keptc && !dropped; base += 32) {
+					const int kk = base + lane;
+					bool ov = false, brk = false; KeptChain kj; kj.i = 0;
+					if (kk < n_keptc) {
+						kj = kp[kk];
+						const int b_max = kj.b > bi ? kj.b : bi, e_min = kj.e < ei ? kj.e : ei;
+						if (e_min > b_max) {
+							const int li = ei - bi, lj = kj.e - kj.b, min_l = li < lj ? li : lj;
+							if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+								ov = true;
+								brk = wv < kj.w * opt.drop_ratio && kj.w - wv >= opt.min_seed_len << 1;
+							}
+						}
+					}
+					const unsigned m_ov = __ballot_sync(FULL, ov), m_brk = __ballot_sync(FULL, brk);
+					const unsigned upto = m_brk ? (0xffffffffu >> (32 - __ffs(m_brk))) : 0xffffffffu; // lanes up to and including the first drop
+					const unsigned eff = m_ov & upto;
+					if (eff) large = 1;
+					if (eff >> lane & 1) { ChainRec &cj = ch[wi[kj.i].idx]; if (cj.first < 0) cj.first = i; }
+					if (m_brk) dropped = true;
+				}
+				__syncwarp();
+				if (!dropped) {
+					if (lane == 0) { kp[n_keptc].b = bi; kp[n_keptc].e = ei; kp[n_keptc].w = wv; kp[n_keptc].i = i; ch[wi[i].idx].kept = large ? 2 : 3; }
+					++n_keptc;
+					__syncwarp();
+				}
+			}
+			if (lane == 0) {
+				int i2, k2;
+				for (i2 = 0; i2 < n_keptc; ++i2) { ChainRec &c = ch[wi[kp[i2].i].idx]; if (c.first >= 0) ch[wi[c.first].idx].kept = 1; }
+				for (i2 = k2 = 0; i2 < n_ch; ++i2) {
+					const int kept = ch[wi[i2].idx].kept;
+					if (kept == 0 || kept == 3) continue;
+					if (++k2 >= opt.max_chain_extend) break;
+				}
+				for (; i2 < n_ch; ++i2) if (ch[wi[i2].idx].kept < 3) ch[wi[i2].idx].kept = 0;
+				for (i2 = k2 = 0; i2 < n_ch; ++i2) if (ch[wi[i2].idx].kept) outc[k2++] = ch[wi[i2].idx];
+				nk = k2;
+			}
+		}
+		if (lane == 0) {
+			u32 ns = 0;
+			for (int c = 0; c < nk; ++c) ns += (u32)outc[c].n;
+			n_kept[r] = nk; n_kseeds[r] = ns;
+		}
+		__syncwarp();
 	}
 }
 
@@ -475,42 +670,143 @@ __global__ void __launch_bounds__(64) k_sw_tasks(ssq_opts_t opt, u64 n, const ss
 }
 
 // --------------------------------------------------------------------------- k_select ----
-// Replays mem_chain2aln()'s seed loop per read over the candidates computed so far.  A read whose replay reaches a seed
-// that must be extended but has no candidate yet flags that seed (need) and stays unfinished; the host runs another
-// extension round for the flagged seeds and replays the unfinished reads again.  force_all: flag every remaining seed of an
-// unfinished read at once (bounds the number of rounds).
-__global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_reads, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
+// mem_chain2aln()'s seed loop per read over the candidates computed so far.  A read whose walk reaches a seed that must be
+// extended but has no candidate yet flags that seed (need), records where it stopped (SelState) and goes on the next round's
+// list; the host runs another extension round for the flagged seeds and the walk RESUMES at that seed.  force_all: flag every
+// remaining seed of an unfinished read at once (bounds the number of rounds).  list_in == 0: all reads (first round).
+__global__ void __launch_bounds__(128) k_select(ssq_opts_t opt, int n_in, const u32 *__restrict__ list_in, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
                                                 const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc, const Seed *__restrict__ sorted,
                                                 const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, const RegCand *__restrict__ cand, u64 *srt,
-                                                RegCand *regs, u32 *n_regs, const uint8_t *__restrict__ have, uint8_t *need, uint8_t *done, int force_all,
-                                                unsigned int *n_unfinished, int *work)
+                                                RegCand *regs, u32 *n_regs, const uint8_t *__restrict__ have, uint8_t *need, SelState *state, int force_all,
+                                                u32 *list_out, unsigned int *n_unfinished, int *work, const int *__restrict__ heavy_thresh, u32 *heavy_list, unsigned int *n_heavy)
 {
-  for (;;) {
-	const int r = atomicAdd(work, 1);
-	if (r >= n_reads) return;
-	if (done[r]) continue;
-	int n_out = 0;
-	bool complete = true;
-	if (n_kept[r] > 0) {
+	const int thresh = *heavy_thresh;
+	for (;;) {
+		const int w = atomicAdd(work, 1);
+		if (w >= n_in) return;
+		const int r = list_in ? (int)list_in[w] : w;
+		const u64 t0 = task_off[r];
+		if ((int)(task_off[r + 1] - t0) > thresh) { heavy_list[atomicAdd(n_heavy, 1u)] = (u32)r; continue; } // taken by a warp of its own
 		const u64 s0 = seed_off[intv_off[r]];
-		const int len = (int)(read_off[r + 1] - read_off[r]);
-		u64 t = task_off[r];
-		RegCand *out = regs + task_off[r];
-		for (int c = 0; c < n_kept[r]; ++c) {
-			const ChainRec ch = outc[s0 + c];
-			const int miss = select_regions(opt, len, ch, sorted + s0 + ch.seed_start, cand + t, srt + t, out, n_out, have + t);
+		SelState st = state[r];
+		const bool complete = select_read(opt, (int)(read_off[r + 1] - read_off[r]), n_kept[r], outc + s0, sorted + s0, cand + t0, srt + t0, regs + t0, have + t0, need + t0, force_all, st);
+		if (complete) n_regs[r] = (u32)st.n_out;
+		else { state[r] = st; list_out[atomicAdd(n_unfinished, 1u)] = (u32)r; }
+	}
+}
+
+// The same walk with the warp's 32 lanes sharing one chain: the seed order comes from a rank sort (keys are unique, so any sort
+// gives the reference's order), and the two inner tests — "is this seed inside an accepted region" and "does a longer seed
+// overlap it off-diagonal" — only ask whether SOME element satisfies a predicate, so 32 elements are tested per step.
+__device__ int select_regions_warp(const ssq_opts_t &opt, int l_query, const ChainRec &c, const Seed *cs, const RegCand *cand, u64 *srt, u64 *tmp,
+                                   RegCand *out, int &n_out, const uint8_t *have, int resume_k, int &stop_k, int lane)
+{
+	int k;
+	if (resume_k >= 0) {
+		k = resume_k;
+		const u32 si = (u32)srt[k];
+		if (!have[si]) { stop_k = k; return (int)si; }
+		if (lane == 0) out[n_out] = cand[si];
+		++n_out; --k;
+		__syncwarp();
+	} else {
+		for (int i = lane; i < c.n; i += 32) tmp[i] = (u64)(u32)cs[i].len << 32 | (u32)i; // seed score == len
+		__syncwarp();
+		for (int i = lane; i < c.n; i += 32) {
+			const u64 key = tmp[i];
+			int rank = 0;
+			for (int j = 0; j < c.n; ++j) rank += tmp[j] < key;
+			srt[rank] = key;
+		}
+		__syncwarp();
+		k = c.n - 1;
+	}
+	for (; k >= 0; --k) {
+		const u32 si = (u32)srt[k];
+		const Seed s = cs[si];
+		bool inside = false;
+		for (int base = 0; base < n_out && !inside; base += 32) {
+			const int i = base + lane;
+			bool h = false;
+			if (i < n_out) {
+				const RegCand &p = out[i];
+				if (!(s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) && !(s.len - p.seedlen0 > .1 * l_query)) {
+					i64 rd; int qd, w, max_gap;
+					qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
+					max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+					w = max_gap < p.w ? max_gap : p.w;
+					if (qd - rd < w && rd - qd < w) h = true;
+					else {
+						qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+						max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+						w = max_gap < p.w ? max_gap : p.w;
+						if (qd - rd < w && rd - qd < w) h = true;
+					}
+				}
+			}
+			inside = __any_sync(FULL, h);
+		}
+		if (inside) {
+			bool overlap = false;
+			for (int base = k + 1; base < c.n && !overlap; base += 32) {
+				const int i = base + lane;
+				bool h = false;
+				if (i < c.n && srt[i] != 0) {
+					const Seed t = cs[(u32)srt[i]];
+					if (!(t.len < s.len * .95)) {
+						if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) h = true;
+						else if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) h = true;
+					}
+				}
+				overlap = __any_sync(FULL, h);
+			}
+			if (!overlap) { __syncwarp(); if (lane == 0) srt[k] = 0; __syncwarp(); continue; }
+		}
+		if (!have[si]) { stop_k = k; return (int)si; }
+		if (lane == 0) out[n_out] = cand[si];
+		++n_out;
+		__syncwarp();
+	}
+	return -1;
+}
+
+__global__ void __launch_bounds__(128) k_select_heavy(ssq_opts_t opt, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
+                                                      const u64 *__restrict__ seed_off, const ChainRec *__restrict__ outc_, const Seed *__restrict__ sorted_,
+                                                      const i32 *__restrict__ n_kept, const u64 *__restrict__ task_off, const RegCand *__restrict__ cand, u64 *srt, u64 *tmp,
+                                                      RegCand *regs, u32 *n_regs, const uint8_t *__restrict__ have, uint8_t *need, SelState *state, int force_all,
+                                                      u32 *list_out, unsigned int *n_unfinished, int *work, const u32 *__restrict__ heavy_list, const unsigned int *__restrict__ n_heavy)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned int nh = *n_heavy;
+	for (;;) {
+		int w = 0;
+		if (lane == 0) w = atomicAdd(work, 1);
+		w = __shfl_sync(FULL, w, 0);
+		if ((unsigned)w >= nh) break;
+		const int r = (int)heavy_list[w];
+		const u64 t0 = task_off[r], s0 = seed_off[intv_off[r]];
+		const int len = (int)(read_off[r + 1] - read_off[r]), nk = n_kept[r];
+		const ChainRec *outc = outc_ + s0; const Seed *sorted = sorted_ + s0;
+		const SelState st = state[r];
+		int c = st.c, n_out = st.n_out, kk = st.kp1 - 1;
+		u32 t = st.t_rel;
+		bool complete = true;
+		for (; c < nk; ++c, kk = -1) {
+			const ChainRec ch = outc[c];
+			int stop_k = -1;
+			const int miss = select_regions_warp(opt, len, ch, sorted + ch.seed_start, cand + t0 + t, srt + t0 + t, tmp + t0 + t, regs + t0, n_out, have + t0 + t, kk, stop_k, lane);
 			if (miss >= 0) {
+				if (force_all) { u32 e = t; for (int cc = c; cc < nk; ++cc) e += (u32)outc[cc].n; for (u32 x = t + lane; x < e; x += 32) need[t0 + x] = 1; }
+				else if (lane == 0) need[t0 + t + miss] = 1;
+				if (lane == 0) { SelState o; o.c = c; o.n_out = n_out; o.kp1 = stop_k + 1; o.t_rel = t; state[r] = o; list_out[atomicAdd(n_unfinished, 1u)] = (u32)r; }
 				complete = false;
-				if (force_all) { u64 e = t; for (int cc = c; cc < n_kept[r]; ++cc) e += outc[s0 + cc].n; for (u64 x = t; x < e; ++x) need[x] = 1; }
-				else need[t + miss] = 1;
 				break;
 			}
-			t += ch.n;
+			t += (u32)ch.n;
 		}
+		if (complete && lane == 0) n_regs[r] = (u32)n_out;
+		__syncwarp();
 	}
-	if (complete) { n_regs[r] = (u32)n_out; done[r] = 1; }
-	else atomicAdd(n_unfinished, 1u);
-  }
 }
 
 __global__ void k_gather_regs(int n_reads, const u64 *__restrict__ task_off, const u64 *__restrict__ reg_off, const u32 *__restrict__ n_regs,
@@ -616,13 +912,13 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xdone, xkp;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2;
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
-	cudaEvent_t ev[6];
+	cudaEvent_t ev[6], evc[3]; // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
 	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
 };
@@ -669,6 +965,7 @@ extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, i
 	b->n_sm = prop.multiProcessorCount;
 	CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
 	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
+	for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&b->evc[i]));
 	if (read_off && (rc = ssq_batch_upload(b, n_reads, seq, read_off))) { ssq_batch_free(b); return rc; }
 	*out = b;
 	return SSQ_OK;
@@ -680,9 +977,10 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xdone, &b->xkp};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
+	for (int i = 0; i < 3; ++i) cudaEventDestroy(b->evc[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
 	delete b;
 }
@@ -777,6 +1075,16 @@ static int run_sa(ssq_batch *b)
 	return SSQ_OK;
 }
 
+// The cut between the thread-per-read and the warp-per-read tier of a stage (work items per read), overridable for tests.
+// Measured on B200 (profiles/r01_tier_sweep.txt): the stage time is flat between 32 and 64 and grows on either side.
+static int tier_threshold(ssq_batch *b, const char *env, int dflt, int *d_thresh)
+{
+	const int v = getenv(env) ? atoi(getenv(env)) : dflt;
+	CK(cudaMemcpyAsync(d_thresh, &v, 4, cudaMemcpyHostToDevice, b->st));
+	CK(cudaStreamSynchronize(b->st)); // v is on the stack
+	return SSQ_OK;
+}
+
 // stage C: chaining + filter
 static int run_chain(ssq_batch *b)
 {
@@ -785,10 +1093,25 @@ static int run_chain(ssq_batch *b)
 	if (b->chain_of.need(ns * 4) || b->ch.need(ns * sizeof(ChainRec)) || b->ord.need(ns * 4) || b->wi.need(ns * sizeof(WIdx)) || b->sorted.need(ns * sizeof(Seed)) ||
 	    b->outc.need(ns * sizeof(ChainRec)) || b->xkp.need(ns * sizeof(KeptChain)) || b->n_kept.need((size_t)(n + 1) * 4) || b->n_kseeds.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
 	if (n) {
+		if (b->xheavy.need((size_t)(n + 1) * 4) || b->xmisc.need(256)) return SSQ_ENOMEM;
+		unsigned int *n_heavy = b->xmisc.as<unsigned int>() + 24;
+		int *heavy_thresh = b->xmisc.as<int>() + 27;
+		const int rc = tier_threshold(b, "SSQ_HEAVY_SEEDS", 64, heavy_thresh);
+		if (rc) return rc;
+		CK(cudaMemsetAsync(n_heavy, 0, 8, b->st));
 		CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+		CK(cudaEventRecord(b->evc[0], b->st));
 		k_chain<<<b->n_sm * 12, 128, 0, b->st>>>(b->idx->dev, b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
 		                                           b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
-		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work);
+		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work, &b->misc.as<Misc>()->cnt, heavy_thresh, b->xheavy.as<u32>(), n_heavy);
+		CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+		CK(cudaEventRecord(b->evc[1], b->st));
+		k_chain_heavy<<<b->n_sm * 4, 128, 0, b->st>>>(b->idx->dev, b->opt, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
+		                                             b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
+		                                             b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work,
+		                                             b->xheavy.as<u32>(), n_heavy);
+		CK(cudaEventRecord(b->evc[2], b->st));
+		++b->launches;
 		++b->launches;
 		CK(cudaGetLastError());
 	}
@@ -814,18 +1137,24 @@ static int run_extend(ssq_batch *b)
 	if (b->xinfo.need((nt + 1) * sizeof(ExtInfo)) || b->xres[0].need((nt + 1) * sizeof(ExtRes)) || b->xres[1].need((nt + 1) * sizeof(ExtRes)) || b->xwide.need(2 * (nt + 1)) ||
 	    b->xkey[0].need((nt + 1) * 4) || b->xkey[1].need((nt + 1) * 4) || b->xidx[0].need((nt + 1) * 4) || b->xidx[1].need((nt + 1) * 4) || b->xretry.need((nt + 1) * 4) ||
 	    b->xmisc.need(256)) return SSQ_ENOMEM;
-	if (b->xneed.need(nt + 1) || b->xhave.need(nt + 1) || b->xdone.need((size_t)n + 1)) return SSQ_ENOMEM;
+	if (b->xneed.need(nt + 1) || b->xhave.need(nt + 1) || b->xsel.need((size_t)(n + 1) * sizeof(SelState)) || b->xlist[0].need((size_t)(n + 1) * 4) || b->xlist[1].need((size_t)(n + 1) * 4) ||
+	    b->srt2.need((nt + 1) * 8) || b->xheavy.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
 	CK(cudaEventRecord(b->ev[3], b->st));
 	float ms_sel = 0.f;
 	if (nt) {
 		k_tasks<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->n_kept.as<i32>(),
 		                                           b->task_off.as<u64>(), b->tasks.as<Task>());
 		const unsigned G = (unsigned)((nt + 255) / 256);
-		uint8_t *wide_l = b->xwide.as<uint8_t>(), *wide_r = wide_l + (nt + 1), *need = b->xneed.as<uint8_t>(), *have = b->xhave.as<uint8_t>(), *done = b->xdone.as<uint8_t>();
+		uint8_t *wide_l = b->xwide.as<uint8_t>(), *wide_r = wide_l + (nt + 1), *need = b->xneed.as<uint8_t>(), *have = b->xhave.as<uint8_t>();
 		u32 *bounds = b->xmisc.as<u32>();                 // [0..6]
-		unsigned int *n_retry = b->xmisc.as<unsigned int>() + 16, *n_unf = b->xmisc.as<unsigned int>() + 17;
+		unsigned int *n_retry = b->xmisc.as<unsigned int>() + 16, *n_unf = b->xmisc.as<unsigned int>() + 17, *n_heavy2 = b->xmisc.as<unsigned int>() + 26;
+		int *sel_thresh = b->xmisc.as<int>() + 28;
+		int n_in = n;
+		rc = tier_threshold(b, "SSQ_HEAVY_TASKS", 32, sel_thresh);
+		if (rc) return rc;
+		CK(cudaMemsetAsync(b->xsel.p, 0, (size_t)(n + 1) * sizeof(SelState), b->st));
 		CK(cudaMemsetAsync(b->xwide.p, 0, 2 * (nt + 1), b->st));
-		CK(cudaMemsetAsync(need, 0, nt + 1, b->st)); CK(cudaMemsetAsync(have, 0, nt + 1, b->st)); CK(cudaMemsetAsync(done, 0, (size_t)n + 1, b->st));
+		CK(cudaMemsetAsync(need, 0, nt + 1, b->st)); CK(cudaMemsetAsync(have, 0, nt + 1, b->st));
 		k_ext_prep<<<G, 256, 0, b->st>>>(b->idx->dev, b->opt, nt, b->tasks.as<Task>(), b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(),
 		                                b->sorted.as<Seed>(), b->xinfo.as<ExtInfo>());
 		const int lazy = getenv("SSQ_EXT_ALL") ? 0 : 1;
@@ -879,15 +1208,23 @@ static int run_extend(ssq_batch *b)
 				}
 				b->launches += 2;
 			}
-			// replay the selection for the reads that are not finished yet
+			// continue the selection for the reads that are not finished yet
 			unsigned int h_unf = 0;
 			CK(cudaMemsetAsync(n_unf, 0, 4, b->st));
+			CK(cudaMemsetAsync(n_heavy2, 0, 4, b->st));
 			CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
 			CK(cudaEventRecord(es0, b->st));
-			k_select<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, n, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+			const u32 *list_in = round == 0 ? (const u32*)0 : b->xlist[(round - 1) & 1].as<u32>();
+			u32 *list_out = b->xlist[round & 1].as<u32>();
+			k_select<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, n_in, list_in, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
 			                                        b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(),
-			                                        have, need, done, round >= 2, n_unf, &b->misc.as<Misc>()->work);
+			                                        have, need, b->xsel.as<SelState>(), round >= 2, list_out, n_unf, &b->misc.as<Misc>()->work, sel_thresh, b->xheavy.as<u32>(), n_heavy2);
+			CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+			k_select_heavy<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
+			                                              b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->srt2.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(),
+			                                              have, need, b->xsel.as<SelState>(), round >= 2, list_out, n_unf, &b->misc.as<Misc>()->work, b->xheavy.as<u32>(), n_heavy2);
 			CK(cudaEventRecord(es1, b->st));
+			++b->launches;
 			++b->launches;
 			CK(cudaGetLastError());
 			CK(cudaMemcpyAsync(&h_unf, n_unf, 4, cudaMemcpyDeviceToHost, b->st));
@@ -895,6 +1232,7 @@ static int run_extend(ssq_batch *b)
 			{ float ms = 0.f; cudaEventElapsedTime(&ms, es0, es1); ms_sel += ms; }
 			b->ext_rounds = round + 1;
 			if (h_unf == 0) break;
+			n_in = (int)h_unf;
 			if (round > 8) { ssq_set_error("seed-extension rounds did not converge"); return SSQ_ECUDA; }
 		}
 		cudaEventDestroy(es0); cudaEventDestroy(es1);
@@ -949,6 +1287,9 @@ extern "C" uint64_t ssq_batch_counter(const ssq_batch_t *b_, int what)
 	case 0: return b->h_cnt.occ_smem; case 1: return b->h_cnt.occ_sa; case 2: return b->h_cnt.sa_reads; case 3: return b->h_cnt.sw_calls;
 	case 4: return b->h_cnt.sw_cells; case 5: return b->h_cnt.sw_bytes; case 6: return (uint64_t)b->launches; case 7: return b->n_seeds; case 8: return b->n_regs_total;
 	case 9: return b->n_intv; case 10: return b->n_tasks; case 11: return (uint64_t)b->ext_rounds;
+	case 12: case 13: case 14: case 15: case 16: return b->h_cnt.dbg[what - 12];
+	case 17: case 18: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[what - 17], b->evc[what - 16]); return (uint64_t)(ms * 1000.f); } // chaining tiers, microseconds
+	case 19: case 20: { u32 v = 0; cudaMemcpy(&v, b->xmisc.as<u32>() + (what == 19 ? 24 : 27), 4, cudaMemcpyDeviceToHost); return v; } // reads in the heavy tier; the cut
 	}
 	return 0;
 }

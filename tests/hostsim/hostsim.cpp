@@ -107,6 +107,7 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 			for (int i = 1; i < cr.n; ++i) if (cs[i].len >= cs[best].len) best = i;
 			need[t + best] = 1; t += cr.n;
 		}
+		SelState st; memset(&st, 0, sizeof(st));
 		for (int round = 0;; ++round) {
 			t = 0;
 			for (int c = 0; c < w.n_kept; ++c) {
@@ -114,14 +115,9 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 				for (int s = 0; s < cr.n; ++s) if (need[t + s] && !have[t + s]) { extend_seed(ix, opt, len, q, cr, w.sorted.data() + cr.seed_start, s, eh, cand[t + s], 0); have[t + s] = 1; }
 				t += cr.n;
 			}
-			n_out = 0; t = 0;
-			bool complete = true;
-			for (int c = 0; c < w.n_kept; ++c) {
-				const ChainRec &cr = w.outc[c];
-				const int miss = select_regions(opt, len, cr, w.sorted.data() + cr.seed_start, cand.data() + t, srt.data() + t, out.data(), n_out, have.data() + t);
-				if (miss >= 0) { complete = false; if (round >= 2) { for (size_t x = t; x < total; ++x) need[x] = 1; } else need[t + miss] = 1; break; }
-				t += cr.n;
-			}
+			// the same resumable per-read step the GPU's k_select takes each round
+			const bool complete = select_read(opt, len, w.n_kept, w.outc.data(), w.sorted.data(), cand.data(), srt.data(), out.data(), have.data(), need.data(), round >= 2, st);
+			n_out = st.n_out;
 			if (complete) break;
 		}
 	}
@@ -291,6 +287,57 @@ int64_t hostsim_align1_batch(const ssqo_idx_t *idx, int n_reads, const uint8_t *
 	}
 	out_off[n_reads] = n;
 	return (int64_t)n;
+}
+
+// randomized check of ChainBuilder's tree-ordered chains against a plain ordered-array restatement (look-up = first chain with
+// an equal pos else the predecessor; insert right after the slot): seed lists dense with equal and near-equal positions
+int hostsim_chain_selftest(int n_trials, unsigned seed)
+{
+	DevIndex ix; memset(&ix, 0, sizeof ix);
+	i64 aoff[1] = {0}; i32 alen[1] = {1 << 30};
+	ix.l_pac = 1 << 30; ix.n_seqs = 1; ix.ann_off = aoff; ix.ann_len = alen;
+	ssq_opts_t opt; ssq_opts_default(&opt);
+	int bad = 0;
+	srand(seed);
+	for (int t = 0; t < n_trials; ++t) {
+		const int n = 1 + rand() % 300;
+		std::vector<Seed> seeds(n);
+		for (int i = 0; i < n; ++i) {
+			seeds[i].rbeg = (rand() % 40) * 50 + (rand() % 3 == 0 ? rand() % 200 : 0) + ((rand() & 1) ? 0 : (1ll << 30)); // both strands, many ties
+			seeds[i].qbeg = rand() % 130; seeds[i].len = 19 + rand() % 30;
+		}
+		// reference: ordered array
+		std::vector<int> chain_ref(n, -1), ord_ref; std::vector<ChainRec> chr(n); int nch = 0;
+		for (int i = 0; i < n; ++i) {
+			const Seed s = seeds[i];
+			int lo = 0, hi = nch;
+			while (lo < hi) { int mid = (lo + hi) >> 1; if (chr[ord_ref[mid]].pos < s.rbeg) lo = mid + 1; else hi = mid; }
+			int slot = (lo < nch && chr[ord_ref[lo]].pos == s.rbeg) ? lo : lo - 1, merged = 0;
+			if (nch && slot >= 0) {
+				ChainRec &c = chr[ord_ref[slot]];
+				i64 qend = c.last_q + c.last_len, rend = c.last_r + c.last_len;
+				if (s.qbeg >= c.first_q && s.qbeg + s.len <= qend && s.rbeg >= c.first_r && s.rbeg + s.len <= rend) merged = 1;
+				else if (!((c.last_r < ix.l_pac || c.first_r < ix.l_pac) && s.rbeg >= ix.l_pac)) {
+					i64 x = s.qbeg - c.last_q, y = s.rbeg - c.last_r;
+					if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - c.last_len < opt.max_chain_gap && y - c.last_len < opt.max_chain_gap) { c.last_q = s.qbeg; c.last_r = s.rbeg; c.last_len = s.len; ++c.n; chain_ref[i] = ord_ref[slot]; merged = 1; }
+				}
+			}
+			if (!merged) {
+				ChainRec &c = chr[nch]; c.pos = s.rbeg; c.first_r = c.last_r = s.rbeg; c.first_q = c.last_q = s.qbeg; c.last_len = s.len; c.rid = 0; c.n = 1;
+				ord_ref.insert(ord_ref.begin() + (slot + 1), nch); chain_ref[i] = nch; ++nch;
+			}
+		}
+		// ChainBuilder
+		std::vector<i32> chain_of(n), ord(n); std::vector<ChainRec> ch(n), outc(n); std::vector<WIdx> wi(n); std::vector<Seed> sorted(n); std::vector<KeptChain> kp(n);
+		ChainBuilder b; b.init(150, n, seeds.data(), 0, chain_of.data(), ch.data(), ord.data(), wi.data(), sorted.data(), outc.data(), kp.data());
+		for (int i = 0; i < n; ++i) b.add_seed(ix, opt, i);
+		b.inorder();
+		bool ok = b.n_ch == nch;
+		for (int i = 0; ok && i < n; ++i) ok = chain_of[i] == chain_ref[i];
+		for (int k = 0; ok && k < nch; ++k) ok = ord[k] == ord_ref[k];
+		bad += !ok;
+	}
+	return bad;
 }
 
 int hostsim_sw_extend_batch(uint64_t n, const api_sw_task_t *t, const uint8_t *qbuf, const uint8_t *tbuf, api_sw_result_t *r)

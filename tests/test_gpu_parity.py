@@ -99,6 +99,37 @@ def test_chain_and_regions_synthetic(ssq, oracle, syn_index, gpu_syn, rl, seed):
     assert np.array_equal(ao, bo) and np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("heavy_seeds,heavy_tasks", [(2, 1), (8, 4)])
+def test_heavy_read_tiers(ssq, oracle, syn_index, gpu_syn, monkeypatch, heavy_seeds, heavy_tasks):
+    """Reads with many seeds / many extension tasks are handled by warp-per-read kernels (k_chain_heavy, k_select_heavy).
+    Lower their thresholds so that nearly every read takes that route, and a repeat-family batch so chains are plentiful."""
+    monkeypatch.setenv("SSQ_HEAVY_SEEDS", str(heavy_seeds))
+    monkeypatch.setenv("SSQ_HEAVY_TASKS", str(heavy_tasks))
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = T.simulate_pairs(g, bounds, 1200, 150, 11, err=0.01, indel=0.002, n_frac=0.002)
+    rng = np.random.default_rng(5)
+    # reads drawn from inside the planted repeat family: find its copies by their shared 40-mer
+    gs = "".join("ACGT"[b] for b in g[:200000])
+    reps = [seqs[i] for i in range(len(seqs))]
+    kmer_hits = {}
+    for i in range(0, len(gs) - 32, 7):
+        kmer_hits.setdefault(gs[i:i + 24], []).append(i)
+    hot = [v for v in kmer_hits.values() if len(v) >= 4]
+    for v in hot[:300]:
+        p0 = max(0, v[int(rng.integers(0, len(v)))] - int(rng.integers(0, 100)))
+        reps.append(gs[p0:p0 + 150])
+    reps = [r for r in reps if len(r) >= 40]
+    seq, off = T.encode_reads(reps)
+    a = oracle.chain_batch(idx, seq, off)
+    b = ssq.chain_batch(gpu_syn, seq, off)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    a, ao = oracle.align_batch(idx, seq, off)
+    b, bo = ssq.align_batch(gpu_syn, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+
+
 def test_regions_example_reads(ssq, oracle, ex_index, ex_reads, gpu_ex):
     idx = oracle.load(ex_index)
     seq, off = T.encode_reads(ex_reads[1])

@@ -54,3 +54,9 @@ def test_sw_extend_random_tasks(oracle, hostsim):
     b = hostsim.sw_extend_batch(tasks, q, t)
     assert np.array_equal(a, b)
     assert (a["score"] >= tasks["h0"]).all()
+
+
+def test_chain_tree_order_equals_ordered_array(hostsim):
+    """ChainBuilder keeps chains in a search tree; its look-up / insert must reproduce the ordered-array semantics of the oracle
+    (first chain with an equal position, else the predecessor; insert right after it) — exercised with many tied positions"""
+    assert hostsim.lib.hostsim_chain_selftest(3000, 12345) == 0
