@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int 
 			t_read0 = tq0;
 			if (ni > 0) { s0 = seed_off[intv_off[r]]; n = (int)(seed_off[intv_off[r] + ni] - s0); }
 			if (n == 0) { n_kept[r] = 0; n_kseeds[r] = 0; continue; }
-			if (n > heavy_thresh) { heavy_list[atomicAdd(n_heavy, 1u)] = (u32)r; continue; } // gets a warp of its own in k_chain_heavy
+			if (n > heavy_thresh) { heavy_list[atomicAdd(n_heavy, 1u)] = (u32)r; continue; } // gets a warp of its own in k_chain_coop
 			b.init((int)(read_off[r + 1] - read_off[r]), n, seeds + s0, l_rep[r], chain_of + s0, ch + s0, ord + s0, wi + s0, sorted + s0, outc + s0, kp + s0);
 			i = 0; have = true;
 			cyc_fetch += clock64() - tq0;
@@ -318,142 +318,205 @@ __global__ void __launch_bounds__(128) k_chain(DevIndex ix, ssq_opts_t opt, int 
 
 // Reads with many seeds (repeat families): one WARP per read.  In the thread-per-read kernel such a read's lane shares its warp with
 // 31 lanes doing unrelated work and gets a fraction of the issue slots, which stretched its sequential critical path ~30x and made one
-// read the duration of the whole kernel.  Here the warp cooperates: the chains' keys live in shared memory as ONE ORDERED ARRAY (the
-// oracle's formulation: look-up = first chain with an equal pos, else the predecessor; insert right after that slot), searched 32
-// keys at a time with ballots and shifted 32 entries at a time on insert; the O(n^2) overlap filter tests 32 kept chains per step and
-// takes the first "drop" position from a ballot.  Everything else (merge test, regrouping, weights, sort) is lane 0's.
-#define HEAVY_CAP 1024 // chains per read held in shared memory; reads beyond that fall back to the tree-based builder on lane 0
+// read the duration of the whole kernel.  Here the warp cooperates and everything hot lives in shared memory:
+//  * build.  A chain's key (pos = rbeg of its first seed) never changes and chains are only ever added, so the ORDER of the chains is
+//    not needed while building — only the answer to mem_chain()'s look-up: "the first chain whose key equals rbeg, else the last chain
+//    with a smaller key", where chains with equal keys stand as (oldest, then the others newest first).  Give every chain the
+//    static 64-bit key ((pos << 13 | tie) << 13) | id with tie = 0 for the first chain of its pos and 8191 - id for later ones:
+//    the reference's order is then simply ascending key, and the look-up is ONE reduction — the largest key <= ((rbeg << 26) | 8191)
+//    (it is the first chain of pos == rbeg if there is one, else the last chain before it).  Each lane scans a 32-strided slice of
+//    the (unsorted) key array, two REDUX instructions merge them.  No insertion shifts, no tree.  Seeds are fetched 32 at a time
+//    and their contig ids computed one per lane.  (pos < 2^37, id < 8192.)
+//  * finish.  Order = rank sort on that key; seed regrouping is a
+//    scatter (each seed knows its rank inside its chain from the build); weights one chain per lane; the weight sort is the
+//    reference's introsort (its order of equal weights matters) run by lane 0 on shared memory; the O(n^2) overlap filter tests 32
+//    kept chains per step and takes the first "drop" position from a ballot.
+// `cap` chains fit (48 bytes each); a read that needs more is passed on (to the same kernel launched with all of an SM's shared
+// memory per warp) or, at the last level, built by lane 0 with the generic ChainBuilder.
+struct CoopSmem {
+	i64 *pos, *last_r; i32 *tie, *rid, *first_q, *last_q, *last_len, *cn, *first, *kept;
+	WIdx *wi; KeptChain *kp; i32 *sstart, *cw;
+	__device__ void carve(unsigned char *base, int cap)
+	{
+		pos = (i64*)base; last_r = (i64*)(base + (size_t)8 * cap); tie = (i32*)(base + (size_t)16 * cap); rid = (i32*)(base + (size_t)20 * cap);
+		first_q = (i32*)(base + (size_t)24 * cap); last_q = (i32*)(base + (size_t)28 * cap); last_len = (i32*)(base + (size_t)32 * cap);
+		cn = (i32*)(base + (size_t)36 * cap); first = (i32*)(base + (size_t)40 * cap); kept = (i32*)(base + (size_t)44 * cap);
+		wi = (WIdx*)pos;         // after the order is known and the chain records are written out
+		kp = (KeptChain*)last_r; // 16 bytes per chain over last_r + tie + rid, all dead by the time the filter starts
+		sstart = tie;            // seed_start per chain, until the filter
+		cw = cn;                 // chain weight replaces the seed count once the count is in the chain record
+	}
+};
 
-__device__ __forceinline__ int warp_lower_bound(const i64 *pos, int n, i64 key, int lane) // first index with pos[idx] >= key (n <= 1024)
+__global__ void __launch_bounds__(32) k_chain_coop(DevIndex ix, ssq_opts_t opt, int cap, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
+                                                   const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
+                                                   const Seed *__restrict__ seeds_, i32 *chain_of_, ChainRec *ch_, i32 *ord_, WIdx *wi_, Seed *sorted_, ChainRec *outc_, KeptChain *kp_,
+                                                   i32 *n_kept, u32 *n_kseeds, int *work, const u32 *__restrict__ list, const unsigned int *__restrict__ n_list,
+                                                   u32 *next_list, unsigned int *n_next)
 {
-	const int stride = (n + 31) >> 5; // <= 32
-	const int p = (lane + 1) * stride - 1; // last element of this lane's segment
-	const int seg = __popc(__ballot_sync(FULL, p < n && pos[p] < key)); // segments entirely below the key (the predicate is monotone)
-	const int lo = seg * stride;
-	const int k = lo + lane;
-	return lo + __popc(__ballot_sync(FULL, lane < stride && k < n && pos[k] < key));
-}
-
-__global__ void __launch_bounds__(128) k_chain_heavy(DevIndex ix, ssq_opts_t opt, const u64 *__restrict__ read_off, const u64 *__restrict__ intv_off,
-                                                     const i32 *__restrict__ intv_cnt, const i32 *__restrict__ l_rep, const u64 *__restrict__ seed_off,
-                                                     const Seed *__restrict__ seeds_, i32 *chain_of_, ChainRec *ch_, i32 *ord_, WIdx *wi_, Seed *sorted_, ChainRec *outc_, KeptChain *kp_,
-                                                     i32 *n_kept, u32 *n_kseeds, int *work, const u32 *__restrict__ heavy_list, const unsigned int *__restrict__ n_heavy)
-{
-	__shared__ i64 s_pos[4][HEAVY_CAP];
-	__shared__ i32 s_idx[4][HEAVY_CAP];
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	i64 *pos = s_pos[wib]; i32 *sidx = s_idx[wib];
-	const unsigned int nh = *n_heavy;
+	extern __shared__ __align__(16) unsigned char coop_smem[];
+	CoopSmem S; S.carve(coop_smem, cap);
+	const int lane = threadIdx.x;
+	const unsigned int nl = *n_list;
+	const i64 l_pac = ix.l_pac;
 	for (;;) {
 		int w = 0;
 		if (lane == 0) w = atomicAdd(work, 1);
 		w = __shfl_sync(FULL, w, 0);
-		if ((unsigned)w >= nh) break;
-		const int r = (int)heavy_list[w];
+		if ((unsigned)w >= nl) break;
+		const int r = (int)list[w];
 		const u64 s0 = seed_off[intv_off[r]];
 		const int n = (int)(seed_off[intv_off[r] + intv_cnt[r]] - s0), len = (int)(read_off[r + 1] - read_off[r]);
-		const Seed *seeds = seeds_ + s0; i32 *chain_of = chain_of_ + s0; ChainRec *ch = ch_ + s0; i32 *ord = ord_ + s0; WIdx *wi = wi_ + s0;
-		Seed *sorted = sorted_ + s0; ChainRec *outc = outc_ + s0; KeptChain *kp = kp_ + s0;
-		const i64 l_pac = ix.l_pac;
+		const Seed *seeds = seeds_ + s0; i32 *chain_of = chain_of_ + s0; ChainRec *ch = ch_ + s0; i32 *ord = ord_ + s0; i32 *rank_in = (i32*)(wi_ + s0);
+		Seed *sorted = sorted_ + s0; ChainRec *outc = outc_ + s0;
 		int n_ch = 0, nk = 0;
+		u32 ns = 0;
 		bool overflow = false;
-		// ---- build: one seed at a time, warp-wide search / shift ----
-		for (int i = 0; i < n && !overflow; ++i) {
-			const Seed s = seeds[i];
-			const int rid = intv2rid(ix, s.rbeg, s.rbeg + s.len);
-			if (rid < 0) { if (lane == 0) chain_of[i] = -1; continue; }
-			const int lo = warp_lower_bound(pos, n_ch, s.rbeg, lane);
-			const int slot = (lo < n_ch && pos[lo] == s.rbeg) ? lo : lo - 1;
-			int merged = 0, cid = -1;
-			if (lane == 0 && slot >= 0) { // merge test on the chain record (global)
-				ChainRec &c = ch[sidx[slot]];
-				const i64 qend = c.last_q + c.last_len, rend = c.last_r + c.last_len;
-				if (rid == c.rid) {
-					if (s.qbeg >= c.first_q && s.qbeg + s.len <= qend && s.rbeg >= c.first_r && s.rbeg + s.len <= rend) merged = 1;
-					else if (!((c.last_r < l_pac || c.first_r < l_pac) && s.rbeg >= l_pac)) {
-						const i64 x = s.qbeg - c.last_q, y = s.rbeg - c.last_r;
-						if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - c.last_len < opt.max_chain_gap && y - c.last_len < opt.max_chain_gap) {
-							c.last_q = s.qbeg; c.last_r = s.rbeg; c.last_len = s.len; ++c.n;
-							cid = sidx[slot]; merged = 1;
+		// ------------------------------------------------------------------ build ----
+		for (int i0 = 0; i0 < n && !overflow; i0 += 32) {
+			Seed my; my.rbeg = 0; my.qbeg = 0; my.len = 0;
+			int myrid = -1;
+			if (i0 + lane < n) { my = seeds[i0 + lane]; myrid = intv2rid(ix, my.rbeg, my.rbeg + my.len); }
+			const int cnt = n - i0 < 32 ? n - i0 : 32;
+			int my_chain = -1, my_rank = 0; // results for the seed this lane fetched
+			for (int j = 0; j < cnt; ++j) {
+				const i64 rbeg = __shfl_sync(FULL, my.rbeg, j);
+				const int qbeg = __shfl_sync(FULL, my.qbeg, j), slen = __shfl_sync(FULL, my.len, j), rid = __shfl_sync(FULL, myrid, j);
+				if (rid < 0) continue;
+				// look-up over the unsorted keys: max key <= limit
+				const i64 limit = (rbeg << 26) | 8191;
+				i64 best = -1;
+				for (int q = lane; q < n_ch; q += 32) { const i64 kq = S.pos[q]; if (kq <= limit && kq > best) best = kq; }
+				{
+					const int hi = (int)(best >> 32); // -1 when the lane found nothing
+					const int ghi = __reduce_max_sync(FULL, hi);
+					const unsigned glo = __reduce_max_sync(FULL, hi == ghi ? (unsigned)best : 0u);
+					best = ghi < 0 ? -1 : ((i64)ghi << 32 | glo);
+				}
+				const bool exact = best >= 0 && (best >> 13) == (rbeg << 13);
+				const int slot = best < 0 ? -1 : (int)(best & 8191);
+				int res_chain = -1, res_rank = 0;
+				bool merged = false;
+				if (slot >= 0) { // every lane evaluates the merge test on the same shared-memory words
+					const i64 c_first_r = S.pos[slot] >> 26, c_last_r = S.last_r[slot];
+					const int c_first_q = S.first_q[slot], c_last_q = S.last_q[slot], c_last_len = S.last_len[slot];
+					const i64 qend = c_last_q + c_last_len, rend = c_last_r + c_last_len;
+					if (rid == S.rid[slot]) {
+						if (qbeg >= c_first_q && qbeg + slen <= qend && rbeg >= c_first_r && rbeg + slen <= rend) merged = true; // contained
+						else if (!((c_last_r < l_pac || c_first_r < l_pac) && rbeg >= l_pac)) {
+							const i64 x = qbeg - c_last_q, y = rbeg - c_last_r;
+							if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - c_last_len < opt.max_chain_gap && y - c_last_len < opt.max_chain_gap) {
+								res_chain = slot; res_rank = S.cn[slot];
+								__syncwarp();
+								if (lane == 0) { S.last_q[slot] = qbeg; S.last_r[slot] = rbeg; S.last_len[slot] = slen; S.cn[slot] = res_rank + 1; }
+								merged = true;
+							}
 						}
 					}
 				}
-			}
-			merged = __shfl_sync(FULL, merged, 0);
-			if (!merged) {
-				if (n_ch >= HEAVY_CAP) { overflow = true; break; }
-				// shift [slot+1, n_ch) up by one, 32 entries at a time from the top
-				for (int hi = n_ch - 1; hi > slot; hi -= 32) {
-					const int kk = hi - lane;
-					i64 pv = 0; i32 iv = 0;
-					if (kk > slot) { pv = pos[kk]; iv = sidx[kk]; }
-					__syncwarp();
-					if (kk > slot) { pos[kk + 1] = pv; sidx[kk + 1] = iv; }
-					__syncwarp();
+				if (!merged) {
+					if (n_ch >= cap) { overflow = true; break; }
+					if (lane == 0) {
+						S.pos[n_ch] = ((rbeg << 13 | (exact ? 8191 - n_ch : 0)) << 13) | n_ch;
+						S.last_r[n_ch] = rbeg; S.first_q[n_ch] = qbeg; S.last_q[n_ch] = qbeg; S.last_len[n_ch] = slen;
+						S.rid[n_ch] = rid; S.cn[n_ch] = 1;
+					}
+					res_chain = n_ch; res_rank = 0;
+					++n_ch;
 				}
-				if (lane == 0) {
-					ChainRec &c = ch[n_ch];
-					c.pos = s.rbeg; c.first_r = c.last_r = s.rbeg; c.first_q = c.last_q = s.qbeg; c.last_len = s.len;
-					c.rid = rid; c.n = 1; c.w = 0; c.first = -1; c.kept = 0; c.seed_start = 0; c.frac_rep = 0.f;
-					pos[slot + 1] = s.rbeg; sidx[slot + 1] = n_ch;
-					cid = n_ch;
-				}
-				++n_ch;
 				__syncwarp();
+				if (lane == j) { my_chain = res_chain; my_rank = res_rank; }
 			}
-			if (lane == 0) chain_of[i] = cid;
+			if (!overflow && i0 + lane < n) { chain_of[i0 + lane] = my_chain; rank_in[i0 + lane] = my_rank; }
 		}
-		if (overflow) { // more chains than the shared array holds: the generic builder, lane 0, from scratch
-			if (lane == 0) {
+		__syncwarp();
+		if (overflow) {
+			if (next_list) { if (lane == 0) next_list[atomicAdd(n_next, 1u)] = (u32)r; continue; } // retried with more shared memory
+			if (lane == 0) { // last level: the generic builder
 				ChainBuilder b;
-				b.init(len, n, seeds, l_rep[r], chain_of, ch, ord, wi, sorted, outc, kp);
+				b.init(len, n, seeds, l_rep[r], chain_of, ch, ord, wi_ + s0, sorted, outc, kp_ + s0);
 				for (int i = 0; i < n; ++i) b.add_seed(ix, opt, i);
 				nk = b.finish(opt);
+				for (int c = 0; c < nk; ++c) ns += (u32)outc[c].n;
+				n_kept[r] = nk; n_kseeds[r] = ns;
 			}
-		} else if (n_ch > 0) {
-			// ---- finish: lane 0 regroups / weighs / sorts, the warp runs the overlap filter ----
-			for (int k = lane; k < n_ch; k += 32) ord[k] = sidx[k];
 			__syncwarp();
-			if (lane == 0) {
-				int off = 0;
-				for (int k = 0; k < n_ch; ++k) { ChainRec &c = ch[ord[k]]; c.seed_start = off; off += c.n; c.n = 0; }
-				for (int i = 0; i < n; ++i) if (chain_of[i] >= 0) { ChainRec &c = ch[chain_of[i]]; sorted[c.seed_start + c.n++] = seeds[i]; }
-				for (int k = 0; k < n_ch; ++k) {
-					ChainRec &c = ch[ord[k]];
-					const Seed *sd = sorted + c.seed_start;
-					i64 end; int j, w2 = 0, tmp;
-					for (j = 0, end = 0; j < c.n; ++j) {
-						if (sd[j].qbeg >= end) w2 += sd[j].len; else if (sd[j].qbeg + sd[j].len > end) w2 += (int)(sd[j].qbeg + sd[j].len - end);
-						end = end > sd[j].qbeg + sd[j].len ? end : sd[j].qbeg + sd[j].len;
-					}
-					tmp = w2; w2 = 0;
-					for (j = 0, end = 0; j < c.n; ++j) {
-						if (sd[j].rbeg >= end) w2 += sd[j].len; else if (sd[j].rbeg + sd[j].len > end) w2 += (int)(sd[j].rbeg + sd[j].len - end);
-						end = end > sd[j].rbeg + sd[j].len ? end : sd[j].rbeg + sd[j].len;
-					}
-					w2 = w2 < tmp ? w2 : tmp;
-					c.w = w2 < 1 << 30 ? w2 : (1 << 30) - 1;
-					c.first = -1; c.kept = 0;
-					c.frac_rep = (float)l_rep[r] / len;
-					wi[k].w = c.w; wi[k].idx = ord[k];
+			continue;
+		}
+		if (n_ch > 0) {
+			// ----------------------------------------------------------- order ----
+			for (int q = lane; q < n_ch; q += 32) {
+				const i64 kq = S.pos[q];
+				int rk = 0;
+				for (int j = 0; j < n_ch; ++j) rk += S.pos[j] < kq;
+				ord[rk] = q;
+			}
+			__syncwarp();
+			// seed_start = exclusive scan of the seed counts in that order
+			for (int base = 0, run = 0; base < n_ch; base += 32) {
+				const int q = base + lane;
+				const int id = q < n_ch ? ord[q] : -1;
+				const int v = id >= 0 ? S.cn[id] : 0;
+				int inc = v;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+				if (id >= 0) S.sstart[id] = run + inc - v;
+				run += __shfl_sync(FULL, inc, 31);
+			}
+			__syncwarp();
+			const float frac_rep = (float)l_rep[r] / len;
+			for (int q = lane; q < n_ch; q += 32) { // the chain records
+				ChainRec c;
+				c.pos = S.pos[q] >> 26; c.first_r = c.pos; c.last_r = S.last_r[q]; c.first_q = S.first_q[q]; c.last_q = S.last_q[q]; c.last_len = S.last_len[q];
+				c.rid = S.rid[q]; c.n = S.cn[q]; c.w = 0; c.first = -1; c.kept = 0; c.seed_start = S.sstart[q]; c.frac_rep = frac_rep;
+				ch[q] = c;
+			}
+			for (int i = lane; i < n; i += 32) { const int co = chain_of[i]; if (co >= 0) sorted[S.sstart[co] + rank_in[i]] = seeds[i]; }
+			__syncwarp();
+			// ---------------------------------------------------------- weights ----
+			for (int q = lane; q < n_ch; q += 32) {
+				const Seed *sd = sorted + S.sstart[q];
+				const int cnq = S.cn[q];
+				i64 end; int j, w2 = 0, tmp;
+				for (j = 0, end = 0; j < cnq; ++j) {
+					const i64 qb = sd[j].qbeg, l = sd[j].len;
+					if (qb >= end) w2 += (int)l; else if (qb + l > end) w2 += (int)(qb + l - end);
+					end = end > qb + l ? end : qb + l;
 				}
-				ks_introsort((long)n_ch, wi, WIdxLt());
-				ChainRec &c0 = ch[wi[0].idx];
-				c0.kept = 3;
-				kp[0].b = c0.first_q; kp[0].e = c0.last_q + c0.last_len; kp[0].w = c0.w; kp[0].i = 0;
+				tmp = w2; w2 = 0;
+				for (j = 0, end = 0; j < cnq; ++j) {
+					const i64 rb = sd[j].rbeg, l = sd[j].len;
+					if (rb >= end) w2 += (int)l; else if (rb + l > end) w2 += (int)(rb + l - end);
+					end = end > rb + l ? end : rb + l;
+				}
+				w2 = w2 < tmp ? w2 : tmp;
+				w2 = w2 < 1 << 30 ? w2 : (1 << 30) - 1;
+				S.cw[q] = w2; // only this lane reads cn[q]
+				ch[q].w = w2;
 			}
 			__syncwarp();
+			for (int q = lane; q < n_ch; q += 32) { const int id = ord[q]; WIdx x; x.w = S.cw[id]; x.idx = id; S.wi[q] = x; S.first[q] = -1; S.kept[q] = 0; } // pos[] is dead
+			__syncwarp();
+			if (lane == 0) ks_introsort((long)n_ch, S.wi, WIdxLt());
+			__syncwarp();
+			// ----------------------------------------------------------- filter ----
 			int n_keptc = 1;
+			if (lane == 0) {
+				const int id = S.wi[0].idx;
+				KeptChain k0; k0.b = S.first_q[id]; k0.e = S.last_q[id] + S.last_len[id]; k0.w = S.cw[id]; k0.i = 0;
+				S.kp[0] = k0; S.kept[0] = 3;
+			}
+			__syncwarp();
 			for (int i = 1; i < n_ch; ++i) {
-				int bi = 0, ei = 0, wv = 0;
-				if (lane == 0) { const ChainRec &ci = ch[wi[i].idx]; bi = ci.first_q; ei = ci.last_q + ci.last_len; wv = ci.w; }
-				bi = __shfl_sync(FULL, bi, 0); ei = __shfl_sync(FULL, ei, 0); wv = __shfl_sync(FULL, wv, 0);
+				const int id = S.wi[i].idx;
+				const int bi = S.first_q[id], ei = S.last_q[id] + S.last_len[id], wv = S.cw[id];
 				int large = 0; bool dropped = false;
 				for (int base = 0; base < n_keptc && !dropped; base += 32) {
 					const int kk = base + lane;
-					bool ov = false, brk = false; KeptChain kj; kj.i = 0;
+					bool ov = false, brk = false; int kji = 0;
 					if (kk < n_keptc) {
-						kj = kp[kk];
+						const KeptChain kj = S.kp[kk];
+						kji = kj.i;
 						const int b_max = kj.b > bi ? kj.b : bi, e_min = kj.e < ei ? kj.e : ei;
 						if (e_min > b_max) {
 							const int li = ei - bi, lj = kj.e - kj.b, min_l = li < lj ? li : lj;
@@ -467,34 +530,45 @@ __global__ void __launch_bounds__(128) k_chain_heavy(DevIndex ix, ssq_opts_t opt
 					const unsigned upto = m_brk ? (0xffffffffu >> (32 - __ffs(m_brk))) : 0xffffffffu; // lanes up to and including the first drop
 					const unsigned eff = m_ov & upto;
 					if (eff) large = 1;
-					if (eff >> lane & 1) { ChainRec &cj = ch[wi[kj.i].idx]; if (cj.first < 0) cj.first = i; }
+					if ((eff >> lane & 1) && S.first[kji] < 0) S.first[kji] = i;
 					if (m_brk) dropped = true;
 				}
 				__syncwarp();
 				if (!dropped) {
-					if (lane == 0) { kp[n_keptc].b = bi; kp[n_keptc].e = ei; kp[n_keptc].w = wv; kp[n_keptc].i = i; ch[wi[i].idx].kept = large ? 2 : 3; }
+					if (lane == 0) { KeptChain kn; kn.b = bi; kn.e = ei; kn.w = wv; kn.i = i; S.kp[n_keptc] = kn; S.kept[i] = large ? 2 : 3; }
 					++n_keptc;
 					__syncwarp();
 				}
 			}
+			for (int q = lane; q < n_keptc; q += 32) { const int f = S.first[S.kp[q].i]; if (f >= 0) S.kept[f] = 1; }
+			__syncwarp();
 			if (lane == 0) {
 				int i2, k2;
-				for (i2 = 0; i2 < n_keptc; ++i2) { ChainRec &c = ch[wi[kp[i2].i].idx]; if (c.first >= 0) ch[wi[c.first].idx].kept = 1; }
 				for (i2 = k2 = 0; i2 < n_ch; ++i2) {
-					const int kept = ch[wi[i2].idx].kept;
+					const int kept = S.kept[i2];
 					if (kept == 0 || kept == 3) continue;
 					if (++k2 >= opt.max_chain_extend) break;
 				}
-				for (; i2 < n_ch; ++i2) if (ch[wi[i2].idx].kept < 3) ch[wi[i2].idx].kept = 0;
-				for (i2 = k2 = 0; i2 < n_ch; ++i2) if (ch[wi[i2].idx].kept) outc[k2++] = ch[wi[i2].idx];
-				nk = k2;
+				for (; i2 < n_ch; ++i2) if (S.kept[i2] < 3) S.kept[i2] = 0;
 			}
+			__syncwarp();
+			// kept chains out, in weight order
+			for (int base = 0; base < n_ch; base += 32) {
+				const int q = base + lane;
+				const bool f = q < n_ch && S.kept[q] != 0;
+				const unsigned m = __ballot_sync(FULL, f);
+				if (f) {
+					ChainRec c = ch[S.wi[q].idx];
+					c.kept = S.kept[q]; c.first = S.first[q];
+					outc[nk + __popc(m & ((1u << lane) - 1))] = c;
+					ns += (u32)c.n;
+				}
+				nk += __popc(m);
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(FULL, ns, o);
 		}
-		if (lane == 0) {
-			u32 ns = 0;
-			for (int c = 0; c < nk; ++c) ns += (u32)outc[c].n;
-			n_kept[r] = nk; n_kseeds[r] = ns;
-		}
+		if (lane == 0) { n_kept[r] = nk; n_kseeds[r] = ns; }
 		__syncwarp();
 	}
 }
@@ -912,13 +986,13 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2;
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
-	cudaEvent_t ev[6], evc[3]; // stage boundaries; chaining tiers (light start, heavy start, end)
+	cudaEvent_t ev[6], evc[4]; // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
 	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
 };
@@ -965,7 +1039,7 @@ extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, i
 	b->n_sm = prop.multiProcessorCount;
 	CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
 	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
-	for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&b->evc[i]));
+	for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&b->evc[i]));
 	if (read_off && (rc = ssq_batch_upload(b, n_reads, seq, read_off))) { ssq_batch_free(b); return rc; }
 	*out = b;
 	return SSQ_OK;
@@ -977,10 +1051,10 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
-	for (int i = 0; i < 3; ++i) cudaEventDestroy(b->evc[i]);
+	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
 	delete b;
 }
@@ -1096,7 +1170,7 @@ static int run_chain(ssq_batch *b)
 		if (b->xheavy.need((size_t)(n + 1) * 4) || b->xmisc.need(256)) return SSQ_ENOMEM;
 		unsigned int *n_heavy = b->xmisc.as<unsigned int>() + 24;
 		int *heavy_thresh = b->xmisc.as<int>() + 27;
-		const int rc = tier_threshold(b, "SSQ_HEAVY_SEEDS", 64, heavy_thresh);
+		const int rc = tier_threshold(b, "SSQ_HEAVY_SEEDS", 16, heavy_thresh);
 		if (rc) return rc;
 		CK(cudaMemsetAsync(n_heavy, 0, 8, b->st));
 		CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
@@ -1106,12 +1180,28 @@ static int run_chain(ssq_batch *b)
 		                                           b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work, &b->misc.as<Misc>()->cnt, heavy_thresh, b->xheavy.as<u32>(), n_heavy);
 		CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
 		CK(cudaEventRecord(b->evc[1], b->st));
-		k_chain_heavy<<<b->n_sm * 4, 128, 0, b->st>>>(b->idx->dev, b->opt, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
-		                                             b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
-		                                             b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work,
-		                                             b->xheavy.as<u32>(), n_heavy);
+		// warp-per-read tiers: a small shared-memory footprint first (many warps per SM); what overflows is retried with 4x the
+		// capacity, and what overflows that with a whole SM's shared memory per warp
+		{
+			static const int caps[3] = {getenv("SSQ_COOP_CAP") ? atoi(getenv("SSQ_COOP_CAP")) : 256, 1024, 4608};
+			unsigned int *n_lvl[3] = {n_heavy, n_heavy + 1, b->xmisc.as<unsigned int>() + 29};
+			if (b->xgiant.need((size_t)(n + 1) * 4) || b->xgiant2.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+			u32 *lists[3] = {b->xheavy.as<u32>(), b->xgiant.as<u32>(), b->xgiant2.as<u32>()};
+			CK(cudaMemsetAsync(n_lvl[2], 0, 4, b->st));
+			CK(cudaFuncSetAttribute(k_chain_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * caps[2]));
+			for (int lvl = 0; lvl < 3; ++lvl) {
+				if (lvl == 1) CK(cudaEventRecord(b->evc[3], b->st));
+				const int fit = (int)(220 * 1024 / (48 * caps[lvl] + 1024));
+				const int per_sm = fit < 1 ? 1 : fit > 24 ? 24 : fit;
+				CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
+				k_chain_coop<<<b->n_sm * per_sm, 32, 48 * caps[lvl], b->st>>>(b->idx->dev, b->opt, caps[lvl], b->read_off.as<u64>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(),
+				        b->seed_off.as<u64>(), b->seeds.as<Seed>(), b->chain_of.as<i32>(), b->ch.as<ChainRec>(), b->ord.as<i32>(), b->wi.as<WIdx>(),
+				        b->sorted.as<Seed>(), b->outc.as<ChainRec>(), b->xkp.as<KeptChain>(), b->n_kept.as<i32>(), b->n_kseeds.as<u32>(), &b->misc.as<Misc>()->work,
+				        lists[lvl], n_lvl[lvl], lvl < 2 ? lists[lvl + 1] : (u32*)0, lvl < 2 ? n_lvl[lvl + 1] : (unsigned int*)0);
+				++b->launches;
+			}
+		}
 		CK(cudaEventRecord(b->evc[2], b->st));
-		++b->launches;
 		++b->launches;
 		CK(cudaGetLastError());
 	}
@@ -1288,8 +1378,9 @@ extern "C" uint64_t ssq_batch_counter(const ssq_batch_t *b_, int what)
 	case 4: return b->h_cnt.sw_cells; case 5: return b->h_cnt.sw_bytes; case 6: return (uint64_t)b->launches; case 7: return b->n_seeds; case 8: return b->n_regs_total;
 	case 9: return b->n_intv; case 10: return b->n_tasks; case 11: return (uint64_t)b->ext_rounds;
 	case 12: case 13: case 14: case 15: case 16: return b->h_cnt.dbg[what - 12];
+	case 22: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[3], b->evc[2]); return (uint64_t)(ms * 1000.f); } // the big-shared-memory tier alone
 	case 17: case 18: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[what - 17], b->evc[what - 16]); return (uint64_t)(ms * 1000.f); } // chaining tiers, microseconds
-	case 19: case 20: { u32 v = 0; cudaMemcpy(&v, b->xmisc.as<u32>() + (what == 19 ? 24 : 27), 4, cudaMemcpyDeviceToHost); return v; } // reads in the heavy tier; the cut
+	case 19: case 20: case 21: { u32 v = 0; cudaMemcpy(&v, b->xmisc.as<u32>() + (what == 19 ? 24 : what == 20 ? 27 : 25), 4, cudaMemcpyDeviceToHost); return v; } // reads in the warp tier; the cut; reads passed on to the big-shared-memory tier
 	}
 	return 0;
 }
