@@ -51,7 +51,10 @@ struct Counters { // device-measured work, feeds roofline.achieved (algorithmic 
 	unsigned long long dbg[8]; // kernel-internal cycle counters (diagnostics)
 };
 
-struct Intv { u64 x0, x1, x2; u32 qb, qe; }; // bi-interval + query span [qb,qe)
+template <class U> struct IntvT { U x0, x1, x2; u32 qb, qe; }; // bi-interval + query span [qb,qe)
+typedef IntvT<u64> Intv;   // any index
+typedef IntvT<u32> Intv32; // indexes with fewer than 2^32 rows (the ones that have the re-blocked bwt32): half the registers and ALU work
+template <class U> SSQ_HD Intv widen(const IntvT<U> &v) { Intv r; r.x0 = v.x0; r.x1 = v.x1; r.x2 = v.x2; r.qb = v.qb; r.qe = v.qe; return r; }
 
 // ----------------------------------------------------------------------- occ / extension ----
 // counts of A,C,G,T in rows [0,k] given the 16 words of the block holding k ('$'-less coordinate kk)
@@ -97,7 +100,8 @@ SSQ_HD Blk32 load_blk32(const u32 *p)
 	return b;
 }
 // occurrences of each base in rows [block start, kk] of a 64-symbol rank block
-SSQ_HD void blk32_count(const Blk32 &b, u64 kk, u64 cnt[4])
+template <class U>
+SSQ_HD void blk32_count(const Blk32 &b, U kk, U cnt[4])
 {
 	const int r = (int)(kk & 63) + 1; // symbols to count, 1..64
 	// two 64-bit lanes of 32 symbols each, MSB-first within each original 32-bit word
@@ -111,7 +115,7 @@ SSQ_HD void blk32_count(const Blk32 &b, u64 kk, u64 cnt[4])
 #else
 	const int p3 = __builtin_popcountll(h0 & l0) + __builtin_popcountll(h1 & l1), ph = __builtin_popcountll(h0) + __builtin_popcountll(h1), pl = __builtin_popcountll(l0) + __builtin_popcountll(l1);
 #endif
-	cnt[3] = (u64)b.c3 + p3; cnt[2] = (u64)b.c2 + (ph - p3); cnt[1] = (u64)b.c1 + (pl - p3); cnt[0] = (u64)b.c0 + (r - ph - pl + p3);
+	cnt[3] = (U)b.c3 + (U)p3; cnt[2] = (U)b.c2 + (U)(ph - p3); cnt[1] = (U)b.c1 + (U)(pl - p3); cnt[0] = (U)b.c0 + (U)(r - ph - pl + p3);
 }
 
 struct ScalarFm {
@@ -141,6 +145,14 @@ struct ScalarFm {
 		++n_blk;
 		occ4_from_block(blk, kk, cnt);
 	}
+	SSQ_HD void occ4(u32 k, u32 cnt[4]) // 32-bit rows: only with bwt32
+	{
+		if (k == (u32)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
+		const u32 kk = k - (k >= (u32)ix.primary);
+		const Blk32 b = load_blk32(ix.bwt32 + ((size_t)(kk >> 6) << 3));
+		++n_blk;
+		blk32_count(b, kk, cnt);
+	}
 	// ok[c] of a forward (is_back=0) or backward (is_back=1) extension of ik by every base c
 	SSQ_HD void extend(const Intv &ik, Intv ok[4], int is_back)
 	{
@@ -164,26 +176,27 @@ struct ScalarFm {
 
 #define SSQ_SEL4(v0, v1, v2, v3, c) ((c) == 0 ? (v0) : (c) == 1 ? (v1) : (c) == 2 ? (v2) : (v3))
 // only ok[c] of an extension, computed without runtime-indexed arrays (keeps everything in registers on the GPU)
-template <class Fm>
-SSQ_HD void extend1(Fm &fm, const Intv &ik, int c, int is_back, Intv &out)
+template <class Fm, class U>
+SSQ_HD void extend1(Fm &fm, const IntvT<U> &ik, int c, int is_back, IntvT<U> &out)
 {
 	const DevIndex &ix = fm.ix;
-	u64 tk[4], tl[4];
-	const u64 kf = is_back ? ik.x0 : ik.x1, ko = is_back ? ik.x1 : ik.x0;
-	fm.occ4(kf - 1, tk);
-	fm.occ4(kf - 1 + ik.x2, tl);
-	const u64 n0 = tl[0] - tk[0], n1 = tl[1] - tk[1], n2 = tl[2] - tk[2], n3 = tl[3] - tk[3];
-	const u64 nf = SSQ_SEL4(ix.L2[0] + 1 + tk[0], ix.L2[1] + 1 + tk[1], ix.L2[2] + 1 + tk[2], ix.L2[3] + 1 + tk[3], c);
-	const u64 base = ko + (kf <= ix.primary && kf + ik.x2 - 1 >= ix.primary);
-	const u64 no = base + (c < 3 ? n3 : 0) + (c < 2 ? n2 : 0) + (c < 1 ? n1 : 0);
+	U tk[4], tl[4];
+	const U kf = is_back ? ik.x0 : ik.x1, ko = is_back ? ik.x1 : ik.x0;
+	fm.occ4((U)(kf - 1), tk);
+	fm.occ4((U)(kf - 1 + ik.x2), tl);
+	const U n0 = tl[0] - tk[0], n1 = tl[1] - tk[1], n2 = tl[2] - tk[2], n3 = tl[3] - tk[3];
+	const U nf = SSQ_SEL4((U)ix.L2[0] + 1 + tk[0], (U)ix.L2[1] + 1 + tk[1], (U)ix.L2[2] + 1 + tk[2], (U)ix.L2[3] + 1 + tk[3], c);
+	const U base = ko + (U)(kf <= (U)ix.primary && (U)(kf + ik.x2 - 1) >= (U)ix.primary);
+	const U no = base + (c < 3 ? n3 : 0) + (c < 2 ? n2 : 0) + (c < 1 ? n1 : 0);
 	out.x2 = SSQ_SEL4(n0, n1, n2, n3, c);
 	if (is_back) { out.x0 = nf; out.x1 = no; } else { out.x1 = nf; out.x0 = no; }
 	out.qb = out.qe = 0;
 }
 
-SSQ_HD void set_intv(const DevIndex &ix, int c, Intv &ik)
+template <class U>
+SSQ_HD void set_intv(const DevIndex &ix, int c, IntvT<U> &ik)
 {
-	ik.x0 = ix.L2[c] + 1; ik.x2 = ix.L2[c + 1] - ix.L2[c]; ik.x1 = ix.L2[3 - c] + 1; ik.qb = ik.qe = 0;
+	ik.x0 = (U)(ix.L2[c] + 1); ik.x2 = (U)(ix.L2[c + 1] - ix.L2[c]); ik.x1 = (U)(ix.L2[3 - c] + 1); ik.qb = ik.qe = 0;
 }
 
 // ------------------------------------------------------------------------ SMEM search ----
@@ -319,70 +332,81 @@ SSQ_HD int collect_intv(Fm &fm, const DevIndex &ix, const ssq_opts_t &opt, int l
 // Lists: the two ping-pong interval lists behind get/set (shared memory with global overflow on the GPU, plain arrays
 // in the host harness); their tails and the tail of the output list are mirrored in registers so that the backward
 // phase never waits on a dependent memory read other than the rank query itself.
-struct HostLists { // plain arrays (hostsim, thread-per-read fallbacks)
-	Intv *a[2];
-	SSQ_HD Intv get(int id, int j) const { return a[id][j]; }
-	SSQ_HD void set(int id, int j, const Intv &v) const { a[id][j] = v; }
+template <class U>
+struct HostListsT { // plain arrays (hostsim, thread-per-read fallbacks)
+	IntvT<U> *a[2];
+	SSQ_HD IntvT<U> get(int id, int j) const { return a[id][j]; }
+	SSQ_HD void set(int id, int j, const IntvT<U> &v) const { a[id][j] = v; }
 };
+typedef HostListsT<u64> HostLists;
 
-template <class Lists>
+// U: row type of the machine's intervals — u64 for any index, u32 when the index has fewer than 2^32 rows.  The output list
+// `mem` always holds 64-bit intervals.
+template <class Lists, class U = u64>
 struct SmemMachineT {
+	typedef IntvT<U> I;
 	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3 };
 	const uint8_t *q; Intv *mem; Lists L;
-	int len, mem_cap, n, base, state, pass, x, i, j, c, qc, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width, prev_id;
+	int len, mem_cap, n, state, pass, x, i, j, c, qc, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width, prev_id;
 	int qi, qnext;     // base at position i (forward phases) and the prefetched base at i+1: the load is issued before the rank
 	                   // query of step i and consumed after it, so the bookkeeping never waits on a query byte
 	int cnext;         // backward phase: prefetched base at i-1
-	u32 last_mem_qb;   // mem[n-1].qb of the current smem1 call
-	u64 curr_tail_x2;  // x2 of the entry last pushed to the current list
-	u64 min_intv, max_mem_intv;
-	Intv ik, in;
+	int cb0, cb1;      // bases at x-1 and x-2 of the current smem1 call, fetched when it starts
+	int rev;           // first backward sweep: the forward list is read from its end (longest match first) instead of being reversed
+	int any_kept;      // this smem1 call has kept an interval (whether or not it was long enough to be stored)
+	u32 last_qe;       // qe of the entry last pushed by the forward phase
+	u32 last_mem_qb;   // qb of the interval this smem1 call kept last
+	U curr_tail_x2;    // x2 of the entry last pushed to the current list
+	U min_intv, max_mem_intv;
+	I ik, in;
 	int is_back;
 
 	SSQ_HD int base_at(int p) const { return p >= 0 && p < len ? (int)q[p] : 4; }
 	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists)
 	{
 		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0;
-		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1;
+		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1; rev = 0;
 		min_seed_len = opt.min_seed_len; split_len = (int)(opt.min_seed_len * opt.split_factor + .499f); split_width = opt.split_width;
-		max_mem_intv = (u64)opt.max_mem_intv;
+		max_mem_intv = (U)opt.max_mem_intv;
 		if (len < opt.min_seed_len) { state = NEXT_P3; pass = 3; x = len; }
 	}
-	SSQ_HD void push_curr(const Intv &v) { L.set(prev_id ^ 1, n_curr++, v); curr_tail_x2 = v.x2; }
-	SSQ_HD void start_smem1(const DevIndex &ix, int x_, u64 min_intv_)
+	SSQ_HD void push_curr(const I &v) { L.set(prev_id ^ 1, n_curr++, v); curr_tail_x2 = v.x2; }
+	SSQ_HD void start_smem1(const DevIndex &ix, int x_, U min_intv_)
 	{
-		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; base = n;
+		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; any_kept = 0;
 		set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
 		i = x + 1; qi = base_at(i); n_curr = 0; state = FWD;
+		{ const int b0 = base_at(x - 1); cb0 = b0 < 4 ? b0 : -1; }
+		{ const int b1 = base_at(x - 2); cb1 = b1 < 4 ? b1 : -1; }
 	}
-	SSQ_HD void end_forward() // forward list complete: longest first, then walk backwards
+	// forward list complete.  smem1() reverses it (longest match first) before walking backwards; here the first backward sweep
+	// reads it from the end instead, and its first entry's qe — smem1()'s return value — is the qe of the last push.
+	SSQ_HD void end_forward()
 	{
-		const int cid = prev_id ^ 1;
-		for (int a = 0; a < n_curr >> 1; ++a) { const Intv t = L.get(cid, a), u = L.get(cid, n_curr - 1 - a); L.set(cid, a, u); L.set(cid, n_curr - 1 - a, t); }
-		ret = (int)L.get(cid, 0).qe;
-		prev_id = cid; n_prev = n_curr;
+		ret = (int)last_qe;
+		prev_id ^= 1; n_prev = n_curr; rev = 1;
 		i = x - 1; j = 0; n_curr = 0;
-		{ const int b0 = base_at(i); c = b0 < 4 ? b0 : -1; }
-		{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
+		c = cb0; cnext = cb1;
 		state = BWD;
 	}
-	SSQ_HD void keep(const Intv &p_) // p is left-maximal at i+1 unless a longer match survived
+	// p is left-maximal at i+1 unless a longer match survived.  smem1() appends it and drops the intervals shorter than
+	// min_seed_len when the call ends; the decision only needs to know THAT something was kept and its qb, so short ones are
+	// not stored in the first place.  (smem1() also reverses the call's output; the final (qb, qe) sort makes that immaterial.)
+	SSQ_HD void keep(const I &p_)
 	{
-		if (n_curr == 0 && (n == base || (u32)(i + 1) < last_mem_qb)) {
-			if (n >= mem_cap) { err = 1; return; }
-			Intv p = p_; p.qb = (u32)(i + 1);
-			mem[n++] = p; last_mem_qb = p.qb;
+		if (n_curr == 0 && (!any_kept || (u32)(i + 1) < last_mem_qb)) {
+			any_kept = 1; last_mem_qb = (u32)(i + 1);
+			if ((int)p_.qe - (i + 1) >= min_seed_len) {
+				if (n >= mem_cap) { err = 1; return; }
+				Intv p = widen(p_); p.qb = (u32)(i + 1);
+				mem[n++] = p;
+			}
 		}
 	}
-	SSQ_HD void end_smem1() // reverse this call's output, drop short ones, pick what comes next
-	{
-		for (int a = 0; a < (n - base) >> 1; ++a) { Intv t = mem[base + a]; mem[base + a] = mem[n - 1 - a]; mem[n - 1 - a] = t; }
-		int k = base;
-		for (int a = base; a < n; ++a) if ((int)(mem[a].qe - mem[a].qb) >= min_seed_len) mem[k++] = mem[a];
-		n = k;
-		if (pass == 1) { x = ret; state = NEXT_P1; } else state = NEXT_P2;
-	}
-	// true: `in` / `qc` / `is_back` describe the next rank query (only ok[qc] is needed); false: the read is complete
+	SSQ_HD void end_smem1() { if (pass == 1) { x = ret; state = NEXT_P1; } else state = NEXT_P2; }
+	// Runs the bookkeeping up to the next rank query.  true: `in` / `qc` / `is_back` describe it (only ok[qc] is needed);
+	// false: the read is complete.  Every transition is a handful of instructions; the only loops are over N bases and over
+	// pass-1 intervals that do not qualify for re-seeding.
 	SSQ_HD bool advance(const DevIndex &ix)
 	{
 		for (;;) {
@@ -399,7 +423,7 @@ struct SmemMachineT {
 					const Intv p = mem[k2++];
 					const int start = (int)p.qb, end = (int)p.qe;
 					if (end - start < split_len || p.x2 > (u64)split_width) continue;
-					start_smem1(ix, (start + end) >> 1, p.x2 + 1);
+					start_smem1(ix, (start + end) >> 1, (U)(p.x2 + 1));
 					started = true;
 					break;
 				}
@@ -413,21 +437,21 @@ struct SmemMachineT {
 				i = x + 1; qi = base_at(i); state = S3;
 				break;
 			case FWD:
-				if (i >= len || qi > 3) { push_curr(ik); end_forward(); break; }
+				if (i >= len || qi > 3) { push_curr(ik); last_qe = ik.qe; end_forward(); break; }
 				in = ik; is_back = 0; qc = 3 - qi;
 				qnext = base_at(i + 1);
 				return true;
 			case BWD:
 				if (j >= n_prev) { // one backward step done for the whole set
 					if (n_curr == 0) { end_smem1(); break; }
-					prev_id ^= 1; n_prev = n_curr;
+					prev_id ^= 1; n_prev = n_curr; rev = 0;
 					--i; j = 0; n_curr = 0;
 					if (i < -1) { end_smem1(); break; }
 					c = cnext;
 					{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
 					break;
 				}
-				in = L.get(prev_id, j);
+				in = L.get(prev_id, rev ? n_prev - 1 - j : j);
 				if (c < 0) { keep(in); ++j; break; }
 				is_back = 1; qc = c;
 				return true;
@@ -440,55 +464,36 @@ struct SmemMachineT {
 			}
 		}
 	}
-	// the common, transition-free way to the next query: returns true and sets in/qc/is_back, or returns false WITHOUT
-	// touching anything when the generic advance() (list reversal, filtering, pass changes, end of read) is needed
-	SSQ_HD bool try_fast_advance()
-	{
-		if (err) return false;
-		if (state == FWD || state == S3) {
-			if (i >= len || qi > 3) return false;
-			in = ik; is_back = 0; qc = 3 - qi;
-			qnext = base_at(i + 1);
-			return true;
-		}
-		if (state == BWD) {
-			if (j >= n_prev || c < 0) return false;
-			in = L.get(prev_id, j);
-			is_back = 1; qc = c;
-			return true;
-		}
-		return false;
-	}
-	SSQ_HD void post(const Intv &okc) // okc = ok[qc] of the query
+	SSQ_HD void post(const I &okc) // okc = ok[qc] of the query
 	{
 		if (state == FWD) {
 			if (okc.x2 != ik.x2) {
-				push_curr(ik);
+				push_curr(ik); last_qe = ik.qe;
 				if (okc.x2 < min_intv) { end_forward(); return; }
 			}
 			ik = okc; ik.qe = (u32)(i + 1);
 			++i; qi = qnext;
 		} else if (state == BWD) {
 			if (okc.x2 < min_intv) keep(in);
-			else if (n_curr == 0 || okc.x2 != curr_tail_x2) { Intv t = okc; t.qb = 0; t.qe = in.qe; push_curr(t); }
+			else if (n_curr == 0 || okc.x2 != curr_tail_x2) { I t = okc; t.qb = 0; t.qe = in.qe; push_curr(t); }
 			++j;
 		} else { // S3
 			if (okc.x2 < max_mem_intv && i - x >= min_seed_len) {
-				Intv m = okc; m.qb = (u32)x; m.qe = (u32)(i + 1);
+				Intv m = widen(okc); m.qb = (u32)x; m.qe = (u32)(i + 1);
 				if (m.x2 > 0) { if (n >= mem_cap) { err = 1; return; } mem[n++] = m; }
 				x = i + 1; state = NEXT_P3;
 			} else { ik = okc; ++i; qi = qnext; }
 		}
 	}
 	// order by (qb,qe): only 4-byte keys (qb | qe | slot) move, the 32-byte records are gathered once when the caller
-	// copies them out through key & 0x3ff.  keys[] needs n entries.  returns the interval count.
+	// copies them out through key & 0xffff.  keys[] needs n entries.  returns the interval count.
 	SSQ_HD int finish(u32 *keys)
 	{
 		if (err) return 0;
 		for (int a = 0; a < n; ++a) {
-			const u32 key = mem[a].qb << 18 | mem[a].qe << 10 | (u32)a; // qb,qe <= 255, a < 1024
+			const u32 key = mem[a].qb << 24 | mem[a].qe << 16 | (u32)a; // qb,qe <= 255, a < 65536
 			int k;
-			for (k = a; k > 0 && (keys[k - 1] >> 10) > (key >> 10); --k) keys[k] = keys[k - 1];
+			for (k = a; k > 0 && (keys[k - 1] >> 16) > (key >> 16); --k) keys[k] = keys[k - 1];
 			keys[k] = key;
 		}
 		return n;

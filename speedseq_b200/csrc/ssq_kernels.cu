@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(128) k_smem_t(DevIndex ix, ssq_opts_t opt, int
 // all lanes of a warp take together is the rank query, whatever phase (forward / backward / pass 3) each is in.
 // The ping-pong lists live in shared memory as 16-byte entries (k, l, s as u32 + query end) when the index has fewer than
 // 2^32 rows, entries beyond `cap` (and every entry of larger indexes) go to the lane's global scratch lists.
-struct DevLists {
+template <class U> struct DevLists;
+template <> struct DevLists<u64> {
 	uint4 *sm; int cap, stride; Intv *g0, *g1;
 	__device__ __forceinline__ Intv get(int id, int j) const
 	{
@@ -163,63 +164,79 @@ struct DevLists {
 		else (id ? g1 : g0)[j] = v;
 	}
 };
+template <> struct DevLists<u32> { // entries are exactly the 16-byte shared-memory words; overflow entries keep the same form in global scratch
+	uint4 *sm; int cap, stride; uint4 *g0, *g1;
+	__device__ __forceinline__ Intv32 get(int id, int j) const
+	{
+		const uint4 v = j < cap ? sm[(id * cap + j) * stride] : (id ? g1 : g0)[j];
+		Intv32 r; r.x0 = v.x; r.x1 = v.y; r.x2 = v.z; r.qb = 0; r.qe = v.w; return r;
+	}
+	__device__ __forceinline__ void set(int id, int j, const Intv32 &v) const
+	{
+		const uint4 w = make_uint4(v.x0, v.x1, v.x2, v.qe);
+		if (j < cap) sm[(id * cap + j) * stride] = w; else (id ? g1 : g0)[j] = w;
+	}
+};
 
-__global__ void __launch_bounds__(128, 5) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+template <class U, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
                                                 int lcap, int list_cap, int slow_batch, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
-                                                u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt)
+                                                u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt,
+                                                const u32 *__restrict__ read_list, u32 *ovf_list, unsigned int *n_ovf)
 {
+	// read_list: the reads to process (0 = all of 0..n_reads).  ovf_list: where to note a read whose intervals do not fit the
+	// lane's scratch (it is redone by a second launch with a much larger scratch); 0 = that is an error.
 	extern __shared__ uint4 list_smem[];
 	const size_t per = (size_t)scratch_cap + 2 * (size_t)(lcap + 1) + (size_t)(scratch_cap + 7) / 8; // + 4-byte sort keys
 	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per, *bufA = mem + scratch_cap, *bufB = bufA + (lcap + 1);
 	u32 *keys = (u32*)(bufB + (lcap + 1));
-	DevLists lists;
-	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = bufA; lists.g1 = bufB;
+	DevLists<U> lists;
+	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = (decltype(lists.g0))bufA; lists.g1 = (decltype(lists.g1))bufB;
 	ScalarFm fm(ix);
-	SmemMachineT<DevLists> m;
-	bool have = false, ready = false, alive = true;
+	SmemMachineT<DevLists<U>, U> m;
+	bool have = false, ready = false, alive = true, fin = false;
 	int r = -1;
 	const int batch = slow_batch > 0 ? slow_batch : 1;
 	for (;;) {
-		// cheap, transition-free advance for lanes in the middle of a forward / backward / greedy run
-		if (alive && have && !ready) ready = m.try_fast_advance();
-		const bool need_slow = alive && !ready;
+		// bookkeeping up to the next rank query: every transition of the machine is short, lanes in different phases diverge only briefly
+		if (have && !fin && !ready) { ready = m.advance(ix); fin = !ready; }
+		const bool need_slow = alive && !ready; // read finished (to be published) or no read yet
 		const unsigned slow_mask = __ballot_sync(FULL, need_slow), alive_mask = __ballot_sync(FULL, alive);
 		if (alive_mask == 0) break;
-		// slow transitions (list reversal, interval filtering, pass changes, publishing a read, fetching the next one) are
-		// batched: a lane that needs one idles until `batch` lanes need one (or nobody can issue a query), then they run together
+		// publishing a read and fetching the next one are long, lane-serial jobs: a lane that needs them idles until `batch` lanes
+		// do (or a quarter of the live lanes, or nobody can issue a query), then they run together
 		const int n_slow = __popc(slow_mask), n_alive = __popc(alive_mask);
 		if (need_slow && (n_slow >= batch || n_slow == n_alive || 4 * n_slow >= n_alive)) {
-			while (alive && !ready) {
-				if (!have) {
-					r = atomicAdd(work, 1);
-					if (r >= n_reads) { alive = false; break; }
-					const u64 off = read_off[r];
-					const int len = (int)(read_off[r + 1] - off);
-					if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
-					m.init(opt, len, seq + off, mem, scratch_cap, lists);
-					have = true;
+			if (fin) { // order the read's intervals, publish them
+				int n = m.finish(keys);
+				bool redo = false;
+				if (m.err) { n = 0; if (ovf_list) { ovf_list[atomicAdd(n_ovf, 1u)] = (u32)r; redo = true; } else atomicMax(err, 1); }
+				int b = 0, en = 0, l_rep = 0;
+				for (int i = 0; i < n; ++i) {
+					const Intv p = mem[keys[i] & 0xffff];
+					if (p.x2 <= (u64)opt.max_occ) continue;
+					if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
 				}
-				ready = m.advance(ix);
-				if (!ready) { // read finished: order its intervals, publish them
-					int n = m.finish(keys);
-					if (m.err) { atomicMax(err, 1); n = 0; }
-					int b = 0, en = 0, l_rep = 0;
-					for (int i = 0; i < n; ++i) {
-						const Intv p = mem[keys[i] & 0x3ff];
-						if (p.x2 <= (u64)opt.max_occ) continue;
-						if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
-					}
-					l_rep += en - b;
-					unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
-					if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
-					for (int i = 0; i < n; ++i) pool[base + i] = mem[keys[i] & 0x3ff];
-					intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep;
-					have = false;
-				}
+				l_rep += en - b;
+				unsigned long long base = atomicAdd(pool_n, (unsigned long long)n);
+				if (base + n > pool_cap) { atomicMax(err, 2); n = 0; }
+				for (int i = 0; i < n; ++i) pool[base + i] = mem[keys[i] & 0xffff];
+				if (!redo) { intv_off[r] = base; intv_cnt[r] = n; l_rep_out[r] = l_rep; }
+				have = false; fin = false;
+			}
+			while (!have) {
+				r = atomicAdd(work, 1);
+				if (r >= n_reads) { alive = false; break; }
+				if (read_list) r = (int)read_list[r];
+				const u64 off = read_off[r];
+				const int len = (int)(read_off[r + 1] - off);
+				if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
+				m.init(opt, len, seq + off, mem, scratch_cap, lists);
+				have = true;
 			}
 		}
 		if (ready) { // the step all lanes that have a query take together
-			Intv okc;
+			IntvT<U> okc;
 			extend1(fm, m.in, m.qc, m.is_back, okc);
 			m.post(okc);
 			ready = false;
@@ -986,7 +1003,7 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2;
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
@@ -998,7 +1015,7 @@ struct ssq_batch {
 };
 
 // misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
-struct Misc { unsigned long long pool_n; int work, err; Counters cnt; };
+struct Misc { unsigned long long pool_n; int work, err; unsigned int n_ovf, pad; Counters cnt; };
 
 static int scan_u64(ssq_batch *b, const u64 *in, u64 *out, size_t n) // exclusive sum, out has n+1 entries (out[n] = total)
 {
@@ -1051,7 +1068,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
@@ -1085,8 +1102,16 @@ static int run_smem(ssq_batch *b)
 	const int warps_per_block = 4, threads = warps_per_block * 32;
 	const size_t smem = variant == 0 ? (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv) : 0;
 	const char *lc_env = getenv("SSQ_LIST_CAP");
-	const int list_cap = variant == 2 && b->idx->dev.seq_len < 0xffffffffull ? (lc_env ? atoi(lc_env) : 10) : 0; // shared-memory list entries per lane
-	if (variant == 2) CK(cudaFuncSetAttribute(k_smem_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)threads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
+	// shared-memory list entries per lane.  Measured (profiles/r01_smem_sweep.txt): the 32-bit machine is fastest with 6 blocks/SM and
+	// short lists — what the lists do not take stays L1 for the query bytes, the output list and the overflow entries
+	const bool m32_ = variant == 2 && b->idx->dev.bwt32 != 0 && !getenv("SSQ_SMEM_M64");
+	const int list_cap = variant == 2 && b->idx->dev.seq_len < 0xffffffffull ? (lc_env ? atoi(lc_env) : m32_ ? 6 : 10) : 0;
+	// 32-bit machine (indexes with bwt32): fewer registers, so more blocks per SM when the shared-memory lists leave room for them
+	const bool m32 = m32_;
+	const int minb = m32 ? (getenv("SSQ_SMEM_BLOCKS") ? atoi(getenv("SSQ_SMEM_BLOCKS")) : 6) : 5;
+	typedef void (*smem_kernel_t)(DevIndex, ssq_opts_t, int, const uint8_t*, const u64*, int, int, int, Intv*, int, Intv*, u64, unsigned long long*, u64*, i32*, i32*, int*, int*, Counters*, const u32*, u32*, unsigned int*);
+	const smem_kernel_t km = !m32 ? k_smem_m<u64, 5> : minb >= 8 ? k_smem_m<u32, 8> : minb == 7 ? k_smem_m<u32, 7> : minb == 6 ? k_smem_m<u32, 6> : k_smem_m<u32, 5>;
+	if (variant == 2) CK(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)threads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
 	int blocks_per_sm = variant == 0 ? (int)((200 * 1024) / (smem + 1024)) : 8;
 	if (blocks_per_sm > 8) blocks_per_sm = 8;
 	if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -1095,7 +1120,7 @@ static int run_smem(ssq_batch *b)
 	const size_t scratch_entries = variant == 0 ? (size_t)grid * warps_per_block * scratch_cap : (size_t)grid * threads * ((size_t)scratch_cap + 2 * (size_t)(lcap + 1) + (size_t)(scratch_cap + 7) / 8);
 	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
 	if (b->scratch.need(scratch_entries * sizeof(Intv))) return SSQ_ENOMEM;
-	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc))) return SSQ_ENOMEM;
+	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc)) || b->xovf.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
 	if (variant == 0) CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	for (int attempt = 0; attempt < 6; ++attempt) {
 		if (b->pool.need(b->pool_cap * sizeof(Intv))) return SSQ_ENOMEM;
@@ -1105,8 +1130,9 @@ static int run_smem(ssq_batch *b)
 			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else if (variant == 2)
-			k_smem_m<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, getenv("SSQ_SLOW_BATCH") ? atoi(getenv("SSQ_SLOW_BATCH")) : 8, b->scratch.as<Intv>(), scratch_cap,
-			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
+			km<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, getenv("SSQ_SLOW_BATCH") ? atoi(getenv("SSQ_SLOW_BATCH")) : 8, b->scratch.as<Intv>(), scratch_cap,
+			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt,
+			                                     (const u32*)0, b->xovf.as<u32>(), &dm->n_ovf);
 		else
 			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
@@ -1115,6 +1141,19 @@ static int run_smem(ssq_batch *b)
 		Misc hm;
 		CK(cudaMemcpyAsync(&hm, b->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, b->st));
 		CK(cudaStreamSynchronize(b->st));
+		if (variant == 2 && hm.err == 0 && hm.n_ovf) { // low-complexity reads with more intervals than a lane's scratch holds: again, few lanes, big scratch
+			const int cap2 = 16384, grid2 = 8;
+			const size_t per2 = (size_t)cap2 + 2 * (size_t)(lcap + 1) + (size_t)(cap2 + 7) / 8;
+			if (b->scratch2.need((size_t)grid2 * threads * per2 * sizeof(Intv))) return SSQ_ENOMEM;
+			CK(cudaMemsetAsync(&dm->work, 0, 4, b->st));
+			km<<<grid2, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, (int)hm.n_ovf, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, 1, b->scratch2.as<Intv>(), cap2,
+			        b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt,
+			        b->xovf.as<u32>(), (u32*)0, (unsigned int*)0);
+			++b->launches;
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(&hm, b->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, b->st));
+			CK(cudaStreamSynchronize(b->st));
+		}
 		if (hm.err == 0) { b->n_intv = hm.pool_n; return SSQ_OK; }
 		if (hm.err == 2) { b->pool_cap = hm.pool_n + hm.pool_n / 8 + 4096; continue; } // pool too small: its true size is now known
 		ssq_set_error(hm.err == 3 ? "read longer than the kernel's length cap" : "a read produced more than %d seed intervals", scratch_cap);

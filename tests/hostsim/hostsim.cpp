@@ -52,14 +52,23 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	w.mem.assign(2048, Intv());
 	int err = 0;
 	if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
-	else { // the state-machine form the GPU kernel runs
+	else if (ix.bwt32 && !getenv("HOSTSIM_M64")) { // the state-machine form the GPU kernel runs, 32-bit rows (what the GPU picks when bwt32 exists)
+		std::vector<Intv32> a32(len + 2), b32(len + 2);
+		SmemMachineT<HostListsT<u32>, u32> m; Intv32 okc;
+		HostListsT<u32> hl; hl.a[0] = a32.data(); hl.a[1] = b32.data();
+		m.init(opt, len, q, w.mem.data(), 2048, hl);
+		for (bool go = m.advance(ix); go; go = m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
+		std::vector<u32> keys(2048);
+		err = m.err; w.n_intv = m.finish(keys.data());
+		{ std::vector<Intv> tmp(w.n_intv); for (int i = 0; i < w.n_intv; ++i) tmp[i] = w.mem[keys[i] & 0xffff]; for (int i = 0; i < w.n_intv; ++i) w.mem[i] = tmp[i]; }
+	} else { // 64-bit rows
 		SmemMachineT<HostLists> m; Intv okc;
 		HostLists hl; hl.a[0] = bufA.data(); hl.a[1] = bufB.data();
 		m.init(opt, len, q, w.mem.data(), 2048, hl);
-		for (bool go = m.advance(ix); go; go = m.try_fast_advance() || m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
+		for (bool go = m.advance(ix); go; go = m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
 		std::vector<u32> keys(2048);
 		err = m.err; w.n_intv = m.finish(keys.data());
-		{ std::vector<Intv> tmp(w.n_intv); for (int i = 0; i < w.n_intv; ++i) tmp[i] = w.mem[keys[i] & 0x3ff]; for (int i = 0; i < w.n_intv; ++i) w.mem[i] = tmp[i]; }
+		{ std::vector<Intv> tmp(w.n_intv); for (int i = 0; i < w.n_intv; ++i) tmp[i] = w.mem[keys[i] & 0xffff]; for (int i = 0; i < w.n_intv; ++i) w.mem[i] = tmp[i]; }
 	}
 	if (err) abort();
 	int b = 0, en = 0; w.l_rep = 0;

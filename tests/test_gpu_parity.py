@@ -70,6 +70,23 @@ def test_smem_edge_cases(ssq, oracle, syn_index, gpu_syn):
     assert len(b) == 0
 
 
+def test_interval_rich_reads(ssq, oracle, syn_index, gpu_syn):
+    """low-complexity reads produce more seed intervals than a seeding lane's scratch holds (768): they must be redone by the
+    overflow pass, not fail the batch"""
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = T.simulate_pairs(g, bounds, 100, 150, 31, err=0.01)
+    seqs = seqs[:60] + ["AC" * 70, "A" * 150, "ACGT" * 37, "AAC" * 50, "AC" * 75] + seqs[60:]
+    seq, off = T.encode_reads(seqs)
+    a, ao = oracle.smem_batch(idx, seq, off)
+    assert int(np.diff(ao).max()) > 768
+    b, bo = ssq.smem_batch(gpu_syn, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    a, ao = oracle.align_batch(idx, seq, off)
+    b, bo = ssq.align_batch(gpu_syn, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+
+
 def test_read_too_long_is_rejected(ssq, gpu_syn):
     seq, off = T.encode_reads(["A" * 256])
     with pytest.raises(RuntimeError, match="rc=-7"):

@@ -2,6 +2,7 @@
 tests/hostsim and compared with the oracle.  This validates the arithmetic the GPU executes on a box without a GPU; the
 GPU parity proper is tests/test_gpu_parity.py.  The harness is not part of the product."""
 import numpy as np
+import pytest
 
 import ssq_testlib as T
 
@@ -32,6 +33,20 @@ def test_synthetic_reads_with_repeats_indels_and_Ns(oracle, hostsim, syn_index):
     for rl, seed in ((75, 1), (150, 2), (250, 3)):
         names, seqs, quals = T.simulate_pairs(g, bounds, 300, rl, seed, err=0.01, indel=0.002, n_frac=0.003)
         _cmp_all(oracle, hostsim, idx, seqs)
+
+
+@pytest.mark.parametrize("env", ["HOSTSIM_M64", "HOSTSIM_STRAIGHT"])
+def test_seeding_formulations_agree(oracle, hostsim, syn_index, monkeypatch, env):
+    """default = the 32-bit-row state machine (what the GPU runs when the index has < 2^32 rows); also the 64-bit machine and the
+    straight-line smem1()/seed_strategy1() form"""
+    monkeypatch.setenv(env, "1")
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = T.simulate_pairs(g, bounds, 400, 150, 21, err=0.015, indel=0.003, n_frac=0.004)
+    seq, off = T.encode_reads(seqs + ["", "N" * 40, "AC" * 70, "T" * 120])
+    a, ao = oracle.smem_batch(idx, seq, off)
+    b, bo = hostsim.smem_batch(idx, seq, off)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
 
 
 def test_edge_cases(oracle, hostsim, syn_index):
