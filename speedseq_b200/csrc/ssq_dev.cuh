@@ -833,20 +833,24 @@ struct EhAcc {
 	SSQ_HD void set(int j, u32 v) const { base[(size_t)j * stride] = v; }
 };
 
-template <class QF, class TF>
-SSQ_HD int sw_extend(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, int w, int end_bonus, int zdrop, int h0, const EhAcc &eh,
-                     int &qle, int &tle, int &gtle, int &gscore_, int &max_off_, unsigned long long &cells)
+// PQ: the query base of column j rides in bits 29..31 of column j's word (H in bits 0..12, E in bits 16..28), so the inner loop reads
+// nothing but that one word per cell — no per-cell query fetch from global memory.  Valid when no score can reach 2^13.
+template <bool PQ, class QF, class TF>
+SSQ_HD int sw_extend_impl(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, int w, int end_bonus, int zdrop, int h0, const EhAcc &eh,
+                          int &qle, int &tle, int &gtle, int &gscore_, int &max_off_, unsigned long long &cells)
 {
 	const int o_del = o.o_del, e_del = o.e_del, o_ins = o.o_ins, e_ins = o.e_ins;
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	const u32 QMASK = PQ ? 0xe0000000u : 0u, VMASK = ~QMASK;
 	int i, j, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
+	auto qbits = [&](int jj) -> u32 { return PQ && jj < qlen ? (u32)Q(jj) << 29 : 0u; };
 	// row -1
-	eh.set(0, (u32)h0);
+	eh.set(0, (u32)h0 | qbits(0));
 	{
 		int h = h0 > oe_ins ? h0 - oe_ins : 0;
-		if (qlen >= 1) eh.set(1, (u32)h);
-		for (j = 2; j <= qlen && h > e_ins; ++j) { h -= e_ins; eh.set(j, (u32)h); }
-		for (; j <= qlen; ++j) eh.set(j, 0);
+		if (qlen >= 1) eh.set(1, (u32)h | qbits(1));
+		for (j = 2; j <= qlen && h > e_ins; ++j) { h -= e_ins; eh.set(j, (u32)h | qbits(j)); }
+		for (; j <= qlen; ++j) eh.set(j, qbits(j));
 	}
 	max = o.a; // largest matrix entry is the match score
 	max_ins = (int)((double)(qlen * max + end_bonus - o_ins) / e_ins + 1.);
@@ -864,25 +868,35 @@ SSQ_HD int sw_extend(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, int w,
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
 		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
-		for (j = beg; j < end; ++j) {
-			u32 p = eh.get(j);
-			int M = (int)(p & 0xffffu), e = (int)(p >> 16), h;
-			const int qb = Q(j);
+		// one cell: consumes the packed (H(i-1,j-1), E(i,j)) word of column j, leaves (H(i,j-1), E(i+1,j)) there
+		auto cell = [&](const u32 p, const int qb, const int jj) {
+			int M = (int)(p & 0xffffu), e = (int)((p & VMASK) >> 16), h;
 			const int sc = (qb > 3 || tb > 3) ? -1 : (qb == tb ? o.a : -o.b);
 			M = M ? M + sc : 0;
 			h = M > e ? M : e;
 			h = h > f ? h : f;
-			mj = m > h ? mj : j;
+			mj = m > h ? mj : jj;
 			m = m > h ? m : h;
 			t = M - oe_del; t = t > 0 ? t : 0;
 			e -= e_del; e = e > t ? e : t;
-			eh.set(j, (u32)h1 | (u32)e << 16); // H(i,j-1) for the next row, E(i+1,j)
+			eh.set(jj, (u32)h1 | (u32)e << 16 | (p & QMASK));
 			h1 = h;
 			t = M - oe_ins; t = t > 0 ? t : 0;
 			f -= e_ins; f = f > t ? f : t;
+		};
+		// four columns per trip: their row-state words are fetched before the first of them is rewritten (column j's store does
+		// not touch columns j+1..j+3), so the loads overlap the dependent arithmetic of the cells
+		for (j = beg; j + 4 <= end; j += 4) {
+			const u32 p0 = eh.get(j), p1 = eh.get(j + 1), p2 = eh.get(j + 2), p3 = eh.get(j + 3);
+			if (PQ) { cell(p0, (int)(p0 >> 29), j); cell(p1, (int)(p1 >> 29), j + 1); cell(p2, (int)(p2 >> 29), j + 2); cell(p3, (int)(p3 >> 29), j + 3); }
+			else {
+				const int q0 = Q(j), q1 = Q(j + 1), q2 = Q(j + 2), q3 = Q(j + 3);
+				cell(p0, q0, j); cell(p1, q1, j + 1); cell(p2, q2, j + 2); cell(p3, q3, j + 3);
+			}
 		}
+		for (; j < end; ++j) { const u32 p = eh.get(j); cell(p, PQ ? (int)(p >> 29) : Q(j), j); }
 		cells += (unsigned long long)(end > beg ? end - beg : 0);
-		eh.set(end, (u32)h1);
+		eh.set(end, PQ ? ((u32)h1 | (eh.get(end) & QMASK)) : (u32)h1);
 		if (j == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
 		if (m == 0) break;
 		if (m > max) {
@@ -893,13 +907,21 @@ SSQ_HD int sw_extend(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, int w,
 			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break; }
 			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
 		}
-		for (j = beg; j < end && eh.get(j) == 0; ++j);
+		for (j = beg; j < end && (eh.get(j) & VMASK) == 0; ++j);
 		beg = j;
-		for (j = end; j >= beg && eh.get(j) == 0; --j);
+		for (j = end; j >= beg && (eh.get(j) & VMASK) == 0; --j);
 		end = j + 2 < qlen ? j + 2 : qlen;
 	}
 	qle = max_j + 1; tle = max_i + 1; gtle = max_ie + 1; gscore_ = gscore; max_off_ = max_off;
 	return max;
+}
+template <class QF, class TF>
+SSQ_HD int sw_extend(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, int w, int end_bonus, int zdrop, int h0, const EhAcc &eh,
+                     int &qle, int &tle, int &gtle, int &gscore_, int &max_off_, unsigned long long &cells)
+{
+	if ((long long)h0 + (long long)qlen * o.a < 8192) // no H or E can exceed h0 + qlen * a
+		return sw_extend_impl<true>(o, qlen, Q, tlen, T, w, end_bonus, zdrop, h0, eh, qle, tle, gtle, gscore_, max_off_, cells);
+	return sw_extend_impl<false>(o, qlen, Q, tlen, T, w, end_bonus, zdrop, h0, eh, qle, tle, gtle, gscore_, max_off_, cells);
 }
 
 // One alignment-region candidate per seed of a kept chain: left then right extension (h0 of the right one is

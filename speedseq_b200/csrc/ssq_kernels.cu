@@ -254,14 +254,21 @@ __global__ void k_occ_count(const Intv *__restrict__ pool, u64 n, int max_occ, u
 	nocc[g] = (u32)intv_occ_count(pool[g].x2, max_occ, step);
 }
 
-__global__ void __launch_bounds__(256) k_sa(DevIndex ix, ssq_opts_t opt, const Intv *__restrict__ pool, const u64 *__restrict__ seed_off, u64 n_intv,
+// owner[t] = the interval seed t comes from = the last g with seed_off[g] <= t: every interval drops its index at its first seed, a
+// running maximum fills the rest (one coalesced pass instead of a 24-step dependent binary search per seed)
+__global__ void k_sa_owner(u64 n_intv, const u64 *__restrict__ seed_off, u32 *owner)
+{
+	const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < n_intv && seed_off[g + 1] > seed_off[g]) owner[seed_off[g]] = (u32)g;
+}
+
+__global__ void __launch_bounds__(256) k_sa(DevIndex ix, ssq_opts_t opt, const Intv *__restrict__ pool, const u64 *__restrict__ seed_off, const u32 *__restrict__ owner,
                                             u64 n_seeds, Seed *seeds, Counters *cnt)
 {
 	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long n_sa = 0, n_blk = 0;
 	if (t < n_seeds) {
-		u64 lo = 0, hi = n_intv; // last g with seed_off[g] <= t
-		while (hi - lo > 1) { u64 mid = (lo + hi) >> 1; if (seed_off[mid] <= t) lo = mid; else hi = mid; }
+		const u64 lo = owner[t];
 		const Intv p = pool[lo];
 		u64 step;
 		intv_occ_count(p.x2, opt.max_occ, step);
@@ -1003,7 +1010,7 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2, xowner;
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
@@ -1068,7 +1075,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2, &b->xowner};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
@@ -1180,9 +1187,17 @@ static int run_sa(ssq_batch *b)
 	CK(cudaStreamSynchronize(b->st));
 	if (b->seeds.need((b->n_seeds + 1) * sizeof(Seed))) return SSQ_ENOMEM;
 	if (b->n_seeds) {
-		k_sa<<<(unsigned)((b->n_seeds + 255) / 256), 256, 0, b->st>>>(b->idx->dev, b->opt, b->pool.as<Intv>(), b->seed_off.as<u64>(), ni, b->n_seeds, b->seeds.as<Seed>(),
+		if (ni >= 0xffffffffull) { ssq_set_error("more than 2^32 seed intervals in one batch"); return SSQ_ECAP; }
+		if (b->xowner.need((b->n_seeds + 1) * 4)) return SSQ_ENOMEM;
+		CK(cudaMemsetAsync(b->xowner.p, 0, b->n_seeds * 4, b->st));
+		k_sa_owner<<<(unsigned)((ni + 255) / 256), 256, 0, b->st>>>(ni, b->seed_off.as<u64>(), b->xowner.as<u32>());
+		size_t tb = 0;
+		cub::DeviceScan::InclusiveScan(0, tb, b->xowner.as<u32>(), b->xowner.as<u32>(), cub::Max(), (int)b->n_seeds, b->st);
+		if (b->cubtmp.need(tb)) return SSQ_ENOMEM;
+		CK(cub::DeviceScan::InclusiveScan(b->cubtmp.p, tb, b->xowner.as<u32>(), b->xowner.as<u32>(), cub::Max(), (int)b->n_seeds, b->st));
+		k_sa<<<(unsigned)((b->n_seeds + 255) / 256), 256, 0, b->st>>>(b->idx->dev, b->opt, b->pool.as<Intv>(), b->seed_off.as<u64>(), b->xowner.as<u32>(), b->n_seeds, b->seeds.as<Seed>(),
 		                                                               &b->misc.as<Misc>()->cnt);
-		++b->launches;
+		b->launches += 3;
 		CK(cudaGetLastError());
 	}
 	return SSQ_OK;
