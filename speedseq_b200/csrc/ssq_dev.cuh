@@ -44,6 +44,9 @@ struct DevIndex {
 	u64 primary, L2[5], seq_len, n_sa;
 	i64 l_pac;
 	i32 n_seqs, sa_intv;
+	// denser suffix-array sample derived at load time (every sad_intv-th row; u32 when positions fit, 0xffffffff = -1): same
+	// values the LF walk would reach, several times fewer dependent steps per look-up.  0 / null: walk to the on-disk sample.
+	const u32 *sad32; const u64 *sad64; i32 sad_intv;
 };
 
 struct Counters { // device-measured work, feeds roofline.achieved (algorithmic bytes)
@@ -509,10 +512,12 @@ SSQ_HD int intv_occ_count(u64 s, int max_occ, u64 &step)
 }
 
 // ------------------------------------------------------------------------- SA look-up ----
-SSQ_HD u64 sa_lookup(ScalarFm &fm, u64 k, unsigned long long &n_sa)
+SSQ_HD u64 sa_lookup(ScalarFm &fm, u64 k, unsigned long long &n_sa, bool use_dense = true)
 {
 	const DevIndex &ix = fm.ix;
-	u64 sa = 0, mask = (u64)ix.sa_intv - 1;
+	const bool dense = use_dense && ix.sad_intv > 0;
+	const u64 intv = dense ? (u64)ix.sad_intv : (u64)ix.sa_intv;
+	u64 sa = 0, mask = intv - 1;
 	while (k & mask) { // walk LF until a sampled row
 		++sa;
 		if (k == ix.primary) { k = 0; continue; }
@@ -534,7 +539,11 @@ SSQ_HD u64 sa_lookup(ScalarFm &fm, u64 k, unsigned long long &n_sa)
 		k = ix.L2[c] + cnt[c];
 	}
 	++n_sa;
-	return sa + ix.sa[k / ix.sa_intv];
+	if (dense) {
+		if (ix.sad32) { const u32 v = ix.sad32[k / intv]; return sa + (v == 0xffffffffu ? (u64)-1 : (u64)v); }
+		return sa + ix.sad64[k / intv];
+	}
+	return sa + ix.sa[k / intv];
 }
 
 // ------------------------------------------------------------------- reference helpers ----
