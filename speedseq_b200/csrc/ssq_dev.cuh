@@ -355,6 +355,7 @@ struct SmemMachineT {
 	                   // query of step i and consumed after it, so the bookkeeping never waits on a query byte
 	int cnext;         // backward phase: prefetched base at i-1
 	int cb0, cb1;      // bases at x-1 and x-2 of the current smem1 call, fetched when it starts
+	int skip_p3;       // the greedy pass is done elsewhere (the GPU runs it as a kernel of its own, k_smem_p3)
 	int rev;           // first backward sweep: the forward list is read from its end (longest match first) instead of being reversed
 	int any_kept;      // this smem1 call has kept an interval (whether or not it was long enough to be stored)
 	u32 last_qe;       // qe of the entry last pushed by the forward phase
@@ -365,9 +366,9 @@ struct SmemMachineT {
 	int is_back;
 
 	SSQ_HD int base_at(int p) const { return p >= 0 && p < len ? (int)q[p] : 4; }
-	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists)
+	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists, int skip_p3_ = 0)
 	{
-		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0;
+		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0; skip_p3 = skip_p3_;
 		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1; rev = 0;
 		min_seed_len = opt.min_seed_len; split_len = (int)(opt.min_seed_len * opt.split_factor + .499f); split_width = opt.split_width;
 		max_mem_intv = (U)opt.max_mem_intv;
@@ -430,7 +431,7 @@ struct SmemMachineT {
 					started = true;
 					break;
 				}
-				if (!started) { pass = 3; x = 0; state = NEXT_P3; if (max_mem_intv == 0) x = len; }
+				if (!started) { pass = 3; x = 0; state = NEXT_P3; if (max_mem_intv == 0 || skip_p3) x = len; }
 				break;
 			}
 			case NEXT_P3:

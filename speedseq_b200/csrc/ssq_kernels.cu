@@ -178,11 +178,65 @@ template <> struct DevLists<u32> { // entries are exactly the 16-byte shared-mem
 	}
 };
 
+// Pass 3 of the seeding (the greedy sweep of seed_strategy1(): walk forward from x until the interval is small enough and long
+// enough, emit it, restart right after it) needs nothing from passes 1 and 2 and has next to no state, so it runs as a kernel of
+// its own in which every lane is in the same phase: ~30 lanes per instruction and 3-4x the occupancy of the full machine.  Its
+// intervals go to a fixed slot range per read; k_smem_m merges them into the read's list before the final sort.
+template <class U>
+__global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                                 int stride, Intv *p3, i32 *p3_cnt, int *work, Counters *cnt)
+{
+	ScalarFm fm(ix);
+	const U max_intv = (U)opt.max_mem_intv;
+	const int min_len = opt.min_seed_len;
+	const uint8_t *q = 0;
+	IntvT<U> ik;
+	int r = -1, len = 0, x = 0, i = 0, qi = 0, qnext = 0, n_out = 0;
+	bool have = false, ready = false, alive = true;
+	ik.x0 = ik.x1 = ik.x2 = 0; ik.qb = ik.qe = 0;
+	for (;;) {
+		while (alive && !ready) { // (re)start a walk, or finish the read and take the next one
+			if (!have) {
+				r = atomicAdd(work, 1);
+				if (r >= n_reads) { alive = false; break; }
+				const u64 off = read_off[r];
+				len = (int)(read_off[r + 1] - off); q = seq + off;
+				x = (len < min_len || max_intv == 0) ? len : 0; n_out = 0; have = true;
+			}
+			while (x < len && q[x] > 3) ++x;
+			if (x >= len) { p3_cnt[r] = n_out; have = false; continue; }
+			set_intv(ix, q[x], ik);
+			i = x + 1;
+			if (i >= len) { x = len; continue; }
+			qi = q[i];
+			if (qi > 3) { x = i + 1; continue; }
+			qnext = i + 1 < len ? (int)q[i + 1] : 4;
+			ready = true;
+		}
+		if (__ballot_sync(FULL, alive) == 0) break;
+		if (ready) {
+			IntvT<U> okc;
+			extend1(fm, ik, 3 - qi, 0, okc);
+			if (okc.x2 < max_intv && i - x >= min_len) {
+				if (okc.x2 > 0 && n_out < stride) { Intv m = widen(okc); m.qb = (u32)x; m.qe = (u32)(i + 1); p3[(size_t)r * stride + n_out] = m; }
+				if (okc.x2 > 0) ++n_out;
+				x = i + 1; ready = false;
+			} else {
+				ik = okc; ++i;
+				if (i >= len) { x = len; ready = false; }
+				else { qi = qnext; if (qi > 3) { x = i + 1; ready = false; } else qnext = i + 1 < len ? (int)q[i + 1] : 4; }
+			}
+		}
+	}
+	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
 template <class U, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
                                                 int lcap, int list_cap, int slow_batch, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
                                                 u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt,
-                                                const u32 *__restrict__ read_list, u32 *ovf_list, unsigned int *n_ovf)
+                                                const u32 *__restrict__ read_list, u32 *ovf_list, unsigned int *n_ovf,
+                                                const Intv *__restrict__ p3, const i32 *__restrict__ p3_cnt, int p3_stride)
 {
 	// read_list: the reads to process (0 = all of 0..n_reads).  ovf_list: where to note a read whose intervals do not fit the
 	// lane's scratch (it is redone by a second launch with a much larger scratch); 0 = that is an error.
@@ -208,6 +262,11 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 		const int n_slow = __popc(slow_mask), n_alive = __popc(alive_mask);
 		if (need_slow && (n_slow >= batch || n_slow == n_alive || 4 * n_slow >= n_alive)) {
 			if (fin) { // order the read's intervals, publish them
+				if (p3 && !m.err) { // the greedy pass's intervals (k_smem_p3) join the list before the sort
+					const int c3 = p3_cnt[r];
+					if (c3 > p3_stride || m.n + c3 > m.mem_cap) m.err = 1;
+					else for (int e = 0; e < c3; ++e) mem[m.n++] = p3[(size_t)r * p3_stride + e];
+				}
 				int n = m.finish(keys);
 				bool redo = false;
 				if (m.err) { n = 0; if (ovf_list) { ovf_list[atomicAdd(n_ovf, 1u)] = (u32)r; redo = true; } else atomicMax(err, 1); }
@@ -231,7 +290,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 				const u64 off = read_off[r];
 				const int len = (int)(read_off[r + 1] - off);
 				if (len > lcap) { atomicMax(err, 3); intv_off[r] = 0; intv_cnt[r] = 0; l_rep_out[r] = 0; continue; }
-				m.init(opt, len, seq + off, mem, scratch_cap, lists);
+				m.init(opt, len, seq + off, mem, scratch_cap, lists, p3 != 0);
 				have = true;
 			}
 		}
@@ -1010,7 +1069,7 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2, xowner;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2, xowner, xp3, xp3n;
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
@@ -1075,7 +1134,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2, &b->xowner};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2, &b->xowner, &b->xp3, &b->xp3n};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
@@ -1116,7 +1175,7 @@ static int run_smem(ssq_batch *b)
 	// 32-bit machine (indexes with bwt32): fewer registers, so more blocks per SM when the shared-memory lists leave room for them
 	const bool m32 = m32_;
 	const int minb = m32 ? (getenv("SSQ_SMEM_BLOCKS") ? atoi(getenv("SSQ_SMEM_BLOCKS")) : 6) : 5;
-	typedef void (*smem_kernel_t)(DevIndex, ssq_opts_t, int, const uint8_t*, const u64*, int, int, int, Intv*, int, Intv*, u64, unsigned long long*, u64*, i32*, i32*, int*, int*, Counters*, const u32*, u32*, unsigned int*);
+	typedef void (*smem_kernel_t)(DevIndex, ssq_opts_t, int, const uint8_t*, const u64*, int, int, int, Intv*, int, Intv*, u64, unsigned long long*, u64*, i32*, i32*, int*, int*, Counters*, const u32*, u32*, unsigned int*, const Intv*, const i32*, int);
 	const smem_kernel_t km = !m32 ? k_smem_m<u64, 5> : minb >= 8 ? k_smem_m<u32, 8> : minb == 7 ? k_smem_m<u32, 7> : minb == 6 ? k_smem_m<u32, 6> : k_smem_m<u32, 5>;
 	if (variant == 2) CK(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)threads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
 	int blocks_per_sm = variant == 0 ? (int)((200 * 1024) / (smem + 1024)) : 8;
@@ -1133,13 +1192,23 @@ static int run_smem(ssq_batch *b)
 		if (b->pool.need(b->pool_cap * sizeof(Intv))) return SSQ_ENOMEM;
 		CK(cudaMemsetAsync(b->misc.p, 0, sizeof(Misc), b->st));
 		Misc *dm = b->misc.as<Misc>();
+		const Intv *p3buf = 0; const i32 *p3cnt = 0;
+		const int p3_stride = lcap / (b->opt.min_seed_len + 1) + 2;
+		if (variant == 2 && b->opt.max_mem_intv > 0 && !getenv("SSQ_NO_P3_KERNEL")) {
+			if (b->xp3.need((size_t)n * p3_stride * sizeof(Intv)) || b->xp3n.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+			if (m32) k_smem_p3<u32><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+			else k_smem_p3<u64><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+			CK(cudaMemsetAsync(&dm->work, 0, 4, b->st));
+			++b->launches;
+			p3buf = b->xp3.as<Intv>(); p3cnt = b->xp3n.as<i32>();
+		}
 		if (variant == 0)
 			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		else if (variant == 2)
 			km<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, getenv("SSQ_SLOW_BATCH") ? atoi(getenv("SSQ_SLOW_BATCH")) : 8, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt,
-			                                     (const u32*)0, b->xovf.as<u32>(), &dm->n_ovf);
+			                                     (const u32*)0, b->xovf.as<u32>(), &dm->n_ovf, p3buf, p3cnt, p3_stride);
 		else
 			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
@@ -1155,7 +1224,7 @@ static int run_smem(ssq_batch *b)
 			CK(cudaMemsetAsync(&dm->work, 0, 4, b->st));
 			km<<<grid2, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, (int)hm.n_ovf, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, 1, b->scratch2.as<Intv>(), cap2,
 			        b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt,
-			        b->xovf.as<u32>(), (u32*)0, (unsigned int*)0);
+			        b->xovf.as<u32>(), (u32*)0, (unsigned int*)0, p3buf, p3cnt, p3_stride);
 			++b->launches;
 			CK(cudaGetLastError());
 			CK(cudaMemcpyAsync(&hm, b->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, b->st));
