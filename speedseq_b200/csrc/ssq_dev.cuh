@@ -345,7 +345,8 @@ typedef HostListsT<u64> HostLists;
 
 // U: row type of the machine's intervals — u64 for any index, u32 when the index has fewer than 2^32 rows.  The output list
 // `mem` always holds 64-bit intervals.
-template <class Lists, class U = u64>
+// P3 = false compiles the greedy pass out (its callers run it elsewhere and always pass skip_p3).
+template <class Lists, class U = u64, bool P3 = true>
 struct SmemMachineT {
 	typedef IntvT<U> I;
 	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3 };
@@ -431,10 +432,11 @@ struct SmemMachineT {
 					started = true;
 					break;
 				}
-				if (!started) { pass = 3; x = 0; state = NEXT_P3; if (max_mem_intv == 0 || skip_p3) x = len; }
+				if (!started) { pass = 3; x = 0; state = NEXT_P3; if (max_mem_intv == 0 || skip_p3 || !P3) x = len; }
 				break;
 			}
 			case NEXT_P3:
+				if (!P3) return false;
 				while (x < len && q[x] > 3) ++x;
 				if (x >= len) return false;
 				set_intv(ix, q[x], ik);
@@ -460,6 +462,7 @@ struct SmemMachineT {
 				is_back = 1; qc = c;
 				return true;
 			case S3:
+				if (!P3) return false;
 				if (i >= len) { x = len; state = NEXT_P3; break; }
 				if (qi > 3) { x = i + 1; state = NEXT_P3; break; }
 				in = ik; is_back = 0; qc = 3 - qi;
@@ -481,7 +484,7 @@ struct SmemMachineT {
 			if (okc.x2 < min_intv) keep(in);
 			else if (n_curr == 0 || okc.x2 != curr_tail_x2) { I t = okc; t.qb = 0; t.qe = in.qe; push_curr(t); }
 			++j;
-		} else { // S3
+		} else if (P3) { // S3
 			if (okc.x2 < max_mem_intv && i - x >= min_seed_len) {
 				Intv m = widen(okc); m.qb = (u32)x; m.qe = (u32)(i + 1);
 				if (m.x2 > 0) { if (n >= mem_cap) { err = 1; return; } mem[n++] = m; }

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, in
 			}
 		}
 	}
-	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+	if (fm.n_blk) { atomicAdd(&cnt->occ_smem, fm.n_blk); atomicAdd(&cnt->dbg[6], fm.n_blk); } // dbg[6]: this kernel's share of occ_smem
 }
 
 template <class U, int MINB>
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 	DevLists<U> lists;
 	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = (decltype(lists.g0))bufA; lists.g1 = (decltype(lists.g1))bufB;
 	ScalarFm fm(ix);
-	SmemMachineT<DevLists<U>, U> m;
+	SmemMachineT<DevLists<U>, U, false> m; // the greedy pass is k_smem_p3's
 	bool have = false, ready = false, alive = true, fin = false;
 	int r = -1;
 	const int batch = slow_batch > 0 ? slow_batch : 1;
@@ -1075,7 +1075,7 @@ struct ssq_batch {
 	u64 pool_cap;
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
-	cudaEvent_t ev[6], evc[4]; // stage boundaries; chaining tiers (light start, heavy start, end)
+	cudaEvent_t ev[6], evc[4], evs[2]; // ... ; k_smem_m alone // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
 	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
 };
@@ -1123,6 +1123,7 @@ extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, i
 	CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
 	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
 	for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&b->evc[i]));
+	for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&b->evs[i]));
 	if (read_off && (rc = ssq_batch_upload(b, n_reads, seq, read_off))) { ssq_batch_free(b); return rc; }
 	*out = b;
 	return SSQ_OK;
@@ -1138,6 +1139,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
+	for (int i = 0; i < 2; ++i) cudaEventDestroy(b->evs[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
 	delete b;
 }
@@ -1194,7 +1196,7 @@ static int run_smem(ssq_batch *b)
 		Misc *dm = b->misc.as<Misc>();
 		const Intv *p3buf = 0; const i32 *p3cnt = 0;
 		const int p3_stride = lcap / (b->opt.min_seed_len + 1) + 2;
-		if (variant == 2 && b->opt.max_mem_intv > 0 && !getenv("SSQ_NO_P3_KERNEL")) {
+		if (variant == 2 && b->opt.max_mem_intv > 0) {
 			if (b->xp3.need((size_t)n * p3_stride * sizeof(Intv)) || b->xp3n.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
 			if (m32) k_smem_p3<u32><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
 			else k_smem_p3<u64><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
@@ -1205,11 +1207,13 @@ static int run_smem(ssq_batch *b)
 		if (variant == 0)
 			k_smem<<<grid, threads, smem, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                      b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
-		else if (variant == 2)
+		else if (variant == 2) {
+			CK(cudaEventRecord(b->evs[0], b->st));
 			km<<<grid, threads, (size_t)threads * 2 * list_cap * sizeof(uint4), b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, getenv("SSQ_SLOW_BATCH") ? atoi(getenv("SSQ_SLOW_BATCH")) : 8, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt,
 			                                     (const u32*)0, b->xovf.as<u32>(), &dm->n_ovf, p3buf, p3cnt, p3_stride);
-		else
+			CK(cudaEventRecord(b->evs[1], b->st));
+		} else
 			k_smem_t<<<grid, threads, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->scratch.as<Intv>(), scratch_cap,
 			                                     b->pool.as<Intv>(), b->pool_cap, &dm->pool_n, b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>(), &dm->work, &dm->err, &dm->cnt);
 		++b->launches;
@@ -1501,6 +1505,8 @@ extern "C" uint64_t ssq_batch_counter(const ssq_batch_t *b_, int what)
 	case 4: return b->h_cnt.sw_cells; case 5: return b->h_cnt.sw_bytes; case 6: return (uint64_t)b->launches; case 7: return b->n_seeds; case 8: return b->n_regs_total;
 	case 9: return b->n_intv; case 10: return b->n_tasks; case 11: return (uint64_t)b->ext_rounds;
 	case 12: case 13: case 14: case 15: case 16: return b->h_cnt.dbg[what - 12];
+	case 23: return b->h_cnt.dbg[6]; // rank blocks dereferenced by k_smem_p3 (part of counter 0)
+	case 24: { float ms = 0.f; if (cudaEventElapsedTime(&ms, b->evs[0], b->evs[1]) != cudaSuccess) { cudaGetLastError(); return 0; } return (uint64_t)(ms * 1000.f); } // k_smem_m alone, microseconds
 	case 22: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[3], b->evc[2]); return (uint64_t)(ms * 1000.f); } // the big-shared-memory tier alone
 	case 17: case 18: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[what - 17], b->evc[what - 16]); return (uint64_t)(ms * 1000.f); } // chaining tiers, microseconds
 	case 19: case 20: case 21: { u32 v = 0; cudaMemcpy(&v, b->xmisc.as<u32>() + (what == 19 ? 24 : what == 20 ? 27 : 25), 4, cudaMemcpyDeviceToHost); return v; } // reads in the warp tier; the cut; reads passed on to the big-shared-memory tier
