@@ -327,6 +327,20 @@ SSQ_HD int collect_intv(Fm &fm, const DevIndex &ix, const ssq_opts_t &opt, int l
 	return n;
 }
 
+// Phase-split seeding (indexes with < 2^32 rows): the forward phase of an smem1() call does not depend on its backward phase (the
+// next call starts at the forward phase's end), so forward walks and backward sweeps can run as separate kernels in which every
+// lane is in the same phase.  A call travels between them as a SeedCall + its forward list (the intervals at which the size changed).
+struct FwdEntry { u32 x0, x1, x2, qe; };
+struct SeedCall { // 32 bytes: everything a lane needs to take the call over with one load
+	u32 read, pk, min_intv, list_n; // pk = x | len << 8 | (base at x-1, 0..4) << 16 | (base at x-2) << 20
+	u64 list_off, seq_off;          // forward list in the list pool; the read's bases
+	SSQ_HD static u32 pack(int x, int len, int b0, int b1) { return (u32)x | (u32)len << 8 | (u32)b0 << 16 | (u32)b1 << 20; }
+	SSQ_HD int x() const { return (int)(pk & 0xff); }
+	SSQ_HD int len() const { return (int)(pk >> 8 & 0xff); }
+	SSQ_HD int b0() const { return (int)(pk >> 16 & 0xf); }
+	SSQ_HD int b1() const { return (int)(pk >> 20 & 0xf); }
+};
+
 // ------------------------------------------------------------- seeding as a state machine ----
 // Same three passes as collect_intv(), unrolled into a machine whose only expensive transition is one rank query.
 // A GPU lane owns one machine; all lanes of a warp meet at the query no matter which phase each is in.  advance() runs
@@ -349,7 +363,8 @@ typedef HostListsT<u64> HostLists;
 template <class Lists, class U = u64, bool P3 = true>
 struct SmemMachineT {
 	typedef IntvT<U> I;
-	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3 };
+	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3, DONE };
+	const FwdEntry *ext; // backward-only use: the forward list of the call, produced elsewhere (read from its end in the first sweep)
 	const uint8_t *q; Intv *mem; Lists L;
 	int len, mem_cap, n, state, pass, x, i, j, c, qc, ret, n_prev, n_curr, old_n, k2, err, min_seed_len, split_len, split_width, prev_id;
 	int qi, qnext;     // base at position i (forward phases) and the prefetched base at i+1: the load is issued before the rank
@@ -370,7 +385,7 @@ struct SmemMachineT {
 	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists, int skip_p3_ = 0)
 	{
 		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0; skip_p3 = skip_p3_;
-		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1; rev = 0;
+		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1; rev = 0; ext = 0;
 		min_seed_len = opt.min_seed_len; split_len = (int)(opt.min_seed_len * opt.split_factor + .499f); split_width = opt.split_width;
 		max_mem_intv = (U)opt.max_mem_intv;
 		if (len < opt.min_seed_len) { state = NEXT_P3; pass = 3; x = len; }
@@ -408,7 +423,23 @@ struct SmemMachineT {
 			}
 		}
 	}
-	SSQ_HD void end_smem1() { if (pass == 1) { x = ret; state = NEXT_P1; } else state = NEXT_P2; }
+	SSQ_HD void end_smem1() { if (pass == 1) { x = ret; state = NEXT_P1; } else if (pass == 0) state = DONE; else state = NEXT_P2; }
+	// backward phase only: the call's forward list comes from outside; advance() returns false when the call is complete and
+	// mem[0..n) holds its intervals (after init(); 32-bit rows only)
+	SSQ_HD void start_backward(int x_, U min_intv_, const FwdEntry *list, int list_n, int b0, int b1) // b0, b1: bases at x-1, x-2 (4 = none / N)
+	{
+		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; any_kept = 0; pass = 0;
+		ext = list; n_prev = list_n; rev = 1; prev_id = 0;
+		ret = (int)list[list_n - 1].qe;
+		i = x - 1; j = 0; n_curr = 0;
+		c = b0 < 4 ? b0 : -1; cnext = b1 < 4 ? b1 : -1;
+		state = BWD;
+	}
+	SSQ_HD I prev_entry(int jj) const
+	{
+		if (rev && ext) { const FwdEntry e = ext[n_prev - 1 - jj]; I r; r.x0 = (U)e.x0; r.x1 = (U)e.x1; r.x2 = (U)e.x2; r.qb = 0; r.qe = e.qe; return r; }
+		return L.get(prev_id, rev ? n_prev - 1 - jj : jj);
+	}
 	// Runs the bookkeeping up to the next rank query.  true: `in` / `qc` / `is_back` describe it (only ok[qc] is needed);
 	// false: the read is complete.  Every transition is a handful of instructions; the only loops are over N bases and over
 	// pass-1 intervals that do not qualify for re-seeding.
@@ -417,6 +448,7 @@ struct SmemMachineT {
 		for (;;) {
 			if (err) return false;
 			switch (state) {
+			case DONE: return false;
 			case NEXT_P1:
 				while (x < len && q[x] > 3) ++x;
 				if (x >= len) { old_n = n; k2 = 0; pass = 2; state = NEXT_P2; break; }
@@ -457,7 +489,7 @@ struct SmemMachineT {
 					{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
 					break;
 				}
-				in = L.get(prev_id, rev ? n_prev - 1 - j : j);
+				in = prev_entry(j);
 				if (c < 0) { keep(in); ++j; break; }
 				is_back = 1; qc = c;
 				return true;

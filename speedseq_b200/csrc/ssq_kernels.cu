@@ -304,6 +304,219 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
 
+// ------------------------------------------------------- phase-split seeding (variant 3) ----
+// Every kernel here has all its lanes in ONE phase of the algorithm (what made k_smem_p3 3.8x as efficient per rank block as the
+// state machine).  Data flow, all in device memory, counters in Split:
+//   k_smem_fwd<1>  per read: the forward walks of pass 1, one after the other (the next starts where the previous ended)
+//                  -> a SeedCall + forward list per walk
+//   k_smem_bwd     per call: its backward sweeps (SmemMachineT started in its backward phase) -> intervals, tagged with the read
+//   k_smem_p2sel   per pass-1 interval: long and rare enough -> a pass-2 call request (x = its middle, min_intv = its size + 1)
+//   k_smem_fwd<2>  per request: the forward walk;  k_smem_bwd again for those calls
+//   k_smem_p3 (+ k_smem_p3_append): the greedy pass
+//   sort by (read, qb, qe) -> pool, intv_off/intv_cnt, l_rep   (equal keys are identical intervals)
+struct Split { unsigned long long n_calls, n_calls1, n_fl, n_mems, n_mems1; int err, pad; int wk[8]; };
+
+// space for n items from a shared counter, one atomic per group of converged lanes
+__device__ __forceinline__ unsigned long long group_alloc(unsigned long long *ctr, unsigned int n)
+{
+	const unsigned mask = __activemask();
+	const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+	unsigned int pre = 0, tot = 0;
+	for (unsigned m = mask; m; m &= m - 1) { const int src = __ffs(m) - 1; const unsigned int v = __shfl_sync(mask, n, src); if (src < lane) pre += v; tot += v; }
+	unsigned long long base = 0;
+	if (lane == leader) base = atomicAdd(ctr, (unsigned long long)tot);
+	base = __shfl_sync(mask, base, leader);
+	return base + pre;
+}
+
+// PASS 1: lane = read, walks x = 0, ret, ret', ...; PASS 2: lane = call request (read, x, min_intv given), one walk
+template <int PASS>
+__global__ void __launch_bounds__(256) k_smem_fwd(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
+                                                  int lcap, FwdEntry *stage, SeedCall *calls, u64 call_cap, FwdEntry *fl, u64 fl_cap, Split *sp, Counters *cnt)
+{
+	ScalarFm fm(ix);
+	FwdEntry *st = stage + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)(lcap + 1);
+	const uint8_t *q = 0;
+	Intv32 ik; ik.x0 = ik.x1 = ik.x2 = 0; ik.qb = ik.qe = 0;
+	int r = -1, len = 0, x = 0, i = 0, qi = 0, qnext = 0, n_list = 0;
+	u32 min_intv = 1;
+	unsigned long long slot = 0; // PASS 2: the request being served
+	bool have = false, ready = false, alive = true;
+	const unsigned long long lo2 = PASS == 2 ? sp->n_calls1 : 0, hi2 = PASS == 2 ? sp->n_calls : 0;
+	auto push = [&]() { FwdEntry e; e.x0 = ik.x0; e.x1 = ik.x1; e.x2 = ik.x2; e.qe = ik.qe; st[n_list++] = e; };
+	auto flush = [&]() { // the walk from x is complete: hand the call over
+		const unsigned long long off = group_alloc(&sp->n_fl, (unsigned)n_list);
+		unsigned long long c = slot;
+		if (PASS == 1) c = group_alloc(&sp->n_calls, 1u);
+		if (off + n_list > fl_cap || c >= call_cap) atomicMax(&sp->err, 2);
+		else {
+			for (int e = 0; e < n_list; ++e) fl[off + e] = st[e];
+			SeedCall sc; sc.read = (u32)r; sc.pk = SeedCall::pack(x, len, x >= 1 ? (int)q[x - 1] : 4, x >= 2 ? (int)q[x - 2] : 4);
+			sc.min_intv = min_intv; sc.list_n = (u32)n_list; sc.list_off = off; sc.seq_off = (u64)(q - seq);
+			calls[c] = sc;
+		}
+		if (PASS == 1) x = (int)st[n_list - 1].qe; else have = false;
+		ready = false;
+	};
+	for (;;) {
+		while (alive && !ready) {
+			if (!have) {
+				if (PASS == 1) {
+					r = atomicAdd(&sp->wk[0], 1);
+					if (r >= n_reads) { alive = false; break; }
+					const u64 off = read_off[r];
+					len = (int)(read_off[r + 1] - off); q = seq + off;
+					x = len < opt.min_seed_len ? len : 0;
+					if (len > lcap) { atomicMax(&sp->err, 3); x = len; }
+				} else {
+					slot = lo2 + (unsigned long long)atomicAdd(&sp->wk[2], 1);
+					if (slot >= hi2) { alive = false; break; }
+					const SeedCall sc = calls[slot];
+					r = (int)sc.read; x = sc.x(); min_intv = sc.min_intv;
+					len = sc.len(); q = seq + sc.seq_off;
+				}
+				have = true;
+			}
+			if (PASS == 1) {
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) { have = false; continue; }
+			}
+			set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
+			i = x + 1; n_list = 0;
+			if (i >= len) { push(); flush(); continue; }
+			qi = q[i];
+			if (qi > 3) { push(); flush(); continue; }
+			qnext = i + 1 < len ? (int)q[i + 1] : 4;
+			ready = true;
+		}
+		if (__ballot_sync(FULL, alive) == 0) break;
+		if (ready) {
+			Intv32 okc;
+			extend1(fm, ik, 3 - qi, 0, okc);
+			bool end = false;
+			if (okc.x2 != ik.x2) { push(); end = okc.x2 < min_intv; }
+			if (!end) {
+				ik = okc; ik.qe = (u32)(i + 1); ++i;
+				if (i >= len) { push(); end = true; }
+				else { qi = qnext; if (qi > 3) { push(); end = true; } else qnext = i + 1 < len ? (int)q[i + 1] : 4; }
+			}
+			if (end) flush();
+		}
+	}
+	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
+// backward sweeps of the calls [lo, hi): lane = call
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_smem_bwd(DevIndex ix, ssq_opts_t opt, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off, int lcap, int list_cap,
+                                                        Intv *scratch, int scratch_cap, const SeedCall *__restrict__ calls, const FwdEntry *__restrict__ fl, int second,
+                                                        Intv *mems, u32 *memr, u64 mem_cap, Split *sp, Counters *cnt)
+{
+	extern __shared__ uint4 list_smem[];
+	const size_t per = (size_t)scratch_cap + (size_t)(lcap + 1); // output of one call + overflow of the two lists as 16-byte entries
+	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per;
+	uint4 *bufA = (uint4*)(mem + scratch_cap), *bufB = bufA + (lcap + 1);
+	DevLists<u32> lists;
+	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = bufA; lists.g1 = bufB;
+	ScalarFm fm(ix);
+	SmemMachineT<DevLists<u32>, u32, false> m;
+	const unsigned long long lo = second ? sp->n_calls1 : 0, hi = second ? sp->n_calls : sp->n_calls1;
+	bool have = false, ready = false, alive = true;
+	u32 rd = 0;
+	for (;;) {
+		while (alive && !ready) {
+			if (have) { // call complete: its intervals go to the pool, tagged with the read
+				if (m.err) atomicMax(&sp->err, 1);
+				else if (m.n > 0) {
+					const unsigned long long base = group_alloc(&sp->n_mems, (unsigned)m.n);
+					if (base + m.n > mem_cap) atomicMax(&sp->err, 2);
+					else for (int e = 0; e < m.n; ++e) { mems[base + e] = mem[e]; memr[base + e] = rd; }
+				}
+				have = false;
+			}
+			const unsigned long long c = lo + (unsigned long long)atomicAdd(&sp->wk[second ? 3 : 1], 1);
+			if (c >= hi) { alive = false; break; }
+			const SeedCall sc = calls[c];
+			rd = sc.read;
+			m.init(opt, sc.len(), seq + sc.seq_off, mem, scratch_cap, lists, 1);
+			m.start_backward(sc.x(), sc.min_intv, fl + sc.list_off, (int)sc.list_n, sc.b0(), sc.b1());
+			have = true;
+			ready = m.advance(ix);
+		}
+		if (__ballot_sync(FULL, alive) == 0) break;
+		if (ready) {
+			Intv32 okc;
+			extend1(fm, m.in, m.qc, m.is_back, okc);
+			m.post(okc);
+			ready = m.advance(ix);
+		}
+	}
+	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
+__global__ void k_smem_snapshot(Split *sp) { sp->n_calls1 = sp->n_calls; sp->n_mems1 = sp->n_mems; }
+
+__global__ void k_smem_p2sel(ssq_opts_t opt, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off, const Intv *__restrict__ mems, const u32 *__restrict__ memr,
+                             SeedCall *calls, u64 call_cap, Split *sp)
+{
+	const unsigned long long n1 = sp->n_mems1;
+	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499f);
+	for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n1; t += (unsigned long long)gridDim.x * blockDim.x) {
+		const Intv p = mems[t];
+		const int start = (int)p.qb, end = (int)p.qe;
+		if (end - start < split_len || p.x2 > (u64)opt.split_width) continue;
+		const unsigned long long c = group_alloc(&sp->n_calls, 1u);
+		if (c >= call_cap) { atomicMax(&sp->err, 2); continue; }
+		SeedCall sc; sc.read = memr[t];
+		const u64 off = read_off[sc.read];
+		const int x = (start + end) >> 1, len = (int)(read_off[sc.read + 1] - off);
+		sc.pk = SeedCall::pack(x, len, x >= 1 ? (int)seq[off + x - 1] : 4, x >= 2 ? (int)seq[off + x - 2] : 4);
+		sc.min_intv = (u32)(p.x2 + 1); sc.list_n = 0; sc.list_off = 0; sc.seq_off = off;
+		calls[c] = sc;
+	}
+}
+
+__global__ void k_smem_p3_append(int n_reads, const Intv *__restrict__ p3, const i32 *__restrict__ p3_cnt, int stride, Intv *mems, u32 *memr, u64 mem_cap, Split *sp)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int c = p3_cnt[r];
+	if (c <= 0) return;
+	const unsigned long long base = group_alloc(&sp->n_mems, (unsigned)c);
+	if (base + c > mem_cap || c > stride) { atomicMax(&sp->err, 2); return; }
+	for (int e = 0; e < c; ++e) { mems[base + e] = p3[(size_t)r * stride + e]; memr[base + e] = (u32)r; }
+}
+
+__global__ void k_smem_keys(u64 n, const Intv *__restrict__ mems, const u32 *__restrict__ memr, u64 *keys, u32 *idx)
+{
+	const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	keys[t] = (u64)memr[t] << 16 | (u64)(mems[t].qb & 0xff) << 8 | (u64)(mems[t].qe & 0xff);
+	idx[t] = (u32)t;
+}
+__global__ void k_smem_publish(u64 n, const u64 *__restrict__ keys, const u32 *__restrict__ idx, const Intv *__restrict__ mems, Intv *pool, u64 *intv_off, i32 *intv_cnt)
+{
+	const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	pool[t] = mems[idx[t]];
+	const u32 r = (u32)(keys[t] >> 16);
+	if (t == 0 || (u32)(keys[t - 1] >> 16) != r) intv_off[r] = t;
+	atomicAdd(&intv_cnt[r], 1);
+}
+__global__ void k_smem_lrep(int n_reads, ssq_opts_t opt, const Intv *__restrict__ pool, const u64 *__restrict__ intv_off, const i32 *__restrict__ intv_cnt, i32 *l_rep_out)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const Intv *mem = pool + intv_off[r];
+	int b = 0, en = 0, l_rep = 0;
+	for (int i = 0; i < intv_cnt[r]; ++i) {
+		const Intv p = mem[i];
+		if (p.x2 <= (u64)opt.max_occ) continue;
+		if ((int)p.qb > en) { l_rep += en - b; b = p.qb; en = p.qe; } else en = en > (int)p.qe ? en : (int)p.qe;
+	}
+	l_rep_out[r] = l_rep + (en - b);
+}
+
 // ------------------------------------------------------------------------------- k_sa ----
 __global__ void k_occ_count(const Intv *__restrict__ pool, u64 n, int max_occ, u32 *nocc)
 {
@@ -1069,12 +1282,13 @@ struct ssq_batch {
 	cudaStream_t st;
 	DBuf seq, read_off, pool, scratch, intv_off, intv_cnt, l_rep, misc, nocc, seed_off, seeds;
 	DBuf chain_of, ch, ord, wi, sorted, outc, n_kept, n_kseeds, task_off, tasks, cand, srt, regs, n_regs, reg_off, cubtmp, out;
-	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2, xowner, xp3, xp3n;
+	DBuf xinfo, xres[2], xwide, xkey[2], xidx[2], xretry, xmisc, xneed, xhave, xkp, xheavy, xsel, xlist[2], srt2, xgiant, xgiant2, xovf, scratch2, xowner, xp3, xp3n, xsplit, xstage, xmems, xmemr, xcalls, xfl, xk64[2], xi32[2];
 	int ext_rounds; float select_ms;
 	u64 n_intv, n_seeds, n_tasks, n_regs_total;
 	u64 pool_cap;
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
+	u64 call_cap = 0, fl_cap = 0; // split seeding: capacities of the call and forward-list pools
 	cudaEvent_t ev[6], evc[4], evs[2]; // ... ; k_smem_m alone // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
 	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
@@ -1135,7 +1349,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	DBuf *all[] = {&b->seq, &b->read_off, &b->pool, &b->scratch, &b->intv_off, &b->intv_cnt, &b->l_rep, &b->misc, &b->nocc, &b->seed_off, &b->seeds,
 	               &b->chain_of, &b->ch, &b->ord, &b->wi, &b->sorted, &b->outc, &b->n_kept, &b->n_kseeds, &b->task_off, &b->tasks, &b->cand, &b->srt,
 	               &b->regs, &b->n_regs, &b->reg_off, &b->cubtmp, &b->out,
-	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2, &b->xowner, &b->xp3, &b->xp3n};
+	               &b->xinfo, &b->xres[0], &b->xres[1], &b->xwide, &b->xkey[0], &b->xkey[1], &b->xidx[0], &b->xidx[1], &b->xretry, &b->xmisc, &b->xneed, &b->xhave, &b->xkp, &b->xheavy, &b->xsel, &b->xlist[0], &b->xlist[1], &b->srt2, &b->xgiant, &b->xgiant2, &b->xovf, &b->scratch2, &b->xowner, &b->xp3, &b->xp3n, &b->xsplit, &b->xstage, &b->xmems, &b->xmemr, &b->xcalls, &b->xfl, &b->xk64[0], &b->xk64[1], &b->xi32[0], &b->xi32[1]};
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
@@ -1162,11 +1376,89 @@ extern "C" int ssq_batch_set_stream(ssq_batch_t *b, void *stream)
 }
 extern "C" int ssq_batch_sync(ssq_batch_t *b) { CK(cudaStreamSynchronize(b->st)); return SSQ_OK; }
 
+// stage A, phase-split form (SSQ_SMEM_VARIANT=3; indexes with bwt32): see the kernels' header comment
+static int run_smem_split(ssq_batch *b)
+{
+	const int n = b->n_reads, lcap = b->max_len > 0 ? b->max_len : 1;
+	const char *lc_env = getenv("SSQ_LIST_CAP");
+	const int list_cap = lc_env ? atoi(lc_env) : 6;
+	const int fgrid = b->n_sm * 5, bgrid = b->n_sm * 6, bthreads = 128;
+	const int scratch_cap = lcap + 1; // a call cannot keep more intervals than the read has positions
+	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc)) ||
+	    b->xsplit.need(sizeof(Split))) return SSQ_ENOMEM;
+	if (b->xstage.need((size_t)fgrid * 256 * (size_t)(lcap + 1) * sizeof(FwdEntry))) return SSQ_ENOMEM;
+	if (b->scratch.need((size_t)bgrid * bthreads * ((size_t)scratch_cap + (size_t)(lcap + 1)) * sizeof(Intv))) return SSQ_ENOMEM;
+	const int p3_stride = lcap / (b->opt.min_seed_len + 1) + 2;
+	const bool with_p3 = b->opt.max_mem_intv > 0;
+	if (with_p3 && (b->xp3.need((size_t)n * p3_stride * sizeof(Intv)) || b->xp3n.need((size_t)(n + 1) * 4))) return SSQ_ENOMEM;
+	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
+	if (b->call_cap == 0) b->call_cap = (u64)n * 10 + 4096;
+	if (b->fl_cap == 0) b->fl_cap = (u64)n * 96 + 65536;
+	CK(cudaFuncSetAttribute(k_smem_bwd<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
+	const size_t lsm = (size_t)bthreads * 2 * list_cap * sizeof(uint4);
+	Misc *dm = b->misc.as<Misc>();
+	Split *sp = b->xsplit.as<Split>();
+	for (int attempt = 0; attempt < 6; ++attempt) {
+		if (b->xmems.need(b->pool_cap * sizeof(Intv)) || b->xmemr.need(b->pool_cap * 4) || b->xcalls.need(b->call_cap * sizeof(SeedCall)) || b->xfl.need(b->fl_cap * sizeof(FwdEntry))) return SSQ_ENOMEM;
+		CK(cudaMemsetAsync(b->misc.p, 0, sizeof(Misc), b->st));
+		CK(cudaMemsetAsync(b->xsplit.p, 0, sizeof(Split), b->st));
+		if (with_p3) k_smem_p3<u32><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+		k_smem_fwd<1><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
+		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
+		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp); // n_calls1 = pass-1 calls (n_mems1 still 0)
+		k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp); // n_mems1 = pass-1 intervals; n_calls1 unchanged (no calls were added)
+		k_smem_p2sel<<<b->n_sm * 8, 256, 0, b->st>>>(b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->xcalls.as<SeedCall>(), b->call_cap, sp);
+		k_smem_fwd<2><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
+		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
+		k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		if (with_p3) k_smem_p3_append<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->xp3.as<Intv>(), b->xp3n.as<i32>(), p3_stride, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp);
+		b->launches += 9;
+		CK(cudaGetLastError());
+		Split hs;
+		CK(cudaMemcpyAsync(&hs, sp, sizeof(Split), cudaMemcpyDeviceToHost, b->st));
+		CK(cudaStreamSynchronize(b->st));
+		if (hs.err == 2) { // a pool was too small; the counters are lower bounds of what is needed
+			if (hs.n_mems + 1 > b->pool_cap) b->pool_cap = hs.n_mems + hs.n_mems / 2 + 4096; else b->pool_cap += b->pool_cap / 2;
+			if (hs.n_calls + 1 > b->call_cap) b->call_cap = hs.n_calls + hs.n_calls / 2 + 4096; else b->call_cap += b->call_cap / 2;
+			if (hs.n_fl + 1 > b->fl_cap) b->fl_cap = hs.n_fl + hs.n_fl / 2 + 65536; else b->fl_cap += b->fl_cap / 2;
+			continue;
+		}
+		if (hs.err) { ssq_set_error(hs.err == 3 ? "read longer than the kernel's length cap" : "seeding (split): a call overflowed its scratch"); return hs.err == 3 ? SSQ_ELEN : SSQ_ECAP; }
+		const u64 N = hs.n_mems;
+		b->n_intv = N;
+		CK(cudaMemsetAsync(b->intv_off.p, 0, (size_t)(n + 1) * 8, b->st));
+		CK(cudaMemsetAsync(b->intv_cnt.p, 0, (size_t)(n + 1) * 4, b->st));
+		if (b->pool.need((N + 1) * sizeof(Intv))) return SSQ_ENOMEM;
+		if (N) {
+			if (N >= 0xffffffffull) { ssq_set_error("more than 2^32 seed intervals in one batch"); return SSQ_ECAP; }
+			if (b->xk64[0].need(N * 8) || b->xk64[1].need(N * 8) || b->xi32[0].need(N * 4) || b->xi32[1].need(N * 4)) return SSQ_ENOMEM;
+			k_smem_keys<<<(unsigned)((N + 255) / 256), 256, 0, b->st>>>(N, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->xk64[0].as<u64>(), b->xi32[0].as<u32>());
+			int rbits = 1; while ((1ull << rbits) < (u64)n + 1) ++rbits;
+			size_t tb = 0;
+			cub::DeviceRadixSort::SortPairs(0, tb, b->xk64[0].as<u64>(), b->xk64[1].as<u64>(), b->xi32[0].as<u32>(), b->xi32[1].as<u32>(), (int)N, 0, 16 + rbits, b->st);
+			if (b->cubtmp.need(tb)) return SSQ_ENOMEM;
+			CK(cub::DeviceRadixSort::SortPairs(b->cubtmp.p, tb, b->xk64[0].as<u64>(), b->xk64[1].as<u64>(), b->xi32[0].as<u32>(), b->xi32[1].as<u32>(), (int)N, 0, 16 + rbits, b->st));
+			k_smem_publish<<<(unsigned)((N + 255) / 256), 256, 0, b->st>>>(N, b->xk64[1].as<u64>(), b->xi32[1].as<u32>(), b->xmems.as<Intv>(), b->pool.as<Intv>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>());
+			b->launches += 3;
+		}
+		k_smem_lrep<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->opt, b->pool.as<Intv>(), b->intv_off.as<u64>(), b->intv_cnt.as<i32>(), b->l_rep.as<i32>());
+		++b->launches;
+		CK(cudaGetLastError());
+		return SSQ_OK;
+	}
+	ssq_set_error("seeding (split): pools kept overflowing");
+	return SSQ_ECAP;
+}
+
 // stage A: seeding (+ pool overflow retry). leaves intervals in pool, per-read (intv_off, intv_cnt, l_rep)
 static int run_smem(ssq_batch *b)
 {
 	const int n = b->n_reads, lcap = b->max_len > 0 ? b->max_len : 1;
-	const int variant = b->smem_variant;
+	if (b->smem_variant == 3 && b->idx->dev.bwt32 && n > 0) return run_smem_split(b);
+	const int variant = b->smem_variant == 3 ? 2 : b->smem_variant;
 	const int warps_per_block = 4, threads = warps_per_block * 32;
 	const size_t smem = variant == 0 ? (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv) : 0;
 	const char *lc_env = getenv("SSQ_LIST_CAP");

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include "../../speedseq_b200/csrc/ssq_dev.cuh"
 #include "../../speedseq_b200/csrc/ssq_mem_host.h"
 extern "C" {
@@ -45,13 +46,86 @@ struct ReadWork {
 	std::vector<RegCand> regs;
 };
 
+// The phase-split formulation of the seeding (k_smem_fwd / k_smem_bwd / k_smem_p3 on the GPU), data flow included: forward walks
+// produce calls + forward lists, every call's backward phase runs on its own from that list, pass 2 is selected from pass 1's
+// intervals, everything is pooled and ordered by (qb, qe) at the end.
+static void fwd_walk(ScalarFm &fm, const DevIndex &ix, int len, const uint8_t *q, int x, u32 min_intv, std::vector<FwdEntry> &list)
+{
+	Intv32 ik, okc;
+	set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
+	auto push = [&]() { FwdEntry e; e.x0 = ik.x0; e.x1 = ik.x1; e.x2 = ik.x2; e.qe = ik.qe; list.push_back(e); };
+	int i;
+	for (i = x + 1; i < len; ++i) {
+		if (q[i] > 3) break;
+		extend1(fm, ik, 3 - q[i], 0, okc);
+		if (okc.x2 != ik.x2) { push(); if (okc.x2 < min_intv) return; }
+		ik = okc; ik.qe = (u32)(i + 1);
+	}
+	push();
+}
+static void run_read_split(const DevIndex &ix, const ssq_opts_t &opt, int len, const uint8_t *q, ReadWork &w)
+{
+	ScalarFm fm(ix);
+	std::vector<Intv> all;
+	std::vector<Intv> mem(2048);
+	std::vector<Intv32> a32(len + 2), b32(len + 2);
+	HostListsT<u32> hl; hl.a[0] = a32.data(); hl.a[1] = b32.data();
+	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499f);
+	auto backward = [&](int x, u32 min_intv, const std::vector<FwdEntry> &list) {
+		SmemMachineT<HostListsT<u32>, u32, false> m; Intv32 okc;
+		m.init(opt, len, q, mem.data(), 2048, hl, 1);
+		m.start_backward(x, min_intv, list.data(), (int)list.size(), x >= 1 ? (int)q[x - 1] : 4, x >= 2 ? (int)q[x - 2] : 4);
+		for (bool go = m.advance(ix); go; go = m.advance(ix)) { extend1(fm, m.in, m.qc, m.is_back, okc); m.post(okc); }
+		if (m.err) abort();
+		for (int k = 0; k < m.n; ++k) all.push_back(mem[k]);
+	};
+	if (len >= opt.min_seed_len) {
+		for (int x = 0; x < len;) { // pass 1
+			if (q[x] > 3) { ++x; continue; }
+			std::vector<FwdEntry> list;
+			fwd_walk(fm, ix, len, q, x, 1, list);
+			backward(x, 1, list);
+			x = (int)list.back().qe;
+		}
+		const size_t n1 = all.size();
+		for (size_t k = 0; k < n1; ++k) { // pass 2
+			const Intv p = all[k];
+			const int start = (int)p.qb, end = (int)p.qe;
+			if (end - start < split_len || p.x2 > (u64)opt.split_width) continue;
+			std::vector<FwdEntry> list;
+			const int x = (start + end) >> 1;
+			fwd_walk(fm, ix, len, q, x, (u32)(p.x2 + 1), list);
+			backward(x, (u32)(p.x2 + 1), list);
+		}
+		if (opt.max_mem_intv > 0) { // pass 3, as in k_smem_p3
+			int x = 0;
+			while (x < len) {
+				if (q[x] > 3) { ++x; continue; }
+				Intv32 ik, okc; set_intv(ix, q[x], ik);
+				int i; bool hit = false;
+				for (i = x + 1; i < len; ++i) {
+					if (q[i] > 3) break;
+					extend1(fm, ik, 3 - q[i], 0, okc);
+					if (okc.x2 < (u32)opt.max_mem_intv && i - x >= opt.min_seed_len) { if (okc.x2 > 0) { Intv m = widen(okc); m.qb = (u32)x; m.qe = (u32)(i + 1); all.push_back(m); } hit = true; break; }
+					ik = okc;
+				}
+				x = (hit || i < len) ? i + 1 : len;
+			}
+		}
+	}
+	std::stable_sort(all.begin(), all.end(), [](const Intv &a, const Intv &b) { return ((u64)a.qb << 32 | a.qe) < ((u64)b.qb << 32 | b.qe); });
+	w.mem.assign(all.begin(), all.end()); w.mem.resize(all.size() + 2048);
+	w.n_intv = (int)all.size();
+}
+
 static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const uint8_t *q, int upto, ReadWork &w)
 {
 	ScalarFm fm(ix);
 	std::vector<Intv> bufA(len + 2), bufB(len + 2);
 	w.mem.assign(2048, Intv());
 	int err = 0;
-	if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
+	if (getenv("HOSTSIM_SPLIT") && ix.bwt32) run_read_split(ix, opt, len, q, w);
+	else if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
 	else if (ix.bwt32 && !getenv("HOSTSIM_M64")) { // the state-machine form the GPU kernel runs, 32-bit rows (what the GPU picks when bwt32 exists)
 		std::vector<Intv32> a32(len + 2), b32(len + 2);
 		SmemMachineT<HostListsT<u32>, u32> m; Intv32 okc;
