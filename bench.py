@@ -334,17 +334,19 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         n_launch = stats_steps * nb
         blk = float(L.ssq_index_info(idx, 7))  # bytes one rank query must fetch: 32 (re-blocked sector) or 64 (on-disk block)
-        kern = {
-            "k_smem_m": {"bytes": blk * (counters[0] - p3_blocks) / n_launch, "ms": smem_m_ms / n_launch},  # passes 1+2 (the state machine)
-            "k_smem_p3": {"bytes": blk * p3_blocks / n_launch, "ms": (stage_ms[0] - smem_m_ms) / n_launch},  # pass 3 + the stage's memsets/copies
-            "k_sa": {"bytes": (blk * counters[1] + 8.0 * counters[2]) / n_launch, "ms": stage_ms[1] / n_launch},
+        kern = {}
+        if smem_m_ms > 0:
+            kern["k_smem_m"] = {"bytes": blk * (counters[0] - p3_blocks) / n_launch, "ms": smem_m_ms / n_launch}  # passes 1+2 (the state machine)
+            kern["k_smem_p3"] = {"bytes": blk * p3_blocks / n_launch, "ms": (stage_ms[0] - smem_m_ms) / n_launch}  # pass 3 + the stage's memsets/copies
+        else:  # SSQ_SMEM_VARIANT=3 (phase-split kernels) or 0/1: the stage as a whole
+            kern["k_smem_stage"] = {"bytes": blk * counters[0] / n_launch, "ms": stage_ms[0] / n_launch}
+        kern.update({
+            "k_sa": {"bytes": (blk * counters[1] + float(L.ssq_index_info(idx, 8)) * counters[2]) / n_launch, "ms": stage_ms[1] / n_launch},
             "k_chain": {"bytes": None, "ms": stage_ms[2] / n_launch},
             "k_extend": {"bytes": counters[5] / n_launch, "ms": stage_ms[3] / n_launch, "gcups": counters[4] / n_launch / (stage_ms[3] / n_launch * 1e6) if stage_ms[3] else None},
             "k_select": {"bytes": None, "ms": stage_ms[4] / n_launch},
-        }
-        dom = max(("k_smem_m", "k_smem_p3", "k_sa", "k_chain", "k_extend"), key=lambda k: kern[k]["ms"])
-        if kern[dom]["bytes"] is None:
-            dom = "k_smem_m"
+        })
+        dom = max((k for k in kern if kern[k]["bytes"] is not None), key=lambda k: kern[k]["ms"])
         ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] else 0.0
         traffic = None
         try:  # DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (same batch size and index)

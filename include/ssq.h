@@ -65,7 +65,8 @@ typedef struct ssq_index ssq_index_t;
 int ssq_index_build(const char *fasta, const char *prefix, int device);
 int ssq_index_load(const char *prefix, int device, ssq_index_t **out);
 void ssq_index_free(ssq_index_t *idx);
-/* what: 0 l_pac, 1 seq_len(=2*l_pac), 2 primary, 3 n_seqs, 4 bwt words, 5 n_sa, 6 device bytes, 7 bytes per rank query (32|64) */
+/* what: 0 l_pac, 1 seq_len(=2*l_pac), 2 primary, 3 n_seqs, 4 bwt words, 5 n_sa, 6 device bytes, 7 bytes per rank query (32|64),
+ * 8 bytes per SA sample read (4|8), 9 SA sampling interval in device memory (on disk: 32; the loader derives a denser sample) */
 uint64_t ssq_index_info(const ssq_index_t *idx, int what);
 
 /* ----------------------------------------------------- kernel-level batches ----

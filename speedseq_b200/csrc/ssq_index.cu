@@ -242,6 +242,8 @@ extern "C" uint64_t ssq_index_info(const ssq_index_t *idx, int what)
 	case 5: return idx->dev.n_sa;
 	case 6: return (uint64_t)idx->dev_bytes;
 	case 7: return idx->dev.bwt32 ? 32 : 64; // bytes fetched per rank query (one re-blocked sector, or one on-disk block)
+	case 8: return idx->dev.sad32 ? 4 : 8;   // bytes per suffix-array sample read
+	case 9: return (uint64_t)(idx->dev.sad_intv ? idx->dev.sad_intv : idx->dev.sa_intv); // rows between the samples the LF walk ends on
 	}
 	return 0;
 }
