@@ -214,7 +214,9 @@ def main():
     idx = s.index_load(fa, local)
     # reads: pinned host copies, one batch object per batch, all sharing one stream
     host_seq, host_off, batches = [], [], []
-    nstreams = max(1, min(a.streams, nb))
+    # stream lanes = host threads that mostly wait on their stream; with several ranks on one box keep them within the host cores
+    # this container may actually use (16 on the GPU boxes, whatever the CPU count says), at least 2 per rank
+    nstreams = max(1, min(a.streams, nb, max(2, ncores // max(1, world))))
     streams = [None] * nstreams
     for b in range(nb):
         seq, off = fast_pairs(g, a.batch // 2, READ_LEN, 1000 + rank * 100 + b)
