@@ -539,6 +539,69 @@ struct SmemMachineT {
 	}
 };
 
+// The backward phase of one smem1() call on its own (phase-split seeding, 32-bit rows): the part of SmemMachineT that a lane of
+// k_smem_bwd2 needs and nothing else (~35 words of state instead of ~58).  Same operations in the same order as the machine's
+// BWD state: sweep the previous list (the call's forward list, read from its end, in the first sweep) one backward extension per
+// entry; an entry whose extension falls below min_intv is left-maximal (keep), one whose extended size differs from the last one
+// pushed survives into the next sweep.
+template <class Lists>
+struct BwdCallT {
+	const uint8_t *q; Intv *mem; Lists L; const FwdEntry *ext;
+	int len, n, i, j, c, cnext, n_prev, n_curr, prev_id, rev, any_kept, err, mem_cap, min_seed_len;
+	u32 last_mem_qb, curr_tail_x2, min_intv;
+	Intv32 in;
+	SSQ_HD int base_at(int p) const { return p >= 0 && p < len ? (int)q[p] : 4; }
+	SSQ_HD void start(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists, int x, u32 min_intv_,
+	                  const FwdEntry *list, int list_n, int b0, int b1)
+	{
+		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; ext = list; min_seed_len = opt.min_seed_len;
+		n = 0; err = 0; any_kept = 0; min_intv = min_intv_ < 1 ? 1 : min_intv_;
+		n_prev = list_n; rev = 1; prev_id = 0; i = x - 1; j = 0; n_curr = 0;
+		c = b0 < 4 ? b0 : -1; cnext = b1 < 4 ? b1 : -1;
+		last_mem_qb = 0; curr_tail_x2 = 0;
+	}
+	SSQ_HD Intv32 entry(int jj) const
+	{
+		if (rev) { const FwdEntry e = ext[n_prev - 1 - jj]; Intv32 r; r.x0 = e.x0; r.x1 = e.x1; r.x2 = e.x2; r.qb = 0; r.qe = e.qe; return r; }
+		return L.get(prev_id, jj);
+	}
+	SSQ_HD void keep(const Intv32 &p_)
+	{
+		if (n_curr == 0 && (!any_kept || (u32)(i + 1) < last_mem_qb)) {
+			any_kept = 1; last_mem_qb = (u32)(i + 1);
+			if ((int)p_.qe - (i + 1) >= min_seed_len) {
+				if (n >= mem_cap) { err = 1; return; }
+				Intv p = widen(p_); p.qb = (u32)(i + 1);
+				mem[n++] = p;
+			}
+		}
+	}
+	// true: extend `in` backwards by base c (only that base's interval is needed); false: the call is complete, mem[0..n) is its output
+	SSQ_HD bool advance()
+	{
+		for (;;) {
+			if (err) return false;
+			if (j >= n_prev) { // one backward step done for the whole set
+				if (n_curr == 0) return false;
+				prev_id ^= 1; n_prev = n_curr; rev = 0;
+				--i; j = 0; n_curr = 0;
+				if (i < -1) return false;
+				c = cnext;
+				{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
+			}
+			in = entry(j);
+			if (c < 0) { keep(in); ++j; continue; }
+			return true;
+		}
+	}
+	SSQ_HD void post(const Intv32 &okc)
+	{
+		if (okc.x2 < min_intv) keep(in);
+		else if (n_curr == 0 || okc.x2 != curr_tail_x2) { Intv32 t = okc; t.qb = 0; t.qe = in.qe; L.set(prev_id ^ 1, n_curr++, t); curr_tail_x2 = t.x2; }
+		++j;
+	}
+};
+
 // number of SA look-ups an interval contributes (max_occ rows, evenly strided when it has more)
 SSQ_HD int intv_occ_count(u64 s, int max_occ, u64 &step)
 {

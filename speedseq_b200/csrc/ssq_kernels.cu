@@ -454,6 +454,55 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd(DevIndex ix, ssq_opts_t 
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
 
+// the same kernel with the lean per-lane state (BwdCallT): fewer registers -> more blocks per SM, fewer instructions per step
+// (SSQ_SMEM_VARIANT=4; CPU-validated through hostsim, first GPU measurement pending)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_smem_bwd2(DevIndex ix, ssq_opts_t opt, const uint8_t *__restrict__ seq, int lcap, int list_cap,
+                                                         Intv *scratch, int scratch_cap, const SeedCall *__restrict__ calls, const FwdEntry *__restrict__ fl, int second,
+                                                         Intv *mems, u32 *memr, u64 mem_cap, Split *sp, Counters *cnt)
+{
+	extern __shared__ uint4 list_smem[];
+	const size_t per = (size_t)scratch_cap + (size_t)(lcap + 1);
+	Intv *mem = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * per;
+	uint4 *bufA = (uint4*)(mem + scratch_cap), *bufB = bufA + (lcap + 1);
+	DevLists<u32> lists;
+	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = bufA; lists.g1 = bufB;
+	ScalarFm fm(ix);
+	BwdCallT<DevLists<u32> > m;
+	m.n = 0; m.err = 0;
+	const unsigned long long lo = second ? sp->n_calls1 : 0, hi = second ? sp->n_calls : sp->n_calls1;
+	bool have = false, ready = false, alive = true;
+	u32 rd = 0;
+	for (;;) {
+		while (alive && !ready) {
+			if (have) { // call complete: its intervals go to the pool, tagged with the read
+				if (m.err) atomicMax(&sp->err, 1);
+				else if (m.n > 0) {
+					const unsigned long long base = group_alloc(&sp->n_mems, (unsigned)m.n);
+					if (base + m.n > mem_cap) atomicMax(&sp->err, 2);
+					else for (int e = 0; e < m.n; ++e) { mems[base + e] = mem[e]; memr[base + e] = rd; }
+				}
+				have = false;
+			}
+			const unsigned long long c = lo + (unsigned long long)atomicAdd(&sp->wk[second ? 3 : 1], 1);
+			if (c >= hi) { alive = false; break; }
+			const SeedCall sc = calls[c];
+			rd = sc.read;
+			m.start(opt, sc.len(), seq + sc.seq_off, mem, scratch_cap, lists, sc.x(), sc.min_intv, fl + sc.list_off, (int)sc.list_n, sc.b0(), sc.b1());
+			have = true;
+			ready = m.advance();
+		}
+		if (__ballot_sync(FULL, alive) == 0) break;
+		if (ready) {
+			Intv32 okc;
+			extend1(fm, m.in, m.c, 1, okc);
+			m.post(okc);
+			ready = m.advance();
+		}
+	}
+	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
+}
+
 __global__ void k_smem_snapshot(Split *sp) { sp->n_calls1 = sp->n_calls; sp->n_mems1 = sp->n_mems; }
 
 __global__ void k_smem_p2sel(ssq_opts_t opt, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off, const Intv *__restrict__ mems, const u32 *__restrict__ memr,
@@ -1382,7 +1431,7 @@ static int run_smem_split(ssq_batch *b)
 	const int n = b->n_reads, lcap = b->max_len > 0 ? b->max_len : 1;
 	const char *lc_env = getenv("SSQ_LIST_CAP");
 	const int list_cap = lc_env ? atoi(lc_env) : 6;
-	const int fgrid = b->n_sm * 5, bgrid = b->n_sm * 6, bthreads = 128;
+	const int fgrid = b->n_sm * 5, bgrid = b->n_sm * 8, bthreads = 128; // persistent lanes; the grid may exceed what is resident
 	const int scratch_cap = lcap + 1; // a call cannot keep more intervals than the read has positions
 	if (b->intv_off.need((size_t)(n + 1) * 8) || b->intv_cnt.need((size_t)(n + 1) * 4) || b->l_rep.need((size_t)(n + 1) * 4) || b->misc.need(sizeof(Misc)) ||
 	    b->xsplit.need(sizeof(Split))) return SSQ_ENOMEM;
@@ -1394,7 +1443,11 @@ static int run_smem_split(ssq_batch *b)
 	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
 	if (b->call_cap == 0) b->call_cap = (u64)n * 10 + 4096;
 	if (b->fl_cap == 0) b->fl_cap = (u64)n * 96 + 65536;
+	const bool lean = b->smem_variant == 4;
+	const int lean_blocks = getenv("SSQ_SMEM_BLOCKS") ? atoi(getenv("SSQ_SMEM_BLOCKS")) : 8;
 	CK(cudaFuncSetAttribute(k_smem_bwd<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
+	CK(cudaFuncSetAttribute(k_smem_bwd2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
+	CK(cudaFuncSetAttribute(k_smem_bwd2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
 	const size_t lsm = (size_t)bthreads * 2 * list_cap * sizeof(uint4);
 	Misc *dm = b->misc.as<Misc>();
 	Split *sp = b->xsplit.as<Split>();
@@ -1406,13 +1459,21 @@ static int run_smem_split(ssq_batch *b)
 		k_smem_fwd<1><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp); // n_calls1 = pass-1 calls (n_mems1 still 0)
-		k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		if (!lean) k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		else if (lean_blocks >= 8) k_smem_bwd2<8><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		else k_smem_bwd2<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp); // n_mems1 = pass-1 intervals; n_calls1 unchanged (no calls were added)
 		k_smem_p2sel<<<b->n_sm * 8, 256, 0, b->st>>>(b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->xcalls.as<SeedCall>(), b->call_cap, sp);
 		k_smem_fwd<2><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
-		k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		if (!lean) k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		else if (lean_blocks >= 8) k_smem_bwd2<8><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		else k_smem_bwd2<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		if (with_p3) k_smem_p3_append<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->xp3.as<Intv>(), b->xp3n.as<i32>(), p3_stride, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp);
 		b->launches += 9;
@@ -1457,8 +1518,8 @@ static int run_smem_split(ssq_batch *b)
 static int run_smem(ssq_batch *b)
 {
 	const int n = b->n_reads, lcap = b->max_len > 0 ? b->max_len : 1;
-	if (b->smem_variant == 3 && b->idx->dev.bwt32 && n > 0) return run_smem_split(b);
-	const int variant = b->smem_variant == 3 ? 2 : b->smem_variant;
+	if ((b->smem_variant == 3 || b->smem_variant == 4) && b->idx->dev.bwt32 && n > 0) return run_smem_split(b);
+	const int variant = b->smem_variant >= 3 ? 2 : b->smem_variant;
 	const int warps_per_block = 4, threads = warps_per_block * 32;
 	const size_t smem = variant == 0 ? (size_t)warps_per_block * 2 * (lcap + 1) * sizeof(Intv) : 0;
 	const char *lc_env = getenv("SSQ_LIST_CAP");

@@ -71,7 +71,16 @@ static void run_read_split(const DevIndex &ix, const ssq_opts_t &opt, int len, c
 	std::vector<Intv32> a32(len + 2), b32(len + 2);
 	HostListsT<u32> hl; hl.a[0] = a32.data(); hl.a[1] = b32.data();
 	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499f);
+	const bool lean = getenv("HOSTSIM_SPLIT_LEAN") != 0; // BwdCallT (k_smem_bwd2) instead of the machine started in its backward phase
 	auto backward = [&](int x, u32 min_intv, const std::vector<FwdEntry> &list) {
+		if (lean) {
+			BwdCallT<HostListsT<u32> > m; Intv32 okc;
+			m.start(opt, len, q, mem.data(), 2048, hl, x, min_intv, list.data(), (int)list.size(), x >= 1 ? (int)q[x - 1] : 4, x >= 2 ? (int)q[x - 2] : 4);
+			while (m.advance()) { extend1(fm, m.in, m.c, 1, okc); m.post(okc); }
+			if (m.err) abort();
+			for (int k = 0; k < m.n; ++k) all.push_back(mem[k]);
+			return;
+		}
 		SmemMachineT<HostListsT<u32>, u32, false> m; Intv32 okc;
 		m.init(opt, len, q, mem.data(), 2048, hl, 1);
 		m.start_backward(x, min_intv, list.data(), (int)list.size(), x >= 1 ? (int)q[x - 1] : 4, x >= 2 ? (int)q[x - 2] : 4);
@@ -124,7 +133,7 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	std::vector<Intv> bufA(len + 2), bufB(len + 2);
 	w.mem.assign(2048, Intv());
 	int err = 0;
-	if (getenv("HOSTSIM_SPLIT") && ix.bwt32) run_read_split(ix, opt, len, q, w);
+	if ((getenv("HOSTSIM_SPLIT") || getenv("HOSTSIM_SPLIT_LEAN")) && ix.bwt32) run_read_split(ix, opt, len, q, w);
 	else if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
 	else if (ix.bwt32 && !getenv("HOSTSIM_M64")) { // the state-machine form the GPU kernel runs, 32-bit rows (what the GPU picks when bwt32 exists)
 		std::vector<Intv32> a32(len + 2), b32(len + 2);
