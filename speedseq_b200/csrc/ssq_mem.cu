@@ -239,10 +239,16 @@ extern "C" int ssq_mem_batch_sam(const ssq_index_t *idx, const ssq_opts_t *opt_,
 	std::vector<u64> off(n_reads + 1, 0);
 	for (int i = 0; i < n_reads; ++i) off[i + 1] = off[i] + strlen(seqs[i]);
 	std::vector<uint8_t> codes(off[n_reads] + 1);
-	for (int i = 0; i < n_reads; ++i) {
-		const char *s = seqs[i];
-		uint8_t *d = codes.data() + off[i];
-		for (size_t k = 0; s[k]; ++k) { switch (s[k]) { case 'A': case 'a': d[k] = 0; break; case 'C': case 'c': d[k] = 1; break; case 'G': case 'g': d[k] = 2; break; case 'T': case 't': d[k] = 3; break; default: d[k] = 4; } }
+	{
+		uint8_t lut[256];
+		memset(lut, 4, sizeof lut);
+		lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+		for (int i = 0; i < n_reads; ++i) {
+			const unsigned char *s = (const unsigned char*)seqs[i];
+			uint8_t *d = codes.data() + off[i];
+			const size_t l = (size_t)(off[i + 1] - off[i]);
+			for (size_t k = 0; k < l; ++k) d[k] = lut[s[k]];
+		}
 	}
 	HostIndexInfo hi; hi.l_pac = idx->dev.l_pac; hi.n_seqs = idx->n_seqs; hi.names = idx->names; hi.ann_off = idx->ann_off;
 	PeStat pes[4];

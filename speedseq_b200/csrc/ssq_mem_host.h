@@ -11,6 +11,7 @@
 #include <string.h>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 #include "ssq_dev2.cuh"
 
@@ -215,22 +216,41 @@ struct ReadPlan { // what is written for one read
 	ReadPlan() : extra_flag(0) {} // XA text per region index (built from xa tasks)
 };
 
-static void put_num(std::string &s, long long v) { char b[24]; snprintf(b, sizeof b, "%lld", v); s += b; }
+static inline void put_num(std::string &s, long long v) // == "%lld"
+{
+	char b[24]; int n = 24;
+	unsigned long long u = v < 0 ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+	do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
+	if (v < 0) b[--n] = '-';
+	s.append(b + n, 24 - n);
+}
 static int get_rlen(const std::vector<u32> &c) { int l = 0; for (size_t k = 0; k < c.size(); ++k) { int op = c[k] & 0xf; if (op == 0 || op == 2) l += c[k] >> 4; } return l; }
 
 static void aln2sam(const HostIndexInfo *ix, std::string &str, const char *name, const char *seq_codes, int l_seq, const char *qual, const std::vector<Aln> &list, int which,
                     const Aln *m_, const char *rg_id, const char *comment)
 {
-	Aln p = list[which], mt;
-	const Aln *m = 0;
-	if (m_) { mt = *m_; m = &mt; }
-	p.flag |= m ? 0x1 : 0;
-	p.flag |= p.rid < 0 ? 0x4 : 0;
-	p.flag |= m && m->rid < 0 ? 0x8 : 0;
-	if (p.rid < 0 && m && m->rid >= 0) { p.rid = m->rid; p.pos = m->pos; p.is_rev = m->is_rev; p.cigar.clear(); }
-	if (m && m->rid < 0 && p.rid >= 0) { mt.rid = p.rid; mt.pos = p.pos; mt.is_rev = p.is_rev; mt.cigar.clear(); }
-	p.flag |= p.is_rev ? 0x10 : 0;
-	p.flag |= m && m->is_rev ? 0x20 : 0;
+	// mem_aln2sam() works on copies of the alignment and its mate and patches them (an unmapped end takes the other end's
+	// coordinates and loses its CIGAR); here the patched scalars live in locals and the records themselves are never copied
+	static const std::vector<u32> no_cigar;
+	const Aln &p0 = list[which];
+	struct { i64 pos; int rid, flag, is_rev, mapq, NM, score, sub; const std::vector<u32> &cigar_ref() const { return *cig; } const std::vector<u32> *cig; const std::string *mdp, *xap; } pv;
+	pv.pos = p0.pos; pv.rid = p0.rid; pv.flag = p0.flag; pv.is_rev = p0.is_rev; pv.mapq = p0.mapq; pv.NM = p0.NM; pv.score = p0.score; pv.sub = p0.sub;
+	pv.cig = &p0.cigar; pv.mdp = &p0.md; pv.xap = &p0.xa;
+	struct { i64 pos; int rid, is_rev; const std::vector<u32> *cig; } mv;
+	const bool has_m = m_ != 0;
+	mv.pos = has_m ? m_->pos : -1; mv.rid = has_m ? m_->rid : -1; mv.is_rev = has_m ? m_->is_rev : 0; mv.cig = has_m ? &m_->cigar : &no_cigar;
+	pv.flag |= has_m ? 0x1 : 0;
+	pv.flag |= pv.rid < 0 ? 0x4 : 0;
+	pv.flag |= has_m && mv.rid < 0 ? 0x8 : 0;
+	if (pv.rid < 0 && has_m && mv.rid >= 0) { pv.rid = mv.rid; pv.pos = mv.pos; pv.is_rev = mv.is_rev; pv.cig = &no_cigar; }
+	if (has_m && mv.rid < 0 && pv.rid >= 0) { mv.rid = pv.rid; mv.pos = pv.pos; mv.is_rev = pv.is_rev; mv.cig = &no_cigar; }
+	pv.flag |= pv.is_rev ? 0x10 : 0;
+	pv.flag |= has_m && mv.is_rev ? 0x20 : 0;
+	struct PView { i64 pos; int rid, flag, is_rev, mapq, NM, score, sub; const std::vector<u32> &cigar; const std::string &md, &xa; };
+	struct MView { i64 pos; int rid, is_rev; const std::vector<u32> &cigar; };
+	const PView p = {pv.pos, pv.rid, pv.flag, pv.is_rev, pv.mapq, pv.NM, pv.score, pv.sub, *pv.cig, *pv.mdp, *pv.xap};
+	const MView mview = {mv.pos, mv.rid, mv.is_rev, *mv.cig};
+	const MView *m = has_m ? &mview : 0;
 	str += name; str += '\t';
 	put_num(str, (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0)); str += '\t';
 	if (p.rid >= 0) {
@@ -265,14 +285,18 @@ static void aln2sam(const HostIndexInfo *ix, std::string &str, const char *name,
 			if (!p.is_rev) { if (c0 == 4 || c0 == 3) qb += p.cigar[0] >> 4; if (c1 == 4 || c1 == 3) qe -= p.cigar.back() >> 4; }
 			else { if (c0 == 4 || c0 == 3) qe -= p.cigar[0] >> 4; if (c1 == 4 || c1 == 3) qb += p.cigar.back() >> 4; }
 		}
+		char buf[2 * SSQ_MAX_READ_LEN + 8];
+		int nb = 0;
 		if (!p.is_rev) {
-			for (int i = qb; i < qe; ++i) str += "ACGTN"[(int)seq_codes[i]];
-			str += '\t';
+			for (int i = qb; i < qe; ++i) buf[nb++] = "ACGTN"[(int)seq_codes[i]];
+			buf[nb++] = '\t';
+			str.append(buf, nb);
 			if (qual) str.append(qual + qb, qe - qb); else str += '*';
 		} else {
-			for (int i = qe - 1; i >= qb; --i) str += "TGCAN"[(int)seq_codes[i]];
-			str += '\t';
-			if (qual) for (int i = qe - 1; i >= qb; --i) str += qual[i]; else str += '*';
+			for (int i = qe - 1; i >= qb; --i) buf[nb++] = "TGCAN"[(int)seq_codes[i]];
+			buf[nb++] = '\t';
+			if (qual) for (int i = qe - 1; i >= qb; --i) buf[nb++] = qual[i]; else buf[nb++] = '*';
+			str.append(buf, nb);
 		}
 	}
 	if (!p.cigar.empty()) { str += "\tNM:i:"; put_num(str, p.NM); str += "\tMD:Z:"; str += p.md; }
@@ -318,6 +342,9 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 	const std::vector<uint8_t> codes(codes_, codes_ + off_[n_reads] + 1);
 	const std::vector<u64> off(off_, off_ + n_reads + 1);
 	int rc;
+	const bool timing = getenv("SSQ_MEM_TIMING") != 0;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_plan = 0, t_dist = 0, t_fmt = 0, t0 = 0;
 	if ((rc = be.align(n_reads, codes_, off_, paired, o.max_matesw))) return rc;
 	PeStat pes[4];
 	memset(pes, 0, sizeof pes);
@@ -443,6 +470,7 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 		}
 	}
 	};
+	t0 = now();
 	{
 		const int units = paired ? n_reads / 2 : n_reads;
 		std::vector<std::thread> th;
@@ -453,6 +481,7 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 		for (size_t t = 0; t < th.size(); ++t) th[t].join();
 		for (int t = 0; t < n_thr; ++t) reqs.insert(reqs.end(), reqs_t[t].begin(), reqs_t[t].end()); // thread order = read order
 	}
+	t_plan = now() - t0;
 	const int nt = (int)reqs.size();
 	std::vector<AlnOut> outs(nt);
 	std::vector<u32> cigs((size_t)nt * CIG_CAP + 1);
@@ -463,29 +492,47 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 		if ((rc = be.cigar(tasks, outs, cigs, mds))) return rc;
 	}
 	// 7. distribute results: output lines, mate headers, XA strings
+	t0 = now();
 	std::vector<std::vector<std::string> > xa(n_reads);
-	for (int r = 0; r < n_reads; ++r) xa[r].resize(na[r]);
-	for (int t = 0; t < nt; ++t) {
-		const CigReq &q = reqs[t];
-		const AlnOut &ao = outs[t];
-		if (ao.n_cigar < 0 || ao.n_cigar > CIG_CAP - 2 || ao.md_len >= MD_CAP) { err = "alignment with too many CIGAR operations / MD characters or a traceback matrix beyond the per-thread capacity"; return SSQ_ECAP; }
-		if (q.kind == 1) {
-			std::string &s = xa[q.read][q.xa_owner];
-			s += idx->names[ao.rid]; s += ','; s += "+-"[ao.is_rev]; put_num(s, ao.pos + 1); s += ',';
-			for (int k = 0; k < ao.n_cigar; ++k) { put_num(s, cigs[(size_t)t * CIG_CAP + k] >> 4); s += "MIDSHN"[cigs[(size_t)t * CIG_CAP + k] & 0xf]; }
-			s += ','; put_num(s, ao.NM); s += ';';
-			continue;
-		}
-		Aln &dst = q.kind == 0 ? plan[q.read].lines[q.line] : mate_hdr[q.read][0];
-		dst.pos = ao.pos; dst.rid = ao.rid; dst.is_rev = ao.is_rev; dst.NM = ao.NM; dst.score = ao.score; dst.sub = ao.sub;
-		dst.flag |= ao.flag;
-		dst.cigar.assign(cigs.begin() + (size_t)t * CIG_CAP, cigs.begin() + (size_t)t * CIG_CAP + ao.n_cigar);
-		dst.md.assign(mds.data() + (size_t)t * MD_CAP, ao.md_len);
-		if (q.kind == 0) plan[q.read].xa_for.resize(1);
+	{
+		// requests are in read order and thread t planned the reads of units [lo_t, hi_t): its slice of `reqs` touches only those
+		// reads' lines, mate headers and XA strings, so the slices can be distributed concurrently
+		std::vector<size_t> req_lo(n_thr + 1, 0);
+		for (int t = 0; t < n_thr; ++t) req_lo[t + 1] = req_lo[t] + reqs_t[t].size();
+		const int units = paired ? n_reads / 2 : n_reads, per_unit = paired ? 2 : 1;
+		std::vector<int> bad(n_thr, 0);
+		auto dist_range = [&](int tid) {
+			const int rlo = (int)((long long)units * tid / n_thr) * per_unit, rhi = (int)((long long)units * (tid + 1) / n_thr) * per_unit;
+			for (int r = rlo; r < rhi; ++r) xa[r].resize(na[r]);
+			for (size_t t = req_lo[tid]; t < req_lo[tid + 1]; ++t) {
+				const CigReq &q = reqs[t];
+				const AlnOut &ao = outs[t];
+				if (ao.n_cigar < 0 || ao.n_cigar > CIG_CAP - 2 || ao.md_len >= MD_CAP) { bad[tid] = 1; return; }
+				if (q.kind == 1) {
+					std::string &s = xa[q.read][q.xa_owner];
+					s += idx->names[ao.rid]; s += ','; s += "+-"[ao.is_rev]; put_num(s, ao.pos + 1); s += ',';
+					for (int k = 0; k < ao.n_cigar; ++k) { put_num(s, cigs[(size_t)t * CIG_CAP + k] >> 4); s += "MIDSHN"[cigs[(size_t)t * CIG_CAP + k] & 0xf]; }
+					s += ','; put_num(s, ao.NM); s += ';';
+					continue;
+				}
+				Aln &dst = q.kind == 0 ? plan[q.read].lines[q.line] : mate_hdr[q.read][0];
+				dst.pos = ao.pos; dst.rid = ao.rid; dst.is_rev = ao.is_rev; dst.NM = ao.NM; dst.score = ao.score; dst.sub = ao.sub;
+				dst.flag |= ao.flag;
+				dst.cigar.assign(cigs.begin() + (size_t)t * CIG_CAP, cigs.begin() + (size_t)t * CIG_CAP + ao.n_cigar);
+				dst.md.assign(mds.data() + (size_t)t * MD_CAP, ao.md_len);
+				if (q.kind == 0) plan[q.read].xa_for.resize(1);
+			}
+			// XA goes to the line built from region xa_owner (all of a read's XA requests precede this pass over its lines)
+			for (size_t t = req_lo[tid]; t < req_lo[tid + 1]; ++t) if (reqs[t].kind == 0) plan[reqs[t].read].lines[reqs[t].line].xa = xa[reqs[t].read][reqs[t].reg_idx];
+		};
+		std::vector<std::thread> th;
+		for (int t = 0; t < n_thr; ++t) { if (n_thr == 1) dist_range(0); else th.emplace_back(dist_range, t); }
+		for (size_t t = 0; t < th.size(); ++t) th[t].join();
+		for (int t = 0; t < n_thr; ++t) if (bad[t]) { err = "alignment with too many CIGAR operations / MD characters or a traceback matrix beyond the per-thread capacity"; return SSQ_ECAP; }
 	}
-	// XA goes to the line built from region xa_owner
-	for (int t = 0; t < nt; ++t) if (reqs[t].kind == 0) plan[reqs[t].read].lines[reqs[t].line].xa = xa[reqs[t].read][reqs[t].reg_idx];
+	t_dist = now() - t0;
 	// 8. SAM text in input order
+	t0 = now();
 	sam.clear();
 	std::vector<std::string> part(n_thr);
 	std::vector<size_t> rel_off(line_off ? n_reads + 1 : 0, 0);
@@ -529,5 +576,7 @@ static int mem_batch_sam(Backend &be, const ssq_opts_t &o, const HostIndexInfo *
 		}
 	}
 	if (line_off) (*line_off)[n_reads] = sam.size();
+	t_fmt = now() - t0;
+	if (timing) fprintf(stderr, "[ssq_mem host] %d reads, %d threads: plan (primary/pair/MAPQ) %.3f s | distribute results %.3f s | SAM text %.3f s\n", n_reads, n_thr, t_plan, t_dist, t_fmt);
 	return SSQ_OK;
 }
