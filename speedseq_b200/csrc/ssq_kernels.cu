@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 //   k_smem_fwd<2>  per request: the forward walk;  k_smem_bwd again for those calls
 //   k_smem_p3 (+ k_smem_p3_append): the greedy pass
 //   sort by (read, qb, qe) -> pool, intv_off/intv_cnt, l_rep   (equal keys are identical intervals)
-struct Split { unsigned long long n_calls, n_calls1, n_fl, n_mems, n_mems1; int err, pad; int wk[8]; };
+struct Split { unsigned long long n_calls, n_calls1, n_fl, n_mems, n_mems1, need_calls; int err, pad; int wk[8]; }; // need_calls: n_calls before clamping to the pool size
 
 // space for n items from a shared counter, one atomic per group of converged lanes
 __device__ __forceinline__ unsigned long long group_alloc(unsigned long long *ctr, unsigned int n)
@@ -348,11 +348,12 @@ __global__ void __launch_bounds__(256) k_smem_fwd(DevIndex ix, ssq_opts_t opt, i
 		const unsigned long long off = group_alloc(&sp->n_fl, (unsigned)n_list);
 		unsigned long long c = slot;
 		if (PASS == 1) c = group_alloc(&sp->n_calls, 1u);
-		if (off + n_list > fl_cap || c >= call_cap) atomicMax(&sp->err, 2);
-		else {
-			for (int e = 0; e < n_list; ++e) fl[off + e] = st[e];
+		const bool fits = off + n_list <= fl_cap;
+		if (!fits || c >= call_cap) atomicMax(&sp->err, 2); // a pool is too small: the host grows it and runs the stage again
+		if (c < call_cap) { // the slot always gets a well-formed record; list_n == 0 tells the backward kernel to skip it
+			if (fits) for (int e = 0; e < n_list; ++e) fl[off + e] = st[e];
 			SeedCall sc; sc.read = (u32)r; sc.pk = SeedCall::pack(x, len, x >= 1 ? (int)q[x - 1] : 4, x >= 2 ? (int)q[x - 2] : 4);
-			sc.min_intv = min_intv; sc.list_n = (u32)n_list; sc.list_off = off; sc.seq_off = (u64)(q - seq);
+			sc.min_intv = min_intv; sc.list_n = fits ? (u32)n_list : 0u; sc.list_off = fits ? off : 0; sc.seq_off = (u64)(q - seq);
 			calls[c] = sc;
 		}
 		if (PASS == 1) x = (int)st[n_list - 1].qe; else have = false;
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd(DevIndex ix, ssq_opts_t 
 			const unsigned long long c = lo + (unsigned long long)atomicAdd(&sp->wk[second ? 3 : 1], 1);
 			if (c >= hi) { alive = false; break; }
 			const SeedCall sc = calls[c];
+			if (sc.list_n == 0) continue; // its forward list did not fit the pool (the stage is being re-run with a larger one)
 			rd = sc.read;
 			m.init(opt, sc.len(), seq + sc.seq_off, mem, scratch_cap, lists, 1);
 			m.start_backward(sc.x(), sc.min_intv, fl + sc.list_off, (int)sc.list_n, sc.b0(), sc.b1());
@@ -487,6 +489,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd2(DevIndex ix, ssq_opts_t
 			const unsigned long long c = lo + (unsigned long long)atomicAdd(&sp->wk[second ? 3 : 1], 1);
 			if (c >= hi) { alive = false; break; }
 			const SeedCall sc = calls[c];
+			if (sc.list_n == 0) continue; // its forward list did not fit the pool (the stage is being re-run with a larger one)
 			rd = sc.read;
 			m.start(opt, sc.len(), seq + sc.seq_off, mem, scratch_cap, lists, sc.x(), sc.min_intv, fl + sc.list_off, (int)sc.list_n, sc.b0(), sc.b1());
 			have = true;
@@ -503,7 +506,13 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd2(DevIndex ix, ssq_opts_t
 	if (fm.n_blk) atomicAdd(&cnt->occ_smem, fm.n_blk);
 }
 
-__global__ void k_smem_snapshot(Split *sp) { sp->n_calls1 = sp->n_calls; sp->n_mems1 = sp->n_mems; }
+// range bookkeeping between the kernels; the counters keep counting when a pool is full, the ranges the next kernels walk must not
+__global__ void k_smem_snapshot(Split *sp, u64 call_cap, u64 mem_cap, int set1)
+{
+	if (sp->n_calls > sp->need_calls) sp->need_calls = sp->n_calls;
+	if (sp->n_calls > call_cap) sp->n_calls = call_cap;
+	if (set1) { sp->n_calls1 = sp->n_calls; sp->n_mems1 = sp->n_mems < mem_cap ? sp->n_mems : mem_cap; }
+}
 
 __global__ void k_smem_p2sel(ssq_opts_t opt, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off, const Intv *__restrict__ mems, const u32 *__restrict__ memr,
                              SeedCall *calls, u64 call_cap, Split *sp)
@@ -1458,15 +1467,16 @@ static int run_smem_split(ssq_batch *b)
 		if (with_p3) k_smem_p3<u32><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
 		k_smem_fwd<1><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
-		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp); // n_calls1 = pass-1 calls (n_mems1 still 0)
+		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 1); // n_calls1 = pass-1 calls (n_mems1 still 0)
 		if (!lean) k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		else if (lean_blocks >= 8) k_smem_bwd2<8><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		else k_smem_bwd2<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
-		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp); // n_mems1 = pass-1 intervals; n_calls1 unchanged (no calls were added)
+		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 1); // n_mems1 = pass-1 intervals; n_calls1 unchanged (no calls were added)
 		k_smem_p2sel<<<b->n_sm * 8, 256, 0, b->st>>>(b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->xcalls.as<SeedCall>(), b->call_cap, sp);
+		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 0); // clamp the request range
 		k_smem_fwd<2><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
 		if (!lean) k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
@@ -1476,14 +1486,14 @@ static int run_smem_split(ssq_batch *b)
 		else k_smem_bwd2<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		if (with_p3) k_smem_p3_append<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->xp3.as<Intv>(), b->xp3n.as<i32>(), p3_stride, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp);
-		b->launches += 9;
+		b->launches += 10;
 		CK(cudaGetLastError());
 		Split hs;
 		CK(cudaMemcpyAsync(&hs, sp, sizeof(Split), cudaMemcpyDeviceToHost, b->st));
 		CK(cudaStreamSynchronize(b->st));
 		if (hs.err == 2) { // a pool was too small; the counters are lower bounds of what is needed
 			if (hs.n_mems + 1 > b->pool_cap) b->pool_cap = hs.n_mems + hs.n_mems / 2 + 4096; else b->pool_cap += b->pool_cap / 2;
-			if (hs.n_calls + 1 > b->call_cap) b->call_cap = hs.n_calls + hs.n_calls / 2 + 4096; else b->call_cap += b->call_cap / 2;
+			{ const u64 nc = hs.need_calls > hs.n_calls ? hs.need_calls : hs.n_calls; if (nc + 1 > b->call_cap) b->call_cap = nc + nc / 2 + 4096; else b->call_cap += b->call_cap / 2; }
 			if (hs.n_fl + 1 > b->fl_cap) b->fl_cap = hs.n_fl + hs.n_fl / 2 + 65536; else b->fl_cap += b->fl_cap / 2;
 			continue;
 		}
