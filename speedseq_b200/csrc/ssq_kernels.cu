@@ -1347,7 +1347,7 @@ struct ssq_batch {
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
 	u64 call_cap = 0, fl_cap = 0; // split seeding: capacities of the call and forward-list pools
-	cudaEvent_t ev[6], evc[4], evs[2]; // ... ; k_smem_m alone // stage boundaries; chaining tiers (light start, heavy start, end)
+	cudaEvent_t ev[6], evc[4], evs[2], evx[2]; // stage boundaries; chaining tiers; k_smem_m alone; selection kernels of one round // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
 	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
 };
@@ -1395,7 +1395,7 @@ extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, i
 	CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
 	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
 	for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&b->evc[i]));
-	for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&b->evs[i]));
+	for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&b->evs[i])); CK(cudaEventCreate(&b->evx[i])); }
 	if (read_off && (rc = ssq_batch_upload(b, n_reads, seq, read_off))) { ssq_batch_free(b); return rc; }
 	*out = b;
 	return SSQ_OK;
@@ -1411,7 +1411,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) all[i]->release();
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
-	for (int i = 0; i < 2; ++i) cudaEventDestroy(b->evs[i]);
+	for (int i = 0; i < 2; ++i) { cudaEventDestroy(b->evs[i]); cudaEventDestroy(b->evx[i]); }
 	if (b->own_stream) cudaStreamDestroy(b->st);
 	delete b;
 }
@@ -1747,8 +1747,7 @@ static int run_extend(ssq_batch *b)
 		const size_t rsmem = (size_t)64 * (b->max_len + 2) * 4;
 		CK(cudaFuncSetAttribute(k_ext_retry<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
 		CK(cudaFuncSetAttribute(k_ext_retry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-		cudaEvent_t es0, es1;
-		CK(cudaEventCreate(&es0)); CK(cudaEventCreate(&es1));
+		const cudaEvent_t es0 = b->evx[0], es1 = b->evx[1];
 		for (int round = 0;; ++round) {
 			for (int dir = 0; dir < 2; ++dir) {
 				size_t tb = 0;
@@ -1815,7 +1814,6 @@ static int run_extend(ssq_batch *b)
 			n_in = (int)h_unf;
 			if (round > 8) { ssq_set_error("seed-extension rounds did not converge"); return SSQ_ECUDA; }
 		}
-		cudaEventDestroy(es0); cudaEventDestroy(es1);
 	} else {
 		CK(cudaMemsetAsync(b->n_regs.p, 0, (size_t)(n + 1) * 4, b->st));
 	}
