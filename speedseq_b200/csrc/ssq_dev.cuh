@@ -47,6 +47,8 @@ struct DevIndex {
 	// denser suffix-array sample derived at load time (every sad_intv-th row; u32 when positions fit, 0xffffffff = -1): same
 	// values the LF walk would reach, several times fewer dependent steps per look-up.  0 / null: walk to the on-disk sample.
 	const u32 *sad32; const u64 *sad64; i32 sad_intv;
+	// k-mer jump-start table (opt-in, SSQ_KMER_K): bi-intervals of every string of length 1..kmer_k, see kmer_off()
+	const struct KmerEnt *kmer; i32 kmer_k;
 };
 
 struct Counters { // device-measured work, feeds roofline.achieved (algorithmic bytes)
@@ -200,6 +202,31 @@ template <class U>
 SSQ_HD void set_intv(const DevIndex &ix, int c, IntvT<U> &ik)
 {
 	ik.x0 = (U)(ix.L2[c] + 1); ik.x2 = (U)(ix.L2[c + 1] - ix.L2[c]); ik.x1 = (U)(ix.L2[3 - c] + 1); ik.qb = ik.qe = 0;
+}
+
+// ---------------------------------------------------------------- k-mer jump-start table ----
+// A third to a half of the seeding's rank queries produce a string of at most 10-12 bases (tests/hostsim diagnostics: 38 % for
+// K = 10, 51 % for K = 12): the first steps of every forward walk and, above all, the short prefixes that survive many backward
+// sweeps.  The bi-interval of a string does not depend on how it was reached, so those queries can be answered — exactly — from a
+// table of the bi-intervals of all strings of length 1..K: entry (L, code) at kmer_off(L) + code, code = the L bases as a 2L-bit
+// number, first base in the top bits.  K = 10: 1.4 M entries x 16 B = 22 MB (L2-resident).  Indexes with < 2^32 rows only.
+struct KmerEnt { u32 x0, x1, x2, pad; };
+SSQ_HD u32 kmer_off(int L) { return ((1u << (2 * L)) - 4u) / 3u; } // 4 + 16 + ... + 4^(L-1)
+SSQ_HD u32 kmer_entries(int K) { return kmer_off(K + 1); }
+template <class Fm>
+SSQ_HD KmerEnt kmer_compute(Fm &fm, const DevIndex &ix, int L, u32 code) // by the same forward extensions a walk would make
+{
+	Intv32 ik, okc;
+	set_intv(ix, (int)(code >> (2 * (L - 1)) & 3u), ik);
+	for (int j = 1; j < L; ++j) { extend1(fm, ik, 3 - (int)(code >> (2 * (L - 1 - j)) & 3u), 0, okc); ik = okc; }
+	KmerEnt e; e.x0 = ik.x0; e.x1 = ik.x1; e.x2 = ik.x2; e.pad = 0;
+	return e;
+}
+SSQ_HD Intv32 kmer_lookup(const DevIndex &ix, int L, u32 code)
+{
+	const KmerEnt e = ix.kmer[kmer_off(L) + code];
+	Intv32 r; r.x0 = e.x0; r.x1 = e.x1; r.x2 = e.x2; r.qb = r.qe = 0;
+	return r;
 }
 
 // ------------------------------------------------------------------------ SMEM search ----
@@ -549,6 +576,7 @@ struct BwdCallT {
 	const uint8_t *q; Intv *mem; Lists L; const FwdEntry *ext;
 	int len, n, i, j, c, cnext, n_prev, n_curr, prev_id, rev, any_kept, err, mem_cap, min_seed_len;
 	u32 last_mem_qb, curr_tail_x2, min_intv;
+	u32 win; int K; // k-mer table in use (K > 0): the K bases from position i on, first base in the top bits (N / beyond the read = 0: never part of a string looked up)
 	Intv32 in;
 	SSQ_HD int base_at(int p) const { return p >= 0 && p < len ? (int)q[p] : 4; }
 	SSQ_HD void start(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists, int x, u32 min_intv_,
@@ -559,6 +587,20 @@ struct BwdCallT {
 		n_prev = list_n; rev = 1; prev_id = 0; i = x - 1; j = 0; n_curr = 0;
 		c = b0 < 4 ? b0 : -1; cnext = b1 < 4 ? b1 : -1;
 		last_mem_qb = 0; curr_tail_x2 = 0;
+		K = 0; win = 0;
+	}
+	SSQ_HD void use_table(int K_) // after start(): window over positions i .. i+K-1
+	{
+		K = K_; win = 0;
+		for (int t = 0; t < K; ++t) { const int b = base_at(i + t); win = win << 2 | (u32)(b < 4 ? b : 0); }
+	}
+	// the query advance() has set up, answered from the table when the string it produces (q[i .. in.qe)) is short enough
+	SSQ_HD bool table_hit(const DevIndex &ix, Intv32 &okc) const
+	{
+		const int L = (int)in.qe - i;
+		if (K == 0 || L > K) return false;
+		okc = kmer_lookup(ix, L, win >> (2 * (K - L)));
+		return true;
 	}
 	SSQ_HD Intv32 entry(int jj) const
 	{
@@ -587,6 +629,7 @@ struct BwdCallT {
 				--i; j = 0; n_curr = 0;
 				if (i < -1) return false;
 				c = cnext;
+				if (K) win = (win >> 2) | (u32)(c < 0 ? 0 : c) << (2 * (K - 1)); // the base at the new i enters at the top, the last one leaves
 				{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
 			}
 			in = entry(j);

@@ -104,6 +104,17 @@ __global__ void k_sa_densify(DevIndex ix, int d, u64 n_dense, T *out)
 	out[j] = (T)v; // -1 truncates to the all-ones sentinel
 }
 
+// k-mer jump-start table (opt-in): entry e = (L, code) with kmer_off(L) <= e < kmer_off(L + 1)
+__global__ void k_kmer_build(DevIndex ix, int K, u32 n_entries, KmerEnt *out)
+{
+	const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_entries) return;
+	int L = 1;
+	while (L < K && kmer_off(L + 1) <= e) ++L;
+	ScalarFm fm(ix);
+	out[e] = kmer_compute(fm, ix, L, e - kmer_off(L));
+}
+
 extern "C" int ssq_index_load(const char *prefix, int device, ssq_index_t **out)
 {
 	if (!prefix || !out) return SSQ_EINVAL;
@@ -178,6 +189,18 @@ extern "C" int ssq_index_load(const char *prefix, int device, ssq_index_t **out)
 			idx->dev.sad_intv = d; idx->dev_bytes += nd * (small ? 4 : 8);
 		}
 	}
+	{ // k-mer jump-start table for the seeding kernels (SSQ_KMER_K=1..12; off by default until measured on the GPU)
+		const int K = getenv("SSQ_KMER_K") ? atoi(getenv("SSQ_KMER_K")) : 0;
+		if (K >= 1 && K <= 12 && idx->dev.bwt32) {
+			const u32 ne = kmer_entries(K);
+			void *dk = 0;
+			CKI(cudaMalloc(&dk, (size_t)ne * sizeof(KmerEnt)));
+			k_kmer_build<<<(ne + 255) / 256, 256>>>(idx->dev, K, ne, (KmerEnt*)dk);
+			CKI(cudaGetLastError());
+			CKI(cudaDeviceSynchronize());
+			idx->dev.kmer = (const KmerEnt*)dk; idx->dev.kmer_k = K; idx->dev_bytes += (size_t)ne * sizeof(KmerEnt);
+		}
+	}
 	// .ann
 	snprintf(fn, sizeof fn, "%s.ann", prefix);
 	{
@@ -224,7 +247,7 @@ extern "C" int ssq_index_load(const char *prefix, int device, ssq_index_t **out)
 extern "C" void ssq_index_free(ssq_index_t *idx)
 {
 	if (!idx) return;
-	cudaFree((void*)idx->dev.bwt); cudaFree((void*)idx->dev.bwt32); cudaFree((void*)idx->dev.sa); cudaFree((void*)idx->dev.pac); cudaFree((void*)idx->dev.sad32); cudaFree((void*)idx->dev.sad64);
+	cudaFree((void*)idx->dev.bwt); cudaFree((void*)idx->dev.bwt32); cudaFree((void*)idx->dev.sa); cudaFree((void*)idx->dev.pac); cudaFree((void*)idx->dev.sad32); cudaFree((void*)idx->dev.sad64); cudaFree((void*)idx->dev.kmer);
 	cudaFree((void*)idx->dev.ann_off); cudaFree((void*)idx->dev.ann_len);
 	for (int i = 0; i < idx->n_seqs && idx->names; ++i) free(idx->names[i]);
 	free(idx->names); free(idx->ann_off); free(idx->ann_len);

@@ -182,7 +182,7 @@ template <> struct DevLists<u32> { // entries are exactly the 16-byte shared-mem
 // enough, emit it, restart right after it) needs nothing from passes 1 and 2 and has next to no state, so it runs as a kernel of
 // its own in which every lane is in the same phase: ~30 lanes per instruction and 3-4x the occupancy of the full machine.  Its
 // intervals go to a fixed slot range per read; k_smem_m merges them into the read's list before the final sort.
-template <class U>
+template <class U, bool TAB>
 __global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
                                                  int stride, Intv *p3, i32 *p3_cnt, int *work, Counters *cnt)
 {
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, in
 	const uint8_t *q = 0;
 	IntvT<U> ik;
 	int r = -1, len = 0, x = 0, i = 0, qi = 0, qnext = 0, n_out = 0;
+	u32 code = 0; // TAB: the walk's string so far (k-mer jump-start table, 32-bit rows only)
 	bool have = false, ready = false, alive = true;
 	ik.x0 = ik.x1 = ik.x2 = 0; ik.qb = ik.qe = 0;
 	for (;;) {
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, in
 			while (x < len && q[x] > 3) ++x;
 			if (x >= len) { p3_cnt[r] = n_out; have = false; continue; }
 			set_intv(ix, q[x], ik);
+			if (TAB) code = q[x];
 			i = x + 1;
 			if (i >= len) { x = len; continue; }
 			qi = q[i];
@@ -216,7 +218,9 @@ __global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, in
 		if (__ballot_sync(FULL, alive) == 0) break;
 		if (ready) {
 			IntvT<U> okc;
-			extend1(fm, ik, 3 - qi, 0, okc);
+			if (TAB) code = code << 2 | (u32)qi;
+			if (TAB && i + 1 - x <= ix.kmer_k) { const Intv32 t = kmer_lookup(ix, i + 1 - x, code); okc.x0 = (U)t.x0; okc.x1 = (U)t.x1; okc.x2 = (U)t.x2; okc.qb = okc.qe = 0; }
+			else extend1(fm, ik, 3 - qi, 0, okc);
 			if (okc.x2 < max_intv && i - x >= min_len) {
 				if (okc.x2 > 0 && n_out < stride) { Intv m = widen(okc); m.qb = (u32)x; m.qe = (u32)(i + 1); p3[(size_t)r * stride + n_out] = m; }
 				if (okc.x2 > 0) ++n_out;
@@ -330,7 +334,7 @@ __device__ __forceinline__ unsigned long long group_alloc(unsigned long long *ct
 }
 
 // PASS 1: lane = read, walks x = 0, ret, ret', ...; PASS 2: lane = call request (read, x, min_intv given), one walk
-template <int PASS>
+template <int PASS, bool TAB>
 __global__ void __launch_bounds__(256) k_smem_fwd(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
                                                   int lcap, FwdEntry *stage, SeedCall *calls, u64 call_cap, FwdEntry *fl, u64 fl_cap, Split *sp, Counters *cnt)
 {
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256) k_smem_fwd(DevIndex ix, ssq_opts_t opt, i
 	const uint8_t *q = 0;
 	Intv32 ik; ik.x0 = ik.x1 = ik.x2 = 0; ik.qb = ik.qe = 0;
 	int r = -1, len = 0, x = 0, i = 0, qi = 0, qnext = 0, n_list = 0;
-	u32 min_intv = 1;
+	u32 min_intv = 1, code = 0; // code (TAB): the walk's string so far, for the k-mer jump-start table
 	unsigned long long slot = 0; // PASS 2: the request being served
 	bool have = false, ready = false, alive = true;
 	const unsigned long long lo2 = PASS == 2 ? sp->n_calls1 : 0, hi2 = PASS == 2 ? sp->n_calls : 0;
@@ -383,6 +387,7 @@ __global__ void __launch_bounds__(256) k_smem_fwd(DevIndex ix, ssq_opts_t opt, i
 				if (x >= len) { have = false; continue; }
 			}
 			set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
+			if (TAB) code = q[x];
 			i = x + 1; n_list = 0;
 			if (i >= len) { push(); flush(); continue; }
 			qi = q[i];
@@ -393,7 +398,8 @@ __global__ void __launch_bounds__(256) k_smem_fwd(DevIndex ix, ssq_opts_t opt, i
 		if (__ballot_sync(FULL, alive) == 0) break;
 		if (ready) {
 			Intv32 okc;
-			extend1(fm, ik, 3 - qi, 0, okc);
+			if (TAB) code = code << 2 | (u32)qi;
+			if (TAB && i + 1 - x <= ix.kmer_k) okc = kmer_lookup(ix, i + 1 - x, code); else extend1(fm, ik, 3 - qi, 0, okc);
 			bool end = false;
 			if (okc.x2 != ik.x2) { push(); end = okc.x2 < min_intv; }
 			if (!end) {
@@ -458,7 +464,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd(DevIndex ix, ssq_opts_t 
 
 // the same kernel with the lean per-lane state (BwdCallT): fewer registers -> more blocks per SM, fewer instructions per step
 // (SSQ_SMEM_VARIANT=4; CPU-validated through hostsim, first GPU measurement pending)
-template <int MINB>
+template <int MINB, bool TAB>
 __global__ void __launch_bounds__(128, MINB) k_smem_bwd2(DevIndex ix, ssq_opts_t opt, const uint8_t *__restrict__ seq, int lcap, int list_cap,
                                                          Intv *scratch, int scratch_cap, const SeedCall *__restrict__ calls, const FwdEntry *__restrict__ fl, int second,
                                                          Intv *mems, u32 *memr, u64 mem_cap, Split *sp, Counters *cnt)
@@ -492,13 +498,14 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd2(DevIndex ix, ssq_opts_t
 			if (sc.list_n == 0) continue; // its forward list did not fit the pool (the stage is being re-run with a larger one)
 			rd = sc.read;
 			m.start(opt, sc.len(), seq + sc.seq_off, mem, scratch_cap, lists, sc.x(), sc.min_intv, fl + sc.list_off, (int)sc.list_n, sc.b0(), sc.b1());
+			if (TAB) m.use_table(ix.kmer_k);
 			have = true;
 			ready = m.advance();
 		}
 		if (__ballot_sync(FULL, alive) == 0) break;
 		if (ready) {
 			Intv32 okc;
-			extend1(fm, m.in, m.c, 1, okc);
+			if (!(TAB && m.table_hit(ix, okc))) extend1(fm, m.in, m.c, 1, okc);
 			m.post(okc);
 			ready = m.advance();
 		}
@@ -1455,8 +1462,12 @@ static int run_smem_split(ssq_batch *b)
 	const bool lean = b->smem_variant == 4;
 	const int lean_blocks = getenv("SSQ_SMEM_BLOCKS") ? atoi(getenv("SSQ_SMEM_BLOCKS")) : 8;
 	CK(cudaFuncSetAttribute(k_smem_bwd<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
-	CK(cudaFuncSetAttribute(k_smem_bwd2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
-	CK(cudaFuncSetAttribute(k_smem_bwd2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
+	const bool tab = b->idx->dev.kmer_k > 0; // k-mer jump-start table loaded (SSQ_KMER_K): forward walks, the greedy pass and the lean backward kernel use it
+	typedef void (*fwd_kernel_t)(DevIndex, ssq_opts_t, int, const uint8_t*, const u64*, int, FwdEntry*, SeedCall*, u64, FwdEntry*, u64, Split*, Counters*);
+	typedef void (*bwd2_kernel_t)(DevIndex, ssq_opts_t, const uint8_t*, int, int, Intv*, int, const SeedCall*, const FwdEntry*, int, Intv*, u32*, u64, Split*, Counters*);
+	const fwd_kernel_t kf1 = tab ? k_smem_fwd<1, true> : k_smem_fwd<1, false>, kf2 = tab ? k_smem_fwd<2, true> : k_smem_fwd<2, false>;
+	const bwd2_kernel_t kb2 = lean_blocks >= 8 ? (tab ? k_smem_bwd2<8, true> : k_smem_bwd2<8, false>) : (tab ? k_smem_bwd2<6, true> : k_smem_bwd2<6, false>);
+	CK(cudaFuncSetAttribute(kb2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)bthreads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
 	const size_t lsm = (size_t)bthreads * 2 * list_cap * sizeof(uint4);
 	Misc *dm = b->misc.as<Misc>();
 	Split *sp = b->xsplit.as<Split>();
@@ -1464,26 +1475,23 @@ static int run_smem_split(ssq_batch *b)
 		if (b->xmems.need(b->pool_cap * sizeof(Intv)) || b->xmemr.need(b->pool_cap * 4) || b->xcalls.need(b->call_cap * sizeof(SeedCall)) || b->xfl.need(b->fl_cap * sizeof(FwdEntry))) return SSQ_ENOMEM;
 		CK(cudaMemsetAsync(b->misc.p, 0, sizeof(Misc), b->st));
 		CK(cudaMemsetAsync(b->xsplit.p, 0, sizeof(Split), b->st));
-		if (with_p3) k_smem_p3<u32><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
-		k_smem_fwd<1><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
+		if (with_p3 && tab) k_smem_p3<u32, true><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+		else if (with_p3) k_smem_p3<u32, false><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+		kf1<<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 1); // n_calls1 = pass-1 calls (n_mems1 still 0)
 		if (!lean) k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
-		else if (lean_blocks >= 8) k_smem_bwd2<8><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
-		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
-		else k_smem_bwd2<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		else kb2<<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 1); // n_mems1 = pass-1 intervals; n_calls1 unchanged (no calls were added)
 		k_smem_p2sel<<<b->n_sm * 8, 256, 0, b->st>>>(b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->xcalls.as<SeedCall>(), b->call_cap, sp);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 0); // clamp the request range
-		k_smem_fwd<2><<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
+		kf2<<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
 		if (!lean) k_smem_bwd<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
-		else if (lean_blocks >= 8) k_smem_bwd2<8><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
-		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
-		else k_smem_bwd2<6><<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
+		else kb2<<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		if (with_p3) k_smem_p3_append<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->xp3.as<Intv>(), b->xp3n.as<i32>(), p3_stride, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp);
 		b->launches += 10;
@@ -1561,8 +1569,8 @@ static int run_smem(ssq_batch *b)
 		const int p3_stride = lcap / (b->opt.min_seed_len + 1) + 2;
 		if (variant == 2 && b->opt.max_mem_intv > 0) {
 			if (b->xp3.need((size_t)n * p3_stride * sizeof(Intv)) || b->xp3n.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
-			if (m32) k_smem_p3<u32><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
-			else k_smem_p3<u64><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+			if (m32) k_smem_p3<u32, false><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+			else k_smem_p3<u64, false><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
 			CK(cudaMemsetAsync(&dm->work, 0, 4, b->st));
 			++b->launches;
 			p3buf = b->xp3.as<Intv>(); p3cnt = b->xp3n.as<i32>();

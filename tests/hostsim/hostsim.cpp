@@ -49,15 +49,39 @@ struct ReadWork {
 // The phase-split formulation of the seeding (k_smem_fwd / k_smem_bwd / k_smem_p3 on the GPU), data flow included: forward walks
 // produce calls + forward lists, every call's backward phase runs on its own from that list, pass 2 is selected from pass 1's
 // intervals, everything is pooled and ordered by (qb, qe) at the end.
+// diagnostics (HOSTSIM_SPLIT): rank queries by the length of the string they produce — sizes a k-mer jump-start table
+static unsigned long long g_ext_hist[3][256], g_tab_hits;
+extern "C" void hostsim_ext_hist(unsigned long long *out) { memcpy(out, g_ext_hist, sizeof g_ext_hist); }
+extern "C" void hostsim_ext_hist_reset() { memset(g_ext_hist, 0, sizeof g_ext_hist); g_tab_hits = 0; }
+extern "C" unsigned long long hostsim_table_hits() { return g_tab_hits; }
+
+// k-mer jump-start table for the diagnostics / HOSTSIM_KMER=K runs: built with the same kmer_compute() the GPU loader uses
+static std::vector<KmerEnt> g_kmer; static int g_kmer_k = 0; static const void *g_kmer_for = 0;
+static void ensure_kmer(DevIndex &ix)
+{
+	const int K = getenv("HOSTSIM_KMER") ? atoi(getenv("HOSTSIM_KMER")) : 0;
+	if (K <= 0 || !ix.bwt32) { ix.kmer = 0; ix.kmer_k = 0; return; }
+	if (g_kmer_k != K || g_kmer_for != (const void*)ix.bwt32) {
+		g_kmer.assign(kmer_entries(K), KmerEnt());
+		ScalarFm fm(ix);
+		for (int L = 1; L <= K; ++L) for (u32 code = 0; code < (1u << (2 * L)); ++code) g_kmer[kmer_off(L) + code] = kmer_compute(fm, ix, L, code);
+		g_kmer_k = K; g_kmer_for = (const void*)ix.bwt32;
+	}
+	ix.kmer = g_kmer.data(); ix.kmer_k = K;
+}
+
 static void fwd_walk(ScalarFm &fm, const DevIndex &ix, int len, const uint8_t *q, int x, u32 min_intv, std::vector<FwdEntry> &list)
 {
+	u32 code = q[x]; // the walk's string so far, for the k-mer table
 	Intv32 ik, okc;
 	set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
 	auto push = [&]() { FwdEntry e; e.x0 = ik.x0; e.x1 = ik.x1; e.x2 = ik.x2; e.qe = ik.qe; list.push_back(e); };
 	int i;
 	for (i = x + 1; i < len; ++i) {
 		if (q[i] > 3) break;
-		extend1(fm, ik, 3 - q[i], 0, okc);
+		code = code << 2 | q[i];
+		if (ix.kmer_k && i + 1 - x <= ix.kmer_k) { okc = kmer_lookup(ix, i + 1 - x, code); ++g_tab_hits; } else extend1(fm, ik, 3 - q[i], 0, okc);
+		++g_ext_hist[0][i + 1 - x < 255 ? i + 1 - x : 255];
 		if (okc.x2 != ik.x2) { push(); if (okc.x2 < min_intv) return; }
 		ik = okc; ik.qe = (u32)(i + 1);
 	}
@@ -76,7 +100,8 @@ static void run_read_split(const DevIndex &ix, const ssq_opts_t &opt, int len, c
 		if (lean) {
 			BwdCallT<HostListsT<u32> > m; Intv32 okc;
 			m.start(opt, len, q, mem.data(), 2048, hl, x, min_intv, list.data(), (int)list.size(), x >= 1 ? (int)q[x - 1] : 4, x >= 2 ? (int)q[x - 2] : 4);
-			while (m.advance()) { extend1(fm, m.in, m.c, 1, okc); m.post(okc); }
+			if (ix.kmer_k) m.use_table(ix.kmer_k);
+			while (m.advance()) { if (!m.table_hit(ix, okc)) extend1(fm, m.in, m.c, 1, okc); else ++g_tab_hits; { const int l = (int)m.in.qe - m.i; ++g_ext_hist[1][l < 255 ? l : 255]; } m.post(okc); }
 			if (m.err) abort();
 			for (int k = 0; k < m.n; ++k) all.push_back(mem[k]);
 			return;
@@ -112,9 +137,12 @@ static void run_read_split(const DevIndex &ix, const ssq_opts_t &opt, int len, c
 				if (q[x] > 3) { ++x; continue; }
 				Intv32 ik, okc; set_intv(ix, q[x], ik);
 				int i; bool hit = false;
+				u32 code = q[x];
 				for (i = x + 1; i < len; ++i) {
 					if (q[i] > 3) break;
-					extend1(fm, ik, 3 - q[i], 0, okc);
+					code = code << 2 | q[i];
+					if (ix.kmer_k && i + 1 - x <= ix.kmer_k) { okc = kmer_lookup(ix, i + 1 - x, code); ++g_tab_hits; } else extend1(fm, ik, 3 - q[i], 0, okc);
+					++g_ext_hist[2][i + 1 - x < 255 ? i + 1 - x : 255];
 					if (okc.x2 < (u32)opt.max_mem_intv && i - x >= opt.min_seed_len) { if (okc.x2 > 0) { Intv m = widen(okc); m.qb = (u32)x; m.qe = (u32)(i + 1); all.push_back(m); } hit = true; break; }
 					ik = okc;
 				}
@@ -133,7 +161,7 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	std::vector<Intv> bufA(len + 2), bufB(len + 2);
 	w.mem.assign(2048, Intv());
 	int err = 0;
-	if ((getenv("HOSTSIM_SPLIT") || getenv("HOSTSIM_SPLIT_LEAN")) && ix.bwt32) run_read_split(ix, opt, len, q, w);
+	if ((getenv("HOSTSIM_SPLIT") || getenv("HOSTSIM_SPLIT_LEAN")) && ix.bwt32) { DevIndex ixk = ix; ensure_kmer(ixk); run_read_split(ixk, opt, len, q, w); }
 	else if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
 	else if (ix.bwt32 && !getenv("HOSTSIM_M64")) { // the state-machine form the GPU kernel runs, 32-bit rows (what the GPU picks when bwt32 exists)
 		std::vector<Intv32> a32(len + 2), b32(len + 2);

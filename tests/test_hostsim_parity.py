@@ -35,12 +35,13 @@ def test_synthetic_reads_with_repeats_indels_and_Ns(oracle, hostsim, syn_index):
         _cmp_all(oracle, hostsim, idx, seqs)
 
 
-@pytest.mark.parametrize("env", ["HOSTSIM_M64", "HOSTSIM_STRAIGHT", "HOSTSIM_SPLIT", "HOSTSIM_SPLIT_LEAN"])
+@pytest.mark.parametrize("env", ["HOSTSIM_M64", "HOSTSIM_STRAIGHT", "HOSTSIM_SPLIT", "HOSTSIM_SPLIT_LEAN", "HOSTSIM_SPLIT_LEAN,HOSTSIM_KMER=7"])
 def test_seeding_formulations_agree(oracle, hostsim, syn_index, monkeypatch, env):
     """default = the 32-bit-row state machine (what the GPU runs when the index has < 2^32 rows); also the 64-bit machine and the
     straight-line smem1()/seed_strategy1() form, and the phase-split form (forward walks, backward sweeps and the greedy
     pass as separate stages connected by call records — what the GPU's split kernels do)"""
-    monkeypatch.setenv(env, "1")
+    for kv in env.split(","):  # the last one: the split form with the short strings answered from the k-mer jump-start table
+        monkeypatch.setenv(*(kv.split("=") if "=" in kv else (kv, "1")))
     fa, g, bounds = syn_index
     idx = oracle.load(fa)
     names, seqs, quals = T.simulate_pairs(g, bounds, 400, 150, 21, err=0.015, indel=0.003, n_frac=0.004)
