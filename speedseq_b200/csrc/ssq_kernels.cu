@@ -1456,6 +1456,7 @@ static int run_smem_split(ssq_batch *b)
 	const int p3_stride = lcap / (b->opt.min_seed_len + 1) + 2;
 	const bool with_p3 = b->opt.max_mem_intv > 0;
 	if (with_p3 && (b->xp3.need((size_t)n * p3_stride * sizeof(Intv)) || b->xp3n.need((size_t)(n + 1) * 4))) return SSQ_ENOMEM;
+	if (getenv("SSQ_SPLIT_TINY_POOLS") && b->call_cap == 0) { b->pool_cap = 256; b->call_cap = 64; b->fl_cap = 512; } // tests: force the overflow retry
 	if (b->pool_cap == 0) b->pool_cap = (u64)n * 48 + 4096;
 	if (b->call_cap == 0) b->call_cap = (u64)n * 10 + 4096;
 	if (b->fl_cap == 0) b->fl_cap = (u64)n * 96 + 65536;
@@ -1471,7 +1472,7 @@ static int run_smem_split(ssq_batch *b)
 	const size_t lsm = (size_t)bthreads * 2 * list_cap * sizeof(uint4);
 	Misc *dm = b->misc.as<Misc>();
 	Split *sp = b->xsplit.as<Split>();
-	for (int attempt = 0; attempt < 6; ++attempt) {
+	for (int attempt = 0; attempt < 12; ++attempt) {
 		if (b->xmems.need(b->pool_cap * sizeof(Intv)) || b->xmemr.need(b->pool_cap * 4) || b->xcalls.need(b->call_cap * sizeof(SeedCall)) || b->xfl.need(b->fl_cap * sizeof(FwdEntry))) return SSQ_ENOMEM;
 		CK(cudaMemsetAsync(b->misc.p, 0, sizeof(Misc), b->st));
 		CK(cudaMemsetAsync(b->xsplit.p, 0, sizeof(Split), b->st));
