@@ -1747,6 +1747,7 @@ static int run_extend(ssq_batch *b)
 		k_ext_prep<<<G, 256, 0, b->st>>>(b->idx->dev, b->opt, nt, b->tasks.as<Task>(), b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(),
 		                                b->sorted.as<Seed>(), b->xinfo.as<ExtInfo>());
 		const int lazy = getenv("SSQ_EXT_ALL") ? 0 : 1;
+		const int force_round = getenv("SSQ_EXT_FORCE_ROUND") ? atoi(getenv("SSQ_EXT_FORCE_ROUND")) : 2; // from this round on an unfinished read gets all its remaining seeds extended
 		if (lazy) k_need_first<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(), b->n_kept.as<i32>(), b->task_off.as<u64>(), need);
 		else CK(cudaMemsetAsync(need, 1, nt, b->st));
 		b->launches += 3;
@@ -1806,11 +1807,11 @@ static int run_extend(ssq_batch *b)
 			u32 *list_out = b->xlist[round & 1].as<u32>();
 			k_select<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, n_in, list_in, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
 			                                        b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(),
-			                                        have, need, b->xsel.as<SelState>(), round >= 2, list_out, n_unf, &b->misc.as<Misc>()->work, sel_thresh, b->xheavy.as<u32>(), n_heavy2);
+			                                        have, need, b->xsel.as<SelState>(), round >= force_round, list_out, n_unf, &b->misc.as<Misc>()->work, sel_thresh, b->xheavy.as<u32>(), n_heavy2);
 			CK(cudaMemsetAsync(&b->misc.as<Misc>()->work, 0, 4, b->st));
 			k_select_heavy<<<b->n_sm * 8, 128, 0, b->st>>>(b->opt, b->read_off.as<u64>(), b->intv_off.as<u64>(), b->seed_off.as<u64>(), b->outc.as<ChainRec>(), b->sorted.as<Seed>(),
 			                                              b->n_kept.as<i32>(), b->task_off.as<u64>(), b->cand.as<RegCand>(), b->srt.as<u64>(), b->srt2.as<u64>(), b->regs.as<RegCand>(), b->n_regs.as<u32>(),
-			                                              have, need, b->xsel.as<SelState>(), round >= 2, list_out, n_unf, &b->misc.as<Misc>()->work, b->xheavy.as<u32>(), n_heavy2);
+			                                              have, need, b->xsel.as<SelState>(), round >= force_round, list_out, n_unf, &b->misc.as<Misc>()->work, b->xheavy.as<u32>(), n_heavy2);
 			CK(cudaEventRecord(es1, b->st));
 			++b->launches;
 			++b->launches;
