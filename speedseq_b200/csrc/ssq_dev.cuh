@@ -387,7 +387,9 @@ typedef HostListsT<u64> HostLists;
 // U: row type of the machine's intervals — u64 for any index, u32 when the index has fewer than 2^32 rows.  The output list
 // `mem` always holds 64-bit intervals.
 // P3 = false compiles the greedy pass out (its callers run it elsewhere and always pass skip_p3).
-template <class Lists, class U = u64, bool P3 = true>
+// TAB = true (32-bit rows, ix.kmer loaded): rank queries that produce a string of at most ix.kmer_k bases are answered from the
+// k-mer jump-start table — table_hit() before extend1().
+template <class Lists, class U = u64, bool P3 = true, bool TAB = false>
 struct SmemMachineT {
 	typedef IntvT<U> I;
 	enum { NEXT_P1, NEXT_P2, NEXT_P3, FWD, BWD, S3, DONE };
@@ -398,6 +400,7 @@ struct SmemMachineT {
 	                   // query of step i and consumed after it, so the bookkeeping never waits on a query byte
 	int cnext;         // backward phase: prefetched base at i-1
 	int cb0, cb1;      // bases at x-1 and x-2 of the current smem1 call, fetched when it starts
+	u32 code, win; int tabK; // TAB: last bases of the forward walk's string; FWD: its first tabK bases (left-aligned), BWD: the tabK bases from position i on
 	int skip_p3;       // the greedy pass is done elsewhere (the GPU runs it as a kernel of its own, k_smem_p3)
 	int rev;           // first backward sweep: the forward list is read from its end (longest match first) instead of being reversed
 	int any_kept;      // this smem1 call has kept an interval (whether or not it was long enough to be stored)
@@ -412,7 +415,7 @@ struct SmemMachineT {
 	SSQ_HD void init(const ssq_opts_t &opt, int len_, const uint8_t *q_, Intv *mem_, int mem_cap_, const Lists &lists, int skip_p3_ = 0)
 	{
 		q = q_; len = len_; mem = mem_; mem_cap = mem_cap_; L = lists; prev_id = 0; skip_p3 = skip_p3_;
-		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1; rev = 0; ext = 0;
+		n = 0; err = 0; x = 0; pass = 1; state = NEXT_P1; rev = 0; ext = 0; code = 0; win = 0; tabK = 0;
 		min_seed_len = opt.min_seed_len; split_len = (int)(opt.min_seed_len * opt.split_factor + .499f); split_width = opt.split_width;
 		max_mem_intv = (U)opt.max_mem_intv;
 		if (len < opt.min_seed_len) { state = NEXT_P3; pass = 3; x = len; }
@@ -422,6 +425,7 @@ struct SmemMachineT {
 	{
 		x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_; any_kept = 0;
 		set_intv(ix, q[x], ik); ik.qe = (u32)(x + 1);
+		if (TAB) { tabK = ix.kmer_k; code = q[x]; win = (u32)q[x] << (2 * (tabK - 1)); }
 		i = x + 1; qi = base_at(i); n_curr = 0; state = FWD;
 		{ const int b0 = base_at(x - 1); cb0 = b0 < 4 ? b0 : -1; }
 		{ const int b1 = base_at(x - 2); cb1 = b1 < 4 ? b1 : -1; }
@@ -434,6 +438,7 @@ struct SmemMachineT {
 		prev_id ^= 1; n_prev = n_curr; rev = 1;
 		i = x - 1; j = 0; n_curr = 0;
 		c = cb0; cnext = cb1;
+		if (TAB) win = (win >> 2) | (u32)(c < 0 ? 0 : c) << (2 * (tabK - 1)); // positions x-1 .. x-1+tabK-1
 		state = BWD;
 	}
 	// p is left-maximal at i+1 unless a longer match survived.  smem1() appends it and drops the intervals shorter than
@@ -504,6 +509,7 @@ struct SmemMachineT {
 			case FWD:
 				if (i >= len || qi > 3) { push_curr(ik); last_qe = ik.qe; end_forward(); break; }
 				in = ik; is_back = 0; qc = 3 - qi;
+				if (TAB) { code = code << 2 | (u32)qi; const int L = i + 1 - x; if (L <= tabK) win |= (u32)qi << (2 * (tabK - L)); }
 				qnext = base_at(i + 1);
 				return true;
 			case BWD:
@@ -513,6 +519,7 @@ struct SmemMachineT {
 					--i; j = 0; n_curr = 0;
 					if (i < -1) { end_smem1(); break; }
 					c = cnext;
+					if (TAB) win = (win >> 2) | (u32)(c < 0 ? 0 : c) << (2 * (tabK - 1));
 					{ const int b1 = base_at(i - 1); cnext = b1 < 4 ? b1 : -1; }
 					break;
 				}
@@ -529,6 +536,18 @@ struct SmemMachineT {
 				return true;
 			}
 		}
+	}
+	// TAB: the query advance() has just set up, answered from the k-mer table when the string it produces is short enough
+	SSQ_HD bool table_hit(const DevIndex &ix, I &okc) const
+	{
+		if (!TAB || tabK == 0) return false;
+		int L; u32 cd;
+		if (state == FWD) { L = i + 1 - x; if (L > tabK) return false; cd = code; }
+		else if (state == BWD) { L = (int)in.qe - i; if (L > tabK) return false; cd = win >> (2 * (tabK - L)); }
+		else return false;
+		const Intv32 t = kmer_lookup(ix, L, cd);
+		okc.x0 = (U)t.x0; okc.x1 = (U)t.x1; okc.x2 = (U)t.x2; okc.qb = okc.qe = 0;
+		return true;
 	}
 	SSQ_HD void post(const I &okc) // okc = ok[qc] of the query
 	{

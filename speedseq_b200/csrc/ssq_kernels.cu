@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_smem_p3(DevIndex ix, ssq_opts_t opt, in
 	if (fm.n_blk) { atomicAdd(&cnt->occ_smem, fm.n_blk); atomicAdd(&cnt->dbg[6], fm.n_blk); } // dbg[6]: this kernel's share of occ_smem
 }
 
-template <class U, int MINB>
+template <class U, int MINB, bool TAB>
 __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t opt, int n_reads, const uint8_t *__restrict__ seq, const u64 *__restrict__ read_off,
                                                 int lcap, int list_cap, int slow_batch, Intv *scratch, int scratch_cap, Intv *pool, u64 pool_cap, unsigned long long *pool_n,
                                                 u64 *intv_off, i32 *intv_cnt, i32 *l_rep_out, int *work, int *err, Counters *cnt,
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 	DevLists<U> lists;
 	lists.sm = list_smem + threadIdx.x; lists.cap = list_cap; lists.stride = blockDim.x; lists.g0 = (decltype(lists.g0))bufA; lists.g1 = (decltype(lists.g1))bufB;
 	ScalarFm fm(ix);
-	SmemMachineT<DevLists<U>, U, false> m; // the greedy pass is k_smem_p3's
+	SmemMachineT<DevLists<U>, U, false, TAB> m; // the greedy pass is k_smem_p3's; TAB: short strings come from the k-mer jump-start table
 	bool have = false, ready = false, alive = true, fin = false;
 	int r = -1;
 	const int batch = slow_batch > 0 ? slow_batch : 1;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128, MINB) k_smem_m(DevIndex ix, ssq_opts_t op
 		}
 		if (ready) { // the step all lanes that have a query take together
 			IntvT<U> okc;
-			extend1(fm, m.in, m.qc, m.is_back, okc);
+			if (!(TAB && m.table_hit(ix, okc))) extend1(fm, m.in, m.qc, m.is_back, okc);
 			m.post(okc);
 			ready = false;
 		}
@@ -1550,7 +1550,8 @@ static int run_smem(ssq_batch *b)
 	const bool m32 = m32_;
 	const int minb = m32 ? (getenv("SSQ_SMEM_BLOCKS") ? atoi(getenv("SSQ_SMEM_BLOCKS")) : 6) : 5;
 	typedef void (*smem_kernel_t)(DevIndex, ssq_opts_t, int, const uint8_t*, const u64*, int, int, int, Intv*, int, Intv*, u64, unsigned long long*, u64*, i32*, i32*, int*, int*, Counters*, const u32*, u32*, unsigned int*, const Intv*, const i32*, int);
-	const smem_kernel_t km = !m32 ? k_smem_m<u64, 5> : minb >= 8 ? k_smem_m<u32, 8> : minb == 7 ? k_smem_m<u32, 7> : minb == 6 ? k_smem_m<u32, 6> : k_smem_m<u32, 5>;
+	const bool mtab = m32 && b->idx->dev.kmer_k > 0; // SSQ_KMER_K loaded the k-mer jump-start table
+	const smem_kernel_t km = !m32 ? k_smem_m<u64, 5, false> : mtab ? k_smem_m<u32, 6, true> : minb >= 8 ? k_smem_m<u32, 8, false> : minb == 7 ? k_smem_m<u32, 7, false> : minb == 6 ? k_smem_m<u32, 6, false> : k_smem_m<u32, 5, false>;
 	if (variant == 2) CK(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)threads * 2 * (list_cap > 0 ? list_cap : 1) * sizeof(uint4))));
 	int blocks_per_sm = variant == 0 ? (int)((200 * 1024) / (smem + 1024)) : 8;
 	if (blocks_per_sm > 8) blocks_per_sm = 8;
@@ -1570,7 +1571,8 @@ static int run_smem(ssq_batch *b)
 		const int p3_stride = lcap / (b->opt.min_seed_len + 1) + 2;
 		if (variant == 2 && b->opt.max_mem_intv > 0) {
 			if (b->xp3.need((size_t)n * p3_stride * sizeof(Intv)) || b->xp3n.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
-			if (m32) k_smem_p3<u32, false><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+			if (mtab) k_smem_p3<u32, true><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
+			else if (m32) k_smem_p3<u32, false><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
 			else k_smem_p3<u64, false><<<b->n_sm * 8, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), p3_stride, b->xp3.as<Intv>(), b->xp3n.as<i32>(), &dm->work, &dm->cnt);
 			CK(cudaMemsetAsync(&dm->work, 0, 4, b->st));
 			++b->launches;

@@ -163,6 +163,17 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	int err = 0;
 	if ((getenv("HOSTSIM_SPLIT") || getenv("HOSTSIM_SPLIT_LEAN")) && ix.bwt32) { DevIndex ixk = ix; ensure_kmer(ixk); run_read_split(ixk, opt, len, q, w); }
 	else if (getenv("HOSTSIM_STRAIGHT")) w.n_intv = collect_intv(fm, ix, opt, len, q, w.mem.data(), 2048, bufA.data(), bufB.data(), err);
+	else if (ix.bwt32 && !getenv("HOSTSIM_M64") && getenv("HOSTSIM_KMER")) { // the 32-bit machine with the k-mer jump-start table (k_smem_m<u32, 6, true>)
+		DevIndex ixk = ix; ensure_kmer(ixk);
+		std::vector<Intv32> a32(len + 2), b32(len + 2);
+		SmemMachineT<HostListsT<u32>, u32, true, true> m; Intv32 okc;
+		HostListsT<u32> hl; hl.a[0] = a32.data(); hl.a[1] = b32.data();
+		m.init(opt, len, q, w.mem.data(), 2048, hl);
+		for (bool go = m.advance(ixk); go; go = m.advance(ixk)) { if (!m.table_hit(ixk, okc)) extend1(fm, m.in, m.qc, m.is_back, okc); else ++g_tab_hits; m.post(okc); }
+		std::vector<u32> keys(2048);
+		err = m.err; w.n_intv = m.finish(keys.data());
+		{ std::vector<Intv> tmp(w.n_intv); for (int i = 0; i < w.n_intv; ++i) tmp[i] = w.mem[keys[i] & 0xffff]; for (int i = 0; i < w.n_intv; ++i) w.mem[i] = tmp[i]; }
+	}
 	else if (ix.bwt32 && !getenv("HOSTSIM_M64")) { // the state-machine form the GPU kernel runs, 32-bit rows (what the GPU picks when bwt32 exists)
 		std::vector<Intv32> a32(len + 2), b32(len + 2);
 		SmemMachineT<HostListsT<u32>, u32> m; Intv32 okc;

@@ -35,7 +35,7 @@ def test_synthetic_reads_with_repeats_indels_and_Ns(oracle, hostsim, syn_index):
         _cmp_all(oracle, hostsim, idx, seqs)
 
 
-@pytest.mark.parametrize("env", ["HOSTSIM_M64", "HOSTSIM_STRAIGHT", "HOSTSIM_SPLIT", "HOSTSIM_SPLIT_LEAN", "HOSTSIM_SPLIT_LEAN,HOSTSIM_KMER=7"])
+@pytest.mark.parametrize("env", ["HOSTSIM_M64", "HOSTSIM_STRAIGHT", "HOSTSIM_SPLIT", "HOSTSIM_SPLIT_LEAN", "HOSTSIM_SPLIT_LEAN,HOSTSIM_KMER=7", "HOSTSIM_KMER=8"])
 def test_seeding_formulations_agree(oracle, hostsim, syn_index, monkeypatch, env):
     """default = the 32-bit-row state machine (what the GPU runs when the index has < 2^32 rows); also the 64-bit machine and the
     straight-line smem1()/seed_strategy1() form, and the phase-split form (forward walks, backward sweeps and the greedy
