@@ -20,7 +20,7 @@
 
 #define SB_VERSION "0.1.22"
 #define PAD 500           /* keeps 5' coordinates left of a contig start non-negative */
-#define CHUNK_BLOCKS (1 << 20)
+#define CHUNK_BLOCKS_MAX (1 << 20) /* QNAME blocks per ssq_dupset_mark call; SSQ_SB_CHUNK lowers it (tests, latency) */
 
 typedef struct {
 	char *text;       /* the line, tabs replaced by NULs */
@@ -111,13 +111,13 @@ typedef struct {
 } opt_t;
 
 /* picks the primary lines, appends MC/MQ, computes the pair's signature; returns 1 when the block can be a duplicate */
-static int block_signature(block_t *b, const opt_t *o, ssq_dupsig_t *sig, int *orphan_out, int *has_pair)
+static int block_signature(block_t *b, const opt_t *o, ssq_dupsig_t *sig, int *orphan_out, int *has_pair, int *disc_out)
 {
 	int i, orphan = 0;
 	line_t *first = 0, *second = 0;
 	memset(sig, 0, sizeof *sig);
 	b->first = b->second = -1;
-	*has_pair = 0; *orphan_out = 0;
+	*has_pair = 0; *orphan_out = 0; *disc_out = 0;
 	for (i = 0; i < b->n; ++i) {
 		line_t *l = &b->lines[i];
 		if (l->flag & 0x900) continue; /* secondary / supplementary lines never define the pair */
@@ -169,6 +169,7 @@ static int block_signature(block_t *b, const opt_t *o, ssq_dupsig_t *sig, int *o
 			else if (ia == ic && (a->flag & 0x10) && !(c->flag & 0x10)) swap = 1;
 		}
 		if (swap) { line_t *t = a; a = c; c = t; i = ia; ia = ic; ic = i; }
+		*disc_out = !(a->flag & 0x2); /* the test looks at the canonically first end (bwa sets 0x2 on both or neither) */
 		sig->pos1 = (uint64_t)(o->ctg.off[ia] + a->pos) + 1;
 		sig->pos2 = (uint64_t)(o->ctg.off[ic] + c->pos) + 1;
 		sig->strand1 = (a->flag & 0x10) ? 1 : 0; sig->strand2 = (c->flag & 0x10) ? 1 : 0;
@@ -212,15 +213,13 @@ static void mark_splitters(block_t *b, const opt_t *o, int mask)
 	}
 }
 
-static void emit_block(block_t *b, opt_t *o, int is_dup, int has_pair, int orphan)
+static void emit_block(block_t *b, opt_t *o, int is_dup, int has_pair, int orphan, int disc)
 {
 	int i;
 	++o->n_ids;
 	if (is_dup) { ++o->n_dup; for (i = 0; i < b->n; ++i) b->lines[i].flag |= 0x400; }
-	if (has_pair && !orphan) { /* both ends mapped and not flagged proper: discordant */
-		line_t *first = &b->lines[b->first], *second = &b->lines[b->second];
-		if (!(first->flag & 0x2) && !(second->flag & 0x2)) first->discordant = second->discordant = 1;
-	}
+	if (has_pair && !orphan && disc) /* both ends mapped and not flagged proper (a pair with both ends unmapped never gets here: disc stays 0) */
+		b->lines[b->first].discordant = b->lines[b->second].discordant = 1;
 	if (o->split) { mark_splitters(b, o, 0x40); mark_splitters(b, o, 0x80); }
 	for (i = 0; i < b->n; ++i) {
 		line_t *l = &b->lines[i];
@@ -247,6 +246,7 @@ int main(int argc, char **argv)
 	ssize_t len;
 	long long total = 0;
 	int i, hdr_done = 0, rc, device = getenv("SSQ_DEVICE") ? atoi(getenv("SSQ_DEVICE")) : 0;
+	const int CHUNK_BLOCKS = getenv("SSQ_SB_CHUNK") && atoi(getenv("SSQ_SB_CHUNK")) > 0 && atoi(getenv("SSQ_SB_CHUNK")) < CHUNK_BLOCKS_MAX ? atoi(getenv("SSQ_SB_CHUNK")) : CHUNK_BLOCKS_MAX;
 	block_t *blocks = (block_t*)calloc(CHUNK_BLOCKS, sizeof(block_t)), cur;
 	ssq_dupsig_t *sigs = (ssq_dupsig_t*)malloc(sizeof(ssq_dupsig_t) * CHUNK_BLOCKS);
 	uint8_t *dups = (uint8_t*)malloc(CHUNK_BLOCKS), *meta = (uint8_t*)malloc(CHUNK_BLOCKS);
@@ -281,11 +281,11 @@ int main(int argc, char **argv)
 #define FLUSH_CHUNK() do { \
 		if (n_blocks) { \
 			if ((rc = ssq_dupset_mark(set, (uint64_t)n_blocks, sigs, dups))) { fprintf(stderr, "samblaster: ssq_dupset_mark failed (%d): %s\n", rc, ssq_last_error()); return 1; } \
-			for (i = 0; i < n_blocks; ++i) { emit_block(&blocks[i], &o, dups[i], meta[i] & 1, (meta[i] >> 1) & 1); free_block(&blocks[i]); } \
+			for (i = 0; i < n_blocks; ++i) { emit_block(&blocks[i], &o, dups[i], meta[i] & 1, (meta[i] >> 1) & 1, (meta[i] >> 2) & 1); free_block(&blocks[i]); } \
 			n_blocks = 0; \
 		} } while (0)
 #define CLOSE_BLOCK() do { \
-		if (cur.n) { int orphan_, pair_; block_signature(&cur, &o, &sigs[n_blocks], &orphan_, &pair_); meta[n_blocks] = (uint8_t)(pair_ | orphan_ << 1); \
+		if (cur.n) { int orphan_, pair_, disc_; block_signature(&cur, &o, &sigs[n_blocks], &orphan_, &pair_, &disc_); meta[n_blocks] = (uint8_t)(pair_ | orphan_ << 1 | disc_ << 2); \
 			blocks[n_blocks++] = cur; memset(&cur, 0, sizeof cur); if (n_blocks == CHUNK_BLOCKS) FLUSH_CHUNK(); } } while (0)
 	while ((len = getline(&line, &cap, stdin)) > 0) {
 		line_t l;

@@ -178,7 +178,7 @@ extern "C" int ssq_index_load(const char *prefix, int device, ssq_index_t **out)
 		const int d = getenv("SSQ_SA_DENSE") ? atoi(getenv("SSQ_SA_DENSE")) : 8;
 		if (d > 0 && d < idx->dev.sa_intv && (d & (d - 1)) == 0) {
 			const u64 nd = idx->dev.seq_len / d + 1;
-			const bool small = idx->dev.seq_len < 0xffffffffull;
+			const bool small = idx->dev.seq_len < 0xffffffffull && !getenv("SSQ_SA_U64"); // SSQ_SA_U64: tests force the u64 sample of >= 2^32-row indexes
 			void *dd = 0;
 			CKI(cudaMalloc(&dd, nd * (small ? 4 : 8)));
 			if (small) k_sa_densify<u32><<<(unsigned)((nd + 255) / 256), 256>>>(idx->dev, d, nd, (u32*)dd);

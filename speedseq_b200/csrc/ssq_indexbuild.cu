@@ -219,9 +219,10 @@ extern "C" int ssq_index_build(const char *fasta, const char *prefix, int device
 	i64 l_pac = 0;
 	if ((rc = parse_fasta(fasta, ctg, holes, pac, l_pac))) { ssq_set_error("cannot read any sequence from %s", fasta); return rc; }
 	pac.resize((size_t)(l_pac >> 2) + 2, 0);
-	if ((rc = write_text_files(prefix, ctg, holes, pac, l_pac))) { ssq_set_error("cannot write %s.{ann,amb,pac}", prefix); return rc; }
 	const i64 n64 = 2 * l_pac;
-	if (n64 + 1 >= 0x7fffffffLL) { ssq_set_error("reference of %lld bases: this build sorts at most 2^31-2 suffixes (see DESIGN.md)", (long long)l_pac); return SSQ_EINVAL; }
+	// checked BEFORE anything is written: a refused build must not leave a partial index (.ann/.amb/.pac) behind
+	if (n64 + 1 >= 0x7fffffffLL) { ssq_set_error("reference of %lld bases: the GPU suffix sort of this build handles at most 2^31-2 suffixes (1.07 Gbp); build a larger index with upstream `bwa index` — libssq loads its files (on-disk format is the same)", (long long)l_pac); return SSQ_EINVAL; }
+	if ((rc = write_text_files(prefix, ctg, holes, pac, l_pac))) { ssq_set_error("cannot write %s.{ann,amb,pac}", prefix); return rc; }
 	const u32 n = (u32)n64, n1 = n + 1;
 	const unsigned G1 = (n1 + 255) / 256;
 	uint8_t *d_pac = 0, *d_bs = 0;

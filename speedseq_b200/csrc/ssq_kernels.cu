@@ -2044,7 +2044,7 @@ extern "C" int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig
 	int rc = ssq_use_device(device);
 	if (rc) return rc;
 	if (n == 0) return SSQ_OK;
-	if (n >= 0xffffffffull) { ssq_set_error("ssq_dupmark_batch: more than 2^32-1 pairs in one call"); return SSQ_EINVAL; }
+	if (n >= 0x7fffffffull) { ssq_set_error("ssq_dupmark_batch: more than 2^31-1 pairs in one call (the sort takes a 32-bit item count)"); return SSQ_EINVAL; }
 	DBuf dsig, k1, k2, k1g, ka, idx_a, idx_b, tmp, dd;
 	if (dsig.need(n * sizeof(ssq_dupsig_t)) || k1.need(n * 8) || k2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dd.need(n)) return SSQ_ENOMEM;
 	CK(cudaMemcpy(dsig.p, sig, n * sizeof(ssq_dupsig_t), cudaMemcpyHostToDevice));
@@ -2178,7 +2178,7 @@ extern "C" int ssq_dupmark_keys_dev(int device, uint64_t n, const uint64_t *d_ke
 	int rc = ssq_use_device(device);
 	if (rc) return rc;
 	if (n == 0) return SSQ_OK;
-	if (n >= 0xffffffffull) { ssq_set_error("ssq_dupmark_keys_dev: more than 2^32-1 pairs in one call"); return SSQ_EINVAL; }
+	if (n >= 0x7fffffffull) { ssq_set_error("ssq_dupmark_keys_dev: more than 2^31-1 pairs in one call (the sort takes a 32-bit item count)"); return SSQ_EINVAL; }
 	cudaStream_t st = (cudaStream_t)stream_;
 	DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp;
 	if (m1.need(n * 8) || m2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4)) return SSQ_ENOMEM;
