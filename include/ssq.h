@@ -161,6 +161,65 @@ int ssq_mem_batch_sam(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads
                       const char *const *comments, int64_t n_processed, int paired, const ssq_pestat_t *pes0, const char *rg_id, int verbose, char **sam_out, size_t *sam_len,
                       size_t *read_sam_off /* optional [n_reads+1]: byte range of each read's lines */);
 void ssq_free(void *p);
+
+/* ----------------------------------------- `bwa mem | samblaster`, HBM-resident ----
+ * The whole pipe of /root/reference/bin/speedseq:438-439 (interleaved) / :468-469 (two files) for one batch of reads:
+ * `$BWA mem -t T [-p] [-C] [-I ..] -R RG REF FQ.. | $SAMBLASTER [--excludeDups] --addMateTags --maxSplitCount C
+ * --minNonOverlap M --splitterFile F --discordantFile F`.  Reads go in as the FASTQ fields (concatenated, with offsets), the three
+ * SAM record streams come out (main, splitters, discordants; headers are the caller's business: they depend on argv).  Between
+ * the two copies everything stays on the device: alignment (upstream mem_process_seqs incl. mem_pestat's batch coupling — only
+ * its histogram reduction runs on the host), pairing, MAPQ, CIGAR/NM/MD, samblaster's signature / discordant / splitter tests,
+ * first-seen-wins duplicate marking against every earlier batch of the same aligner object, and the SAM text itself.
+ * With sb == NULL or sb->enabled == 0 only text[0] is produced and it is exactly `bwa mem`'s records (what ssq_mem_batch_sam
+ * returns).  One aligner object = one `bwa mem | samblaster` run: create, run batch after batch in input order, free. */
+typedef struct {
+	int32_t enabled;            /* 0: plain `bwa mem` records */
+	int32_t exclude_dups;       /* --excludeDups: duplicates stay out of the splitter / discordant streams (speedseq:241) */
+	int32_t add_mate_tags;      /* --addMateTags: MC:Z / MQ:i on every record of a pair (speedseq:439) */
+	int32_t max_split_count;    /* --maxSplitCount (speedseq:242) */
+	int32_t min_non_overlap;    /* --minNonOverlap (speedseq:243) */
+	int32_t min_indel_size, max_unmapped_bases; /* samblaster defaults 50 / 50 */
+	int32_t remove_dups;        /* --removeDups */
+	int32_t want_split, want_disc; /* --splitterFile / --discordantFile given */
+} ssq_sb_opts_t;
+void ssq_sb_opts_default(ssq_sb_opts_t *o);
+
+typedef struct {
+	int32_t n_reads, paired;              /* paired: adjacent reads are mates (`-p` after smart pairing, or two files interleaved) */
+	const char *seq; const uint64_t *seq_off;   /* bases as in the FASTQ (ASCII, any case), concatenated; seq_off[n_reads + 1] */
+	const char *qual;                     /* qualities at the same offsets; NULL = none (FASTA input) */
+	const char *name; const uint32_t *name_off; /* names without the /1 /2 suffix, concatenated, no terminators; name_off[n_reads + 1] */
+	const char *comment; const uint32_t *comment_off; /* FASTQ comments for `-C`; NULL = none */
+	int64_t n_processed;                  /* global ordinal of reads[0] (tie-breaking hashes use it) */
+} ssq_reads_t;
+
+typedef struct {
+	const char *text[3]; size_t len[3];   /* 0 main SAM records, 1 splitters, 2 discordants; owned by the aligner, valid until its next run */
+	const uint64_t *read_off;             /* [n_reads + 1]: byte range of each read's records in text[0] */
+	uint64_t n_ids, n_dup;                /* QNAME blocks seen / marked duplicate in this batch */
+	ssq_pestat_t pes[4];                  /* the insert-size statistics the batch was paired with */
+} ssq_sam_t;
+
+typedef struct ssq_aligner ssq_aligner_t;
+int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt, const ssq_sb_opts_t *sb, const char *rg_id, ssq_aligner_t **out);
+/* pes0 != NULL overrides the per-batch insert-size statistics (`-I`); verbose: mem_pestat's log lines on stderr like bwa */
+int ssq_aligner_run(ssq_aligner_t *al, const ssq_reads_t *reads, const ssq_pestat_t *pes0, int verbose, ssq_sam_t *out);
+/* the three phases of ssq_aligner_run, separately (bench.py times `compute` with the reads resident in HBM) */
+int ssq_aligner_upload(ssq_aligner_t *al, const ssq_reads_t *reads);
+int ssq_aligner_compute(ssq_aligner_t *al, const ssq_pestat_t *pes0, int verbose);
+int ssq_aligner_fetch(ssq_aligner_t *al, ssq_sam_t *out);
+int ssq_aligner_reset_dups(ssq_aligner_t *al);     /* forget every signature seen so far (a new run) */
+void *ssq_aligner_stream(ssq_aligner_t *al);       /* cudaStream_t of the object, for event timing on the launching stream */
+/* milliseconds of the last batch per stage (CUDA events): 0 upload, 1 seed..extend, 2 sort/dedup/patch, 3 insert-size statistics,
+ * 4 mate rescue, 5 pairing/MAPQ/planning, 6 CIGAR/NM/MD, 7 samblaster + dup-set, 8 text, 9 fetch; 10.. = ssq_batch_stage_ms(0..4) */
+float ssq_aligner_stage_ms(const ssq_aligner_t *al, int stage);
+/* what < 100: ssq_batch_counter of the alignment stage; 100 alignments written (CIGAR tasks), 101-103 bytes of the three streams, 104 dup-set size */
+uint64_t ssq_aligner_counter(const ssq_aligner_t *al, int what);
+void ssq_aligner_free(ssq_aligner_t *al);
+
+/* streaming dup-set on device pointers (what the aligner uses; also the owner-side step of the multi-GPU exchange) */
+int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t *d_key1, const uint64_t *d_key2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);
+int ssq_dupset_reset(ssq_dupset_t *set);
 /* contig table for the SAM header: name/length of contig i (0 <= i < ssq_index_info(idx,3)) */
 const char *ssq_index_contig(const ssq_index_t *idx, int i, int64_t *len);
 

@@ -363,7 +363,8 @@ SSQ_HD int infer_dir(i64 l_pac, i64 b1, i64 b2, i64 *dist)
 struct MateScratch { uint8_t *seq, *ref; int ref_cap; LocalScratch L; AlnScratch A; };
 
 // one mem_matesw(): rescue the mate `ms` of hit `a` inside the windows the insert-size bounds allow; ma[0..*n_ma) is the mate's
-// region list (capacity ma_cap), kept sorted by score and de-duplicated
+// region list (capacity ma_cap), kept sorted by score and de-duplicated.  Returns the number of windows aligned, -1 when a window
+// does not fit S.ref_cap (callers size the scratch from the batch's insert-size bounds and treat -1 as an error)
 SSQ_HD int mate_rescue(const DevIndex &ix, const ssq_opts_t &o, const PeStat pes[4], const AlnReg &a, int l_ms, const uint8_t *ms, AlnReg *ma, int *n_ma, int ma_cap,
                        const MateScratch &S)
 {
@@ -400,7 +401,8 @@ SSQ_HD int mate_rescue(const DevIndex &ix, const ssq_opts_t &o, const PeStat pes
 			rb = rb > far_beg ? rb : far_beg;
 			re = re < far_end ? re : far_end;
 		}
-		if (a.rid == rid && re - rb >= o.min_seed_len && re - rb <= S.ref_cap) {
+		if (a.rid == rid && re - rb >= o.min_seed_len) {
+			if (re - rb > S.ref_cap) return -1; // window beyond the caller's scratch: reported, never skipped silently (the reference has no limit)
 			const int tlen = (int)(re - rb);
 			for (i = 0; i < tlen; ++i) S.ref[i] = (uint8_t)ref_base(ix, rb + i);
 			const int xtra = SSQ_XSUBO | SSQ_XSTART | (l_ms * o.a < 250 ? SSQ_XBYTE : 0) | (o.min_seed_len * o.a);

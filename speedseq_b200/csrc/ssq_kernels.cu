@@ -1325,20 +1325,6 @@ __global__ void k_dup_mark(u64 n, const u32 *__restrict__ idx, const u64 *__rest
 // ===================================================================== host-side launch code ====
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ssq_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return SSQ_ECUDA; } } while (0)
 
-struct DBuf { // growable device buffer
-	void *p; size_t cap;
-	DBuf() : p(0), cap(0) {}
-	~DBuf() { release(); }
-	int need(size_t bytes) {
-		if (bytes <= cap) return 0;
-		if (p) cudaFree(p);
-		size_t want = bytes + bytes / 4 + 256;
-		if (cudaMalloc(&p, want) != cudaSuccess) { p = 0; cap = 0; ssq_set_error("cudaMalloc(%zu) failed", want); return SSQ_ENOMEM; }
-		cap = want; return 0;
-	}
-	void release() { if (p) cudaFree(p); p = 0; cap = 0; }
-	template <class T> T *as() { return (T*)p; }
-};
 
 struct ssq_batch {
 	const ssq_index *idx;
@@ -1356,7 +1342,7 @@ struct ssq_batch {
 	u64 call_cap = 0, fl_cap = 0; // split seeding: capacities of the call and forward-list pools
 	cudaEvent_t ev[6], evc[4], evs[2], evx[2]; // stage boundaries; chaining tiers; k_smem_m alone; selection kernels of one round // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
-	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 2; } memset(stage_ms, 0, sizeof stage_ms); }
+	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 3; /* phase-split seeding (r02: 48.9 ms vs 59.9 ms for the state machine on the bench workload); indexes without bwt32 use the 64-bit state machine */ } memset(stage_ms, 0, sizeof stage_ms); }
 };
 
 // misc buffer layout (device): [0] pool_n (u64)  [1] work (int) + err (int)  [2..] Counters
@@ -1386,6 +1372,17 @@ extern "C" int ssq_batch_upload(ssq_batch_t *b, int n_reads, const uint8_t *seq,
 	CK(cudaMemcpyAsync(b->read_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->st));
 	CK(cudaStreamSynchronize(b->st));
 	b->n_intv = b->n_seeds = b->n_tasks = b->n_regs_total = 0;
+	return SSQ_OK;
+}
+
+int ssq_batch_reserve(ssq_batch_t *b, int n_reads, u64 total_bases, int max_len, uint8_t **d_seq, u64 **d_off)
+{
+	if (!b || n_reads < 0) return SSQ_EINVAL;
+	if (max_len > SSQ_MAX_READ_LEN) { ssq_set_error("read longer than %d bases", SSQ_MAX_READ_LEN); return SSQ_ELEN; }
+	b->n_reads = n_reads; b->max_len = max_len;
+	if (b->seq.need(total_bases + 16) || b->read_off.need((size_t)(n_reads + 1) * 8)) return SSQ_ENOMEM;
+	b->n_intv = b->n_seeds = b->n_tasks = b->n_regs_total = 0;
+	*d_seq = b->seq.as<uint8_t>(); *d_off = b->read_off.as<u64>();
 	return SSQ_OK;
 }
 
@@ -2069,7 +2066,7 @@ extern "C" int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig
 // signatures seen so far is kept on the device as two parallel arrays sorted by (key1, key2); a batch is (1) marked within
 // itself by the two-pass stable sort above, (2) its survivors are looked up in the set by binary search, (3) the new ones
 // are appended and the set is re-sorted (two stable LSD passes).
-struct ssq_dupset { int device; u64 n, cap; u64 *k1, *k2; };
+struct ssq_dupset { int device; u64 n, cap; u64 *k1, *k2; DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp, dnew, nk1, nk2, cnt, t1, t2; /* scratch kept across calls */ };
 
 __global__ void k_dupset_lookup(u64 n, const ssq_dupsig_t *__restrict__ sig, const u64 *__restrict__ key1, const u64 *__restrict__ key2, uint8_t *is_dup,
                                 const u64 *__restrict__ s1, const u64 *__restrict__ s2, u64 sn, uint8_t *is_new)
@@ -2090,13 +2087,97 @@ extern "C" int ssq_dupset_create(int device, ssq_dupset_t **out)
 {
 	int rc = ssq_use_device(device);
 	if (rc) return rc;
-	ssq_dupset *s = (ssq_dupset*)calloc(1, sizeof(ssq_dupset));
-	s->device = device;
+	ssq_dupset *s = new ssq_dupset();
+	s->device = device; s->n = s->cap = 0; s->k1 = s->k2 = 0;
 	*out = s;
 	return SSQ_OK;
 }
-extern "C" void ssq_dupset_free(ssq_dupset_t *s) { if (!s) return; cudaFree(s->k1); cudaFree(s->k2); free(s); }
+extern "C" void ssq_dupset_free(ssq_dupset_t *s) { if (!s) return; cudaFree(s->k1); cudaFree(s->k2); delete s; }
 extern "C" uint64_t ssq_dupset_size(const ssq_dupset_t *s) { return s ? s->n : 0; }
+
+__global__ void k_dupset_lookup_keys(u64 n, const uint8_t *__restrict__ valid, const u64 *__restrict__ key1, const u64 *__restrict__ key2, uint8_t *is_dup,
+                                     const u64 *__restrict__ s1, const u64 *__restrict__ s2, u64 sn, uint8_t *is_new)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint8_t nw = 0;
+	if (valid[i] && !is_dup[i]) {
+		const u64 a = key1[i], b = key2[i];
+		u64 lo = 0, hi = sn;
+		while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (s1[mid] < a || (s1[mid] == a && s2[mid] < b)) lo = mid + 1; else hi = mid; }
+		if (lo < sn && s1[lo] == a && s2[lo] == b) is_dup[i] = 1; else nw = 1;
+	}
+	is_new[i] = nw;
+}
+__global__ void k_dup_sig_keys(u64 n, const ssq_dupsig_t *__restrict__ sig, u64 *key1, u64 *key2, uint8_t *valid)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	key1[i] = sig[i].pos1 << 1 | (sig[i].strand1 & 1); key2[i] = sig[i].pos2 << 1 | (sig[i].strand2 & 1); valid[i] = sig[i].valid ? 1 : 0;
+}
+__global__ void k_dup_iota(u64 n, u32 *idx);
+__global__ void k_dup_mask(u64 n, const uint8_t *__restrict__ valid, const u64 *__restrict__ k1, const u64 *__restrict__ k2, u64 *m1, u64 *m2);
+__global__ void k_dup_mark_keys(u64 n, const u32 *__restrict__ idx, const u64 *__restrict__ key1s, const u64 *__restrict__ key2, const uint8_t *__restrict__ valid, uint8_t *is_dup);
+
+extern "C" int ssq_dupset_reset(ssq_dupset_t *set) { if (!set) return SSQ_EINVAL; set->n = 0; return SSQ_OK; }
+
+// Device-pointer form (the fused `bwa mem | samblaster` path, ssq_pipe.cu): key1/key2 = (5' position << 1 | strand) of the
+// canonically ordered ends, element order = input order.  Marks duplicates within the chunk (two stable radix-sort passes +
+// adjacent-equal test), then against the sorted set of every earlier chunk (binary search), then absorbs the new signatures.
+extern "C" int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t *d_k1, const uint64_t *d_k2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream_)
+{
+	if (!set) return SSQ_EINVAL;
+	int rc = ssq_use_device(set->device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	if (n >= 0x7fffffffull) { ssq_set_error("ssq_dupset_mark: more than 2^31-1 pairs in one call"); return SSQ_EINVAL; }
+	cudaStream_t st = (cudaStream_t)stream_;
+	DBuf &m1 = set->m1, &m2 = set->m2, &k1g = set->k1g, &ka = set->ka, &idx_a = set->idx_a, &idx_b = set->idx_b, &tmp = set->tmp, &dnew = set->dnew, &nk1 = set->nk1, &nk2 = set->nk2, &cnt = set->cnt;
+	if (m1.need(n * 8) || m2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dnew.need(n) || nk1.need(n * 8) || nk2.need(n * 8) || cnt.need(16)) return SSQ_ENOMEM;
+	const unsigned g = (unsigned)((n + 255) / 256);
+	size_t tb = 0, tb2 = 0;
+	cub::DeviceRadixSort::SortPairs(0, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st);
+	cub::DeviceSelect::Flagged(0, tb2, m1.as<u64>(), dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n, st);
+	if (tb2 > tb) tb = tb2;
+	const u64 grown = set->n + n;
+	if (grown >= 0x7fffffffull) { ssq_set_error("ssq_dupset: more than 2^31-1 distinct signatures"); return SSQ_ECAP; }
+	cub::DeviceRadixSort::SortPairs(0, tb2, (u64*)0, (u64*)0, (u64*)0, (u64*)0, (int)grown, 0, 64, st);
+	if (tb2 > tb) tb = tb2;
+	if (tmp.need(tb)) return SSQ_ENOMEM;
+	k_dup_mask<<<g, 256, 0, st>>>(n, d_valid, d_k1, d_k2, m1.as<u64>(), m2.as<u64>());
+	k_dup_iota<<<g, 256, 0, st>>>(n, idx_a.as<u32>());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st)); // stable, by key2
+	k_dup_gather<<<g, 256, 0, st>>>(n, idx_b.as<u32>(), m1.as<u64>(), k1g.as<u64>());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n, 0, 64, st)); // stable, by key1
+	k_dup_mark_keys<<<g, 256, 0, st>>>(n, idx_a.as<u32>(), ka.as<u64>(), m2.as<u64>(), d_valid, d_is_dup);
+	k_dupset_lookup_keys<<<g, 256, 0, st>>>(n, d_valid, d_k1, d_k2, d_is_dup, set->k1, set->k2, set->n, dnew.as<uint8_t>());
+	CK(cudaGetLastError());
+	// absorb the new signatures
+	u64 n_new = 0;
+	CK(cub::DeviceSelect::Flagged(tmp.p, tb, d_k1, dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n, st));
+	CK(cub::DeviceSelect::Flagged(tmp.p, tb, d_k2, dnew.as<uint8_t>(), nk2.as<u64>(), cnt.as<u64>(), (int)n, st));
+	CK(cudaMemcpyAsync(&n_new, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (n_new) {
+		const u64 total = set->n + n_new;
+		if (total > set->cap) { // grow, keeping the content
+			const u64 ncap = total + total / 2 + 1024;
+			u64 *a = 0, *b = 0;
+			CK(cudaMalloc(&a, ncap * 8)); CK(cudaMalloc(&b, ncap * 8));
+			if (set->n) { CK(cudaMemcpyAsync(a, set->k1, set->n * 8, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(b, set->k2, set->n * 8, cudaMemcpyDeviceToDevice, st)); }
+			CK(cudaStreamSynchronize(st));
+			cudaFree(set->k1); cudaFree(set->k2);
+			set->k1 = a; set->k2 = b; set->cap = ncap;
+		}
+		CK(cudaMemcpyAsync(set->k1 + set->n, nk1.p, n_new * 8, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(set->k2 + set->n, nk2.p, n_new * 8, cudaMemcpyDeviceToDevice, st));
+		if (set->t1.need(total * 8) || set->t2.need(total * 8)) return SSQ_ENOMEM;
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, set->k2, set->t2.as<u64>(), set->k1, set->t1.as<u64>(), (int)total, 0, 64, st)); // by key2, key1 rides along
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, set->t1.as<u64>(), set->k1, set->t2.as<u64>(), set->k2, (int)total, 0, 64, st)); // stable by key1
+		set->n = total;
+	}
+	return SSQ_OK;
+}
 
 extern "C" int ssq_dupset_mark(ssq_dupset_t *set, uint64_t n, const ssq_dupsig_t *sig, uint8_t *is_dup)
 {
@@ -2105,52 +2186,14 @@ extern "C" int ssq_dupset_mark(ssq_dupset_t *set, uint64_t n, const ssq_dupsig_t
 	if (rc) return rc;
 	if (n == 0) return SSQ_OK;
 	if (n >= 0x7fffffffull) { ssq_set_error("ssq_dupset_mark: more than 2^31-1 pairs in one call"); return SSQ_EINVAL; }
-	DBuf dsig, k1, k2, k1g, ka, idx_a, idx_b, tmp, dd, dnew, nk1, nk2, cnt;
-	if (dsig.need(n * sizeof(ssq_dupsig_t)) || k1.need(n * 8) || k2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dd.need(n) || dnew.need(n) ||
-	    nk1.need(n * 8) || nk2.need(n * 8) || cnt.need(16)) return SSQ_ENOMEM;
+	DBuf dsig, k1, k2, va, dd;
+	if (dsig.need(n * sizeof(ssq_dupsig_t)) || k1.need(n * 8) || k2.need(n * 8) || va.need(n) || dd.need(n)) return SSQ_ENOMEM;
 	CK(cudaMemcpy(dsig.p, sig, n * sizeof(ssq_dupsig_t), cudaMemcpyHostToDevice));
-	const unsigned g = (unsigned)((n + 255) / 256);
-	k_dup_keys<<<g, 256>>>(n, dsig.as<ssq_dupsig_t>(), k1.as<u64>(), k2.as<u64>(), idx_a.as<u32>());
-	size_t tb = 0, tb2 = 0;
-	cub::DeviceRadixSort::SortPairs(0, tb, k2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n);
-	cub::DeviceSelect::Flagged(0, tb2, k1.as<u64>(), dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n);
-	if (tb2 > tb) tb = tb2;
-	const u64 grown = set->n + n;
-	cub::DeviceRadixSort::SortPairs(0, tb2, (u64*)0, (u64*)0, (u64*)0, (u64*)0, (int)(grown < 0x7fffffffull ? grown : 0x7ffffffe));
-	if (tb2 > tb) tb = tb2;
-	if (grown >= 0x7fffffffull) { ssq_set_error("ssq_dupset: more than 2^31-1 distinct signatures"); return SSQ_ECAP; }
-	if (tmp.need(tb)) return SSQ_ENOMEM;
-	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n));
-	k_dup_gather<<<g, 256>>>(n, idx_b.as<u32>(), k1.as<u64>(), k1g.as<u64>());
-	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n));
-	k_dup_mark<<<g, 256>>>(n, idx_a.as<u32>(), ka.as<u64>(), k2.as<u64>(), dsig.as<ssq_dupsig_t>(), dd.as<uint8_t>());
-	k_dupset_lookup<<<g, 256>>>(n, dsig.as<ssq_dupsig_t>(), k1.as<u64>(), k2.as<u64>(), dd.as<uint8_t>(), set->k1, set->k2, set->n, dnew.as<uint8_t>());
+	k_dup_sig_keys<<<(unsigned)((n + 255) / 256), 256>>>(n, dsig.as<ssq_dupsig_t>(), k1.as<u64>(), k2.as<u64>(), va.as<uint8_t>());
 	CK(cudaGetLastError());
-	CK(cudaMemcpy(is_dup, dd.p, n, cudaMemcpyDeviceToHost));
-	// absorb the new signatures
-	u64 n_new = 0;
-	CK(cub::DeviceSelect::Flagged(tmp.p, tb, k1.as<u64>(), dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n));
-	CK(cub::DeviceSelect::Flagged(tmp.p, tb, k2.as<u64>(), dnew.as<uint8_t>(), nk2.as<u64>(), cnt.as<u64>(), (int)n));
-	CK(cudaMemcpy(&n_new, cnt.p, 8, cudaMemcpyDeviceToHost));
-	if (n_new) {
-		const u64 total = set->n + n_new;
-		if (total > set->cap) { // grow, keeping the content
-			const u64 ncap = total + total / 2 + 1024;
-			u64 *a = 0, *b = 0;
-			CK(cudaMalloc(&a, ncap * 8)); CK(cudaMalloc(&b, ncap * 8));
-			if (set->n) { CK(cudaMemcpy(a, set->k1, set->n * 8, cudaMemcpyDeviceToDevice)); CK(cudaMemcpy(b, set->k2, set->n * 8, cudaMemcpyDeviceToDevice)); }
-			cudaFree(set->k1); cudaFree(set->k2);
-			set->k1 = a; set->k2 = b; set->cap = ncap;
-		}
-		CK(cudaMemcpy(set->k1 + set->n, nk1.p, n_new * 8, cudaMemcpyDeviceToDevice));
-		CK(cudaMemcpy(set->k2 + set->n, nk2.p, n_new * 8, cudaMemcpyDeviceToDevice));
-		DBuf t1, t2;
-		if (t1.need(total * 8) || t2.need(total * 8)) return SSQ_ENOMEM;
-		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, set->k2, t2.as<u64>(), set->k1, t1.as<u64>(), (int)total)); // by key2, key1 rides along
-		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, t1.as<u64>(), set->k1, t2.as<u64>(), set->k2, (int)total)); // stable by key1
-		set->n = total;
-	}
 	CK(cudaDeviceSynchronize());
+	if ((rc = ssq_dupset_mark_dev(set, n, k1.as<u64>(), k2.as<u64>(), va.as<uint8_t>(), dd.as<uint8_t>(), 0))) return rc;
+	CK(cudaMemcpy(is_dup, dd.p, n, cudaMemcpyDeviceToHost));
 	return SSQ_OK;
 }
 

@@ -1,0 +1,558 @@
+// ssq_pipe.cu — `bwa mem | samblaster` for a batch of reads with everything between the FASTQ bytes and the three SAM streams
+// resident in HBM.
+//
+// Reference call sites: `$BWA mem -t T [-p] [-C] [-I ..] -R RG REF FQ1 [FQ2] | $SAMBLASTER [--excludeDups] --addMateTags
+// --maxSplitCount C --minNonOverlap M --splitterFile F --discordantFile F` at /root/reference/bin/speedseq:438-439,468-469.
+// Upstream routines replaced (un-vendored submodules of the reference): mem_process_seqs, mem_pestat, mem_sam_pe, mem_matesw,
+// mem_pair, mem_mark_primary_se, mem_approx_mapq_se, mem_reg2aln, mem_gen_alt, mem_reg2sam, mem_aln2sam; samblaster's
+// markDupsDiscordants, markSplitterUnmappedClipped and its line writer.
+//
+// Stages (all kernels hand-written for sm_100a; CUB only for scans and the radix sort inside the dup-set):
+//   k_encode        ASCII bases -> one code per base
+//   ssq_batch_run   seeding, SA look-up, chaining, extension                                   (ssq_kernels.cu)
+//   k_dedup         sort / de-duplicate / patch the regions of a read                          (thread per read)
+//   k_pestat        insert-size histogram of the batch                                         (thread per pair, atomics)
+//     host:         quartiles / mean / std from the histogram (the reference's double sums replayed in sorted order),
+//                   penalty table .721*log(2*erfc(|z|/sqrt2))*a over the integer insert sizes  -> back to the device
+//   k_rescue_mark   which pairs trigger a mate-rescue alignment at all                         (thread per pair)
+//   k_rescue        mate rescue, striped-order local SW                                        (thread per marked pair)
+//   k_plan          primary marking, pairing, MAPQ, list of alignments to write                (thread per pair / read)
+//   k_cigar         global banded DP + traceback -> position / CIGAR / NM / MD                 (thread per alignment)
+//   k_sb            samblaster: pair signature, discordant bit, splitter masks                 (thread per pair / read)
+//   dup-set         first-seen-wins over all batches of the run                                (ssq_kernels.cu)
+//   k_text<false>   byte counts of each read's records in the three streams; scans
+//   k_text<true>    the text
+// Host round trips per batch: the size queries inside ssq_batch_run, the histogram, the task count and the text sizes.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "ssq_dev3.cuh"
+#include "ssq_pipe_host.h"
+#include "ssq_host.h"
+#include "ssq_batch.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ssq_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return SSQ_ECUDA; } } while (0)
+#define QMAX 256
+
+// streaming dup-set, device-pointer form (ssq_kernels.cu)
+extern "C" int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t *d_k1, const uint64_t *d_k2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);
+extern "C" int ssq_dupset_reset(ssq_dupset_t *set);
+
+// ================================================================================ kernels ====
+__global__ void __launch_bounds__(256) k_encode(u64 n, const char *__restrict__ ascii, uint8_t *__restrict__ codes)
+{
+	const u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i >= n) return;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		if (i + k >= n) break;
+		const int c = ascii[i + k] | 0x20;
+		codes[i + k] = c == 'a' ? 0 : c == 'c' ? 1 : c == 'g' ? 2 : c == 't' ? 3 : 4;
+	}
+}
+
+// capacity of a read's region list: its own regions plus at most 4 rescued ones per mate hit that may trigger a rescue
+__global__ void k_areg_cap(int n, int paired, int max_matesw, const u32 *__restrict__ n_regs, u64 *cap)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	u32 m = paired ? n_regs[i ^ 1] : 0;
+	if (m > (u32)max_matesw) m = (u32)max_matesw;
+	cap[i] = (u64)n_regs[i] + 4ull * m + (paired ? 4 : 0);
+}
+
+struct DedupSlab { i32 h[QMAX + 16], e[QMAX + 16]; uint8_t qbuf[QMAX], rbuf[2048]; };
+__global__ void __launch_bounds__(128) k_dedup(PipeView V, DedupSlab *slabs, int *work)
+{
+	DedupSlab &s = slabs[(size_t)blockIdx.x * blockDim.x + threadIdx.x];
+	AlnScratch A; A.qbuf = s.qbuf; A.rbuf = s.rbuf; A.rcap = 2048; A.g.h = s.h; A.g.e = s.e; A.g.z = 0; A.g.zcap = 0;
+	for (;;) {
+		const int r = atomicAdd(work, 1);
+		if (r >= V.n_reads) break;
+		body_dedup(V, r, A);
+	}
+}
+
+__global__ void __launch_bounds__(256) k_pestat(PipeView V)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= V.n_reads >> 1) return;
+	int dir; i64 is;
+	if (body_pestat(V, p, &dir, &is)) atomicAdd(&V.hist[(size_t)dir * V.hist_n + is], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_rescue_mark(PipeView V, u32 *list, unsigned int *n_list)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= V.n_reads >> 1) return;
+	if (rescue_wanted(V, p)) list[atomicAdd(n_list, 1u)] = (u32)p;
+}
+
+// per-thread scratch of the rescue kernel: DP rows of the striped-order local SW, the mate in both orientations, the reference
+// window (win_cap bases) and the list of sub-optimal rows (win_cap entries), the snapshot of the near-best hits of both ends
+struct RescueCfg { int win_cap; size_t slab_bytes; };
+__global__ void __launch_bounds__(128) k_rescue(PipeView V, const u32 *__restrict__ list, const unsigned int *__restrict__ n_list, uint8_t *slabs, RescueCfg cfg, int *work)
+{
+	uint8_t *p = slabs + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * cfg.slab_bytes;
+	MateScratch M;
+	M.L.H0 = (i32*)p; p += (QMAX + 16) * 4; M.L.H1 = (i32*)p; p += (QMAX + 16) * 4; M.L.E = (i32*)p; p += (QMAX + 16) * 4; M.L.Hmax = (i32*)p; p += (QMAX + 16) * 4;
+	AlnReg *bbuf = (AlnReg*)p; p += 128 * sizeof(AlnReg);
+	M.L.b = (u64*)p; p += (size_t)cfg.win_cap * 8; M.L.b_cap = cfg.win_cap;
+	M.seq = p; p += QMAX + 64;
+	M.ref = p; M.ref_cap = cfg.win_cap;
+	M.A.qbuf = M.A.rbuf = 0; M.A.rcap = 0; M.A.g.h = M.A.g.e = 0; M.A.g.z = 0; M.A.g.zcap = 0; // sort_dedup_patch(query = 0) never aligns
+	const unsigned int n = *n_list;
+	for (;;) {
+		const unsigned int k = (unsigned int)atomicAdd(work, 1);
+		if (k >= n) break;
+		body_rescue(V, (int)list[k], bbuf, M);
+	}
+}
+
+__global__ void k_tslot_cap(int n, const u32 *__restrict__ n_areg, u64 *cap)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) cap[i] = 2ull * n_areg[i] + 1;
+}
+__global__ void __launch_bounds__(128) k_plan(PipeView V)
+{
+	const int u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= (V.paired ? V.n_reads >> 1 : V.n_reads)) return;
+	body_plan(V, u);
+}
+__global__ void k_ntasks(int n, const ReadMeta *__restrict__ meta, u64 *out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = meta[i].n_tasks;
+}
+__global__ void k_compact(PipeView V)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= V.n_reads) return;
+	const PTask *src = V.tslots + V.tslot_off[r];
+	PTask *dst = V.tasks + V.tk_base[r];
+	const int n = V.meta[r].n_tasks;
+	for (int i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+// CIGAR generation in two tiers: every task first runs with a small traceback slab (enough for the narrow bands almost all
+// alignments have); the ones whose band needs more are listed and redone by a second launch with full-size slabs
+struct CigCfg { int zcap; size_t slab_bytes; };
+__global__ void __launch_bounds__(128) k_cigar(PipeView V, u64 n_tasks, const u32 *__restrict__ redo_in, const unsigned int *__restrict__ n_redo_in, uint8_t *slabs, CigCfg cfg,
+                                               u32 *redo_out, unsigned int *n_redo_out, int *work)
+{
+	uint8_t *p = slabs + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * cfg.slab_bytes;
+	AlnScratch A;
+	A.g.h = (i32*)p; p += (QMAX + 16) * 4; A.g.e = (i32*)p; p += (QMAX + 16) * 4;
+	A.qbuf = p; p += QMAX; A.rbuf = p; p += 2048; A.rcap = 2048;
+	A.g.z = p; A.g.zcap = cfg.zcap;
+	const u64 n = redo_in ? (u64)*n_redo_in : n_tasks;
+	for (;;) {
+		const u64 k = (u64)(unsigned int)atomicAdd(work, 1);
+		if (k >= n) break;
+		const u64 t = redo_in ? (u64)redo_in[k] : k;
+		if (redo_out) { // first tier: a traceback matrix beyond the small slab defers the task instead of failing it
+			const PTask tk = V.tasks[t];
+			const AlnReg &reg = V.areg[V.areg_off[tk.read] + tk.reg_idx];
+			AlnOut a;
+			reg2aln(V.ix, V.opt, (int)(V.tc.read_off[tk.read + 1] - V.tc.read_off[tk.read]), V.tc.seq + V.tc.read_off[tk.read], reg, A, a, V.cigs + t * CIG_CAP, CIG_CAP, V.mds + t * MD_CAP, MD_CAP);
+			if (a.n_cigar < 0) { redo_out[atomicAdd(n_redo_out, 1u)] = (u32)t; continue; }
+			if (a.n_cigar > CIG_CAP - 2 || a.md_len >= MD_CAP) PIPE_ERR(V, 4);
+			V.outs[t] = a;
+		} else body_cigar(V, t, A);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_sb(PipeView V)
+{
+	const int u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= (V.paired ? V.n_reads >> 1 : V.n_reads)) return;
+	body_sb(V, u);
+}
+template <bool W>
+__global__ void __launch_bounds__(128) k_text(PipeView V)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= V.n_reads) return;
+	body_text<W>(V, r);
+}
+__global__ void k_count_u8(u64 n, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, unsigned long long *out) // out[0] += #a, out[1] += #b
+{
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (a[i]) atomicAdd(out, 1ull);
+	if (b && b[i]) atomicAdd(out + 1, 1ull);
+}
+
+// ================================================================================== host ====
+struct PinBuf { // growable pinned host buffer
+	void *p; size_t cap;
+	PinBuf() : p(0), cap(0) {}
+	~PinBuf() { if (p) cudaFreeHost(p); }
+	int need(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFreeHost(p);
+		const size_t want = bytes + bytes / 4 + 4096;
+		if (cudaMallocHost(&p, want) != cudaSuccess) { p = 0; cap = 0; ssq_set_error("cudaMallocHost(%zu) failed", want); return SSQ_ENOMEM; }
+		cap = want; return 0;
+	}
+};
+
+enum { ST_UPLOAD, ST_ALIGN, ST_DEDUP, ST_PESTAT, ST_RESCUE, ST_PLAN, ST_CIGAR, ST_SB, ST_TEXT, ST_FETCH, ST_N };
+
+struct ssq_aligner {
+	const ssq_index *idx; ssq_opts_t opt; SbOpts sb; int device, n_sm;
+	char rg_id[256];
+	cudaStream_t st;
+	ssq_batch_t *b;
+	ssq_dupset_t *dups;
+	// static tables
+	DBuf d_logn, d_lg, d_ctg_names, d_ctg_off, d_sb_off, d_rg;
+	// batch inputs
+	DBuf d_ascii, d_qual, d_names, d_name_off, d_cmt, d_cmt_off;
+	int n_reads, paired, has_qual, has_cmt; i64 n_processed; u64 total_bases; int max_len;
+	// stages
+	DBuf cubtmp, d_cap, d_aoff, d_na, d_areg, d_work, d_pes, d_hist, d_pen, d_dslab, d_rlist, d_rslab, d_tcap, d_tsoff, d_tslots, d_meta, d_pv, d_xcnt,
+	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_cslab, d_cslab_big, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
+	PinBuf h_text[3], h_roff, h_hist, h_small;
+	PeStat pes[4];
+	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines;
+	cudaEvent_t ev[ST_N + 1];
+	float stage_ms[ST_N];
+	int computed;
+};
+
+static int scan_u64(ssq_aligner *a, const u64 *in, u64 *out, size_t n) // exclusive sum, out[n] = total
+{
+	size_t tmp = 0;
+	cub::DeviceScan::ExclusiveSum(0, tmp, in, out, (int)n, a->st);
+	if (a->cubtmp.need(tmp)) return SSQ_ENOMEM;
+	CK(cub::DeviceScan::ExclusiveSum(a->cubtmp.p, tmp, in, out, (int)n, a->st));
+	return 0;
+}
+
+extern "C" void ssq_sb_opts_default(ssq_sb_opts_t *o)
+{
+	memset(o, 0, sizeof *o);
+	o->max_split_count = 2; o->min_non_overlap = 20; o->min_indel_size = 50; o->max_unmapped_bases = 50;
+}
+
+extern "C" void ssq_aligner_free(ssq_aligner_t *a)
+{
+	if (!a) return;
+	cudaSetDevice(a->device);
+	if (a->b) ssq_batch_free(a->b);
+	if (a->dups) ssq_dupset_free(a->dups);
+	for (int i = 0; i <= ST_N; ++i) if (a->ev[i]) cudaEventDestroy(a->ev[i]);
+	delete a;
+}
+
+extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt, const ssq_sb_opts_t *sb, const char *rg_id, ssq_aligner_t **out)
+{
+	if (!idx || !opt || !out) return SSQ_EINVAL;
+	int rc = ssq_use_device(idx->device);
+	if (rc) return rc;
+	ssq_aligner *a = new ssq_aligner();
+	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->dups = 0; a->computed = 0; a->n_reads = 0;
+	memset(a->ev, 0, sizeof a->ev); memset(a->stage_ms, 0, sizeof a->stage_ms); memset(a->pes, 0, sizeof a->pes);
+	memset(&a->sb, 0, sizeof a->sb);
+	if (sb) {
+		a->sb.enabled = sb->enabled; a->sb.excludeDups = sb->exclude_dups; a->sb.addMateTags = sb->add_mate_tags; a->sb.maxSplitCount = sb->max_split_count;
+		a->sb.minNonOverlap = sb->min_non_overlap; a->sb.minIndelSize = sb->min_indel_size; a->sb.maxUnmappedBases = sb->max_unmapped_bases;
+		a->sb.removeDups = sb->remove_dups; a->sb.want_split = sb->want_split; a->sb.want_disc = sb->want_disc;
+	}
+	snprintf(a->rg_id, sizeof a->rg_id, "%s", rg_id ? rg_id : "");
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, idx->device));
+	a->n_sm = prop.multiProcessorCount;
+	if ((rc = ssq_batch_create(idx, opt, 0, 0, 0, &a->b))) { ssq_aligner_free(a); return rc; }
+	a->st = (cudaStream_t)ssq_batch_stream(a->b);
+	if ((rc = ssq_dupset_create(idx->device, &a->dups))) { ssq_aligner_free(a); return rc; }
+	for (int i = 0; i <= ST_N; ++i) CK(cudaEventCreate(&a->ev[i]));
+	{ // tables over integers, computed with the host's libm exactly as the reference evaluates them (see ssq_dev3.cuh)
+		const int n_logn = 8192, n_lg = 65536;
+		std::vector<double> logn(n_logn); std::vector<i32> lg(n_lg);
+		for (int i = 0; i < n_logn; ++i) logn[i] = i ? log((double)i) : 0.;
+		for (int i = 0; i < n_lg; ++i) lg[i] = (int)(4.343 * log((double)(i + 1)) + .499);
+		if (a->d_logn.need(n_logn * 8) || a->d_lg.need(n_lg * 4)) { ssq_aligner_free(a); return SSQ_ENOMEM; }
+		CK(cudaMemcpy(a->d_logn.p, logn.data(), n_logn * 8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(a->d_lg.p, lg.data(), n_lg * 4, cudaMemcpyHostToDevice));
+	}
+	{ // contig names and samblaster's padded coordinate offsets
+		const int ns = idx->n_seqs;
+		std::vector<char> names; std::vector<u32> off(ns + 1, 0); std::vector<i64> sboff(ns + 1, 0);
+		i64 total = 0;
+		for (int i = 0; i < ns; ++i) {
+			const size_t l = strlen(idx->names[i]);
+			names.insert(names.end(), idx->names[i], idx->names[i] + l);
+			off[i + 1] = (u32)names.size();
+			sboff[i] = total; total += (i64)idx->ann_len[i] + 2 * SB_PAD + 1;
+		}
+		if (a->d_ctg_names.need(names.size() + 16) || a->d_ctg_off.need((ns + 1) * 4) || a->d_sb_off.need((ns + 1) * 8) || a->d_rg.need(256)) { ssq_aligner_free(a); return SSQ_ENOMEM; }
+		CK(cudaMemcpy(a->d_ctg_names.p, names.data(), names.size(), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(a->d_ctg_off.p, off.data(), (ns + 1) * 4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(a->d_sb_off.p, sboff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(a->d_rg.p, a->rg_id, 256, cudaMemcpyHostToDevice));
+	}
+	if (a->d_work.need(256) || a->d_err.need(64) || a->d_cnt.need(64) || a->d_pes.need(4 * sizeof(PeStat))) { ssq_aligner_free(a); return SSQ_ENOMEM; }
+	*out = a;
+	return SSQ_OK;
+}
+
+extern "C" int ssq_aligner_reset_dups(ssq_aligner_t *a) { return a ? ssq_dupset_reset(a->dups) : SSQ_EINVAL; }
+extern "C" void *ssq_aligner_stream(ssq_aligner_t *a) { return a ? (void*)a->st : 0; }
+extern "C" float ssq_aligner_stage_ms(const ssq_aligner_t *a, int stage)
+{
+	if (!a || stage < 0) return -1.f;
+	if (stage < ST_N) return a->stage_ms[stage];
+	if (stage < ST_N + 5) return ssq_batch_stage_ms(a->b, stage - ST_N); // 0 smem, 1 sa, 2 chain, 3 extend, 4 select
+	return -1.f;
+}
+extern "C" uint64_t ssq_aligner_counter(const ssq_aligner_t *a, int what)
+{
+	if (!a) return 0;
+	if (what < 100) return ssq_batch_counter(a->b, what);
+	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); }
+	return 0;
+}
+
+// ---- stage 0: host blobs -> HBM ----
+extern "C" int ssq_aligner_upload(ssq_aligner_t *a, const ssq_reads_t *rd)
+{
+	if (!a || !rd || rd->n_reads < 0 || (rd->n_reads && (!rd->seq || !rd->seq_off || !rd->name || !rd->name_off))) return SSQ_EINVAL;
+	if (rd->paired && (rd->n_reads & 1)) { ssq_set_error("paired batch with an odd number of reads"); return SSQ_EINVAL; }
+	int rc = ssq_use_device(a->device);
+	if (rc) return rc;
+	const int n = rd->n_reads;
+	CK(cudaEventRecord(a->ev[ST_UPLOAD], a->st));
+	a->n_reads = n; a->paired = rd->paired ? 1 : 0; a->n_processed = rd->n_processed; a->has_qual = rd->qual != 0; a->has_cmt = rd->comment != 0 && rd->comment_off != 0;
+	a->computed = 0;
+	const u64 total = n ? rd->seq_off[n] : 0;
+	int max_len = 0;
+	for (int i = 0; i < n; ++i) { const int l = (int)(rd->seq_off[i + 1] - rd->seq_off[i]); if (l > max_len) max_len = l; }
+	a->total_bases = total; a->max_len = max_len;
+	uint8_t *d_seq; u64 *d_off;
+	if ((rc = ssq_batch_reserve(a->b, n, total, max_len, &d_seq, &d_off))) return rc;
+	const size_t name_bytes = n ? rd->name_off[n] : 0, cmt_bytes = a->has_cmt && n ? rd->comment_off[n] : 0;
+	if (a->d_ascii.need(total + 16) || a->d_qual.need(total + 16) || a->d_names.need(name_bytes + 16) || a->d_name_off.need((size_t)(n + 1) * 4) ||
+	    a->d_cmt.need(cmt_bytes + 16) || a->d_cmt_off.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+	if (n) {
+		CK(cudaMemcpyAsync(a->d_ascii.p, rd->seq, total, cudaMemcpyHostToDevice, a->st));
+		CK(cudaMemcpyAsync(d_off, rd->seq_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, a->st));
+		if (a->has_qual) CK(cudaMemcpyAsync(a->d_qual.p, rd->qual, total, cudaMemcpyHostToDevice, a->st));
+		CK(cudaMemcpyAsync(a->d_names.p, rd->name, name_bytes, cudaMemcpyHostToDevice, a->st));
+		CK(cudaMemcpyAsync(a->d_name_off.p, rd->name_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, a->st));
+		if (a->has_cmt) {
+			CK(cudaMemcpyAsync(a->d_cmt.p, rd->comment, cmt_bytes, cudaMemcpyHostToDevice, a->st));
+			CK(cudaMemcpyAsync(a->d_cmt_off.p, rd->comment_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, a->st));
+		}
+		if (total) k_encode<<<(unsigned)((total / 4 + 256) / 256), 256, 0, a->st>>>(total, a->d_ascii.as<char>(), d_seq);
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(a->ev[ST_ALIGN], a->st));
+	CK(cudaStreamSynchronize(a->st)); // the caller may reuse its host buffers
+	return SSQ_OK;
+}
+
+static PipeView make_view(ssq_aligner *a)
+{
+	PipeView V;
+	memset(&V, 0, sizeof V);
+	const BatchView bv = ssq_batch_view(a->b);
+	V.ix = bv.ix; V.opt = a->opt; V.sb = a->sb;
+	V.T.logn = a->d_logn.as<double>(); V.T.n_logn = 8192; V.T.lg4343 = a->d_lg.as<i32>(); V.T.n_lg = 65536;
+	V.tc.ctg_names = a->d_ctg_names.as<char>(); V.tc.ctg_name_off = a->d_ctg_off.as<u32>();
+	V.tc.names = a->d_names.as<char>(); V.tc.name_off = a->d_name_off.as<u32>();
+	V.tc.seq = bv.seq; V.tc.read_off = bv.read_off;
+	V.tc.qual = a->has_qual ? a->d_qual.as<char>() : 0;
+	V.tc.cmt = a->has_cmt ? a->d_cmt.as<char>() : 0; V.tc.cmt_off = a->has_cmt ? a->d_cmt_off.as<u32>() : 0;
+	V.tc.rg_id = a->d_rg.as<char>(); V.tc.rg_len = (i32)strlen(a->rg_id);
+	V.n_reads = a->n_reads; V.paired = a->paired; V.n_processed = a->n_processed;
+	V.task_off = bv.task_off; V.n_regs = bv.n_regs; V.regs = bv.regs;
+	V.sb_off = a->d_sb_off.as<i64>();
+	V.err = a->d_err.as<i32>();
+	return V;
+}
+
+// ---- stages 1..8: everything on the device; leaves the text of the three streams in HBM ----
+extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
+{
+	if (!a) return SSQ_EINVAL;
+	int rc = ssq_use_device(a->device);
+	if (rc) return rc;
+	const int n = a->n_reads, n_pairs = a->paired ? n >> 1 : 0, n_units = a->paired ? n >> 1 : n;
+	cudaStream_t st = a->st;
+	a->text_len[0] = a->text_len[1] = a->text_len[2] = 0; a->n_tasks_total = 0; a->n_ids = a->n_dup = a->n_disc_lines = a->n_split_lines = 0;
+	CK(cudaEventRecord(a->ev[ST_ALIGN], st));
+	if (n == 0) { for (int i = ST_ALIGN + 1; i <= ST_N; ++i) CK(cudaEventRecord(a->ev[i], st)); a->computed = 1; return SSQ_OK; }
+	if ((rc = ssq_batch_run(a->b))) return rc;
+	CK(cudaEventRecord(a->ev[ST_DEDUP], st));
+	PipeView V = make_view(a);
+	CK(cudaMemsetAsync(a->d_err.p, 0, 64, st));
+	CK(cudaMemsetAsync(a->d_cnt.p, 0, 64, st));
+	// region lists
+	u64 total_cap = 0;
+	if (a->d_cap.need((size_t)(n + 2) * 8) || a->d_aoff.need((size_t)(n + 2) * 8) || a->d_na.need((size_t)(n + 1) * 4)) return SSQ_ENOMEM;
+	k_areg_cap<<<(n + 255) / 256, 256, 0, st>>>(n, a->paired, a->opt.max_matesw, V.n_regs, a->d_cap.as<u64>());
+	if ((rc = scan_u64(a, a->d_cap.as<u64>(), a->d_aoff.as<u64>(), (size_t)n + 1))) return rc;
+	CK(cudaMemcpyAsync(&total_cap, a->d_aoff.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (a->d_areg.need((total_cap + 1) * sizeof(AlnReg)) || a->d_pv.need((total_cap + 2) * sizeof(P64)) || a->d_xcnt.need((total_cap + 2) * 4)) return SSQ_ENOMEM;
+	V.areg_off = a->d_aoff.as<u64>(); V.areg = a->d_areg.as<AlnReg>(); V.n_areg = a->d_na.as<u32>();
+	V.pv = a->d_pv.as<P64>(); V.xcnt = a->d_xcnt.as<i32>();
+	const int dedup_blocks = a->n_sm * 8;
+	if (a->d_dslab.need((size_t)dedup_blocks * 128 * sizeof(DedupSlab))) return SSQ_ENOMEM;
+	int *work = a->d_work.as<int>();
+	CK(cudaMemsetAsync(work, 0, 256, st));
+	k_dedup<<<dedup_blocks, 128, 0, st>>>(V, a->d_dslab.as<DedupSlab>(), work);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(a->ev[ST_PESTAT], st));
+	// insert-size statistics and the pairing penalty table
+	PeStat *pes = a->pes;
+	memset(pes, 0, 4 * sizeof(PeStat));
+	V.pes = a->d_pes.as<PeStat>();
+	if (a->paired) {
+		if (pes0) for (int d = 0; d < 4; ++d) { pes[d].low = pes0[d].low; pes[d].high = pes0[d].high; pes[d].failed = pes0[d].failed; pes[d].pad = 0; pes[d].avg = pes0[d].avg; pes[d].std = pes0[d].std; }
+		else {
+			const int hist_n = a->opt.max_ins + 1;
+			if (a->d_hist.need((size_t)4 * hist_n * 4) || a->h_hist.need((size_t)4 * hist_n * 4)) return SSQ_ENOMEM;
+			CK(cudaMemsetAsync(a->d_hist.p, 0, (size_t)4 * hist_n * 4, st));
+			V.hist = a->d_hist.as<u32>(); V.hist_n = hist_n;
+			k_pestat<<<(n_pairs + 255) / 256, 256, 0, st>>>(V);
+			CK(cudaMemcpyAsync(a->h_hist.p, a->d_hist.p, (size_t)4 * hist_n * 4, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			pestat_from_hist(a->opt, (const u32*)a->h_hist.p, hist_n, pes, verbose ? stderr : 0);
+		}
+		// penalty table over the integer distances each orientation admits
+		std::vector<double> pen; int pn[4]; size_t pat[4];
+		const size_t tot = pen_table(a->opt, pes, pen, pn, pat);
+		if (a->d_pen.need((tot + 1) * 8)) return SSQ_ENOMEM;
+		for (int d = 0; d < 4; ++d) { V.T.pen[d] = a->d_pen.as<double>() + pat[d]; V.T.pen_low[d] = pes[d].low; V.T.pen_n[d] = pn[d]; }
+		if (tot) CK(cudaMemcpyAsync(a->d_pen.p, pen.data(), tot * 8, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(a->d_pes.p, pes, 4 * sizeof(PeStat), cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st)); // pen is a host temporary
+	}
+	CK(cudaEventRecord(a->ev[ST_RESCUE], st));
+	if (a->paired) { // mate rescue
+		int win = 0;
+		for (int d = 0; d < 4; ++d) if (!pes[d].failed && pes[d].high - pes[d].low > win) win = pes[d].high - pes[d].low;
+		RescueCfg cfg;
+		cfg.win_cap = win + a->max_len + 16;
+		if (cfg.win_cap > (1 << 20)) { ssq_set_error("insert-size bounds admit rescue windows of %d bases (limit 2^20)", cfg.win_cap); return SSQ_EINVAL; }
+		cfg.slab_bytes = (size_t)4 * (QMAX + 16) * 4 + 128 * sizeof(AlnReg) + (size_t)cfg.win_cap * 8 + QMAX + 64 + (size_t)cfg.win_cap;
+		cfg.slab_bytes = (cfg.slab_bytes + 15) & ~(size_t)15;
+		int blocks = a->n_sm * 4;
+		while (blocks > a->n_sm && (size_t)blocks * 128 * cfg.slab_bytes > ((size_t)6 << 30)) blocks >>= 1;
+		if (a->d_rlist.need((size_t)(n_pairs + 1) * 4) || a->d_rslab.need((size_t)blocks * 128 * cfg.slab_bytes)) return SSQ_ENOMEM;
+		unsigned int *n_list = (unsigned int*)(work + 16);
+		k_rescue_mark<<<(n_pairs + 255) / 256, 256, 0, st>>>(V, a->d_rlist.as<u32>(), n_list);
+		k_rescue<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), n_list, a->d_rslab.as<uint8_t>(), cfg, work + 1);
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(a->ev[ST_PLAN], st));
+	// planning: task slots, plan, compaction
+	u64 total_slots = 0, total_tasks = 0;
+	if (a->d_tcap.need((size_t)(n + 2) * 8) || a->d_tsoff.need((size_t)(n + 2) * 8) || a->d_meta.need((size_t)(n + 1) * sizeof(ReadMeta)) || a->d_ntk.need((size_t)(n + 2) * 8) || a->d_tkbase.need((size_t)(n + 2) * 8)) return SSQ_ENOMEM;
+	k_tslot_cap<<<(n + 255) / 256, 256, 0, st>>>(n, V.n_areg, a->d_tcap.as<u64>());
+	if ((rc = scan_u64(a, a->d_tcap.as<u64>(), a->d_tsoff.as<u64>(), (size_t)n + 1))) return rc;
+	CK(cudaMemcpyAsync(&total_slots, a->d_tsoff.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (a->d_tslots.need((total_slots + 1) * sizeof(PTask))) return SSQ_ENOMEM;
+	V.tslot_off = a->d_tsoff.as<u64>(); V.tslots = a->d_tslots.as<PTask>(); V.meta = a->d_meta.as<ReadMeta>();
+	k_plan<<<(n_units + 127) / 128, 128, 0, st>>>(V);
+	k_ntasks<<<(n + 255) / 256, 256, 0, st>>>(n, V.meta, a->d_ntk.as<u64>());
+	if ((rc = scan_u64(a, a->d_ntk.as<u64>(), a->d_tkbase.as<u64>(), (size_t)n + 1))) return rc;
+	CK(cudaMemcpyAsync(&total_tasks, a->d_tkbase.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	a->n_tasks_total = total_tasks;
+	if (total_tasks >= 0xffffffffull) { ssq_set_error("more than 2^32-1 alignments to write in one batch"); return SSQ_EINVAL; }
+	if (a->d_tasks.need((total_tasks + 1) * sizeof(PTask)) || a->d_outs.need((total_tasks + 1) * sizeof(AlnOut)) || a->d_cigs.need((total_tasks + 1) * CIG_CAP * 4) || a->d_mds.need((total_tasks + 1) * MD_CAP) ||
+	    a->d_redo.need((total_tasks + 1) * 4)) return SSQ_ENOMEM;
+	V.tk_base = a->d_tkbase.as<u64>(); V.tasks = a->d_tasks.as<PTask>(); V.outs = a->d_outs.as<AlnOut>(); V.cigs = a->d_cigs.as<u32>(); V.mds = a->d_mds.as<char>();
+	k_compact<<<(n + 255) / 256, 256, 0, st>>>(V);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(a->ev[ST_CIGAR], st));
+	if (total_tasks) { // CIGARs: small-slab tier, then the deferred ones with full-size slabs
+		CigCfg small, big;
+		small.zcap = 12 * 1024; small.slab_bytes = (size_t)2 * (QMAX + 16) * 4 + QMAX + 2048 + small.zcap;
+		big.zcap = QMAX * 768; big.slab_bytes = (size_t)2 * (QMAX + 16) * 4 + QMAX + 2048 + big.zcap;
+		const int blocks = a->n_sm * 8, big_blocks = a->n_sm;
+		if (a->d_cslab.need((size_t)blocks * 128 * small.slab_bytes) || a->d_cslab_big.need((size_t)big_blocks * 128 * big.slab_bytes)) return SSQ_ENOMEM;
+		unsigned int *n_redo = (unsigned int*)(work + 17);
+		k_cigar<<<blocks, 128, 0, st>>>(V, total_tasks, 0, 0, a->d_cslab.as<uint8_t>(), small, a->d_redo.as<u32>(), n_redo, work + 2);
+		k_cigar<<<big_blocks, 128, 0, st>>>(V, total_tasks, a->d_redo.as<u32>(), n_redo, a->d_cslab_big.as<uint8_t>(), big, 0, 0, work + 3);
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(a->ev[ST_SB], st));
+	if (a->d_k1.need((size_t)(n_units + 1) * 8) || a->d_k2.need((size_t)(n_units + 1) * 8) || a->d_valid.need(n_units + 16) || a->d_dup.need(n_units + 16) || a->d_disc.need(n_units + 16) || a->d_smask.need((size_t)(n + 1) * 8)) return SSQ_ENOMEM;
+	V.k1 = a->d_k1.as<u64>(); V.k2 = a->d_k2.as<u64>(); V.valid = a->d_valid.as<uint8_t>(); V.dup = a->d_dup.as<uint8_t>(); V.disc = a->d_disc.as<uint8_t>(); V.split_mask = a->d_smask.as<u64>();
+	if (a->sb.enabled) {
+		k_sb<<<(n_units + 127) / 128, 128, 0, st>>>(V);
+		CK(cudaGetLastError());
+		if ((rc = ssq_dupset_mark_dev(a->dups, (u64)n_units, V.k1, V.k2, V.valid, V.dup, (void*)st))) return rc;
+		k_count_u8<<<(n_units + 255) / 256, 256, 0, st>>>((u64)n_units, V.dup, 0, (unsigned long long*)a->d_cnt.p);
+	}
+	CK(cudaEventRecord(a->ev[ST_TEXT], st));
+	// text: sizes, offsets, bytes
+	for (int k = 0; k < 3; ++k) { if (a->d_len[k].need((size_t)(n + 2) * 8) || a->d_off[k].need((size_t)(n + 2) * 8)) return SSQ_ENOMEM; V.len[k] = a->d_len[k].as<u64>(); V.off[k] = a->d_off[k].as<u64>(); }
+	k_text<false><<<(n + 127) / 128, 128, 0, st>>>(V);
+	CK(cudaGetLastError());
+	const int n_streams = a->sb.enabled ? 3 : 1;
+	for (int k = 0; k < n_streams; ++k) {
+		if ((rc = scan_u64(a, a->d_len[k].as<u64>(), a->d_off[k].as<u64>(), (size_t)n + 1))) return rc;
+		CK(cudaMemcpyAsync(&a->text_len[k], a->d_off[k].as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+	}
+	int h_err = 0; unsigned long long h_cnt[2] = {0, 0};
+	CK(cudaMemcpyAsync(&h_err, a->d_err.p, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h_cnt, a->d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (h_err) {
+		ssq_set_error("batch capacity error (flags 0x%x):%s%s%s%s%s", h_err, h_err & 1 ? " mate rescue overflowed a region list;" : "", h_err & 2 ? " more alignments to write than task slots;" : "",
+		              h_err & 4 ? " an alignment with too many CIGAR operations / MD characters or a traceback matrix beyond the per-thread capacity;" : "", h_err & 8 ? " a rescue window beyond the scratch sized from the insert-size bounds;" : "", h_err & ~15 ? " internal;" : "");
+		return SSQ_ECAP;
+	}
+	for (int k = 0; k < 3; ++k) { if (a->d_text[k].need(a->text_len[k] + 64)) return SSQ_ENOMEM; V.text[k] = a->d_text[k].as<char>(); }
+	k_text<true><<<(n + 127) / 128, 128, 0, st>>>(V);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(a->ev[ST_FETCH], st));
+	a->n_ids = (u64)n_units; a->n_dup = h_cnt[0];
+	a->computed = 1;
+	return SSQ_OK;
+}
+
+// ---- stage 9: the three streams back to (pinned) host memory ----
+extern "C" int ssq_aligner_fetch(ssq_aligner_t *a, ssq_sam_t *out)
+{
+	if (!a || !out || !a->computed) return SSQ_EINVAL;
+	int rc = ssq_use_device(a->device);
+	if (rc) return rc;
+	const int n = a->n_reads;
+	memset(out, 0, sizeof *out);
+	for (int k = 0; k < 3; ++k) {
+		if (a->h_text[k].need(a->text_len[k] + 1)) return SSQ_ENOMEM;
+		if (a->text_len[k]) CK(cudaMemcpyAsync(a->h_text[k].p, a->d_text[k].p, a->text_len[k], cudaMemcpyDeviceToHost, a->st));
+	}
+	if (a->h_roff.need((size_t)(n + 1) * 8)) return SSQ_ENOMEM;
+	if (n) CK(cudaMemcpyAsync(a->h_roff.p, a->d_off[0].p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, a->st));
+	else *(u64*)a->h_roff.p = 0;
+	CK(cudaEventRecord(a->ev[ST_N], a->st));
+	CK(cudaStreamSynchronize(a->st));
+	for (int i = 0; i < ST_N; ++i) { float ms = 0.f; if (cudaEventElapsedTime(&ms, a->ev[i], a->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; } a->stage_ms[i] = ms; }
+	for (int k = 0; k < 3; ++k) { ((char*)a->h_text[k].p)[a->text_len[k]] = 0; out->text[k] = (const char*)a->h_text[k].p; out->len[k] = a->text_len[k]; }
+	out->read_off = (const uint64_t*)a->h_roff.p;
+	out->n_ids = a->n_ids; out->n_dup = a->n_dup;
+	for (int d = 0; d < 4; ++d) { out->pes[d].low = a->pes[d].low; out->pes[d].high = a->pes[d].high; out->pes[d].failed = a->pes[d].failed; out->pes[d].pad = 0; out->pes[d].avg = a->pes[d].avg; out->pes[d].std = a->pes[d].std; }
+	return SSQ_OK;
+}
+
+extern "C" int ssq_aligner_run(ssq_aligner_t *a, const ssq_reads_t *reads, const ssq_pestat_t *pes0, int verbose, ssq_sam_t *out)
+{
+	int rc;
+	if ((rc = ssq_aligner_upload(a, reads))) return rc;
+	if ((rc = ssq_aligner_compute(a, pes0, verbose))) return rc;
+	return ssq_aligner_fetch(a, out);
+}

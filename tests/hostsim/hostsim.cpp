@@ -7,7 +7,10 @@
 #include <vector>
 #include <algorithm>
 #include "../../speedseq_b200/csrc/ssq_dev.cuh"
-#include "../../speedseq_b200/csrc/ssq_mem_host.h"
+#include "../../speedseq_b200/csrc/ssq_dev3.cuh"
+#include "../../speedseq_b200/csrc/ssq_pipe_host.h"
+#include <set>
+#include <string>
 extern "C" {
 #include "../../oracle/ssqo.h"
 }
@@ -255,64 +258,109 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 	w.regs.assign(out.begin(), out.begin() + n_out);
 }
 
-// ---- backend for mem_batch_sam(): the three base-level stages executed by the SSQ_HD routines on the host ----
-struct HostBackend {
-	const DevIndex &ix; ssq_opts_t o;
-	std::vector<uint8_t> codes; std::vector<u64> off; int n_reads;
-	std::vector<u64> aoff; std::vector<u32> na; std::vector<AlnReg> areg;
-	// scratch
-	std::vector<uint8_t> qbuf, rbuf, z, seq, ref; std::vector<i32> h, e, H0, H1, E, Hmax; std::vector<u64> b;
-	AlnScratch A; MateScratch M;
-	HostBackend(const DevIndex &i, const ssq_opts_t &o_) : ix(i), o(o_), n_reads(0), qbuf(256), rbuf(2048), z(256 * 768), seq(256), ref(12288), h(272), e(272), H0(272), H1(272), E(272), Hmax(272), b(12288)
+// ---- the HBM-resident `bwa mem | samblaster` pipeline of ssq_pipe.cu, stage by stage, with the kernels' per-thread bodies
+// (ssq_dev3.cuh) run in plain loops over host vectors.  Same order of stages, same host-side reductions (ssq_pipe_host.h). ----
+struct HostPipe {
+	std::set<std::pair<u64, u64> > seen; // the streaming dup-set: signatures of every earlier batch
+	std::string text[3];
+	std::vector<u64> read_off;
+	PeStat pes[4];
+	int err;
+	int run(const DevIndex &ix, const ssq_opts_t &opt, const SbOpts &sb, int n, const char *const *names, const char *const *seqs, const char *const *quals, const char *const *comments,
+	        i64 n_processed, int paired, const PeStat *pes0, const char *rg_id, const std::vector<std::string> &ctg, const std::vector<i32> &ctg_len)
 	{
-		A.qbuf = qbuf.data(); A.rbuf = rbuf.data(); A.rcap = 2048; A.g.h = h.data(); A.g.e = e.data(); A.g.z = z.data(); A.g.zcap = 256 * 768;
-		M.seq = seq.data(); M.ref = ref.data(); M.ref_cap = 12288; M.L.H0 = H0.data(); M.L.H1 = H1.data(); M.L.E = E.data(); M.L.Hmax = Hmax.data(); M.L.b = b.data(); M.L.b_cap = 12288; M.A = A;
-	}
-	int align(int n, const uint8_t *codes_, const u64 *off_, int paired, int max_matesw)
-	{
-		n_reads = n; codes.assign(codes_, codes_ + off_[n] + 1); off.assign(off_, off_ + n + 1);
-		std::vector<std::vector<RegCand> > r0(n);
-		for (int r = 0; r < n; ++r) { ReadWork w; run_read(ix, o, (int)(off[r + 1] - off[r]), codes.data() + off[r], 2, w); r0[r] = w.regs; }
-		aoff.assign(n + 1, 0); na.assign(n + 1, 0);
-		for (int r = 0; r < n; ++r) {
-			u64 m = paired ? r0[r ^ 1].size() : 0;
-			if (m > (u64)max_matesw) m = max_matesw;
-			aoff[r + 1] = aoff[r] + r0[r].size() + 4 * m + (paired ? 4 : 0);
-		}
-		areg.assign(aoff[n] + 1, AlnReg());
-		for (int r = 0; r < n; ++r) {
-			AlnReg *a = areg.data() + aoff[r];
-			for (size_t i = 0; i < r0[r].size(); ++i) reg_from_cand(r0[r][i], a[i]);
-			na[r] = (u32)sort_dedup_patch(ix, o, codes.data() + off[r], (int)r0[r].size(), a, A);
-		}
-		return 0;
-	}
-	int rescue(const PeStat pes[4])
-	{
-		for (int p = 0; p < n_reads / 2; ++p) {
-			AlnReg bb[2][64]; int nb[2] = {0, 0}, n[2]; AlnReg *a[2];
-			for (int i = 0; i < 2; ++i) {
-				a[i] = areg.data() + aoff[2 * p + i]; n[i] = (int)na[2 * p + i];
-				for (int j = 0; j < n[i]; ++j) if (a[i][j].score >= a[i][0].score - o.pen_unpaired && nb[i] < 64) bb[i][nb[i]++] = a[i][j];
+		err = 0;
+		// inputs as the aligner lays them out
+		std::vector<u64> off(n + 1, 0); std::vector<u32> name_off(n + 1, 0), cmt_off(n + 1, 0);
+		std::string nameb, qualb, cmtb;
+		for (int i = 0; i < n; ++i) { off[i + 1] = off[i] + strlen(seqs[i]); nameb += names[i]; name_off[i + 1] = (u32)nameb.size(); if (quals && quals[i]) qualb += quals[i]; if (comments && comments[i]) cmtb += comments[i]; cmt_off[i + 1] = (u32)cmtb.size(); }
+		std::vector<uint8_t> codes(off[n] + 16);
+		for (int i = 0; i < n; ++i) for (size_t k = 0; seqs[i][k]; ++k) { const int c = seqs[i][k] | 0x20; codes[off[i] + k] = c == 'a' ? 0 : c == 'c' ? 1 : c == 'g' ? 2 : c == 't' ? 3 : 4; }
+		std::string ctgb; std::vector<u32> ctg_off(ctg.size() + 1, 0); std::vector<i64> sb_off(ctg.size() + 1, 0);
+		{ i64 total = 0; for (size_t i = 0; i < ctg.size(); ++i) { ctgb += ctg[i]; ctg_off[i + 1] = (u32)ctgb.size(); sb_off[i] = total; total += (i64)ctg_len[i] + 2 * SB_PAD + 1; } }
+		std::vector<double> logn(8192); std::vector<i32> lg(65536);
+		for (int i = 0; i < 8192; ++i) logn[i] = i ? log((double)i) : 0.;
+		for (int i = 0; i < 65536; ++i) lg[i] = (int)(4.343 * log((double)(i + 1)) + .499);
+		// stage 0: regions out of seed extension
+		std::vector<RegCand> regs; std::vector<u64> task_off(n + 1, 0); std::vector<u32> n_regs(n + 1, 0);
+		for (int r = 0; r < n; ++r) { ReadWork w; run_read(ix, opt, (int)(off[r + 1] - off[r]), codes.data() + off[r], 2, w); task_off[r] = regs.size(); n_regs[r] = (u32)w.regs.size(); regs.insert(regs.end(), w.regs.begin(), w.regs.end()); }
+		regs.push_back(RegCand());
+		PipeView V; memset(&V, 0, sizeof V);
+		V.ix = ix; V.opt = opt; V.sb = sb;
+		V.T.logn = logn.data(); V.T.n_logn = 8192; V.T.lg4343 = lg.data(); V.T.n_lg = 65536;
+		V.tc.ctg_names = ctgb.data(); V.tc.ctg_name_off = ctg_off.data(); V.tc.names = nameb.data(); V.tc.name_off = name_off.data();
+		V.tc.seq = codes.data(); V.tc.read_off = off.data(); V.tc.qual = quals && qualb.size() == off[n] && n ? qualb.data() : 0;
+		V.tc.cmt = comments ? cmtb.data() : 0; V.tc.cmt_off = comments ? cmt_off.data() : 0;
+		V.tc.rg_id = rg_id ? rg_id : ""; V.tc.rg_len = rg_id ? (i32)strlen(rg_id) : 0;
+		V.n_reads = n; V.paired = paired; V.n_processed = n_processed;
+		V.task_off = task_off.data(); V.n_regs = n_regs.data(); V.regs = regs.data();
+		V.sb_off = sb_off.data(); V.err = &err;
+		const int n_pairs = paired ? n / 2 : 0, n_units = paired ? n / 2 : n;
+		// region lists
+		std::vector<u64> aoff(n + 1, 0); std::vector<u32> na(n + 1, 0);
+		for (int i = 0; i < n; ++i) { u32 m = paired ? n_regs[i ^ 1] : 0; if (m > (u32)opt.max_matesw) m = (u32)opt.max_matesw; aoff[i + 1] = aoff[i] + n_regs[i] + 4ull * m + (paired ? 4 : 0); }
+		std::vector<AlnReg> areg(aoff[n] + 1); std::vector<P64> pv(aoff[n] + 2); std::vector<i32> xcnt(aoff[n] + 2);
+		V.areg_off = aoff.data(); V.areg = areg.data(); V.n_areg = na.data(); V.pv = pv.data(); V.xcnt = xcnt.data();
+		std::vector<uint8_t> qbuf(256), rbuf(2048), zb(256 * 768), sq(256 + 64); std::vector<i32> h(272), e(272), H0(272), H1(272), E(272), Hm(272);
+		AlnScratch A; A.qbuf = qbuf.data(); A.rbuf = rbuf.data(); A.rcap = 2048; A.g.h = h.data(); A.g.e = e.data(); A.g.z = 0; A.g.zcap = 0;
+		for (int r = 0; r < n; ++r) body_dedup(V, r, A);
+		// insert-size statistics
+		memset(pes, 0, sizeof pes);
+		V.pes = pes;
+		std::vector<double> pen; int pn[4]; size_t pat[4];
+		if (paired) {
+			if (pes0) for (int d = 0; d < 4; ++d) pes[d] = pes0[d];
+			else {
+				const int hist_n = opt.max_ins + 1;
+				std::vector<u32> hist((size_t)4 * hist_n, 0);
+				V.hist = hist.data(); V.hist_n = hist_n;
+				for (int p = 0; p < n_pairs; ++p) { int dir; i64 is; if (body_pestat(V, p, &dir, &is)) ++hist[(size_t)dir * hist_n + is]; }
+				pestat_from_hist(opt, hist.data(), hist_n, pes, 0);
 			}
-			for (int i = 0; i < 2; ++i) {
-				const int cap = (int)(aoff[2 * p + !i + 1] - aoff[2 * p + !i]);
-				for (int j = 0; j < nb[i] && j < o.max_matesw; ++j)
-					mate_rescue(ix, o, pes, bb[i][j], (int)(off[2 * p + !i + 1] - off[2 * p + !i]), codes.data() + off[2 * p + !i], a[!i], &n[!i], cap, M);
-			}
-			na[2 * p] = (u32)n[0]; na[2 * p + 1] = (u32)n[1];
+			pen_table(opt, pes, pen, pn, pat);
+			for (int d = 0; d < 4; ++d) { V.T.pen[d] = pen.data() + pat[d]; V.T.pen_low[d] = pes[d].low; V.T.pen_n[d] = pn[d]; }
+			// mate rescue
+			int win = 0;
+			for (int d = 0; d < 4; ++d) if (!pes[d].failed && pes[d].high - pes[d].low > win) win = pes[d].high - pes[d].low;
+			int max_len = 0; for (int i = 0; i < n; ++i) if ((int)(off[i + 1] - off[i]) > max_len) max_len = (int)(off[i + 1] - off[i]);
+			const int win_cap = win + max_len + 16;
+			std::vector<uint8_t> ref(win_cap); std::vector<u64> bl(win_cap); std::vector<AlnReg> bbuf(128);
+			MateScratch M; M.seq = sq.data(); M.ref = ref.data(); M.ref_cap = win_cap; M.L.H0 = H0.data(); M.L.H1 = H1.data(); M.L.E = E.data(); M.L.Hmax = Hm.data(); M.L.b = bl.data(); M.L.b_cap = win_cap;
+			M.A.qbuf = M.A.rbuf = 0; M.A.rcap = 0; M.A.g.h = M.A.g.e = 0; M.A.g.z = 0; M.A.g.zcap = 0;
+			for (int p = 0; p < n_pairs; ++p) if (rescue_wanted(V, p)) body_rescue(V, p, bbuf.data(), M);
 		}
-		return 0;
-	}
-	int cigar(const std::vector<CigTask> &tasks, std::vector<AlnOut> &outs, std::vector<u32> &cigs, std::vector<char> &mds)
-	{
-		for (size_t t = 0; t < tasks.size(); ++t) {
-			const int r = tasks[t].read;
-			reg2aln(ix, o, (int)(off[r + 1] - off[r]), codes.data() + off[r], tasks[t].reg, A, outs[t], cigs.data() + t * CIG_CAP, CIG_CAP, mds.data() + t * MD_CAP, MD_CAP);
+		// planning
+		std::vector<u64> tsoff(n + 1, 0);
+		for (int i = 0; i < n; ++i) tsoff[i + 1] = tsoff[i] + 2ull * na[i] + 1;
+		std::vector<PTask> tslots(tsoff[n] + 1); std::vector<ReadMeta> meta(n + 1);
+		V.tslot_off = tsoff.data(); V.tslots = tslots.data(); V.meta = meta.data();
+		for (int u = 0; u < n_units; ++u) body_plan(V, u);
+		std::vector<u64> tkb(n + 1, 0);
+		for (int i = 0; i < n; ++i) tkb[i + 1] = tkb[i] + meta[i].n_tasks;
+		const u64 nt = tkb[n];
+		std::vector<PTask> tasks(nt + 1); std::vector<AlnOut> outs(nt + 1); std::vector<u32> cigs((nt + 1) * CIG_CAP); std::vector<char> mds((nt + 1) * MD_CAP);
+		V.tk_base = tkb.data(); V.tasks = tasks.data(); V.outs = outs.data(); V.cigs = cigs.data(); V.mds = mds.data();
+		for (int r = 0; r < n; ++r) for (u32 i = 0; i < meta[r].n_tasks; ++i) tasks[tkb[r] + i] = tslots[tsoff[r] + i];
+		A.g.z = zb.data(); A.g.zcap = 256 * 768;
+		for (u64 t = 0; t < nt; ++t) body_cigar(V, t, A);
+		// samblaster + dup-set
+		std::vector<u64> k1(n_units + 1), k2(n_units + 1), smask(n + 1, 0); std::vector<uint8_t> valid(n_units + 1, 0), dup(n_units + 1, 0), disc(n_units + 1, 0);
+		V.k1 = k1.data(); V.k2 = k2.data(); V.valid = valid.data(); V.dup = dup.data(); V.disc = disc.data(); V.split_mask = smask.data();
+		if (sb.enabled) {
+			for (int u = 0; u < n_units; ++u) body_sb(V, u);
+			for (int u = 0; u < n_units; ++u) if (valid[u]) dup[u] = seen.insert(std::make_pair(k1[u], k2[u])).second ? 0 : 1;
 		}
-		return 0;
+		// text
+		std::vector<u64> len[3], toff[3];
+		for (int k = 0; k < 3; ++k) { len[k].assign(n + 1, 0); toff[k].assign(n + 1, 0); V.len[k] = len[k].data(); V.off[k] = toff[k].data(); }
+		for (int r = 0; r < n; ++r) body_text<false>(V, r);
+		for (int k = 0; k < 3; ++k) { for (int r = 0; r < n; ++r) toff[k][r + 1] = toff[k][r] + len[k][r]; text[k].assign(toff[k][n], '\0'); V.text[k] = &text[k][0]; }
+		for (int r = 0; r < n; ++r) body_text<true>(V, r);
+		read_off = toff[0];
+		return err;
 	}
 };
+static HostPipe g_pipe;
 
 extern "C" {
 
@@ -379,45 +427,41 @@ int64_t hostsim_align_batch(const ssqo_idx_t *idx, int n_reads, const uint8_t *s
 }
 
 // `bwa mem` for a batch of pairs through the product's host orchestration + the host backend -> malloc'd SAM text
+static void pipe_index_names(const ssqo_idx_t *idx, std::vector<std::string> &ctg, std::vector<i32> &len)
+{
+	for (int i = 0; i < idx->bns.n_seqs; ++i) { ctg.push_back(idx->bns.anns[i].name); len.push_back(idx->bns.anns[i].len); }
+}
+// `bwa mem` records for a batch (plain: no samblaster stage) -> malloc'd SAM text
 char *hostsim_mem_pe(const ssqo_idx_t *idx, int n_reads, const char **names, const char **seqs, const char **quals, int64_t n_processed, const char *rg_id, int paired)
 {
 	std::vector<i64> aoff_; std::vector<i32> alen_; DevIndex ix = make_ix(idx, aoff_, alen_);
 	ssq_opts_t opt; ssq_opts_default(&opt);
-	if (getenv("HOSTSIM_THREADS")) opt.n_threads = atoi(getenv("HOSTSIM_THREADS"));
-	std::vector<u64> off(n_reads + 1, 0);
-	for (int i = 0; i < n_reads; ++i) off[i + 1] = off[i] + strlen(seqs[i]);
-	std::vector<uint8_t> codes(off[n_reads] + 1);
-	for (int i = 0; i < n_reads; ++i) for (size_t k = 0; seqs[i][k]; ++k) { char c = seqs[i][k]; codes[off[i] + k] = c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2 : c == 'T' || c == 't' ? 3 : 4; }
-	std::vector<char*> nm(idx->bns.n_seqs);
-	for (int i = 0; i < idx->bns.n_seqs; ++i) nm[i] = idx->bns.anns[i].name;
-	HostIndexInfo hi; hi.l_pac = idx->bns.l_pac; hi.n_seqs = idx->bns.n_seqs; hi.names = nm.data(); hi.ann_off = aoff_.data();
-	HostBackend be(ix, opt);
-	std::string sam, err;
-	int rc = mem_batch_sam(be, opt, &hi, n_reads, names, codes.data(), off.data(), quals, (const char *const *)0, n_processed, paired, (const PeStat*)0, rg_id, (FILE*)0, sam, err);
-	if (rc) return 0;
-	char *out = (char*)malloc(sam.size() + 1);
-	memcpy(out, sam.c_str(), sam.size() + 1);
+	SbOpts sb; memset(&sb, 0, sizeof sb);
+	std::vector<std::string> ctg; std::vector<i32> clen; pipe_index_names(idx, ctg, clen);
+	HostPipe hp;
+	if (hp.run(ix, opt, sb, n_reads, names, seqs, quals, 0, n_processed, paired, 0, rg_id, ctg, clen)) return 0;
+	char *out = (char*)malloc(hp.text[0].size() + 1);
+	memcpy(out, hp.text[0].c_str(), hp.text[0].size() + 1);
 	return out;
 }
-
-int64_t hostsim_align1_batch(const ssqo_idx_t *idx, int n_reads, const uint8_t *seq, const uint64_t *read_off, api_alnreg_t *out, uint64_t cap, uint64_t *out_off)
+// the fused `bwa mem | samblaster` pipeline for one batch; sbv = {excludeDups, addMateTags, maxSplitCount, minNonOverlap, removeDups};
+// reset != 0 starts a new run (empties the dup-set); pes_in: optional 4 x {low, high, failed, avg, std} as doubles (-I)
+int hostsim_pipe(const ssqo_idx_t *idx, int n_reads, const char **names, const char **seqs, const char **quals, const char **comments, int64_t n_processed, const char *rg_id, int paired,
+                 const int *sbv, int reset, const double *pes_in, char **out_main, char **out_split, char **out_disc)
 {
 	std::vector<i64> aoff_; std::vector<i32> alen_; DevIndex ix = make_ix(idx, aoff_, alen_);
 	ssq_opts_t opt; ssq_opts_default(&opt);
-	HostBackend be(ix, opt);
-	be.align(n_reads, seq, read_off, 0, opt.max_matesw);
-	uint64_t n = 0;
-	for (int r = 0; r < n_reads; ++r) {
-		out_off[r] = n;
-		for (u32 i = 0; i < be.na[r]; ++i, ++n) {
-			if (n >= cap) return -1;
-			const AlnReg &a = be.areg[be.aoff[r] + i];
-			out[n].rb = a.rb; out[n].re = a.re; out[n].qb = a.qb; out[n].qe = a.qe; out[n].rid = a.rid; out[n].score = a.score; out[n].truesc = a.truesc;
-			out[n].w = a.w; out[n].seedcov = a.seedcov; out[n].seedlen0 = a.seedlen0; out[n].frac_rep = a.frac_rep; out[n].read_id = r;
-		}
-	}
-	out_off[n_reads] = n;
-	return (int64_t)n;
+	SbOpts sb; memset(&sb, 0, sizeof sb);
+	sb.enabled = 1; sb.excludeDups = sbv[0]; sb.addMateTags = sbv[1]; sb.maxSplitCount = sbv[2]; sb.minNonOverlap = sbv[3]; sb.removeDups = sbv[4]; sb.minIndelSize = 50; sb.maxUnmappedBases = 50; sb.want_split = sb.want_disc = 1;
+	std::vector<std::string> ctg; std::vector<i32> clen; pipe_index_names(idx, ctg, clen);
+	if (reset) g_pipe.seen.clear();
+	PeStat pes[4]; memset(pes, 0, sizeof pes);
+	if (pes_in) for (int d = 0; d < 4; ++d) { pes[d].low = (int)pes_in[5 * d]; pes[d].high = (int)pes_in[5 * d + 1]; pes[d].failed = (int)pes_in[5 * d + 2]; pes[d].avg = pes_in[5 * d + 3]; pes[d].std = pes_in[5 * d + 4]; }
+	const int rc = g_pipe.run(ix, opt, sb, n_reads, names, seqs, quals, comments, n_processed, paired, pes_in ? pes : 0, rg_id, ctg, clen);
+	if (rc) return rc;
+	char **outs[3] = {out_main, out_split, out_disc};
+	for (int k = 0; k < 3; ++k) { *outs[k] = (char*)malloc(g_pipe.text[k].size() + 1); memcpy(*outs[k], g_pipe.text[k].c_str(), g_pipe.text[k].size() + 1); }
+	return 0;
 }
 
 // randomized check of ChainBuilder's tree-ordered chains against a plain ordered-array restatement (look-up = first chain with

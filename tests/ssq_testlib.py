@@ -5,26 +5,19 @@ import ctypes as C
 import gzip
 import os
 import subprocess
+import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 ORACLE_SO = os.path.join(ROOT, "oracle", "libssqo.so")
 ORACLE_BIN = os.path.join(ROOT, "oracle", "ssqo")
 HOSTSIM_SO = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
 SSQ_SO = os.path.join(ROOT, "speedseq_b200", "libssq.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-SMEM_DT = np.dtype([("k", "<u8"), ("l", "<u8"), ("s", "<u8"), ("qbeg", "<u4"), ("qend", "<u4")])
-SEED_DT = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])
-SWTASK_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("h0", "<i4"), ("w", "<i4"),
-                      ("end_bonus", "<i4"), ("zdrop", "<i4")])
-SWRES_DT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("gscore", "<i4"), ("max_off", "<i4")])
-REG_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
-                   ("w", "<i4"), ("seedcov", "<i4"), ("seedlen0", "<i4"), ("frac_rep", "<f4"), ("read_id", "<i4")])
-DUPSIG_DT = np.dtype([("pos1", "<u8"), ("pos2", "<u8"), ("strand1", "u1"), ("strand2", "u1"), ("valid", "u1"), ("pad", "u1", (5,))])
+from speedseq_b200.capi import SMEM_DT, SEED_DT, SWTASK_DT, SWRES_DT, REG_DT, DUPSIG_DT, SSQ, pack_reads  # noqa: E402,F401  (the product's own bindings)
 ODUPSIG_DT = np.dtype([("pos1", "<u8"), ("pos2", "<u8"), ("strand1", "u1"), ("strand2", "u1"), ("valid", "u1")], align=True)
-
-assert SMEM_DT.itemsize == 32 and SEED_DT.itemsize == 16 and SWTASK_DT.itemsize == 40 and REG_DT.itemsize == 56 and DUPSIG_DT.itemsize == 24
 
 
 def build_oracle():
@@ -34,7 +27,7 @@ def build_oracle():
 def build_hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     src, out = os.path.join(d, "hostsim.cpp"), HOSTSIM_SO
-    hdrs = [os.path.join(ROOT, "speedseq_b200", "csrc", f) for f in ("ssq_dev.cuh", "ssq_dev2.cuh", "ssq_mem_host.h")]
+    hdrs = [os.path.join(ROOT, "speedseq_b200", "csrc", f) for f in ("ssq_dev.cuh", "ssq_dev2.cuh", "ssq_dev3.cuh", "ssq_pipe_host.h")]
     if not os.path.exists(out) or os.path.getmtime(out) < max([os.path.getmtime(src), os.path.getmtime(ORACLE_SO)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread", "-o", out, src, "-L" + os.path.join(ROOT, "oracle"), "-lssqo",
                                "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
@@ -167,17 +160,22 @@ class HostSim:
         self.o.lib.ssqo_api_free(C.c_void_p(p))
         return s
 
-    def align1_batch(self, idx, seq, off):
-        n = len(off) - 1
-        cap = max(1024, 16 * n)
-        self.lib.hostsim_align1_batch.restype = C.c_int64
-        while True:
-            out = np.zeros(cap, REG_DT)
-            ooff = np.zeros(n + 1, np.uint64)
-            r = self.lib.hostsim_align1_batch(C.c_void_p(idx), C.c_int(n), _ptr(seq), _ptr(off), _ptr(out), C.c_uint64(cap), _ptr(ooff))
-            if r >= 0:
-                return out[:r], ooff
-            cap *= 4
+    def pipe(self, idx, names, seqs, quals, n_processed=0, rg_id=b"", paired=1, sb=(1, 1, 2, 20, 0), reset=1, comments=None, pes=None):
+        """the fused `bwa mem | samblaster` pipeline (bodies of ssq_pipe.cu's kernels run on the host) -> (main, splitters, discordants)
+        sb = (excludeDups, addMateTags, maxSplitCount, minNonOverlap, removeDups); pes = 4 x (low, high, failed, avg, std) for -I"""
+        n = len(names)
+        arr = lambda xs: (C.c_char_p * n)(*[x if isinstance(x, bytes) else x.encode() for x in xs])
+        outs = [C.c_void_p() for _ in range(3)]
+        sbv = (C.c_int * 5)(*sb)
+        pv = (C.c_double * 20)(*[float(x) for row in pes for x in row]) if pes is not None else None
+        rc = self.lib.hostsim_pipe(C.c_void_p(idx), C.c_int(n), arr(names), arr(seqs), arr(quals) if quals is not None else None, arr(comments) if comments is not None else None,
+                                   C.c_int64(n_processed), rg_id, C.c_int(paired), sbv, C.c_int(reset), pv, C.byref(outs[0]), C.byref(outs[1]), C.byref(outs[2]))
+        assert rc == 0, "hostsim_pipe failed: flags 0x%x" % rc
+        res = []
+        for o in outs:
+            res.append(C.string_at(o).decode())
+            self.o.lib.ssqo_api_free(o)
+        return tuple(res)
 
     def align_batch(self, idx, seq, off):
         n = len(off) - 1
@@ -190,106 +188,6 @@ class HostSim:
             if r >= 0:
                 return out[:r], ooff
             cap *= 4
-
-
-class SSQ:
-    """the product's C-ABI (include/ssq.h); raises when libssq.so is missing — there is no fallback"""
-    OPTS_WORDS = 30
-
-    def __init__(self):
-        if not os.path.exists(SSQ_SO):
-            raise RuntimeError("speedseq_b200/libssq.so is not built; run __graft_entry__.build()")
-        self.lib = C.CDLL(SSQ_SO)
-        L = self.lib
-        L.ssq_last_error.restype = C.c_char_p
-        L.ssq_index_info.restype = C.c_uint64
-        L.ssq_index_info.argtypes = [C.c_void_p, C.c_int]
-        L.ssq_batch_counter.restype = C.c_uint64
-        L.ssq_batch_counter.argtypes = [C.c_void_p, C.c_int]
-        L.ssq_batch_stage_ms.restype = C.c_float
-        L.ssq_batch_stage_ms.argtypes = [C.c_void_p, C.c_int]
-        L.ssq_batch_stream.restype = C.c_void_p
-        L.ssq_batch_stream.argtypes = [C.c_void_p]
-        self.opts = (C.c_int32 * self.OPTS_WORDS)()
-        L.ssq_opts_default(self.opts)
-
-    def err(self):
-        return self.lib.ssq_last_error().decode()
-
-    def ck(self, rc, what):
-        if rc != 0:
-            raise RuntimeError("%s failed: rc=%d: %s" % (what, rc, self.err()))
-
-    def index_load(self, prefix, device=0):
-        h = C.c_void_p()
-        self.ck(self.lib.ssq_index_load(prefix.encode(), C.c_int(device), C.byref(h)), "ssq_index_load")
-        return h
-
-    def index_build(self, fasta, prefix=None, device=0):
-        self.ck(self.lib.ssq_index_build(fasta.encode(), (prefix or fasta).encode(), C.c_int(device)), "ssq_index_build")
-
-    def index_free(self, h):
-        self.lib.ssq_index_free(h)
-
-    def smem_batch(self, idx, seq, off):
-        n = len(off) - 1
-        cap = max(1024, 64 * n)
-        while True:
-            out = np.zeros(cap, SMEM_DT)
-            ooff = np.zeros(n + 1, np.uint64)
-            need = C.c_uint64(0)
-            rc = self.lib.ssq_smem_batch(idx, self.opts, C.c_int(n), _ptr(seq), _ptr(off), _ptr(out), C.c_uint64(cap), _ptr(ooff), C.byref(need))
-            if rc == -5:
-                cap = int(need.value) + 16
-                continue
-            self.ck(rc, "ssq_smem_batch")
-            return out[: int(need.value)], ooff
-
-    def sa_lookup_batch(self, idx, rows):
-        pos = np.zeros(len(rows), np.uint64)
-        self.ck(self.lib.ssq_sa_lookup_batch(idx, C.c_uint64(len(rows)), _ptr(rows), _ptr(pos)), "ssq_sa_lookup_batch")
-        return pos
-
-    def sw_extend_batch(self, tasks, qbuf, tbuf, device=0):
-        res = np.zeros(len(tasks), SWRES_DT)
-        self.ck(self.lib.ssq_sw_extend_batch(self.opts, C.c_int(device), C.c_uint64(len(tasks)), _ptr(tasks), _ptr(qbuf), C.c_uint64(len(qbuf)), _ptr(tbuf),
-                                             C.c_uint64(len(tbuf)), _ptr(res)), "ssq_sw_extend_batch")
-        return res
-
-    def chain_batch(self, idx, seq, off):
-        n = len(off) - 1
-        scap, ccap = max(4096, 256 * n), max(1024, 64 * n)
-        while True:
-            seeds = np.zeros(scap, SEED_DT)
-            cso = np.zeros(ccap + 1, np.uint64)
-            rco = np.zeros(n + 1, np.uint64)
-            nc, ns = C.c_uint64(0), C.c_uint64(0)
-            rc = self.lib.ssq_chain_batch(idx, self.opts, C.c_int(n), _ptr(seq), _ptr(off), _ptr(seeds), C.c_uint64(scap), _ptr(cso), C.c_uint64(ccap), _ptr(rco),
-                                          C.byref(nc), C.byref(ns))
-            if rc == -5:
-                scap, ccap = int(ns.value) + 16, int(nc.value) + 16
-                continue
-            self.ck(rc, "ssq_chain_batch")
-            return seeds[: int(ns.value)], cso[: int(nc.value) + 1], rco
-
-    def align_batch(self, idx, seq, off):
-        n = len(off) - 1
-        cap = max(1024, 16 * n)
-        while True:
-            out = np.zeros(cap, REG_DT)
-            ooff = np.zeros(n + 1, np.uint64)
-            need = C.c_uint64(0)
-            rc = self.lib.ssq_align_batch(idx, self.opts, C.c_int(n), _ptr(seq), _ptr(off), C.c_int(0), _ptr(out), C.c_uint64(cap), _ptr(ooff), C.byref(need))
-            if rc == -5:
-                cap = int(need.value) + 16
-                continue
-            self.ck(rc, "ssq_align_batch")
-            return out[: int(need.value)], ooff
-
-    def dupmark_batch(self, sig, device=0):
-        d = np.zeros(len(sig), np.uint8)
-        self.ck(self.lib.ssq_dupmark_batch(C.c_int(device), C.c_uint64(len(sig)), _ptr(sig), _ptr(d)), "ssq_dupmark_batch")
-        return d
 
 
 # ------------------------------------------------------------------------------------ data ----
