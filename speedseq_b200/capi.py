@@ -191,7 +191,7 @@ class SSQ:
         return h
 
     def aligner_run(self, al, reads, pes=None, verbose=0):
-        """reads: Reads (pack_reads) -> (main, splitters, discordants) as bytes + the ssq_sam_t"""
+        """reads: Reads (pack_reads) -> ((main, splitters, discordants) as bytes, info dict)"""
         out = Sam()
         pv = None
         if pes is not None:
@@ -199,7 +199,10 @@ class SSQ:
             for d in range(4):
                 pv[d].low, pv[d].high, pv[d].failed, pv[d].avg, pv[d].std = int(pes[d][0]), int(pes[d][1]), int(pes[d][2]), float(pes[d][3]), float(pes[d][4])
         self.ck(self.lib.ssq_aligner_run(al, C.byref(reads), pv, C.c_int(verbose), C.byref(out)), "ssq_aligner_run")
-        return tuple(C.string_at(out.text[k], out.len[k]) for k in range(3)), out
+        # everything is copied here: the buffers behind `out` belong to the aligner and are reused by its next run
+        info = {"n_ids": int(out.n_ids), "n_dup": int(out.n_dup), "pes": [(p.low, p.high, p.failed, p.avg, p.std) for p in out.pes],
+                "read_off": np.ctypeslib.as_array((C.c_uint64 * (reads.n_reads + 1)).from_address(out.read_off)).copy()}
+        return tuple(C.string_at(out.text[k], out.len[k]) for k in range(3)), info
 
     def aligner_free(self, al):
         self.lib.ssq_aligner_free(al)
