@@ -89,6 +89,18 @@ typedef struct { int32_t score, qle, tle, gtle, gscore, max_off; } ssq_sw_result
 int ssq_sw_extend_batch(const ssq_opts_t *opt, int device, uint64_t n, const ssq_sw_task_t *tasks,
                         const uint8_t *qbuf, uint64_t qbuf_len, const uint8_t *tbuf, uint64_t tbuf_len, ssq_sw_result_t *out);
 
+/* Local alignment in the evaluation order of the reference's striped SSE2 kernel.  Replaces upstream ksw_align2() as called from
+ * mem_matesw() (mate rescue inside `$BWA mem`, speedseq:438): xtra = KSW_XSUBO|KSW_XSTART|(KSW_XBYTE if qlen*a < 250)|minsc.
+ * One warp per problem, the SSE lanes mapped onto warp lanes (csrc/ssq_warp.cuh). */
+typedef struct { uint64_t q_off, t_off; int32_t qlen, tlen, xtra, pad; } ssq_swl_task_t;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb; } ssq_swl_result_t;
+#define SSQ_KSW_XBYTE  0x10000
+#define SSQ_KSW_XSTOP  0x20000
+#define SSQ_KSW_XSUBO  0x40000
+#define SSQ_KSW_XSTART 0x80000
+int ssq_sw_local_batch(const ssq_opts_t *opt, int device, uint64_t n, const ssq_swl_task_t *tasks, const uint8_t *qbuf, uint64_t qbuf_len,
+                       const uint8_t *tbuf, uint64_t tbuf_len, ssq_swl_result_t *out);
+
 /* Chains after seeding + SA lookup + chaining + chain filter.  Replaces upstream mem_chain() +
  * mem_chain_flt() (speedseq:438).  Flattened: read i owns chains [read_chain_off[i], read_chain_off[i+1]),
  * chain c owns seeds [chain_seed_off[c], chain_seed_off[c+1]). */
@@ -209,6 +221,10 @@ int ssq_aligner_upload(ssq_aligner_t *al, const ssq_reads_t *reads);
 int ssq_aligner_compute(ssq_aligner_t *al, const ssq_pestat_t *pes0, int verbose);
 int ssq_aligner_fetch(ssq_aligner_t *al, ssq_sam_t *out);
 int ssq_aligner_reset_dups(ssq_aligner_t *al);     /* forget every signature seen so far (a new run) */
+/* several aligner objects (one host thread + stream each) can work on consecutive batches of ONE run: they share a dup-set, and
+ * each batch is given its turn number (0, 1, 2, ... since the last reset) so that "first seen wins" still follows input order */
+int ssq_aligner_share_dupset(ssq_aligner_t *al, ssq_dupset_t *set);
+int ssq_aligner_set_turn(ssq_aligner_t *al, long long turn); /* -1 (default): no ordering (a single aligner runs its batches in order anyway) */
 void *ssq_aligner_stream(ssq_aligner_t *al);       /* cudaStream_t of the object, for event timing on the launching stream */
 /* milliseconds of the last batch per stage (CUDA events): 0 upload, 1 seed..extend, 2 sort/dedup/patch, 3 insert-size statistics,
  * 4 mate rescue, 5 pairing/MAPQ/planning, 6 CIGAR/NM/MD, 7 samblaster + dup-set, 8 text, 9 fetch; 10.. = ssq_batch_stage_ms(0..4) */

@@ -12,6 +12,8 @@
 // Scans use CUB (plumbing).  No CPU fallback exists in this library.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <mutex>
+#include <condition_variable>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -2066,7 +2068,10 @@ extern "C" int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig
 // signatures seen so far is kept on the device as two parallel arrays sorted by (key1, key2); a batch is (1) marked within
 // itself by the two-pass stable sort above, (2) its survivors are looked up in the set by binary search, (3) the new ones
 // are appended and the set is re-sorted (two stable LSD passes).
-struct ssq_dupset { int device; u64 n, cap; u64 *k1, *k2; DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp, dnew, nk1, nk2, cnt, t1, t2; /* scratch kept across calls */ };
+struct ssq_dupset {
+	int device; u64 n, cap; u64 *k1, *k2; DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp, dnew, nk1, nk2, cnt, t1, t2; /* scratch kept across calls */
+	std::mutex mu; std::condition_variable cv; long long turn; // batches of one run mark in batch order even when several host threads drive them
+};
 
 __global__ void k_dupset_lookup(u64 n, const ssq_dupsig_t *__restrict__ sig, const u64 *__restrict__ key1, const u64 *__restrict__ key2, uint8_t *is_dup,
                                 const u64 *__restrict__ s1, const u64 *__restrict__ s2, u64 sn, uint8_t *is_new)
@@ -2088,7 +2093,7 @@ extern "C" int ssq_dupset_create(int device, ssq_dupset_t **out)
 	int rc = ssq_use_device(device);
 	if (rc) return rc;
 	ssq_dupset *s = new ssq_dupset();
-	s->device = device; s->n = s->cap = 0; s->k1 = s->k2 = 0;
+	s->device = device; s->n = s->cap = 0; s->k1 = s->k2 = 0; s->turn = 0;
 	*out = s;
 	return SSQ_OK;
 }
@@ -2119,7 +2124,11 @@ __global__ void k_dup_iota(u64 n, u32 *idx);
 __global__ void k_dup_mask(u64 n, const uint8_t *__restrict__ valid, const u64 *__restrict__ k1, const u64 *__restrict__ k2, u64 *m1, u64 *m2);
 __global__ void k_dup_mark_keys(u64 n, const u32 *__restrict__ idx, const u64 *__restrict__ key1s, const u64 *__restrict__ key2, const uint8_t *__restrict__ valid, uint8_t *is_dup);
 
-extern "C" int ssq_dupset_reset(ssq_dupset_t *set) { if (!set) return SSQ_EINVAL; set->n = 0; return SSQ_OK; }
+extern "C" int ssq_dupset_reset(ssq_dupset_t *set) { if (!set) return SSQ_EINVAL; std::lock_guard<std::mutex> g(set->mu); set->n = 0; set->turn = 0; set->cv.notify_all(); return SSQ_OK; }
+// "first seen wins" is defined by input order: when batches are driven concurrently (one host thread and stream per batch), each
+// waits here until every earlier batch (turn = 0, 1, 2, ... since the last reset) has gone through the set
+extern "C" void ssq_dupset_wait_turn(ssq_dupset_t *set, long long turn) { std::unique_lock<std::mutex> l(set->mu); set->cv.wait(l, [&] { return set->turn >= turn; }); }
+extern "C" void ssq_dupset_end_turn(ssq_dupset_t *set, long long turn) { std::lock_guard<std::mutex> g(set->mu); if (set->turn == turn) set->turn = turn + 1; set->cv.notify_all(); }
 
 // Device-pointer form (the fused `bwa mem | samblaster` path, ssq_pipe.cu): key1/key2 = (5' position << 1 | strand) of the
 // canonically ordered ends, element order = input order.  Marks duplicates within the chunk (two stable radix-sort passes +

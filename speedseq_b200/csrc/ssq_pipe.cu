@@ -31,6 +31,7 @@
 #include <string.h>
 #include <vector>
 #include "ssq_dev3.cuh"
+#include "ssq_warp.cuh"
 #include "ssq_pipe_host.h"
 #include "ssq_host.h"
 #include "ssq_batch.h"
@@ -41,6 +42,8 @@
 // streaming dup-set, device-pointer form (ssq_kernels.cu)
 extern "C" int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t *d_k1, const uint64_t *d_k2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);
 extern "C" int ssq_dupset_reset(ssq_dupset_t *set);
+extern "C" void ssq_dupset_wait_turn(ssq_dupset_t *set, long long turn);
+extern "C" void ssq_dupset_end_turn(ssq_dupset_t *set, long long turn);
 
 // ================================================================================ kernels ====
 __global__ void __launch_bounds__(256) k_encode(u64 n, const char *__restrict__ ascii, uint8_t *__restrict__ codes)
@@ -92,24 +95,23 @@ __global__ void __launch_bounds__(256) k_rescue_mark(PipeView V, u32 *list, unsi
 	if (rescue_wanted(V, p)) list[atomicAdd(n_list, 1u)] = (u32)p;
 }
 
-// per-thread scratch of the rescue kernel: DP rows of the striped-order local SW, the mate in both orientations, the reference
-// window (win_cap bases) and the list of sub-optimal rows (win_cap entries), the snapshot of the near-best hits of both ends
+// mate rescue: one warp per marked pair (ssq_warp.cuh).  Per-warp global scratch: the snapshot of the near-best hits of both ends
+// (2 x 64 regions) and the list of sub-optimal rows of the current alignment (win_cap entries); DP state lives in shared memory
 struct RescueCfg { int win_cap; size_t slab_bytes; };
 __global__ void __launch_bounds__(128) k_rescue(PipeView V, const u32 *__restrict__ list, const unsigned int *__restrict__ n_list, uint8_t *slabs, RescueCfg cfg, int *work)
 {
-	uint8_t *p = slabs + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * cfg.slab_bytes;
-	MateScratch M;
-	M.L.H0 = (i32*)p; p += (QMAX + 16) * 4; M.L.H1 = (i32*)p; p += (QMAX + 16) * 4; M.L.E = (i32*)p; p += (QMAX + 16) * 4; M.L.Hmax = (i32*)p; p += (QMAX + 16) * 4;
-	AlnReg *bbuf = (AlnReg*)p; p += 128 * sizeof(AlnReg);
-	M.L.b = (u64*)p; p += (size_t)cfg.win_cap * 8; M.L.b_cap = cfg.win_cap;
-	M.seq = p; p += QMAX + 64;
-	M.ref = p; M.ref_cap = cfg.win_cap;
-	M.A.qbuf = M.A.rbuf = 0; M.A.rcap = 0; M.A.g.h = M.A.g.e = 0; M.A.g.z = 0; M.A.g.zcap = 0; // sort_dedup_patch(query = 0) never aligns
+	__shared__ WarpSwSmem sm[4];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint8_t *p = slabs + ((size_t)blockIdx.x * 4 + wid) * cfg.slab_bytes;
+	AlnReg *bbuf = (AlnReg*)p;
+	u64 *bl = (u64*)(p + 128 * sizeof(AlnReg));
 	const unsigned int n = *n_list;
 	for (;;) {
-		const unsigned int k = (unsigned int)atomicAdd(work, 1);
+		unsigned int k = 0;
+		if (lane == 0) k = (unsigned int)atomicAdd(work, 1);
+		k = __shfl_sync(WFULL, k, 0);
 		if (k >= n) break;
-		body_rescue(V, (int)list[k], bbuf, M);
+		body_rescue_warp(V, (int)list[k], bbuf, sm[wid], bl, cfg.win_cap, lane);
 	}
 }
 
@@ -139,32 +141,68 @@ __global__ void k_compact(PipeView V)
 	for (int i = 0; i < n; ++i) dst[i] = src[i];
 }
 
-// CIGAR generation in two tiers: every task first runs with a small traceback slab (enough for the narrow bands almost all
-// alignments have); the ones whose band needs more are listed and redone by a second launch with full-size slabs
-struct CigCfg { int zcap; size_t slab_bytes; };
-__global__ void __launch_bounds__(128) k_cigar(PipeView V, u64 n_tasks, const u32 *__restrict__ redo_in, const unsigned int *__restrict__ n_redo_in, uint8_t *slabs, CigCfg cfg,
-                                               u32 *redo_out, unsigned int *n_redo_out, int *work)
+// CIGAR generation in two kernels.  k_cigar_fast (thread per alignment) finishes the alignments that need no dynamic programming
+// — query and reference span of equal length and a zero band, i.e. at most two mismatches and no indel: more than nine in ten —
+// and lists the others; k_cigar_warp gives every listed alignment a warp (banded global DP with lanes = band columns, ssq_warp.cuh).
+__global__ void __launch_bounds__(128) k_cigar_fast(PipeView V, u64 n_tasks, u32 *gapped, unsigned int *n_gapped)
 {
-	uint8_t *p = slabs + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * cfg.slab_bytes;
-	AlnScratch A;
-	A.g.h = (i32*)p; p += (QMAX + 16) * 4; A.g.e = (i32*)p; p += (QMAX + 16) * 4;
-	A.qbuf = p; p += QMAX; A.rbuf = p; p += 2048; A.rcap = 2048;
-	A.g.z = p; A.g.zcap = cfg.zcap;
-	const u64 n = redo_in ? (u64)*n_redo_in : n_tasks;
+	const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tasks) return;
+	const PTask tk = V.tasks[t];
+	const AlnReg &ar = V.areg[V.areg_off[tk.read] + tk.reg_idx];
+	const ssq_opts_t &o = V.opt;
+	const int lq = ar.qe - ar.qb, lr = (int)(ar.re - ar.rb);
+	int tmp = infer_bw(lq, lr, ar.truesc, o.a, o.o_del, o.e_del), w2 = infer_bw(lq, lr, ar.truesc, o.a, o.o_ins, o.e_ins);
+	w2 = w2 > tmp ? w2 : tmp;
+	if (w2 > o.w) w2 = w2 < ar.w ? w2 : ar.w;
+	const bool invalid = lq <= 0 || ar.rb >= ar.re || (ar.rb < V.ix.l_pac && ar.re > V.ix.l_pac);
+	if (!invalid && !(lq == lr && w2 == 0)) { gapped[atomicAdd(n_gapped, 1u)] = (u32)t; return; } // (a zero band stays zero when the reference doubles it)
+	uint8_t qbuf[QMAX], rbuf[QMAX];
+	AlnScratch A; A.qbuf = qbuf; A.rbuf = rbuf; A.rcap = QMAX; A.g.h = A.g.e = 0; A.g.z = 0; A.g.zcap = 0;
+	AlnOut a;
+	reg2aln(V.ix, o, (int)(V.tc.read_off[tk.read + 1] - V.tc.read_off[tk.read]), V.tc.seq + V.tc.read_off[tk.read], ar, A, a, V.cigs + t * CIG_CAP, CIG_CAP, V.mds + t * MD_CAP, MD_CAP);
+	if (a.n_cigar < 0 || a.n_cigar > CIG_CAP - 2 || a.md_len >= MD_CAP) PIPE_ERR(V, 4);
+	V.outs[t] = a;
+}
+__global__ void __launch_bounds__(128) k_cigar_warp(PipeView V, const u32 *__restrict__ gapped, const unsigned int *__restrict__ n_gapped, uint8_t *zslabs, long zcap, int *work)
+{
+	__shared__ WarpGlSmem sm[4];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint8_t *z = zslabs + ((size_t)blockIdx.x * 4 + wid) * (size_t)zcap;
+	const unsigned int n = *n_gapped;
 	for (;;) {
-		const u64 k = (u64)(unsigned int)atomicAdd(work, 1);
+		unsigned int k = 0;
+		if (lane == 0) k = (unsigned int)atomicAdd(work, 1);
+		k = __shfl_sync(WFULL, k, 0);
 		if (k >= n) break;
-		const u64 t = redo_in ? (u64)redo_in[k] : k;
-		if (redo_out) { // first tier: a traceback matrix beyond the small slab defers the task instead of failing it
-			const PTask tk = V.tasks[t];
-			const AlnReg &reg = V.areg[V.areg_off[tk.read] + tk.reg_idx];
-			AlnOut a;
-			reg2aln(V.ix, V.opt, (int)(V.tc.read_off[tk.read + 1] - V.tc.read_off[tk.read]), V.tc.seq + V.tc.read_off[tk.read], reg, A, a, V.cigs + t * CIG_CAP, CIG_CAP, V.mds + t * MD_CAP, MD_CAP);
-			if (a.n_cigar < 0) { redo_out[atomicAdd(n_redo_out, 1u)] = (u32)t; continue; }
-			if (a.n_cigar > CIG_CAP - 2 || a.md_len >= MD_CAP) PIPE_ERR(V, 4);
+		const u64 t = gapped[k];
+		const PTask tk = V.tasks[t];
+		const AlnReg &ar = V.areg[V.areg_off[tk.read] + tk.reg_idx];
+		AlnOut a;
+		reg2aln_warp(V.ix, V.opt, (int)(V.tc.read_off[tk.read + 1] - V.tc.read_off[tk.read]), V.tc.seq + V.tc.read_off[tk.read], ar, sm[wid], z, zcap, a, V.cigs + t * CIG_CAP, CIG_CAP,
+		             V.mds + t * MD_CAP, MD_CAP, lane);
+		if (lane == 0) {
+			if (a.n_cigar < 0 || a.n_cigar > CIG_CAP - 2 || a.md_len >= MD_CAP) PIPE_ERR(V, 4);
 			V.outs[t] = a;
-		} else body_cigar(V, t, A);
+		}
 	}
+}
+
+// kernel-level entry: ksw_align2 problems over caller-supplied sequences, one warp each (parity target: the oracle's ssqo_ksw_align2)
+__global__ void __launch_bounds__(128) k_sw_local_tasks(ssq_opts_t opt, u64 n, const ssq_swl_task_t *__restrict__ tk, const uint8_t *__restrict__ qbuf, const uint8_t *__restrict__ tbuf, ssq_swl_result_t *out,
+                                                        u64 *bl_all, int b_cap)
+{
+	__shared__ WarpSwSmem sm[4];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const u64 t = (u64)blockIdx.x * 4 + wid;
+	if (t >= n) return;
+	WarpSwSmem &W = sm[wid];
+	const ssq_swl_task_t k = tk[t];
+	for (int i = lane; i < k.qlen; i += 32) W.q[i] = qbuf[k.q_off + i];
+	__syncwarp();
+	TgtBuf tg; tg.t = tbuf + k.t_off;
+	const LocalRes r = sw_local_warp(opt, k.qlen, k.tlen, tg, k.xtra, W, bl_all + t * (u64)b_cap, b_cap, lane);
+	if (lane == 0) { ssq_swl_result_t o; o.score = r.score; o.te = r.te; o.qe = r.qe; o.score2 = r.score2; o.te2 = r.te2; o.tb = r.tb; o.qb = r.qb; out[t] = o; }
 }
 
 __global__ void __launch_bounds__(128) k_sb(PipeView V)
@@ -209,15 +247,15 @@ struct ssq_aligner {
 	char rg_id[256];
 	cudaStream_t st;
 	ssq_batch_t *b;
-	ssq_dupset_t *dups;
+	ssq_dupset_t *dups; int own_dups; long long turn; // turn >= 0: the dup stage waits for the batches with smaller turn numbers (shared set)
 	// static tables
 	DBuf d_logn, d_lg, d_ctg_names, d_ctg_off, d_sb_off, d_rg;
 	// batch inputs
 	DBuf d_ascii, d_qual, d_names, d_name_off, d_cmt, d_cmt_off;
 	int n_reads, paired, has_qual, has_cmt; i64 n_processed; u64 total_bases; int max_len;
 	// stages
-	DBuf cubtmp, d_cap, d_aoff, d_na, d_areg, d_work, d_pes, d_hist, d_pen, d_dslab, d_rlist, d_rslab, d_tcap, d_tsoff, d_tslots, d_meta, d_pv, d_xcnt,
-	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_cslab, d_cslab_big, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
+	DBuf cubtmp, d_cap, d_aoff, d_na, d_areg, d_work, d_pes, d_hist, d_pen, d_slab /* per-thread scratch of whichever slab kernel runs (dedup, rescue, CIGAR tiers: never live together) */, d_rlist, d_tcap, d_tsoff, d_tslots, d_meta, d_pv, d_xcnt,
+	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
 	PinBuf h_text[3], h_roff, h_hist, h_small;
 	PeStat pes[4];
 	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines;
@@ -246,7 +284,7 @@ extern "C" void ssq_aligner_free(ssq_aligner_t *a)
 	if (!a) return;
 	cudaSetDevice(a->device);
 	if (a->b) ssq_batch_free(a->b);
-	if (a->dups) ssq_dupset_free(a->dups);
+	if (a->dups && a->own_dups) ssq_dupset_free(a->dups);
 	for (int i = 0; i <= ST_N; ++i) if (a->ev[i]) cudaEventDestroy(a->ev[i]);
 	delete a;
 }
@@ -257,7 +295,7 @@ extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt,
 	int rc = ssq_use_device(idx->device);
 	if (rc) return rc;
 	ssq_aligner *a = new ssq_aligner();
-	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->dups = 0; a->computed = 0; a->n_reads = 0;
+	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->computed = 0; a->n_reads = 0;
 	memset(a->ev, 0, sizeof a->ev); memset(a->stage_ms, 0, sizeof a->stage_ms); memset(a->pes, 0, sizeof a->pes);
 	memset(&a->sb, 0, sizeof a->sb);
 	if (sb) {
@@ -304,6 +342,14 @@ extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt,
 }
 
 extern "C" int ssq_aligner_reset_dups(ssq_aligner_t *a) { return a ? ssq_dupset_reset(a->dups) : SSQ_EINVAL; }
+extern "C" int ssq_aligner_share_dupset(ssq_aligner_t *a, ssq_dupset_t *set)
+{
+	if (!a || !set) return SSQ_EINVAL;
+	if (a->dups && a->own_dups) ssq_dupset_free(a->dups);
+	a->dups = set; a->own_dups = 0;
+	return SSQ_OK;
+}
+extern "C" int ssq_aligner_set_turn(ssq_aligner_t *a, long long turn) { if (!a) return SSQ_EINVAL; a->turn = turn; return SSQ_OK; }
 extern "C" void *ssq_aligner_stream(ssq_aligner_t *a) { return a ? (void*)a->st : 0; }
 extern "C" float ssq_aligner_stage_ms(const ssq_aligner_t *a, int stage)
 {
@@ -379,9 +425,16 @@ static PipeView make_view(ssq_aligner *a)
 }
 
 // ---- stages 1..8: everything on the device; leaves the text of the three streams in HBM ----
+static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose);
 extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 {
 	if (!a) return SSQ_EINVAL;
+	const int rc = compute_impl(a, pes0, verbose);
+	if (a->turn >= 0) { ssq_dupset_wait_turn(a->dups, a->turn); ssq_dupset_end_turn(a->dups, a->turn); } // whatever happened, later batches must not wait for this one
+	return rc;
+}
+static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
+{
 	int rc = ssq_use_device(a->device);
 	if (rc) return rc;
 	const int n = a->n_reads, n_pairs = a->paired ? n >> 1 : 0, n_units = a->paired ? n >> 1 : n;
@@ -405,10 +458,10 @@ extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, i
 	V.areg_off = a->d_aoff.as<u64>(); V.areg = a->d_areg.as<AlnReg>(); V.n_areg = a->d_na.as<u32>();
 	V.pv = a->d_pv.as<P64>(); V.xcnt = a->d_xcnt.as<i32>();
 	const int dedup_blocks = a->n_sm * 8;
-	if (a->d_dslab.need((size_t)dedup_blocks * 128 * sizeof(DedupSlab))) return SSQ_ENOMEM;
+	if (a->d_slab.need((size_t)dedup_blocks * 128 * sizeof(DedupSlab))) return SSQ_ENOMEM;
 	int *work = a->d_work.as<int>();
 	CK(cudaMemsetAsync(work, 0, 256, st));
-	k_dedup<<<dedup_blocks, 128, 0, st>>>(V, a->d_dslab.as<DedupSlab>(), work);
+	k_dedup<<<dedup_blocks, 128, 0, st>>>(V, a->d_slab.as<DedupSlab>(), work);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(a->ev[ST_PESTAT], st));
 	// insert-size statistics and the pairing penalty table
@@ -443,14 +496,12 @@ extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, i
 		RescueCfg cfg;
 		cfg.win_cap = win + a->max_len + 16;
 		if (cfg.win_cap > (1 << 20)) { ssq_set_error("insert-size bounds admit rescue windows of %d bases (limit 2^20)", cfg.win_cap); return SSQ_EINVAL; }
-		cfg.slab_bytes = (size_t)4 * (QMAX + 16) * 4 + 128 * sizeof(AlnReg) + (size_t)cfg.win_cap * 8 + QMAX + 64 + (size_t)cfg.win_cap;
-		cfg.slab_bytes = (cfg.slab_bytes + 15) & ~(size_t)15;
-		int blocks = a->n_sm * 4;
-		while (blocks > a->n_sm && (size_t)blocks * 128 * cfg.slab_bytes > ((size_t)6 << 30)) blocks >>= 1;
-		if (a->d_rlist.need((size_t)(n_pairs + 1) * 4) || a->d_rslab.need((size_t)blocks * 128 * cfg.slab_bytes)) return SSQ_ENOMEM;
+		cfg.slab_bytes = ((size_t)128 * sizeof(AlnReg) + (size_t)cfg.win_cap * 8 + 15) & ~(size_t)15;
+		const int blocks = a->n_sm * 8; // 4 warps per block, 32 warps per SM
+		if (a->d_rlist.need((size_t)(n_pairs + 1) * 4) || a->d_slab.need((size_t)blocks * 4 * cfg.slab_bytes)) return SSQ_ENOMEM;
 		unsigned int *n_list = (unsigned int*)(work + 16);
 		k_rescue_mark<<<(n_pairs + 255) / 256, 256, 0, st>>>(V, a->d_rlist.as<u32>(), n_list);
-		k_rescue<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), n_list, a->d_rslab.as<uint8_t>(), cfg, work + 1);
+		k_rescue<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), n_list, a->d_slab.as<uint8_t>(), cfg, work + 1);
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(a->ev[ST_PLAN], st));
@@ -476,15 +527,13 @@ extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, i
 	k_compact<<<(n + 255) / 256, 256, 0, st>>>(V);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(a->ev[ST_CIGAR], st));
-	if (total_tasks) { // CIGARs: small-slab tier, then the deferred ones with full-size slabs
-		CigCfg small, big;
-		small.zcap = 12 * 1024; small.slab_bytes = (size_t)2 * (QMAX + 16) * 4 + QMAX + 2048 + small.zcap;
-		big.zcap = QMAX * 768; big.slab_bytes = (size_t)2 * (QMAX + 16) * 4 + QMAX + 2048 + big.zcap;
-		const int blocks = a->n_sm * 8, big_blocks = a->n_sm;
-		if (a->d_cslab.need((size_t)blocks * 128 * small.slab_bytes) || a->d_cslab_big.need((size_t)big_blocks * 128 * big.slab_bytes)) return SSQ_ENOMEM;
-		unsigned int *n_redo = (unsigned int*)(work + 17);
-		k_cigar<<<blocks, 128, 0, st>>>(V, total_tasks, 0, 0, a->d_cslab.as<uint8_t>(), small, a->d_redo.as<u32>(), n_redo, work + 2);
-		k_cigar<<<big_blocks, 128, 0, st>>>(V, total_tasks, a->d_redo.as<u32>(), n_redo, a->d_cslab_big.as<uint8_t>(), big, 0, 0, work + 3);
+	if (total_tasks) { // CIGARs: the ones without dynamic programming per thread, the others per warp
+		const long zcap = (long)QMAX * 768;
+		const int blocks = a->n_sm * 6; // 4 warps per block, 24 warps per SM (22 KB of shared memory per block)
+		if (a->d_slab.need((size_t)blocks * 4 * (size_t)zcap)) return SSQ_ENOMEM;
+		unsigned int *n_gapped = (unsigned int*)(work + 17);
+		k_cigar_fast<<<(unsigned)((total_tasks + 127) / 128), 128, 0, st>>>(V, total_tasks, a->d_redo.as<u32>(), n_gapped);
+		k_cigar_warp<<<blocks, 128, 0, st>>>(V, a->d_redo.as<u32>(), n_gapped, a->d_slab.as<uint8_t>(), zcap, work + 2);
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(a->ev[ST_SB], st));
@@ -493,7 +542,10 @@ extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, i
 	if (a->sb.enabled) {
 		k_sb<<<(n_units + 127) / 128, 128, 0, st>>>(V);
 		CK(cudaGetLastError());
-		if ((rc = ssq_dupset_mark_dev(a->dups, (u64)n_units, V.k1, V.k2, V.valid, V.dup, (void*)st))) return rc;
+		if (a->turn >= 0) ssq_dupset_wait_turn(a->dups, a->turn);
+		rc = ssq_dupset_mark_dev(a->dups, (u64)n_units, V.k1, V.k2, V.valid, V.dup, (void*)st);
+		if (a->turn >= 0) { cudaStreamSynchronize(st); ssq_dupset_end_turn(a->dups, a->turn); } // the set must be complete before the next batch looks it up from another stream
+		if (rc) return rc;
 		k_count_u8<<<(n_units + 255) / 256, 256, 0, st>>>((u64)n_units, V.dup, 0, (unsigned long long*)a->d_cnt.p);
 	}
 	CK(cudaEventRecord(a->ev[ST_TEXT], st));
@@ -555,4 +607,27 @@ extern "C" int ssq_aligner_run(ssq_aligner_t *a, const ssq_reads_t *reads, const
 	if ((rc = ssq_aligner_upload(a, reads))) return rc;
 	if ((rc = ssq_aligner_compute(a, pes0, verbose))) return rc;
 	return ssq_aligner_fetch(a, out);
+}
+
+extern "C" int ssq_sw_local_batch(const ssq_opts_t *opt, int device, uint64_t n, const ssq_swl_task_t *tasks, const uint8_t *qbuf, uint64_t qbuf_len, const uint8_t *tbuf, uint64_t tbuf_len,
+                                  ssq_swl_result_t *out)
+{
+	if (!opt || (n && (!tasks || !qbuf || !tbuf || !out))) return SSQ_EINVAL;
+	int rc = ssq_use_device(device);
+	if (rc) return rc;
+	if (n == 0) return SSQ_OK;
+	int b_cap = 1;
+	for (u64 i = 0; i < n; ++i) {
+		if (tasks[i].qlen < 0 || tasks[i].qlen > SSQ_MAX_READ_LEN || tasks[i].tlen < 0 || tasks[i].q_off + tasks[i].qlen > qbuf_len || tasks[i].t_off + tasks[i].tlen > tbuf_len) { ssq_set_error("ssq_sw_local_batch: task %llu out of range", (unsigned long long)i); return SSQ_EINVAL; }
+		if (tasks[i].tlen > b_cap) b_cap = tasks[i].tlen;
+	}
+	DBuf dt, dq, dtb, dout, dbl;
+	if (dt.need(n * sizeof(ssq_swl_task_t)) || dq.need(qbuf_len + 16) || dtb.need(tbuf_len + 16) || dout.need(n * sizeof(ssq_swl_result_t)) || dbl.need(n * (size_t)b_cap * 8)) return SSQ_ENOMEM;
+	CK(cudaMemcpy(dt.p, tasks, n * sizeof(ssq_swl_task_t), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(dq.p, qbuf, qbuf_len, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(dtb.p, tbuf, tbuf_len, cudaMemcpyHostToDevice));
+	k_sw_local_tasks<<<(unsigned)((n + 3) / 4), 128>>>(*opt, n, dt.as<ssq_swl_task_t>(), dq.as<uint8_t>(), dtb.as<uint8_t>(), dout.as<ssq_swl_result_t>(), dbl.as<u64>(), b_cap);
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(out, dout.p, n * sizeof(ssq_swl_result_t), cudaMemcpyDeviceToHost));
+	return SSQ_OK;
 }

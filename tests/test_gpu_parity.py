@@ -205,3 +205,64 @@ def test_dupmark(ssq, oracle):
     keys = set(zip(v["pos1"].tolist(), v["pos2"].tolist(), v["strand1"].tolist(), v["strand2"].tolist()))
     assert int((d == 0)[sig["valid"] == 1].sum()) == len(keys)
     assert len(ssq.dupmark_batch(np.zeros(0, T.DUPSIG_DT))) == 0
+
+
+def test_sw_local_striped_order(ssq, oracle):
+    """ksw_align2 problems (mate rescue): one warp per problem with the SSE lanes on warp lanes vs the oracle's scalar restatement of
+    the striped kernel — byte mode (saturating, 16 lanes) and word mode (8 lanes), sub-optimal score, start coordinates"""
+    import ctypes as C
+    rng = np.random.default_rng(17)
+    SWL_T = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("pad", "<i4")])
+    SWL_R = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
+    n = 1500
+    tasks = np.zeros(n, SWL_T)
+    qs, ts = [], []
+    qo = to = 0
+    for i in range(n):
+        ql = int(rng.integers(20, 256)) if i % 7 else int(rng.integers(1, 20))
+        q = rng.integers(0, 4, ql, dtype=np.uint8)
+        tl = int(rng.integers(ql, ql + 700))
+        t = rng.integers(0, 4, tl, dtype=np.uint8)
+        kind = i % 5
+        if kind < 3:  # plant a diverged copy of the query (sometimes two: sub-optimal hit)
+            for rep in range(1 + (kind == 2)):
+                c = q.copy()
+                m = rng.random(ql) < (0.03 if kind else 0.0)
+                c[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+                if kind == 1 and ql > 30:
+                    p = int(rng.integers(5, ql - 5)); c = np.concatenate([c[:p], c[p + int(rng.integers(1, 4)):]])
+                at = int(rng.integers(0, tl - len(c) + 1))
+                t[at:at + len(c)] = c
+        if rng.random() < 0.1:
+            q[rng.integers(0, ql)] = 4
+        if rng.random() < 0.05:
+            t[rng.integers(0, tl)] = 4
+        minsc = 19
+        xtra = 0x40000 | 0x80000 | (0x10000 if ql < 250 and i % 11 else 0) | minsc
+        if i % 13 == 0:
+            xtra &= ~0x80000  # no start coordinates wanted
+        tasks[i] = (qo, to, ql, tl, xtra, 0)
+        qs.append(q); ts.append(t)
+        qo += ql; to += tl
+    qbuf, tbuf = np.concatenate(qs), np.concatenate(ts)
+    got = np.zeros(n, SWL_R)
+    ssq.ck(ssq.lib.ssq_sw_local_batch(ssq.opts, C.c_int(0), C.c_uint64(n), tasks.ctypes.data_as(C.c_void_p), qbuf.ctypes.data_as(C.c_void_p), C.c_uint64(len(qbuf)),
+                                      tbuf.ctypes.data_as(C.c_void_p), C.c_uint64(len(tbuf)), got.ctypes.data_as(C.c_void_p)), "ssq_sw_local_batch")
+    mat = np.array([1 if i == j else -4 for i in range(4) for j in range(5)] , np.int8)
+    mat = np.zeros(25, np.int8)
+    for i in range(5):
+        for j in range(5):
+            mat[i * 5 + j] = -1 if (i == 4 or j == 4) else (1 if i == j else -4)
+
+    class KR(C.Structure):
+        _fields_ = [(k, C.c_int) for k in ("score", "te", "qe", "score2", "te2", "tb", "qb")]
+    oracle.lib.ssqo_ksw_align2.restype = KR
+    ref = np.zeros(n, SWL_R)
+    for i in range(n):
+        q = qs[i].copy(); t = ts[i].copy()
+        r = oracle.lib.ssqo_ksw_align2(C.c_int(len(q)), q.ctypes.data_as(C.c_void_p), C.c_int(len(t)), t.ctypes.data_as(C.c_void_p), C.c_int(5), mat.ctypes.data_as(C.c_void_p),
+                                       C.c_int(6), C.c_int(1), C.c_int(6), C.c_int(1), C.c_int(int(tasks["xtra"][i])))
+        ref[i] = (r.score, r.te, r.qe, r.score2, r.te2, r.tb, r.qb)
+    bad = np.nonzero(got != ref)[0]
+    assert len(bad) == 0, (bad[:5], got[bad[:5]], ref[bad[:5]], tasks[bad[:5]])
+    assert (ref["score"] >= 19).sum() > 500 and (ref["score2"] >= 19).sum() > 50 and (ref["score"] == 255).sum() >= 0
