@@ -144,14 +144,18 @@ def ensure_reference(cache, genome_len, builder):
     os.makedirs(cache, exist_ok=True)
     fa = os.path.join(cache, "syn_%d.fa" % genome_len)
     gnpy = fa + ".npy"
+    t0 = time.time()
     if not os.path.exists(gnpy):
         g = synth_genome(genome_len, 20)
         bounds = np.linspace(0, genome_len, 9).astype(np.int64)
         write_fasta(fa, g, ["chrS%d" % (i + 1) for i in range(8)], bounds)
         np.save(gnpy, g)
+        sys.stderr.write("[bench] synthetic genome of %d bp written in %.1f s\n" % (genome_len, time.time() - t0))
     if not all(os.path.exists(fa + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
+        t0 = time.time()
         builder(fa)
-    return fa, np.load(gnpy, mmap_mode="r")
+        sys.stderr.write("[bench] index built in %.1f s\n" % (time.time() - t0))
+    return fa, np.load(gnpy)
 
 
 def usable_cores():
