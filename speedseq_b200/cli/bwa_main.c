@@ -3,10 +3,18 @@
  * libssq.so.  Honours the argv/stdio contract of the reference's call sites:
  *     $BWA index REF                                              /root/reference/bin/speedseq:389
  *     $BWA mem -t T [-p] [-C] [-I f[,f[,i[,i]]]] -R '@RG\tID:..' REF FQ1 [FQ2]   speedseq:438,468,1961
- * stdout = SAM (header, then records name-grouped in input order).  All base-level work happens on the GPU inside
- * libssq (ssq_index_build, ssq_mem_batch_sam); this file only parses argv, tokenises FASTQ, forms batches the way the
- * reference's `bwa mem` does (bases >= 10 M x T and an even read count) and writes text.
+ * stdout = SAM (header, then records name-grouped in input order).  All base-level work AND the SAM text come from the GPU
+ * (ssq_index_build, ssq_aligner_run: include/ssq.h); this file parses argv, tokenises FASTQ straight into the concatenated
+ * layout the aligner takes, forms batches the way the reference's `bwa mem` does (bases >= 10 M x T and an even read count), and
+ * writes what comes back.
  * FASTQ tokenisation follows the reference's in-tree parser /root/reference/src/samtools-1.3.1/htslib-1.3.1/htslib/kseq.h:189-231.
+ *
+ * Fused mode.  speedseq pipes `$BWA mem | $SAMBLASTER ...` (speedseq:438-439).  When the environment variable
+ * SSQ_FUSE_SAMBLASTER holds samblaster's option string (speedseq.config can export it from speedseq's own variables, see
+ * INTEGRATION.md), this program also runs samblaster's stage on the device — duplicate marking, MC/MQ tags, discordant and
+ * splitter selection — and writes the three record streams as length-prefixed frames behind a marker line; the `samblaster` shim
+ * recognises the marker, checks that its own argv asks for the same options, and only routes the frames to stdout and to the two
+ * side files.  Without the variable the output is plain `bwa mem` SAM and `samblaster` does its own work.
  */
 #include <ctype.h>
 #include <stdio.h>
@@ -15,6 +23,7 @@
 #include <unistd.h>
 #include <zlib.h>
 #include "ssq.h"
+#include "ssq_fuse.h"
 
 #define SHIM_VERSION "0.7.12-r1039" /* the bwa release whose behaviour libssq reproduces */
 
@@ -28,29 +37,34 @@ static fq_t *fq_open(const char *fn)
 	gzFile fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(0, "r");
 	fq_t *f;
 	if (!fp) return 0;
+	gzbuffer(fp, 1 << 20);
 	f = (fq_t*)calloc(1, sizeof(fq_t));
-	f->fp = fp; f->buf = (unsigned char*)malloc(1 << 16);
+	f->fp = fp; f->buf = (unsigned char*)malloc(1 << 18);
 	return f;
 }
 static inline int fq_getc(fq_t *f)
 {
 	if (f->beg >= f->end) {
 		if (f->eof) return -1;
-		f->beg = 0; f->end = gzread(f->fp, f->buf, 1 << 16);
+		f->beg = 0; f->end = gzread(f->fp, f->buf, 1 << 18);
 		if (f->end <= 0) { f->eof = 1; f->end = 0; return -1; }
 	}
 	return f->buf[f->beg++];
 }
-static inline void s_push(str_t *s, int c)
-{
-	if (s->l + 2 > s->m) { s->m = s->m ? s->m * 2 : 128; s->s = (char*)realloc(s->s, s->m); }
-	s->s[s->l++] = (char)c; s->s[s->l] = 0;
-}
-static inline void s_clear(str_t *s) { s->l = 0; if (!s->s) { s->m = 128; s->s = (char*)malloc(s->m); } s->s[0] = 0; }
+static inline void s_reserve(str_t *s, size_t add) { if (s->l + add + 1 > s->m) { s->m = (s->l + add + 1) * 2; s->s = (char*)realloc(s->s, s->m); } }
+static inline void s_push(str_t *s, int c) { s_reserve(s, 1); s->s[s->l++] = (char)c; s->s[s->l] = 0; }
+static inline void s_clear(str_t *s) { s->l = 0; if (!s->s) { s->m = 256; s->s = (char*)malloc(s->m); } s->s[0] = 0; }
 static int fq_line(fq_t *f, str_t *s) /* appends the rest of the current line, returns -1 at EOF with nothing read */
 {
-	int c, got = 0;
-	while ((c = fq_getc(f)) >= 0) { got = 1; if (c == '\n') break; s_push(s, c); }
+	int got = 0;
+	for (;;) {
+		unsigned char *p, *e;
+		if (f->beg >= f->end) { int c = fq_getc(f); if (c < 0) break; --f->beg; }
+		got = 1;
+		p = f->buf + f->beg; e = (unsigned char*)memchr(p, '\n', (size_t)(f->end - f->beg));
+		if (e) { s_reserve(s, (size_t)(e - p)); memcpy(s->s + s->l, p, (size_t)(e - p)); s->l += (size_t)(e - p); s->s[s->l] = 0; f->beg += (int)(e - p) + 1; break; }
+		s_reserve(s, (size_t)(f->end - f->beg)); memcpy(s->s + s->l, p, (size_t)(f->end - f->beg)); s->l += (size_t)(f->end - f->beg); s->s[s->l] = 0; f->beg = f->end;
+	}
 	if (s->l && s->s[s->l - 1] == '\r') s->s[--s->l] = 0;
 	return got ? 0 : -1;
 }
@@ -82,31 +96,52 @@ static int fq_read(fq_t *f, rec_t *r)
 }
 
 /* --------------------------------------------------------------------------- batches ---- */
-typedef struct { char *name, *comment, *seq, *qual; int id; } read_t;
-typedef struct { read_t *a; int n, m; } reads_t;
+/* one batch in the aligner's layout: concatenated fields + offsets (ssq_reads_t) */
+typedef struct {
+	str_t seq, qual, name, cmt;
+	uint64_t *seq_off; uint32_t *name_off, *cmt_off;
+	int n, m, all_qual, any_cmt;
+} blob_t;
 
+static void blob_clear(blob_t *b) { b->seq.l = b->qual.l = b->name.l = b->cmt.l = 0; b->n = 0; b->all_qual = 1; b->any_cmt = 0; }
 static void trim_readno(str_t *s) { if (s->l > 2 && s->s[s->l - 2] == '/' && isdigit((unsigned char)s->s[s->l - 1])) { s->l -= 2; s->s[s->l] = 0; } }
-
-static void reads_push(reads_t *v, const rec_t *r, int keep_comment)
+static void blob_push(blob_t *b, const char *name, size_t ln, const char *seq, size_t ls, const char *qual, size_t lq, const char *cmt, size_t lc)
 {
-	read_t *x;
-	if (v->n == v->m) { v->m = v->m ? v->m * 2 : 1024; v->a = (read_t*)realloc(v->a, sizeof(read_t) * v->m); }
-	x = &v->a[v->n];
-	x->name = strdup(r->name.s); x->seq = strdup(r->seq.s);
-	x->qual = r->qual.l ? strdup(r->qual.s) : 0;
-	x->comment = keep_comment && r->comment.l ? strdup(r->comment.s) : 0;
-	x->id = v->n++;
+	if (b->n + 2 > b->m) {
+		b->m = b->m ? b->m * 2 : 1 << 16;
+		b->seq_off = (uint64_t*)realloc(b->seq_off, sizeof(uint64_t) * (b->m + 1)); b->name_off = (uint32_t*)realloc(b->name_off, 4 * (b->m + 1)); b->cmt_off = (uint32_t*)realloc(b->cmt_off, 4 * (b->m + 1));
+	}
+	if (b->n == 0) { b->seq_off[0] = 0; b->name_off[0] = 0; b->cmt_off[0] = 0; }
+	s_reserve(&b->seq, ls); memcpy(b->seq.s + b->seq.l, seq, ls); b->seq.l += ls;
+	s_reserve(&b->qual, ls);
+	if (lq == ls && ls) memcpy(b->qual.s + b->qual.l, qual, ls); else { memset(b->qual.s + b->qual.l, '*', ls); if (ls) b->all_qual = 0; }
+	b->qual.l += ls;
+	s_reserve(&b->name, ln); memcpy(b->name.s + b->name.l, name, ln); b->name.l += ln;
+	if (lc) { s_reserve(&b->cmt, lc); memcpy(b->cmt.s + b->cmt.l, cmt, lc); b->cmt.l += lc; b->any_cmt = 1; }
+	++b->n;
+	b->seq_off[b->n] = b->seq.l; b->name_off[b->n] = (uint32_t)b->name.l; b->cmt_off[b->n] = (uint32_t)b->cmt.l;
+}
+static void blob_push_rec(blob_t *b, const rec_t *r, int keep_comment)
+{
+	blob_push(b, r->name.s, r->name.l, r->seq.s, r->seq.l, r->qual.s, r->qual.l, r->comment.s, keep_comment ? r->comment.l : 0);
+}
+static void blob_push_from(blob_t *b, const blob_t *src, int i)
+{
+	const size_t ls = (size_t)(src->seq_off[i + 1] - src->seq_off[i]);
+	if (!src->all_qual) b->all_qual = 0; /* mixed inputs: a read without qualities makes the sub-batch quality-less, like the parent */
+	blob_push(b, src->name.s + src->name_off[i], src->name_off[i + 1] - src->name_off[i], src->seq.s + src->seq_off[i], ls, src->qual.s + src->seq_off[i], ls,
+	          src->cmt.s + src->cmt_off[i], src->cmt_off[i + 1] - src->cmt_off[i]);
 }
 
 /* one batch: until the base count reaches chunk and the read count is even */
-static long read_batch(long chunk, fq_t *f1, fq_t *f2, rec_t *r1, rec_t *r2, reads_t *v, int keep_comment)
+static long read_batch(long chunk, fq_t *f1, fq_t *f2, rec_t *r1, rec_t *r2, blob_t *v, int keep_comment)
 {
 	long size = 0;
-	v->n = 0;
+	blob_clear(v);
 	while (fq_read(f1, r1) >= 0) {
 		if (f2 && fq_read(f2, r2) < 0) { fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n"); break; }
-		trim_readno(&r1->name); reads_push(v, r1, keep_comment); size += (long)r1->seq.l;
-		if (f2) { trim_readno(&r2->name); reads_push(v, r2, keep_comment); size += (long)r2->seq.l; }
+		trim_readno(&r1->name); blob_push_rec(v, r1, keep_comment); size += (long)r1->seq.l;
+		if (f2) { trim_readno(&r2->name); blob_push_rec(v, r2, keep_comment); size += (long)r2->seq.l; }
 		if (size >= chunk && (v->n & 1) == 0) break;
 	}
 	if (size == 0 && f2 && fq_read(f2, r2) >= 0) fprintf(stderr, "[W::bseq_read] the 1st file has fewer sequences.\n");
@@ -114,27 +149,26 @@ static long read_batch(long chunk, fq_t *f1, fq_t *f2, rec_t *r1, rec_t *r2, rea
 }
 
 static void die(const char *what, int rc) { fprintf(stderr, "[E::bwa] %s failed (%d): %s\n", what, rc, ssq_last_error()); exit(1); }
-
-/* runs one homogeneous (all single-end or all paired) sub-batch and scatters each read's SAM lines to out[id] */
-static void run_sub(const ssq_index_t *idx, const ssq_opts_t *opt, read_t **sub, int n, long long n_processed, int paired, const ssq_pestat_t *pes0,
-                    const char *rg_id, char **out)
+static int same_name(const blob_t *v, int i, int j)
 {
-	const char **names = (const char**)malloc(sizeof(char*) * n), **seqs = (const char**)malloc(sizeof(char*) * n);
-	const char **quals = (const char**)malloc(sizeof(char*) * n), **comments = (const char**)malloc(sizeof(char*) * n);
-	size_t *offs = (size_t*)malloc(sizeof(size_t) * (n + 1)), len = 0;
-	char *sam = 0;
-	int i, rc, any_comment = 0;
-	for (i = 0; i < n; ++i) { names[i] = sub[i]->name; seqs[i] = sub[i]->seq; quals[i] = sub[i]->qual; comments[i] = sub[i]->comment; any_comment |= sub[i]->comment != 0; }
-	if (paired) for (i = 0; i < n; i += 2) if (strcmp(names[i], names[i + 1]) != 0) { fprintf(stderr, "[E::mem_sam_pe] paired reads have different names: \"%s\", \"%s\"\n", names[i], names[i + 1]); exit(1); }
-	rc = ssq_mem_batch_sam(idx, opt, n, names, seqs, quals, any_comment ? comments : 0, n_processed, paired, pes0, rg_id, 1, &sam, &len, offs);
-	if (rc) die("ssq_mem_batch_sam", rc);
-	for (i = 0; i < n; ++i) {
-		const size_t l = offs[i + 1] - offs[i];
-		out[sub[i]->id] = (char*)malloc(l + 1);
-		memcpy(out[sub[i]->id], sam + offs[i], l); out[sub[i]->id][l] = 0;
-	}
-	ssq_free(sam);
-	free(names); free(seqs); free(quals); free(comments); free(offs);
+	const uint32_t li = v->name_off[i + 1] - v->name_off[i], lj = v->name_off[j + 1] - v->name_off[j];
+	return li == lj && memcmp(v->name.s + v->name_off[i], v->name.s + v->name_off[j], li) == 0;
+}
+static void fill_reads(ssq_reads_t *rd, const blob_t *b, int paired, long long n_processed)
+{
+	memset(rd, 0, sizeof *rd);
+	rd->n_reads = b->n; rd->paired = paired; rd->seq = b->seq.s; rd->seq_off = b->seq_off; rd->qual = b->all_qual && b->n ? b->qual.s : 0;
+	rd->name = b->name.s; rd->name_off = b->name_off; rd->comment = b->any_cmt ? b->cmt.s : 0; rd->comment_off = b->any_cmt ? b->cmt_off : 0; rd->n_processed = n_processed;
+}
+static void check_pair_names(const blob_t *b)
+{
+	int i;
+	for (i = 0; i + 1 < b->n; i += 2)
+		if (!same_name(b, i, i + 1)) {
+			fprintf(stderr, "[E::mem_sam_pe] paired reads have different names: \"%.*s\", \"%.*s\"\n", (int)(b->name_off[i + 1] - b->name_off[i]), b->name.s + b->name_off[i],
+			        (int)(b->name_off[i + 2] - b->name_off[i + 1]), b->name.s + b->name_off[i + 1]);
+			exit(1);
+		}
 }
 
 static char *unescape(char *s)
@@ -150,21 +184,32 @@ static char *unescape(char *s)
 	return s;
 }
 
+static void put_frame(int stream, const char *p, size_t len)
+{
+	ssq_frame_hdr_t h;
+	if (!len) return;
+	memcpy(h.magic, SSQ_FRAME_MAGIC, 8); h.stream = (uint64_t)stream; h.len = (uint64_t)len;
+	fwrite(&h, sizeof h, 1, stdout); fwrite(p, 1, len, stdout);
+}
+
 static int main_mem(int argc, char **argv, const char *prog)
 {
 	ssq_opts_t opt;
+	ssq_sb_opts_t sb;
 	ssq_pestat_t pes[4], *pes0 = 0;
 	ssq_index_t *idx = 0;
+	ssq_aligner_t *al = 0;
 	fq_t *f1, *f2 = 0;
 	rec_t r1, r2;
-	reads_t v = {0, 0, 0};
-	char *rg_line = 0, rg_id[256] = "", *p;
-	int c, i, n_threads = 1, smart_pe = 0, paired = 0, keep_comment = 0, device = getenv("SSQ_DEVICE") ? atoi(getenv("SSQ_DEVICE")) : 0, rc;
+	blob_t v, se, pe;
+	char *rg_line = 0, rg_id[256] = "", *p, fuse_opts[1024] = "";
+	int c, i, n_threads = 1, smart_pe = 0, paired = 0, keep_comment = 0, device = getenv("SSQ_DEVICE") ? atoi(getenv("SSQ_DEVICE")) : 0, rc, fused = 0;
 	long long n_processed = 0;
 	const long chunk_size = 10000000;
-	memset(&r1, 0, sizeof r1); memset(&r2, 0, sizeof r2); memset(pes, 0, sizeof pes);
+	memset(&r1, 0, sizeof r1); memset(&r2, 0, sizeof r2); memset(pes, 0, sizeof pes); memset(&v, 0, sizeof v); memset(&se, 0, sizeof se); memset(&pe, 0, sizeof pe);
 	pes[0].failed = pes[1].failed = pes[2].failed = pes[3].failed = 1;
 	ssq_opts_default(&opt);
+	ssq_sb_opts_default(&sb);
 	while ((c = getopt(argc, argv, "t:pR:I:Cv:")) >= 0) {
 		if (c == 't') n_threads = atoi(optarg) > 1 ? atoi(optarg) : 1;
 		else if (c == 'p') smart_pe = paired = 1;
@@ -189,7 +234,24 @@ static int main_mem(int argc, char **argv, const char *prog)
 	}
 	opt.n_threads = n_threads;
 	if (optind + 1 >= argc || optind + 3 < argc) { fprintf(stderr, "Usage: bwa mem [-t INT] [-p] [-C] [-I FLOAT[,FLOAT[,INT[,INT]]]] [-R STR] <idxbase> <in1.fq> [in2.fq]\n"); return 1; }
+	if (getenv("SSQ_FUSE_SAMBLASTER") && getenv("SSQ_FUSE_SAMBLASTER")[0]) { /* samblaster's options: its stage runs here, on the device */
+		char tmp[1024], *tok;
+		snprintf(tmp, sizeof tmp, "%s", getenv("SSQ_FUSE_SAMBLASTER"));
+		fused = 1; sb.enabled = 1; sb.want_split = sb.want_disc = 1;
+		for (tok = strtok(tmp, " \t"); tok; tok = strtok(0, " \t")) {
+			if (!strcmp(tok, "--excludeDups") || !strcmp(tok, "-e")) sb.exclude_dups = 1;
+			else if (!strcmp(tok, "--addMateTags")) sb.add_mate_tags = 1;
+			else if (!strcmp(tok, "--removeDups") || !strcmp(tok, "-r")) sb.remove_dups = 1;
+			else if (!strcmp(tok, "--maxSplitCount")) { if ((tok = strtok(0, " \t"))) sb.max_split_count = atoi(tok); }
+			else if (!strcmp(tok, "--minNonOverlap")) { if ((tok = strtok(0, " \t"))) sb.min_non_overlap = atoi(tok); }
+			else if (!strcmp(tok, "--minIndelSize")) { if ((tok = strtok(0, " \t"))) sb.min_indel_size = atoi(tok); }
+			else if (!strcmp(tok, "--maxUnmappedBases")) { if ((tok = strtok(0, " \t"))) sb.max_unmapped_bases = atoi(tok); }
+			else { fprintf(stderr, "[E::bwa] SSQ_FUSE_SAMBLASTER: option '%s' is not one the fused stage implements\n", tok); return 1; }
+		}
+		ssq_fuse_describe(fuse_opts, sizeof fuse_opts, sb.exclude_dups, sb.add_mate_tags, sb.remove_dups, sb.max_split_count, sb.min_non_overlap, sb.min_indel_size, sb.max_unmapped_bases);
+	}
 	if ((rc = ssq_index_load(argv[optind], device, &idx))) die("ssq_index_load", rc);
+	if ((rc = ssq_aligner_create(idx, &opt, fused ? &sb : 0, rg_id, &al))) die("ssq_aligner_create", rc);
 	if (!(f1 = fq_open(argv[optind + 1]))) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 1]); return 1; }
 	if (optind + 2 < argc) {
 		if (smart_pe) fprintf(stderr, "[W::main_mem] when '-p' is in use, the second query file is ignored.\n");
@@ -197,43 +259,63 @@ static int main_mem(int argc, char **argv, const char *prog)
 	}
 	{ /* header: @SQ from the index, @RG as given, @PG with the command line */
 		const int ns = (int)ssq_index_info(idx, 3);
+		static char obuf[1 << 22];
+		setvbuf(stdout, obuf, _IOFBF, sizeof obuf);
 		for (i = 0; i < ns; ++i) { int64_t len; const char *nm = ssq_index_contig(idx, i, &len); printf("@SQ\tSN:%s\tLN:%lld\n", nm, (long long)len); }
 		if (rg_line) printf("%s\n", rg_line);
 		printf("@PG\tID:bwa\tPN:bwa\tVN:%s\tCL:%s", SHIM_VERSION, prog);
 		for (i = 0; i < argc; ++i) printf(" %s", argv[i]);
 		printf("\n");
+		if (fused) printf("%s%s\n", SSQ_FUSE_MARKER, fuse_opts);
 	}
 	for (;;) {
 		const long size = read_batch(chunk_size * n_threads, f1, f2, &r1, &r2, &v, keep_comment);
-		char **out;
-		read_t **se, **pe;
-		int n_se = 0, n_pe = 0;
+		ssq_reads_t rd;
+		ssq_sam_t out;
+		int n_se = 0, n_pe = 0, mixed = 0;
 		if (v.n == 0) break;
 		fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", v.n, size);
-		out = (char**)calloc(v.n, sizeof(char*));
-		se = (read_t**)malloc(sizeof(read_t*) * v.n); pe = (read_t**)malloc(sizeof(read_t*) * v.n);
 		if (smart_pe) { /* interleaved input: adjacent reads with equal names are mates, the others single-end */
 			int has_last = 1;
 			for (i = 1; i < v.n; ++i) {
+				if (has_last) { if (same_name(&v, i, i - 1)) { n_pe += 2; has_last = 0; } else ++n_se; }
+				else has_last = 1;
+			}
+			if (has_last) ++n_se;
+			fprintf(stderr, "[M::process] %d single-end sequences; %d paired-end sequences\n", n_se, n_pe);
+			mixed = n_se && n_pe;
+		} else if (paired) n_pe = v.n; else n_se = v.n;
+		if (!mixed) { /* the whole batch is one call; its text is already in input order */
+			if (n_pe) check_pair_names(&v);
+			fill_reads(&rd, &v, n_pe ? 1 : 0, n_processed);
+			if ((rc = ssq_aligner_run(al, &rd, n_pe ? pes0 : 0, 1, &out))) die("ssq_aligner_run", rc);
+			if (fused) { put_frame(0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
+			else fwrite(out.text[0], 1, out.len[0], stdout);
+		} else { /* single-end reads first, then the pairs (the reference's order of work); records go out in input order */
+			int *id_se = (int*)malloc(sizeof(int) * v.n), *id_pe = (int*)malloc(sizeof(int) * v.n), has_last = 1, k_se = 0, k_pe = 0;
+			char **txt = (char**)calloc(v.n, sizeof(char*)); size_t *len = (size_t*)calloc(v.n, sizeof(size_t));
+			if (fused) { fprintf(stderr, "[E::bwa] interleaved input with unpaired reads in one batch cannot go through the fused samblaster stage; unset SSQ_FUSE_SAMBLASTER\n"); return 1; }
+			blob_clear(&se); blob_clear(&pe);
+			for (i = 1; i < v.n; ++i) {
 				if (has_last) {
-					if (strcmp(v.a[i].name, v.a[i - 1].name) == 0) { pe[n_pe++] = &v.a[i - 1]; pe[n_pe++] = &v.a[i]; has_last = 0; }
-					else se[n_se++] = &v.a[i - 1];
+					if (same_name(&v, i, i - 1)) { id_pe[k_pe++] = i - 1; id_pe[k_pe++] = i; blob_push_from(&pe, &v, i - 1); blob_push_from(&pe, &v, i); has_last = 0; }
+					else { id_se[k_se++] = i - 1; blob_push_from(&se, &v, i - 1); }
 				} else has_last = 1;
 			}
-			if (has_last) se[n_se++] = &v.a[v.n - 1];
-			fprintf(stderr, "[M::process] %d single-end sequences; %d paired-end sequences\n", n_se, n_pe);
-		} else if (paired) { for (i = 0; i < v.n; ++i) pe[n_pe++] = &v.a[i]; }
-		else { for (i = 0; i < v.n; ++i) se[n_se++] = &v.a[i]; }
-		if (n_se) run_sub(idx, &opt, se, n_se, n_processed, 0, 0, rg_id, out);
-		if (n_pe) run_sub(idx, &opt, pe, n_pe, n_processed + n_se, 1, pes0, rg_id, out);
-		n_processed += v.n;
-		for (i = 0; i < v.n; ++i) {
-			if (out[i]) { fputs(out[i], stdout); free(out[i]); }
-			free(v.a[i].name); free(v.a[i].seq); free(v.a[i].qual); free(v.a[i].comment);
+			if (has_last) { id_se[k_se++] = v.n - 1; blob_push_from(&se, &v, v.n - 1); }
+			for (c = 0; c < 2; ++c) {
+				const blob_t *b = c ? &pe : &se; const int *ids = c ? id_pe : id_se;
+				fill_reads(&rd, b, c, n_processed + (c ? n_se : 0));
+				if ((rc = ssq_aligner_run(al, &rd, c ? pes0 : 0, 1, &out))) die("ssq_aligner_run", rc);
+				for (i = 0; i < b->n; ++i) { len[ids[i]] = (size_t)(out.read_off[i + 1] - out.read_off[i]); txt[ids[i]] = (char*)malloc(len[ids[i]] + 1); memcpy(txt[ids[i]], out.text[0] + out.read_off[i], len[ids[i]]); }
+			}
+			for (i = 0; i < v.n; ++i) { fwrite(txt[i], 1, len[i], stdout); free(txt[i]); }
+			free(txt); free(len); free(id_se); free(id_pe);
 		}
-		free(out); free(se); free(pe);
+		n_processed += v.n;
 	}
 	fflush(stdout);
+	ssq_aligner_free(al);
 	ssq_index_free(idx);
 	return 0;
 }

@@ -17,6 +17,7 @@
 #include <string.h>
 #include <stdint.h>
 #include "ssq.h"
+#include "ssq_fuse.h"
 
 #define SB_VERSION "0.1.22"
 #define PAD 500           /* keeps 5' coordinates left of a contig start non-negative */
@@ -269,7 +270,6 @@ int main(int argc, char **argv)
 		else { fprintf(stderr, "samblaster: Unrecognized option: %s\n", argv[i]); return 1; }
 	}
 	fprintf(stderr, "samblaster: Version %s (B200 shim over libssq)\n", SB_VERSION);
-	if ((rc = ssq_dupset_create(device, &set))) { fprintf(stderr, "samblaster: %s\n", ssq_last_error()); return 1; }
 	if (discfn && !(o.disc = fopen(discfn, "w"))) { fprintf(stderr, "samblaster: Unable to open %s\n", discfn); return 1; }
 	if (splitfn && !(o.split = fopen(splitfn, "w"))) { fprintf(stderr, "samblaster: Unable to open %s\n", splitfn); return 1; }
 	strcpy(cl, "samblaster -i stdin -o stdout");
@@ -280,6 +280,7 @@ int main(int argc, char **argv)
 	if (splitfn) sprintf(cl + strlen(cl), " --maxSplitCount %d --maxUnmappedBases %d --minIndelSize %d --minNonOverlap %d", o.maxSplitCount, o.maxUnmappedBases, o.minIndelSize, o.minNonOverlap);
 #define FLUSH_CHUNK() do { \
 		if (n_blocks) { \
+			if (!set && (rc = ssq_dupset_create(device, &set))) { fprintf(stderr, "samblaster: %s\n", ssq_last_error()); return 1; } /* the GPU is only touched when there is work for it (not in fused mode) */ \
 			if ((rc = ssq_dupset_mark(set, (uint64_t)n_blocks, sigs, dups))) { fprintf(stderr, "samblaster: ssq_dupset_mark failed (%d): %s\n", rc, ssq_last_error()); return 1; } \
 			for (i = 0; i < n_blocks; ++i) { emit_block(&blocks[i], &o, dups[i], meta[i] & 1, (meta[i] >> 1) & 1, (meta[i] >> 2) & 1); free_block(&blocks[i]); } \
 			n_blocks = 0; \
@@ -289,6 +290,38 @@ int main(int argc, char **argv)
 			blocks[n_blocks++] = cur; memset(&cur, 0, sizeof cur); if (n_blocks == CHUNK_BLOCKS) FLUSH_CHUNK(); } } while (0)
 	while ((len = getline(&line, &cap, stdin)) > 0) {
 		line_t l;
+		if (line[0] == '@' && !hdr_done && !strncmp(line, SSQ_FUSE_MARKER, strlen(SSQ_FUSE_MARKER))) {
+			/* fused mode: `bwa` already ran this program's stage on the device under the options described on the marker line */
+			char mine[1024];
+			FILE *fps[3] = {o.out, o.split, o.disc};
+			ssq_frame_hdr_t h;
+			char *buf = 0; size_t bcap = 0;
+			unsigned long long n_rec[3] = {0, 0, 0};
+			ssq_fuse_describe(mine, sizeof mine, o.excludeDups, o.addMateTags, o.removeDups, o.maxSplitCount, o.minNonOverlap, o.minIndelSize, o.maxUnmappedBases);
+			if (len && line[len - 1] == '\n') line[len - 1] = 0;
+			if (strcmp(line + strlen(SSQ_FUSE_MARKER), mine) != 0) {
+				fprintf(stderr, "samblaster: the fused stream was produced under other options (SSQ_FUSE_SAMBLASTER: %s; this command line: %s)\n", line + strlen(SSQ_FUSE_MARKER), mine);
+				return 1;
+			}
+			for (i = 0; i < 3; ++i) if (fps[i]) fprintf(fps[i], "@PG\tID:SAMBLASTER\tVN:%s\tCL:%s\n", SB_VERSION, cl);
+			hdr_done = 1;
+			while (fread(&h, sizeof h, 1, stdin) == 1) {
+				size_t k;
+				if (memcmp(h.magic, SSQ_FRAME_MAGIC, 8) != 0 || h.stream > 2) { fprintf(stderr, "samblaster: corrupt fused stream\n"); return 1; }
+				if (h.len > bcap) { bcap = h.len + h.len / 4; buf = (char*)realloc(buf, bcap); }
+				if (fread(buf, 1, h.len, stdin) != h.len) { fprintf(stderr, "samblaster: truncated fused stream\n"); return 1; }
+				if (fps[h.stream]) fwrite(buf, 1, h.len, fps[h.stream]);
+				for (k = 0; k < h.len; ++k) n_rec[h.stream] += buf[k] == '\n';
+			}
+			free(buf);
+			fflush(o.out);
+			if (o.disc) fclose(o.disc);
+			if (o.split) fclose(o.split);
+			if (discfn) fprintf(stderr, "samblaster: Output %llu discordant read pairs to %s\n", n_rec[2] / 2, discfn);
+			if (splitfn) fprintf(stderr, "samblaster: Output %llu split reads to %s\n", n_rec[1] / 2, splitfn);
+			fprintf(stderr, "samblaster: routed %llu records marked on the device by `bwa mem` (fused mode).\n", n_rec[0]);
+			return 0;
+		}
 		if (line[0] == '@' && !hdr_done) {
 			if (!strncmp(line, "@SQ\t", 4)) {
 				char name[1024] = "";
@@ -322,7 +355,7 @@ int main(int argc, char **argv)
 	if (discfn) fprintf(stderr, "samblaster: Output %llu discordant read pairs to %s\n", o.n_disc / 2, discfn);
 	if (splitfn) fprintf(stderr, "samblaster: Output %llu split reads to %s\n", o.n_split / 2, splitfn);
 	fprintf(stderr, "samblaster: Marked %llu of %llu (%.2f%%) read ids as duplicates.\n", o.n_dup, o.n_ids, o.n_ids ? 100.0 * o.n_dup / o.n_ids : 0.0);
-	ssq_dupset_free(set);
+	if (set) ssq_dupset_free(set);
 	free(line); free(blocks); free(sigs); free(dups); free(meta);
 	return 0;
 }

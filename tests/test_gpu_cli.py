@@ -117,3 +117,81 @@ def test_dupset_streaming_equals_one_shot(ssq, oracle):
     assert np.array_equal(got, ref)
     assert int(ssq.lib.ssq_dupset_size(h)) == int(((ref == 0) & (sig["valid"] == 1)).sum())
     ssq.lib.ssq_dupset_free(h)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the invocation modes of /root/reference/bin/speedseq that one interleaved single-batch run does not reach: two FASTQ files
+# (:468, the default), -I (:286), -C (:1961), several batches (per-batch insert-size statistics + global read ordinals), smart
+# pairing with unpaired reads, gz input, and the fused samblaster stage behind the same two executables
+def _records(b):
+    return b"".join(l for l in b.splitlines(True) if not l.startswith(b"@"))
+
+
+def _both(args, stdin=None):
+    return [subprocess.run(exe + args, input=stdin, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout for exe in ([T.ORACLE_BIN], [BWA])]
+
+
+@pytest.fixture(scope="module")
+def cli_ref(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cliref")
+    g, bounds = T.synth_genome(600000, 31, n_contigs=4)
+    fa = str(d / "ref.fa")
+    T.write_fasta(fa, g, bounds)
+    subprocess.check_call([BWA, "index", fa], stderr=subprocess.DEVNULL)
+    return d, fa, g, bounds
+
+
+def test_cli_two_files_insert_override_and_comments(ssq, cli_ref):
+    from test_hostsim_pipe import stress_reads
+    d, fa, g, bounds = cli_ref
+    names, seqs, quals = stress_reads(g, bounds, 1500, 150, 3)
+    fq1, fq2 = str(d / "r1.fq.gz"), str(d / "r2.fq")
+    with gzip.open(fq1, "wt") as f1, open(fq2, "w") as f2:
+        for i, (n, s, q) in enumerate(zip(names, seqs, quals)):
+            (f2 if i & 1 else f1).write("@%s/%d BC:Z:x%d\n%s\n+\n%s\n" % (n, 1 + (i & 1), i % 5, s, q))
+    for extra in ([], ["-I", "300,30"], ["-C"], ["-I", "420,60,900,50", "-C"]):
+        a, b = _both(["mem", "-t", "3", "-R", RG] + extra + [fa, fq1, fq2])
+        assert _records(a) == _records(b), extra
+        assert _records(b).count(b"\n") >= 3000
+        assert (b"BC:Z:x" in b) == ("-C" in extra)
+
+
+def test_cli_several_batches_and_smart_pairing(ssq, cli_ref):
+    """-t 1: a batch closes at 10 Mbp (67 k reads of 150 bp), so 150 k reads make three batches — each with its own insert-size
+    statistics, read ordinals continuing across them; the interleaved file also holds unpaired reads (smart pairing)"""
+    d, fa, g, bounds = cli_ref
+    names, seqs, quals = T.simulate_pairs(g, bounds, 75000, 150, 5)
+    fq = str(d / "big.fq")
+    with open(fq, "w") as f:
+        for i, (n, s, q) in enumerate(zip(names, seqs, quals)):
+            if i % 9001 == 17:  # drop one end now and then: its mate becomes a single-end read in the middle of the stream
+                continue
+            f.write("@%s/%d\n%s\n+\n%s\n" % (n, 1 + (i & 1), s, q))
+    a, b = _both(["mem", "-t", "1", "-p", fa, fq])
+    assert _records(a) == _records(b)
+    a, b = _both(["mem", "-t", "1", fa, fq])  # the same file as single-end reads
+    assert _records(a) == _records(b)
+
+
+def test_cli_fused_samblaster_stage(ssq, cli_ref, tmp_path, monkeypatch):
+    """SSQ_FUSE_SAMBLASTER: `bwa mem | samblaster` with samblaster's stage executed on the device inside `bwa mem`; the three streams
+    must equal the oracle's pipe, and the unfused product pipe, byte for byte (minus @PG)"""
+    from test_hostsim_pipe import stress_reads
+    d, fa, g, bounds = cli_ref
+    names, seqs, quals = stress_reads(g, bounds, 40000, 150, 8)  # -t 1: two batches (dups across them)
+    fq = str(d / "fused.fq")
+    T.write_fastq(fq, names, seqs, quals)
+    sb_args = ["--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20"]
+    outs = {}
+    for tag, bwa, sb, env in (("oracle", [T.ORACLE_BIN], [T.ORACLE_BIN, "samblaster"], {}), ("unfused", [BWA], [SAMBLASTER], {}),
+                              ("fused", [BWA], [SAMBLASTER], {"SSQ_FUSE_SAMBLASTER": " ".join(sb_args)})):
+        e = dict(os.environ); e.update(env)
+        spl, disc = str(tmp_path / (tag + ".spl")), str(tmp_path / (tag + ".disc"))
+        p1 = subprocess.Popen(bwa + ["mem", "-t", "1", "-p", "-R", RG, fa, fq], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e)
+        p2 = subprocess.run(sb + sb_args + ["--splitterFile", spl, "--discordantFile", disc], stdin=p1.stdout, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e, check=True)
+        assert p1.wait() == 0
+        outs[tag] = (_strip_pg(p2.stdout), _strip_pg(open(spl, "rb").read()), _strip_pg(open(disc, "rb").read()))
+    for i, what in enumerate(("main", "splitters", "discordants")):
+        assert outs["oracle"][i] == outs["unfused"][i], what
+        assert outs["oracle"][i] == outs["fused"][i], what
+    assert outs["fused"][0].count(b"\n") > 80000 and outs["fused"][1].count(b"\n") > 100 and outs["fused"][2].count(b"\n") > 500

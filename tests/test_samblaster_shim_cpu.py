@@ -15,7 +15,7 @@ import ssq_testlib as T
 def shim(tmp_path_factory, oracle):
     d = tmp_path_factory.mktemp("shim")
     exe = str(d / "samblaster_stub")
-    subprocess.check_call(["gcc", "-O1", "-w", "-I" + os.path.join(T.ROOT, "include"), "-o", exe,
+    subprocess.check_call(["gcc", "-O1", "-w", "-I" + os.path.join(T.ROOT, "include"), "-I" + os.path.join(T.ROOT, "speedseq_b200", "cli"), "-o", exe,
                            os.path.join(T.ROOT, "speedseq_b200", "cli", "samblaster_main.c"), os.path.join(T.ROOT, "tests", "stubs", "dupset_stub.c")])
     return exe
 
@@ -99,3 +99,23 @@ def test_shim_text_logic_matches_oracle(shim, oracle, tmp_path, seed, chunk, ext
     assert b"\t77\t" in res["shim"][0] and b"\t77\t" not in res["shim"][2]          # unmapped pairs pass through, never discordant
     assert res["shim"][2].count(b"\n") > 50 and res["shim"][1].count(b"\n") > 20    # both side streams are exercised
     assert any((int(l.split(b"\t")[1]) & 0x400) for l in res["shim"][0].splitlines() if not l.startswith(b"@"))
+
+
+def test_fused_stream_is_only_routed(shim, tmp_path):
+    """fused mode (speedseq_b200/cli/ssq_fuse.h): behind the marker line the shim copies frames to stdout / --splitterFile /
+    --discordantFile and never touches the GPU; a marker written under other options is refused"""
+    import struct
+    hdr = b"@SQ\tSN:c1\tLN:5000\n@PG\tID:bwa\tPN:bwa\n"
+    marker = b"@CO\tssq-fused-v1\texcludeDups=1 addMateTags=1 removeDups=0 maxSplitCount=2 minNonOverlap=20 minIndelSize=50 maxUnmappedBases=50\n"
+    frame = lambda k, p: b"SSQFRAME" + struct.pack("<QQ", k, len(p)) + p
+    main1, main2, spl, disc = b"a\t99\tc1\t1\n" * 3, b"b\t1171\tc1\t9\n", b"a_1\t65\tc1\t1\n" * 2, b"d\t65\tc1\t1\nd\t129\tc1\t7\n"
+    data = hdr + marker + frame(0, main1) + frame(1, spl) + frame(0, main2) + frame(2, disc)
+    s, d = str(tmp_path / "s"), str(tmp_path / "d")
+    args = ["--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20", "--splitterFile", s, "--discordantFile", d]
+    out = subprocess.run([shim] + args, input=data, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    body = lambda b: b"".join(l for l in b.splitlines(True) if not l.startswith(b"@PG\tID:SAMBLASTER"))
+    assert body(out) == hdr + main1 + main2 and b"ssq-fused" not in out
+    assert body(open(s, "rb").read()) == hdr + spl and body(open(d, "rb").read()) == hdr + disc
+    assert out.count(b"@PG\tID:SAMBLASTER") == 1
+    bad = subprocess.run([shim, "--addMateTags", "--splitterFile", s, "--discordantFile", d], input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert bad.returncode != 0 and b"other options" in bad.stderr
