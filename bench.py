@@ -373,7 +373,7 @@ def main():
               "k_smem", "k_sa", "k_chain", "k_extend", "k_select"]
     stage_ms = np.zeros(len(STAGES))
     counters = np.zeros(12)
-    n_tasks = text_bytes = 0
+    n_tasks = text_bytes = n_rescue = n_gapped = 0
     out = capi.Sam()
     s.ck(L.ssq_dupset_reset(dset), "reset")
     for b, al in enumerate(aligners):
@@ -384,6 +384,8 @@ def main():
         counters += [L.ssq_aligner_counter(al, i) for i in range(12)]
         n_tasks += L.ssq_aligner_counter(al, 100)
         text_bytes += sum(L.ssq_aligner_counter(al, 101 + k) for k in range(3))
+        n_rescue += L.ssq_aligner_counter(al, 105)
+        n_gapped += L.ssq_aligner_counter(al, 106)
     dup_frac_seen = None
     # ---- e2e: host buffers through the C-ABI (upload + compute + fetch per batch) ----
     d2h_step = [0]
@@ -464,7 +466,7 @@ def main():
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"], "rank_block_bytes": blk},
                "kernels": kern,
                "work_per_step": {"occ_blocks_smem": counters[0], "occ_blocks_sa": counters[1], "sa_samples": counters[2], "sw_calls": counters[3], "sw_cells": counters[4], "seeds": counters[7],
-                                 "alignments_written": n_tasks, "sam_bytes": text_bytes},
+                                 "alignments_written": n_tasks, "sam_bytes": text_bytes, "pairs_through_mate_rescue": n_rescue, "alignments_with_banded_dp": n_gapped},
                "kernel_stats_note": "kernels{} come from one extra step after the timed region with the batches run one after the other (stage boundaries by CUDA events on each batch's stream)"}
         if world == 1 and not a.no_cpu_baseline:
             T = oracle_lib()

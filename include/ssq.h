@@ -229,9 +229,27 @@ void *ssq_aligner_stream(ssq_aligner_t *al);       /* cudaStream_t of the object
 /* milliseconds of the last batch per stage (CUDA events): 0 upload, 1 seed..extend, 2 sort/dedup/patch, 3 insert-size statistics,
  * 4 mate rescue, 5 pairing/MAPQ/planning, 6 CIGAR/NM/MD, 7 samblaster + dup-set, 8 text, 9 fetch; 10.. = ssq_batch_stage_ms(0..4) */
 float ssq_aligner_stage_ms(const ssq_aligner_t *al, int stage);
-/* what < 100: ssq_batch_counter of the alignment stage; 100 alignments written (CIGAR tasks), 101-103 bytes of the three streams, 104 dup-set size */
+/* what < 100: ssq_batch_counter of the alignment stage; 100 alignments written (CIGAR tasks), 101-103 bytes of the three streams, 104 dup-set size,
+ * 105 pairs that went through mate rescue, 106 alignments that needed the banded global DP for their CIGAR */
 uint64_t ssq_aligner_counter(const ssq_aligner_t *al, int what);
 void ssq_aligner_free(ssq_aligner_t *al);
+
+/* ------------------------------------------------------------------ several GPUs ----
+ * Batches are dealt to the ranks round-robin with the index replicated (no collective); "first pair seen with a signature is
+ * kept" (`$SAMBLASTER`, speedseq:439) stays global through one exchange per round, in C over NCCL: signatures go to the owner rank
+ * hash(signature) mod N (grouped ncclSend/ncclRecv, 16 B per pair), the owner marks them against everything it has owned so far,
+ * one byte per pair comes back (csrc/ssq_dist.cu).  One process per GPU: rank 0 makes the id, every rank creates its communicator
+ * and hands it to its aligner object(s); ssq_aligner_compute then performs the round inside its duplicate stage (a collective: all
+ * ranks run the same number of batches, empty ones included). */
+typedef struct ssq_comm ssq_comm_t;
+int ssq_comm_unique_id(void *id128);  /* 128 bytes, to be broadcast to the other ranks by whatever launched them */
+int ssq_comm_create(const void *id128, int rank, int world, int device, ssq_comm_t **out);
+int ssq_aligner_set_comm(ssq_aligner_t *al, ssq_comm_t *comm);
+/* one round on explicit device arrays (key = 5' position << 1 | strand of the canonically ordered ends, array order = input order) */
+int ssq_comm_mark_round(ssq_comm_t *comm, uint64_t n, const uint64_t *d_key1, const uint64_t *d_key2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);
+ssq_dupset_t *ssq_comm_dupset(ssq_comm_t *comm);            /* the signatures this rank owns (reset it on every rank to start a new run) */
+uint64_t ssq_comm_counter(const ssq_comm_t *comm, int what); /* 0 bytes sent to other ranks, 1 bytes received back, 2 rounds */
+void ssq_comm_free(ssq_comm_t *comm);
 
 /* streaming dup-set on device pointers (what the aligner uses; also the owner-side step of the multi-GPU exchange) */
 int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t *d_key1, const uint64_t *d_key2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);

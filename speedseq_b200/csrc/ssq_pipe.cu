@@ -44,6 +44,9 @@ extern "C" int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t
 extern "C" int ssq_dupset_reset(ssq_dupset_t *set);
 extern "C" void ssq_dupset_wait_turn(ssq_dupset_t *set, long long turn);
 extern "C" void ssq_dupset_end_turn(ssq_dupset_t *set, long long turn);
+// multi-GPU exchange (ssq_dist.cu)
+extern "C" int ssq_comm_mark_round(ssq_comm_t *c, uint64_t n, const uint64_t *d_k1, const uint64_t *d_k2, const uint8_t *d_valid, uint8_t *d_is_dup, void *stream);
+extern "C" ssq_dupset_t *ssq_comm_dupset(ssq_comm_t *c);
 
 // ================================================================================ kernels ====
 __global__ void __launch_bounds__(256) k_encode(u64 n, const char *__restrict__ ascii, uint8_t *__restrict__ codes)
@@ -73,11 +76,8 @@ __global__ void __launch_bounds__(128) k_dedup(PipeView V, DedupSlab *slabs, int
 {
 	DedupSlab &s = slabs[(size_t)blockIdx.x * blockDim.x + threadIdx.x];
 	AlnScratch A; A.qbuf = s.qbuf; A.rbuf = s.rbuf; A.rcap = 2048; A.g.h = s.h; A.g.e = s.e; A.g.z = 0; A.g.zcap = 0;
-	for (;;) {
-		const int r = atomicAdd(work, 1);
-		if (r >= V.n_reads) break;
-		body_dedup(V, r, A);
-	}
+	(void)work;
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < V.n_reads; r += gridDim.x * blockDim.x) body_dedup(V, r, A); // neighbouring lanes take neighbouring reads: their region lists are adjacent in memory
 }
 
 __global__ void __launch_bounds__(256) k_pestat(PipeView V)
@@ -247,6 +247,7 @@ struct ssq_aligner {
 	char rg_id[256];
 	cudaStream_t st;
 	ssq_batch_t *b;
+	ssq_comm_t *comm; // set: the dup stage is one round of the cross-GPU exchange instead of a local look-up
 	ssq_dupset_t *dups; int own_dups; long long turn; // turn >= 0: the dup stage waits for the batches with smaller turn numbers (shared set)
 	// static tables
 	DBuf d_logn, d_lg, d_ctg_names, d_ctg_off, d_sb_off, d_rg;
@@ -258,7 +259,7 @@ struct ssq_aligner {
 	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
 	PinBuf h_text[3], h_roff, h_hist, h_small;
 	PeStat pes[4];
-	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines;
+	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines, n_rescue_pairs, n_gapped;
 	cudaEvent_t ev[ST_N + 1];
 	float stage_ms[ST_N];
 	int computed;
@@ -295,7 +296,7 @@ extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt,
 	int rc = ssq_use_device(idx->device);
 	if (rc) return rc;
 	ssq_aligner *a = new ssq_aligner();
-	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->computed = 0; a->n_reads = 0;
+	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->comm = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->computed = 0; a->n_reads = 0;
 	memset(a->ev, 0, sizeof a->ev); memset(a->stage_ms, 0, sizeof a->stage_ms); memset(a->pes, 0, sizeof a->pes);
 	memset(&a->sb, 0, sizeof a->sb);
 	if (sb) {
@@ -349,6 +350,13 @@ extern "C" int ssq_aligner_share_dupset(ssq_aligner_t *a, ssq_dupset_t *set)
 	a->dups = set; a->own_dups = 0;
 	return SSQ_OK;
 }
+extern "C" int ssq_aligner_set_comm(ssq_aligner_t *a, ssq_comm_t *comm)
+{
+	if (!a || !comm) return SSQ_EINVAL;
+	if (a->dups && a->own_dups) ssq_dupset_free(a->dups);
+	a->comm = comm; a->dups = ssq_comm_dupset(comm); a->own_dups = 0; // the owner-side set also keeps the turn counter of this rank's lanes
+	return SSQ_OK;
+}
 extern "C" int ssq_aligner_set_turn(ssq_aligner_t *a, long long turn) { if (!a) return SSQ_EINVAL; a->turn = turn; return SSQ_OK; }
 extern "C" void *ssq_aligner_stream(ssq_aligner_t *a) { return a ? (void*)a->st : 0; }
 extern "C" float ssq_aligner_stage_ms(const ssq_aligner_t *a, int stage)
@@ -362,7 +370,7 @@ extern "C" uint64_t ssq_aligner_counter(const ssq_aligner_t *a, int what)
 {
 	if (!a) return 0;
 	if (what < 100) return ssq_batch_counter(a->b, what);
-	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); }
+	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); case 105: return a->n_rescue_pairs; case 106: return a->n_gapped; }
 	return 0;
 }
 
@@ -441,7 +449,17 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 	cudaStream_t st = a->st;
 	a->text_len[0] = a->text_len[1] = a->text_len[2] = 0; a->n_tasks_total = 0; a->n_ids = a->n_dup = a->n_disc_lines = a->n_split_lines = 0;
 	CK(cudaEventRecord(a->ev[ST_ALIGN], st));
-	if (n == 0) { for (int i = ST_ALIGN + 1; i <= ST_N; ++i) CK(cudaEventRecord(a->ev[i], st)); a->computed = 1; return SSQ_OK; }
+	if (n == 0) {
+		if (a->comm && a->sb.enabled) { // an empty batch still takes part in its round of the exchange (the other ranks are waiting in it)
+			if (a->turn >= 0) ssq_dupset_wait_turn(a->dups, a->turn);
+			rc = ssq_comm_mark_round(a->comm, 0, 0, 0, 0, 0, (void*)st);
+			if (a->turn >= 0) ssq_dupset_end_turn(a->dups, a->turn);
+			if (rc) return rc;
+		}
+		for (int i = ST_ALIGN + 1; i <= ST_N; ++i) CK(cudaEventRecord(a->ev[i], st));
+		a->computed = 1;
+		return SSQ_OK;
+	}
 	if ((rc = ssq_batch_run(a->b))) return rc;
 	CK(cudaEventRecord(a->ev[ST_DEDUP], st));
 	PipeView V = make_view(a);
@@ -543,7 +561,7 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 		k_sb<<<(n_units + 127) / 128, 128, 0, st>>>(V);
 		CK(cudaGetLastError());
 		if (a->turn >= 0) ssq_dupset_wait_turn(a->dups, a->turn);
-		rc = ssq_dupset_mark_dev(a->dups, (u64)n_units, V.k1, V.k2, V.valid, V.dup, (void*)st);
+		rc = a->comm ? ssq_comm_mark_round(a->comm, (u64)n_units, V.k1, V.k2, V.valid, V.dup, (void*)st) : ssq_dupset_mark_dev(a->dups, (u64)n_units, V.k1, V.k2, V.valid, V.dup, (void*)st);
 		if (a->turn >= 0) { cudaStreamSynchronize(st); ssq_dupset_end_turn(a->dups, a->turn); } // the set must be complete before the next batch looks it up from another stream
 		if (rc) return rc;
 		k_count_u8<<<(n_units + 255) / 256, 256, 0, st>>>((u64)n_units, V.dup, 0, (unsigned long long*)a->d_cnt.p);
@@ -558,7 +576,8 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 		if ((rc = scan_u64(a, a->d_len[k].as<u64>(), a->d_off[k].as<u64>(), (size_t)n + 1))) return rc;
 		CK(cudaMemcpyAsync(&a->text_len[k], a->d_off[k].as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
 	}
-	int h_err = 0; unsigned long long h_cnt[2] = {0, 0};
+	int h_err = 0; unsigned long long h_cnt[2] = {0, 0}; unsigned int h_work[2] = {0, 0};
+	CK(cudaMemcpyAsync(h_work, work + 16, 8, cudaMemcpyDeviceToHost, st)); // pairs that went through mate rescue, alignments that needed the banded DP
 	CK(cudaMemcpyAsync(&h_err, a->d_err.p, 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_cnt, a->d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
@@ -571,7 +590,7 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 	k_text<true><<<(n + 127) / 128, 128, 0, st>>>(V);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(a->ev[ST_FETCH], st));
-	a->n_ids = (u64)n_units; a->n_dup = h_cnt[0];
+	a->n_ids = (u64)n_units; a->n_dup = h_cnt[0]; a->n_rescue_pairs = h_work[0]; a->n_gapped = h_work[1];
 	a->computed = 1;
 	return SSQ_OK;
 }
