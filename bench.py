@@ -311,8 +311,24 @@ def main():
     # batches: pinned host copies + one aligner object (own stream, own scratch) per batch, all sharing one dup-set
     nstreams = max(1, min(a.streams, nb, max(1, ncores // max(1, world))))
     L.ssq_dupset_create.argtypes = [C.c_int, C.c_void_p]
-    dset = C.c_void_p()
-    s.ck(L.ssq_dupset_create(local, C.byref(dset)), "ssq_dupset_create")
+    L.ssq_comm_dupset.restype = C.c_void_p
+    L.ssq_comm_dupset.argtypes = [C.c_void_p]
+    L.ssq_comm_counter.restype = C.c_uint64
+    L.ssq_comm_counter.argtypes = [C.c_void_p, C.c_int]
+    dset, comm = C.c_void_p(), None
+    if world > 1:  # the duplicate stage of every batch is one round of libssq's NCCL exchange (csrc/ssq_dist.cu): rank 0 makes the id, torch carries it
+        idb = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            s.ck(L.ssq_comm_unique_id(buf), "ssq_comm_unique_id")
+            idb = torch.tensor(list(buf), dtype=torch.uint8)
+        idb = idb.cuda()
+        dist.broadcast(idb, 0)
+        comm = C.c_void_p()
+        s.ck(L.ssq_comm_create(bytes(idb.cpu().tolist()), C.c_int(rank), C.c_int(world), C.c_int(local), C.byref(comm)), "ssq_comm_create")
+        dset = C.c_void_p(L.ssq_comm_dupset(comm))
+    else:
+        s.ck(L.ssq_dupset_create(local, C.byref(dset)), "ssq_dupset_create")
     L.ssq_aligner_set_turn.argtypes = [C.c_void_p, C.c_longlong]
     batches, aligners = [], []
     pool0 = None
@@ -320,9 +336,12 @@ def main():
         codes = fast_pairs(g, a.batch // 2, READ_LEN, 1000 + rank * 100 + b, dup_pool=pool0)
         if b == 0:
             pool0 = codes[: a.batch // 4 + 2].copy()
-        batches.append(Batch(torch, codes, (rank * nb + b) * (a.batch // 2)))
+        batches.append(Batch(torch, codes, (b * world + rank) * (a.batch // 2)))  # round b: rank r holds global batch b * world + r
         al = s.aligner_create(idx, SB, b"bench")
-        s.ck(L.ssq_aligner_share_dupset(al, dset), "ssq_aligner_share_dupset")
+        if comm is not None:
+            s.ck(L.ssq_aligner_set_comm(al, comm), "ssq_aligner_set_comm")
+        else:
+            s.ck(L.ssq_aligner_share_dupset(al, dset), "ssq_aligner_share_dupset")
         aligners.append(al)
     exts = [torch.cuda.ExternalStream(L.ssq_aligner_stream(al)) for al in aligners]
     for al, bt in zip(aligners, batches):
@@ -373,7 +392,7 @@ def main():
               "k_smem", "k_sa", "k_chain", "k_extend", "k_select"]
     stage_ms = np.zeros(len(STAGES))
     counters = np.zeros(12)
-    n_tasks = text_bytes = n_rescue = n_gapped = 0
+    n_tasks = text_bytes = n_rescue = n_gapped = n_swl = swl_cells = 0
     out = capi.Sam()
     s.ck(L.ssq_dupset_reset(dset), "reset")
     for b, al in enumerate(aligners):
@@ -386,6 +405,8 @@ def main():
         text_bytes += sum(L.ssq_aligner_counter(al, 101 + k) for k in range(3))
         n_rescue += L.ssq_aligner_counter(al, 105)
         n_gapped += L.ssq_aligner_counter(al, 106)
+        n_swl += L.ssq_aligner_counter(al, 107)
+        swl_cells += L.ssq_aligner_counter(al, 108)
     dup_frac_seen = None
     # ---- e2e: host buffers through the C-ABI (upload + compute + fetch per batch) ----
     d2h_step = [0]
@@ -442,7 +463,7 @@ def main():
             "k_select": {"ms": st["k_select"], "bytes": None},
             "k_dedup (sort/dedup/patch)": {"ms": st["sort_dedup_patch"], "bytes": None},
             "k_pestat + host reduction": {"ms": st["insert_size_stats"], "bytes": None},
-            "k_rescue (mate rescue, ksw_align2)": {"ms": st["mate_rescue"], "bytes": None},
+            "k_rescue (mate rescue, ksw_align2)": {"ms": st["mate_rescue"], "bytes": None, "gcups": swl_cells / nb / (st["mate_rescue"] * 1e6) if st["mate_rescue"] else None},
             "k_plan (primary/pair/MAPQ)": {"ms": st["pair_mapq_plan"], "bytes": None},
             "k_cigar (ksw_global2 + traceback)": {"ms": st["cigar_nm_md"], "bytes": None},
             "k_sb + dup-set (radix sort + mark)": {"ms": st["samblaster_dupset"], "bytes": 25.0 * a.batch / 2},
@@ -459,14 +480,15 @@ def main():
                "config": {"workload": workload, "batch_reads": a.batch, "batches_per_step": nb, "streams": nstreams, "genome_bp": a.genome_len,
                           "l2": "inputs + scratch per step exceed L2 (%.1f GB of FASTQ fields, %.1f GB of SAM text per step)" % (h2d / 1e9, text_bytes / 1e9),
                           "index": "replicated per GPU, %.0f MB on the device, loaded in %.1f s" % (L.ssq_index_info(idx, 6) / 1e6, t_load),
-                          "parallelism": "whole batches per rank; dup-marking per rank (see DESIGN.md §6)", "samblaster": " ".join(SB_ARGS)},
+                          "parallelism": ("batches dealt round-robin to %d ranks, index replicated; duplicate stage = one NCCL exchange per round (signatures to owner rank hash mod N, 16 B/pair out, 1 B/pair back): rank 0 sent %.1f MB / received back %.1f MB per step" % (world, L.ssq_comm_counter(comm, 0) / 1e6 / max(1, L.ssq_comm_counter(comm, 2) // nb), L.ssq_comm_counter(comm, 1) / 1e6 / max(1, L.ssq_comm_counter(comm, 2) // nb))) if comm is not None else "single GPU: no collective",
+                          "samblaster": " ".join(SB_ARGS)},
                "clocks": clocks, "gpu_launches": int(counters[6]) * a.steps + 14 * nb * a.steps,
                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step[0], "ms_per_step": ms_e2e / a.steps},
                "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"], "rank_block_bytes": blk},
                "kernels": kern,
                "work_per_step": {"occ_blocks_smem": counters[0], "occ_blocks_sa": counters[1], "sa_samples": counters[2], "sw_calls": counters[3], "sw_cells": counters[4], "seeds": counters[7],
-                                 "alignments_written": n_tasks, "sam_bytes": text_bytes, "pairs_through_mate_rescue": n_rescue, "alignments_with_banded_dp": n_gapped},
+                                 "alignments_written": n_tasks, "sam_bytes": text_bytes, "pairs_through_mate_rescue": n_rescue, "alignments_with_banded_dp": n_gapped, "rescue_sw_passes": n_swl, "rescue_sw_cells": swl_cells},
                "kernel_stats_note": "kernels{} come from one extra step after the timed region with the batches run one after the other (stage boundaries by CUDA events on each batch's stream)"}
         if world == 1 and not a.no_cpu_baseline:
             T = oracle_lib()
@@ -493,7 +515,10 @@ def main():
         print(json.dumps(res))
     for al in aligners:
         s.aligner_free(al)
-    L.ssq_dupset_free(dset)
+    if comm is not None:
+        L.ssq_comm_free(comm)
+    else:
+        L.ssq_dupset_free(dset)
     s.index_free(idx)
     if world > 1:
         dist.destroy_process_group()

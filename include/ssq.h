@@ -230,7 +230,8 @@ void *ssq_aligner_stream(ssq_aligner_t *al);       /* cudaStream_t of the object
  * 4 mate rescue, 5 pairing/MAPQ/planning, 6 CIGAR/NM/MD, 7 samblaster + dup-set, 8 text, 9 fetch; 10.. = ssq_batch_stage_ms(0..4) */
 float ssq_aligner_stage_ms(const ssq_aligner_t *al, int stage);
 /* what < 100: ssq_batch_counter of the alignment stage; 100 alignments written (CIGAR tasks), 101-103 bytes of the three streams, 104 dup-set size,
- * 105 pairs that went through mate rescue, 106 alignments that needed the banded global DP for their CIGAR */
+ * 105 pairs that went through mate rescue, 106 alignments that needed the banded global DP for their CIGAR,
+ * 107 local-SW passes run by the mate rescue, 108 their cells */
 uint64_t ssq_aligner_counter(const ssq_aligner_t *al, int what);
 void ssq_aligner_free(ssq_aligner_t *al);
 

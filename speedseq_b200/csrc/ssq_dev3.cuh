@@ -559,6 +559,7 @@ struct PipeView {
 	const i64 *sb_off; u64 *k1, *k2; uint8_t *valid, *dup, *disc; u64 *split_mask;
 	// text: per-read byte counts / offsets of the three streams (0 main, 1 splitters, 2 discordants) and the buffers
 	u64 *len[3]; const u64 *off[3]; char *text[3];
+	unsigned long long *cnt; // device-measured work: [0] duplicate blocks, [2] local-SW passes of the mate rescue, [3] their cells (rows x query length), [4] banded-DP cells of CIGAR generation
 	i32 *err; // sticky error flags: 1 region-list overflow, 2 task-slot overflow, 4 CIGAR/MD/traceback capacity, 8 rescue window capacity
 };
 #ifdef __CUDA_ARCH__

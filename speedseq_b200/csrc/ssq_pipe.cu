@@ -259,7 +259,7 @@ struct ssq_aligner {
 	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
 	PinBuf h_text[3], h_roff, h_hist, h_small;
 	PeStat pes[4];
-	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines, n_rescue_pairs, n_gapped;
+	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines, n_rescue_pairs, n_gapped, n_sw_local, sw_local_cells;
 	cudaEvent_t ev[ST_N + 1];
 	float stage_ms[ST_N];
 	int computed;
@@ -370,7 +370,7 @@ extern "C" uint64_t ssq_aligner_counter(const ssq_aligner_t *a, int what)
 {
 	if (!a) return 0;
 	if (what < 100) return ssq_batch_counter(a->b, what);
-	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); case 105: return a->n_rescue_pairs; case 106: return a->n_gapped; }
+	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); case 105: return a->n_rescue_pairs; case 106: return a->n_gapped; case 107: return a->n_sw_local; case 108: return a->sw_local_cells; }
 	return 0;
 }
 
@@ -428,7 +428,7 @@ static PipeView make_view(ssq_aligner *a)
 	V.n_reads = a->n_reads; V.paired = a->paired; V.n_processed = a->n_processed;
 	V.task_off = bv.task_off; V.n_regs = bv.n_regs; V.regs = bv.regs;
 	V.sb_off = a->d_sb_off.as<i64>();
-	V.err = a->d_err.as<i32>();
+	V.err = a->d_err.as<i32>(); V.cnt = (unsigned long long*)a->d_cnt.p;
 	return V;
 }
 
@@ -576,10 +576,10 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 		if ((rc = scan_u64(a, a->d_len[k].as<u64>(), a->d_off[k].as<u64>(), (size_t)n + 1))) return rc;
 		CK(cudaMemcpyAsync(&a->text_len[k], a->d_off[k].as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
 	}
-	int h_err = 0; unsigned long long h_cnt[2] = {0, 0}; unsigned int h_work[2] = {0, 0};
+	int h_err = 0; unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned int h_work[2] = {0, 0};
 	CK(cudaMemcpyAsync(h_work, work + 16, 8, cudaMemcpyDeviceToHost, st)); // pairs that went through mate rescue, alignments that needed the banded DP
 	CK(cudaMemcpyAsync(&h_err, a->d_err.p, 4, cudaMemcpyDeviceToHost, st));
-	CK(cudaMemcpyAsync(h_cnt, a->d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h_cnt, a->d_cnt.p, 64, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	if (h_err) {
 		ssq_set_error("batch capacity error (flags 0x%x):%s%s%s%s%s", h_err, h_err & 1 ? " mate rescue overflowed a region list;" : "", h_err & 2 ? " more alignments to write than task slots;" : "",
@@ -590,7 +590,7 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 	k_text<true><<<(n + 127) / 128, 128, 0, st>>>(V);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(a->ev[ST_FETCH], st));
-	a->n_ids = (u64)n_units; a->n_dup = h_cnt[0]; a->n_rescue_pairs = h_work[0]; a->n_gapped = h_work[1];
+	a->n_ids = (u64)n_units; a->n_dup = h_cnt[0]; a->n_rescue_pairs = h_work[0]; a->n_gapped = h_work[1]; a->n_sw_local = h_cnt[2]; a->sw_local_cells = h_cnt[3];
 	a->computed = 1;
 	return SSQ_OK;
 }

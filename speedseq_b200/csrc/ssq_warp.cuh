@@ -33,7 +33,7 @@ struct TgtBuf { const uint8_t *t; __device__ __forceinline__ int operator()(int 
 template <class T> struct TgtRev { T t; int te; __device__ __forceinline__ int operator()(int i) const { return i <= te ? t(te - i) : t(i); } };
 
 template <class TGT>
-__device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane)
+__device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt = 0)
 {
 	const int P = bytes ? 16 : 8, slen = (qlen + P - 1) / P, n = slen * P;
 	const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
@@ -117,6 +117,7 @@ __device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen
 		cur ^= 1;
 	}
 	n_b = __shfl_sync(WFULL, n_b, 0);
+	if (cnt && lane == 0) { atomicAdd(cnt + 2, 1ull); atomicAdd(cnt + 3, (unsigned long long)(te < 0 ? tlen : (te + 1 < tlen ? te + 1 : tlen)) * qlen); }
 	r.score = bytes ? (gmax + shift < 255 ? gmax : 255) : gmax;
 	r.te = te;
 	if (!bytes || r.score != 255) {
@@ -142,15 +143,15 @@ __device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen
 
 // forward pass for score/end, then a pass over the reversed prefixes for the start.  q: the query in shared memory (W.q)
 template <class TGT>
-__device__ LocalRes sw_local_warp(const ssq_opts_t &o, int qlen, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane)
+__device__ LocalRes sw_local_warp(const ssq_opts_t &o, int qlen, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt = 0)
 {
 	const bool bytes = (xtra & SSQ_XBYTE) != 0;
-	LocalRes r = sw_local_pass_warp(o, bytes, qlen, W.q, tlen, tgt, xtra, W, b, b_cap, lane);
+	LocalRes r = sw_local_pass_warp(o, bytes, qlen, W.q, tlen, tgt, xtra, W, b, b_cap, lane, cnt);
 	if ((xtra & SSQ_XSTART) == 0 || ((xtra & SSQ_XSUBO) && r.score < (xtra & 0xffff))) return r;
 	for (int i = lane; i <= r.qe; i += 32) W.q2[i] = W.q[r.qe - i];
 	__syncwarp();
 	TgtRev<TGT> rt; rt.t = tgt; rt.te = r.te;
-	const LocalRes rr = sw_local_pass_warp(o, bytes, r.qe + 1, W.q2, tlen, rt, SSQ_XSTOP | r.score, W, b, b_cap, lane);
+	const LocalRes rr = sw_local_pass_warp(o, bytes, r.qe + 1, W.q2, tlen, rt, SSQ_XSTOP | r.score, W, b, b_cap, lane, cnt);
 	if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
 	return r;
 }
@@ -158,7 +159,7 @@ __device__ LocalRes sw_local_warp(const ssq_opts_t &o, int qlen, int tlen, TGT t
 // one mem_matesw() by a warp: control flow is uniform (every lane evaluates the same scalars), lane 0 owns the writes to the
 // mate's region list.  Same contract as ssq_dev2.cuh::mate_rescue
 __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const PeStat *pes, const AlnReg &a, int l_ms, const uint8_t *ms, AlnReg *ma, int *n_ma, int ma_cap,
-                                WarpSwSmem &W, u64 *bl, int b_cap, int lane)
+                                WarpSwSmem &W, u64 *bl, int b_cap, int lane, unsigned long long *wcnt = 0)
 {
 	const i64 l_pac = ix.l_pac;
 	int i, r, skip[4], n = 0, cnt = *n_ma; // cnt: the list length, kept uniform across the lanes (lane 0 changes the list, then broadcasts)
@@ -201,7 +202,7 @@ __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const P
 			const int tlen = (int)(re - rb);
 			const int xtra = SSQ_XSUBO | SSQ_XSTART | (l_ms * o.a < 250 ? SSQ_XBYTE : 0) | (o.min_seed_len * o.a);
 			TgtPac tg; tg.ix = &ix; tg.rb = rb;
-			const LocalRes aln = sw_local_warp(o, l_ms, tlen, tg, xtra, W, bl, b_cap, lane);
+			const LocalRes aln = sw_local_warp(o, l_ms, tlen, tg, xtra, W, bl, b_cap, lane, wcnt);
 			if (aln.score >= o.min_seed_len && aln.qb >= 0) {
 				if (lane == 0 && cnt < ma_cap) {
 					AlnReg b;
@@ -239,11 +240,12 @@ struct WarpGlSmem { i32 H[2][QMAX_W + 16], E[QMAX_W + 16]; uint8_t q[QMAX_W], r[
 
 // banded global alignment of W.q[0..qlen) vs W.r[0..tlen), traceback into cig (lane 0 writes).  z: per-warp global scratch of
 // zcap bytes (null / too small: score only when cig == null, else *n_cig = -1).  Same contract and results as sw_global()
-__device__ int sw_global_warp(const ssq_opts_t &o, int qlen, int tlen, int w, WarpGlSmem &W, uint8_t *z, long zcap, u32 *cig, int cig_cap, int *n_cig, int lane)
+__device__ int sw_global_warp(const ssq_opts_t &o, int qlen, int tlen, int w, WarpGlSmem &W, uint8_t *z, long zcap, u32 *cig, int cig_cap, int *n_cig, int lane, unsigned long long *cells = 0)
 {
 	const int o_del = o.o_del, e_del = o.e_del, o_ins = o.o_ins, e_ins = o.e_ins, oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
 	const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
 	const bool tb = cig != 0 && n_cig != 0;
+	if (cells && lane == 0) atomicAdd(cells, (unsigned long long)n_col * tlen);
 	if (n_cig) *n_cig = 0;
 	if (tb && (long)n_col * tlen > zcap) { *n_cig = -1; return 0; }
 	for (int j = lane; j <= qlen; j += 32) {
@@ -449,7 +451,7 @@ __device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwS
 		const int cap = (int)(V.areg_off[2 * p + !i + 1] - V.areg_off[2 * p + !i]);
 		for (int j = 0; j < nb[i] && j < V.opt.max_matesw; ++j) {
 			const int before = na[!i];
-			if (mate_rescue_warp(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, W, bl, b_cap, lane) < 0 && lane == 0) PIPE_ERR(V, 8);
+			if (mate_rescue_warp(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, W, bl, b_cap, lane, V.cnt) < 0 && lane == 0) PIPE_ERR(V, 8);
 			if (na[!i] >= cap && before < cap && lane == 0) PIPE_ERR(V, 1);
 		}
 	}
