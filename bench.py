@@ -42,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from speedseq_b200 import capi  # noqa: E402  (ctypes bindings of the product's C-ABI; no compute)
 
-GENOME_LEN = 63025520
+GENOME_LEN = 1000000000  # the largest round size the GPU index builder handles (2 x 10^9 suffixes < 2^31); chr20-sized: --genome-len 63025520
 READ_LEN = 150
 SB = dict(exclude_dups=1, add_mate_tags=1, max_split_count=2, min_non_overlap=20)  # bin/speedseq:439 with its defaults (:241-243)
 SB_ARGS = ["--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20"]
