@@ -191,12 +191,32 @@ SSQ_HD int patch_reg(const DevIndex &ix, const ssq_opts_t &o, const uint8_t *que
 	return score;
 }
 
-// query == null disables patching (the call made from mate rescue)
-SSQ_HD int sort_dedup_patch(const DevIndex &ix, const ssq_opts_t &o, const uint8_t *query, int n, AlnReg *a, const AlnScratch &S)
+// The reference sorts the 96-byte records themselves; the order it leaves equal keys in is part of its behaviour, so the SAME
+// introsort runs here — on an index array, comparing through it (identical comparisons and swaps, hence the identical
+// permutation) — and the records are then moved once, cycle by cycle.  idx: n scratch ints; null: sort the records directly
+template <class LT> struct IdxLt { const AlnReg *a; LT lt; SSQ_HD bool operator()(i32 x, i32 y) const { return lt(a[x], a[y]); } };
+template <class LT>
+SSQ_HD void sort_regs(int n, AlnReg *a, i32 *idx, LT lt)
+{
+	if (!idx || n < 8) { ks_introsort((long)n, a, lt); return; }
+	for (int i = 0; i < n; ++i) idx[i] = i;
+	IdxLt<LT> il; il.a = a; il.lt = lt;
+	ks_introsort((long)n, idx, il);
+	for (int s = 0; s < n; ++s) { // position k takes record idx[k]
+		if (idx[s] == s) continue;
+		const AlnReg tmp = a[s];
+		int j = s;
+		while (idx[j] != s) { const int nj = idx[j]; a[j] = a[nj]; idx[j] = j; j = nj; }
+		a[j] = tmp; idx[j] = j;
+	}
+}
+
+// query == null disables patching (the call made from mate rescue); idx: optional n scratch ints (see sort_regs)
+SSQ_HD int sort_dedup_patch(const DevIndex &ix, const ssq_opts_t &o, const uint8_t *query, int n, AlnReg *a, const AlnScratch &S, i32 *idx = 0)
 {
 	int m, i, j;
 	if (n <= 1) return n;
-	ks_introsort((long)n, a, Ars2Lt());
+	sort_regs(n, a, idx, Ars2Lt());
 	for (i = 0; i < n; ++i) a[i].n_comp = 1;
 	for (i = 1; i < n; ++i) {
 		AlnReg &p = a[i];
@@ -227,7 +247,7 @@ SSQ_HD int sort_dedup_patch(const DevIndex &ix, const ssq_opts_t &o, const uint8
 	}
 	for (i = 0, m = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
 	n = m;
-	ks_introsort((long)n, a, ArsLt());
+	sort_regs(n, a, idx, ArsLt());
 	for (i = 1; i < n; ++i) if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
 	for (i = 1, m = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
 	return m;
@@ -366,7 +386,7 @@ struct MateScratch { uint8_t *seq, *ref; int ref_cap; LocalScratch L; AlnScratch
 // region list (capacity ma_cap), kept sorted by score and de-duplicated.  Returns the number of windows aligned, -1 when a window
 // does not fit S.ref_cap (callers size the scratch from the batch's insert-size bounds and treat -1 as an error)
 SSQ_HD int mate_rescue(const DevIndex &ix, const ssq_opts_t &o, const PeStat pes[4], const AlnReg &a, int l_ms, const uint8_t *ms, AlnReg *ma, int *n_ma, int ma_cap,
-                       const MateScratch &S)
+                       const MateScratch &S, i32 *idx = 0)
 {
 	const i64 l_pac = ix.l_pac;
 	int i, r, skip[4], n = 0;
@@ -427,7 +447,7 @@ SSQ_HD int mate_rescue(const DevIndex &ix, const ssq_opts_t &o, const PeStat pes
 			}
 			++n;
 		}
-		if (n) *n_ma = sort_dedup_patch(ix, o, 0, *n_ma, ma, S.A);
+		if (n) *n_ma = sort_dedup_patch(ix, o, 0, *n_ma, ma, S.A, idx);
 	}
 	return n;
 }

@@ -62,12 +62,12 @@ SSQ_HD bool pestat_pair(const ssq_opts_t &o, i64 l_pac, const AlnReg *r0, int n0
 }
 
 // ---- primary marking ----
-SSQ_HD int mark_primary_d(const ssq_opts_t &o, int n, AlnReg *a, i64 id)
+SSQ_HD int mark_primary_d(const ssq_opts_t &o, int n, AlnReg *a, i64 id, i32 *idx = 0)
 {
 	if (n == 0) return 0;
 	for (int i = 0; i < n; ++i) { a[i].sub = 0; a[i].secondary = a[i].secondary_all = -1; a[i].hash = hash64_d((u64)(id + i)); }
 	// (score desc, hash asc) is a total order (hash64 is a bijection), so any sort gives the reference's permutation
-	if (n <= 12) ks_isort(a, 0, n, ArsHashLt()); else ks_introsort((long)n, a, ArsHashLt());
+	if (n <= 12) ks_isort(a, 0, n, ArsHashLt()); else sort_regs(n, a, idx, ArsHashLt());
 	int tmp = o.a + o.b;
 	tmp = o.o_del + o.e_del > tmp ? o.o_del + o.e_del : tmp;
 	tmp = o.o_ins + o.e_ins > tmp ? o.o_ins + o.e_ins : tmp;
@@ -223,7 +223,7 @@ SSQ_HD void plan_reg2sam(const ssq_opts_t &o, const MathTabs &T, TaskSink &s, in
 }
 SSQ_HD void plan_single(const ssq_opts_t &o, const MathTabs &T, int read, AlnReg *a, int n, i64 id, TaskSink &s, ReadMeta &m, i32 *cnt)
 {
-	mark_primary_d(o, n, a, id);
+	mark_primary_d(o, n, a, id, cnt);
 	plan_reg2sam(o, T, s, read, a, n, 0, cnt);
 	m.n_tasks = (u32)s.n; m.n_lines = (u32)s.lines; m.extra_flag = 0; m.mode = 1; m.has_hdr = 0;
 }
@@ -233,8 +233,8 @@ SSQ_HD void plan_pair(const ssq_opts_t &o, const DevIndex &ix, const MathTabs &T
                       TaskSink s[2], ReadMeta m[2], P64 *v, i32 *cnt[2])
 {
 	int z[2] = {0, 0}, osc = 0, subo = 0, n_sub = 0, extra_flag = 1;
-	mark_primary_d(o, n[0], a[0], id << 1 | 0);
-	mark_primary_d(o, n[1], a[1], id << 1 | 1);
+	mark_primary_d(o, n[0], a[0], id << 1 | 0, cnt[0]);
+	mark_primary_d(o, n[1], a[1], id << 1 | 1, cnt[1]);
 	bool pairing = false;
 	if (n[0] && n[1] && (osc = mem_pair_d(o, ix, T, pes, a, n, id, &subo, &n_sub, z, v)) > 0) {
 		bool multi = false;
@@ -574,7 +574,7 @@ SSQ_HD void body_dedup(const PipeView &V, int r, const AlnScratch &A)
 	const int n0 = (int)V.n_regs[r];
 	AlnReg *a = V.areg + V.areg_off[r];
 	for (int i = 0; i < n0; ++i) reg_from_cand(V.regs[V.task_off[r] + i], a[i]);
-	V.n_areg[r] = (u32)sort_dedup_patch(V.ix, V.opt, V.tc.seq + V.tc.read_off[r], n0, a, A);
+	V.n_areg[r] = (u32)sort_dedup_patch(V.ix, V.opt, V.tc.seq + V.tc.read_off[r], n0, a, A, V.xcnt + V.areg_off[r]);
 }
 // stage 2: a pair's vote in the insert-size histogram; returns true when it voted
 SSQ_HD bool body_pestat(const PipeView &V, int p, int *dir, i64 *is)
@@ -621,7 +621,7 @@ SSQ_HD void body_rescue(const PipeView &V, int p, AlnReg *bbuf, const MateScratc
 		const int cap = (int)(V.areg_off[2 * p + !i + 1] - V.areg_off[2 * p + !i]);
 		for (int j = 0; j < nb[i] && j < V.opt.max_matesw; ++j) {
 			const int before = na[!i];
-			if (mate_rescue(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, M) < 0) PIPE_ERR(V, 8);
+			if (mate_rescue(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, M, V.xcnt + V.areg_off[2 * p + !i]) < 0) PIPE_ERR(V, 8);
 			if (na[!i] >= cap && before < cap) PIPE_ERR(V, 1);
 		}
 	}

@@ -159,15 +159,19 @@ __device__ LocalRes sw_local_warp(const ssq_opts_t &o, int qlen, int tlen, TGT t
 // one mem_matesw() by a warp: control flow is uniform (every lane evaluates the same scalars), lane 0 owns the writes to the
 // mate's region list.  Same contract as ssq_dev2.cuh::mate_rescue
 __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const PeStat *pes, const AlnReg &a, int l_ms, const uint8_t *ms, AlnReg *ma, int *n_ma, int ma_cap,
-                                WarpSwSmem &W, u64 *bl, int b_cap, int lane, unsigned long long *wcnt = 0)
+                                WarpSwSmem &W, u64 *bl, int b_cap, int lane, unsigned long long *wcnt = 0, i32 *idx = 0)
 {
 	const i64 l_pac = ix.l_pac;
 	int i, r, skip[4], n = 0, cnt = *n_ma; // cnt: the list length, kept uniform across the lanes (lane 0 changes the list, then broadcasts)
-	for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
-	for (i = 0; i < cnt; ++i) {
-		i64 dist;
-		r = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
-		if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+	{ // the skip test looks at every hit of the mate: lanes take hits round-robin, one vote per orientation
+		int mine = 0;
+		for (i = lane; i < cnt; i += 32) {
+			i64 dist;
+			r = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
+			if (dist >= pes[r].low && dist <= pes[r].high) mine |= 1 << r;
+		}
+		mine = __reduce_or_sync(WFULL, mine);
+		for (r = 0; r < 4; ++r) skip[r] = (pes[r].failed || (mine >> r & 1)) ? 1 : 0;
 	}
 	if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
 	AlnScratch noA; noA.qbuf = noA.rbuf = 0; noA.rcap = 0; noA.g.h = noA.g.e = 0; noA.g.z = 0; noA.g.zcap = 0;
@@ -225,7 +229,7 @@ __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const P
 		}
 		if (n) {
 			int c2 = cnt;
-			if (lane == 0) c2 = sort_dedup_patch(ix, o, 0, cnt, ma, noA);
+			if (lane == 0) c2 = sort_dedup_patch(ix, o, 0, cnt, ma, noA, idx);
 			cnt = __shfl_sync(WFULL, c2, 0);
 			__syncwarp();
 		}
@@ -441,17 +445,24 @@ __device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwS
 	AlnReg *b[2] = {bbuf, bbuf + 64};
 	int nb[2] = {0, 0}, na[2];
 	AlnReg *a[2];
-	for (int i = 0; i < 2; ++i) {
+	for (int i = 0; i < 2; ++i) { // snapshot of the near-best hits of both ends: lanes pick the qualifying hits by ballot, then copy them 16 bytes at a time
 		a[i] = V.areg + V.areg_off[2 * p + i]; na[i] = (int)V.n_areg[2 * p + i];
-		for (int j = 0; j < na[i]; ++j)
-			if (a[i][j].score >= a[i][0].score - V.opt.pen_unpaired && nb[i] < 64) { if (lane == 0) b[i][nb[i]] = a[i][j]; ++nb[i]; }
+		const int thr = na[i] ? a[i][0].score - V.opt.pen_unpaired : 0;
+		for (int j0 = 0; j0 < na[i] && nb[i] < 64; j0 += 32) {
+			const int j = j0 + lane;
+			const bool q = j < na[i] && a[i][j].score >= thr;
+			const unsigned m = __ballot_sync(WFULL, q);
+			const int at = nb[i] + __popc(m & ((1u << lane) - 1));
+			if (q && at < 64) { const uint4 *src = (const uint4*)&a[i][j]; uint4 *dst = (uint4*)&b[i][at]; for (int k = 0; k < (int)(sizeof(AlnReg) / 16); ++k) dst[k] = src[k]; }
+			nb[i] += __popc(m); if (nb[i] > 64) nb[i] = 64;
+		}
 	}
 	__syncwarp();
 	for (int i = 0; i < 2; ++i) {
 		const int cap = (int)(V.areg_off[2 * p + !i + 1] - V.areg_off[2 * p + !i]);
 		for (int j = 0; j < nb[i] && j < V.opt.max_matesw; ++j) {
 			const int before = na[!i];
-			if (mate_rescue_warp(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, W, bl, b_cap, lane, V.cnt) < 0 && lane == 0) PIPE_ERR(V, 8);
+			if (mate_rescue_warp(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, W, bl, b_cap, lane, V.cnt, V.xcnt + V.areg_off[2 * p + !i]) < 0 && lane == 0) PIPE_ERR(V, 8);
 			if (na[!i] >= cap && before < cap && lane == 0) PIPE_ERR(V, 1);
 		}
 	}
