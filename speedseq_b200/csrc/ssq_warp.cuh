@@ -445,7 +445,7 @@ __device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwS
 	AlnReg *b[2] = {bbuf, bbuf + 64};
 	int nb[2] = {0, 0}, na[2];
 	AlnReg *a[2];
-	for (int i = 0; i < 2; ++i) { // snapshot of the near-best hits of both ends: lanes pick the qualifying hits by ballot, then copy them 16 bytes at a time
+	for (int i = 0; i < 2; ++i) { // snapshot of the near-best hits of both ends: lanes pick the qualifying hits by ballot and copy one record each
 		a[i] = V.areg + V.areg_off[2 * p + i]; na[i] = (int)V.n_areg[2 * p + i];
 		const int thr = na[i] ? a[i][0].score - V.opt.pen_unpaired : 0;
 		for (int j0 = 0; j0 < na[i] && nb[i] < 64; j0 += 32) {
@@ -453,7 +453,7 @@ __device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwS
 			const bool q = j < na[i] && a[i][j].score >= thr;
 			const unsigned m = __ballot_sync(WFULL, q);
 			const int at = nb[i] + __popc(m & ((1u << lane) - 1));
-			if (q && at < 64) { const uint4 *src = (const uint4*)&a[i][j]; uint4 *dst = (uint4*)&b[i][at]; for (int k = 0; k < (int)(sizeof(AlnReg) / 16); ++k) dst[k] = src[k]; }
+			if (q && at < 64) b[i][at] = a[i][j];
 			nb[i] += __popc(m); if (nb[i] > 64) nb[i] = 64;
 		}
 	}
