@@ -32,6 +32,7 @@ extern "C" {
 #define SSQ_ECAP     (-5)  /* caller buffer too small; required size returned through *needed */
 #define SSQ_ECUDA    (-6)  /* a CUDA call failed; see ssq_last_error() */
 #define SSQ_ELEN     (-7)  /* a read is longer than SSQ_MAX_READ_LEN */
+#define SSQ_EFORMAT  (-8)  /* FASTQ text the device tokeniser does not take (see ssq_aligner_upload_fastq); use the host tokeniser */
 
 #define SSQ_MAX_READ_LEN 255
 
@@ -219,6 +220,18 @@ int ssq_aligner_run(ssq_aligner_t *al, const ssq_reads_t *reads, const ssq_pesta
 /* the three phases of ssq_aligner_run, separately (bench.py times `compute` with the reads resident in HBM) */
 int ssq_aligner_upload(ssq_aligner_t *al, const ssq_reads_t *reads);
 int ssq_aligner_compute(ssq_aligner_t *al, const ssq_pestat_t *pes0, int verbose);
+/* FASTQ ingest on the device instead of ssq_aligner_upload (upstream bseq_read -> kseq_read inside `$BWA mem`, speedseq:438,468;
+ * tokenisation rules of /root/reference/src/samtools-1.3.1/htslib-1.3.1/htslib/kseq.h:189-231).  fq1 / fq2: raw, uncompressed text of
+ * the FASTQ input(s) from a record boundary on (fq2 == NULL: one file; interleaved: adjacent records are mates, `-p`); final: no
+ * more text follows.  The device finds the records, closes the batch where bwa would (bases >= chunk_bases and an even number of
+ * reads), strips /1 /2, and packs names, bases, qualities and (keep_comment, `-C`) comments into the aligner's batch buffers;
+ * *used1 / *used2 = bytes of each text the batch covers (the caller keeps the rest for the next call).  *need_more: no complete
+ * batch in the text and more text exists -> call again with more.  SSQ_EFORMAT: not the four-lines-per-record layout (multi-line
+ * records, FASTA, unpaired reads in an interleaved file, files of different lengths): nothing was consumed, tokenise on the host. */
+int ssq_aligner_upload_fastq(ssq_aligner_t *al, const char *fq1, size_t len1, int final1, const char *fq2, size_t len2, int final2, int interleaved, int keep_comment,
+                             int64_t chunk_bases, int64_t n_processed, size_t *used1, size_t *used2, int *n_reads, int *need_more);
+void *ssq_host_alloc(size_t bytes); /* page-locked host memory for the text buffers (full-rate host->device copies) */
+void ssq_host_free(void *p);
 int ssq_aligner_fetch(ssq_aligner_t *al, ssq_sam_t *out);
 int ssq_aligner_reset_dups(ssq_aligner_t *al);     /* forget every signature seen so far (a new run) */
 /* several aligner objects (one host thread + stream each) can work on consecutive batches of ONE run: they share a dup-set, and
@@ -231,7 +244,7 @@ void *ssq_aligner_stream(ssq_aligner_t *al);       /* cudaStream_t of the object
 float ssq_aligner_stage_ms(const ssq_aligner_t *al, int stage);
 /* what < 100: ssq_batch_counter of the alignment stage; 100 alignments written (CIGAR tasks), 101-103 bytes of the three streams, 104 dup-set size,
  * 105 pairs that went through mate rescue, 106 alignments that needed the banded global DP for their CIGAR,
- * 107 local-SW passes run by the mate rescue, 108 their cells */
+ * 107 local-SW passes run by the mate rescue, 108 their cells, 109 bases / 110 reads of the batch in the aligner */
 uint64_t ssq_aligner_counter(const ssq_aligner_t *al, int what);
 void ssq_aligner_free(ssq_aligner_t *al);
 

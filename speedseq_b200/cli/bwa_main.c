@@ -32,14 +32,40 @@ typedef struct { gzFile fp; unsigned char *buf; int beg, end, eof, last; } fq_t;
 typedef struct { char *s; size_t l, m; } str_t;
 typedef struct { str_t name, comment, seq, qual; } rec_t;
 
-static fq_t *fq_open(const char *fn)
+/* raw text of an input for the device tokeniser (ssq_aligner_upload_fastq): page-locked, refilled from the (possibly gzipped) file */
+typedef struct { gzFile fp; char *buf; size_t len, cap; int eof; } raw_t;
+static int raw_open(raw_t *r, const char *fn)
 {
-	gzFile fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(0, "r");
-	fq_t *f;
-	if (!fp) return 0;
-	gzbuffer(fp, 1 << 20);
-	f = (fq_t*)calloc(1, sizeof(fq_t));
-	f->fp = fp; f->buf = (unsigned char*)malloc(1 << 18);
+	memset(r, 0, sizeof *r);
+	r->fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(0, "r");
+	if (!r->fp) return -1;
+	gzbuffer(r->fp, 1 << 20);
+	return 0;
+}
+static void raw_fill(raw_t *r, size_t want)
+{
+	while (!r->eof && r->len < want) {
+		int n;
+		if (r->cap < want) {
+			const size_t ncap = want + want / 4;
+			char *nb = (char*)ssq_host_alloc(ncap);
+			if (!nb) { fprintf(stderr, "[E::bwa] cannot allocate %zu bytes of page-locked memory\n", ncap); exit(1); }
+			if (r->len) memcpy(nb, r->buf, r->len);
+			ssq_host_free(r->buf); r->buf = nb; r->cap = ncap;
+		}
+		n = gzread(r->fp, r->buf + r->len, (unsigned)((r->cap - r->len) < (1u << 30) ? (r->cap - r->len) : (1u << 30)));
+		if (n <= 0) r->eof = 1; else r->len += (size_t)n;
+	}
+}
+/* hand the rest of a raw reader (its unconsumed bytes, then the file) to the host tokeniser */
+static fq_t *fq_from_raw(raw_t *r)
+{
+	fq_t *f = (fq_t*)calloc(1, sizeof(fq_t));
+	const size_t cap = r->len > (1u << 18) ? r->len : (1u << 18);
+	f->fp = r->fp; f->buf = (unsigned char*)malloc(cap);
+	if (r->len) memcpy(f->buf, r->buf, r->len);
+	f->beg = 0; f->end = (int)r->len; f->eof = 0; /* a further gzread reports the end again */
+	ssq_host_free(r->buf); r->buf = 0; r->len = r->cap = 0;
 	return f;
 }
 static inline int fq_getc(fq_t *f)
@@ -199,8 +225,11 @@ static int main_mem(int argc, char **argv, const char *prog)
 	ssq_pestat_t pes[4], *pes0 = 0;
 	ssq_index_t *idx = 0;
 	ssq_aligner_t *al = 0;
-	fq_t *f1, *f2 = 0;
+	fq_t *f1 = 0, *f2 = 0;
+	raw_t R1, R2;
 	rec_t r1, r2;
+	int dev_ingest = 0, two_files = 0;
+	size_t raw_target;
 	blob_t v, se, pe;
 	char *rg_line = 0, rg_id[256] = "", *p, fuse_opts[1024] = "";
 	int c, i, n_threads = 1, smart_pe = 0, paired = 0, keep_comment = 0, device = getenv("SSQ_DEVICE") ? atoi(getenv("SSQ_DEVICE")) : 0, rc, fused = 0;
@@ -252,11 +281,13 @@ static int main_mem(int argc, char **argv, const char *prog)
 	}
 	if ((rc = ssq_index_load(argv[optind], device, &idx))) die("ssq_index_load", rc);
 	if ((rc = ssq_aligner_create(idx, &opt, fused ? &sb : 0, rg_id, &al))) die("ssq_aligner_create", rc);
-	if (!(f1 = fq_open(argv[optind + 1]))) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 1]); return 1; }
+	if (raw_open(&R1, argv[optind + 1])) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 1]); return 1; }
 	if (optind + 2 < argc) {
 		if (smart_pe) fprintf(stderr, "[W::main_mem] when '-p' is in use, the second query file is ignored.\n");
-		else { if (!(f2 = fq_open(argv[optind + 2]))) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 2]); return 1; } paired = 1; }
+		else { if (raw_open(&R2, argv[optind + 2])) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 2]); return 1; } paired = 1; two_files = 1; }
 	}
+	dev_ingest = !(getenv("SSQ_HOST_FASTQ") && atoi(getenv("SSQ_HOST_FASTQ"))); /* the device tokenises; the host tokeniser takes over when the text is not four-line FASTQ */
+	if (!dev_ingest) { f1 = fq_from_raw(&R1); if (two_files) f2 = fq_from_raw(&R2); }
 	{ /* header: @SQ from the index, @RG as given, @PG with the command line */
 		const int ns = (int)ssq_index_info(idx, 3);
 		static char obuf[1 << 22];
@@ -268,11 +299,41 @@ static int main_mem(int argc, char **argv, const char *prog)
 		printf("\n");
 		if (fused) printf("%s%s\n", SSQ_FUSE_MARKER, fuse_opts);
 	}
+	if (!two_files) memset(&R2, 0, sizeof R2);
+	raw_target = (size_t)((double)chunk_size * n_threads * 2.7 / (two_files ? 2 : 1)) + (1u << 20); /* bytes of text one batch is expected to span */
 	for (;;) {
-		const long size = read_batch(chunk_size * n_threads, f1, f2, &r1, &r2, &v, keep_comment);
+		long size;
 		ssq_reads_t rd;
 		ssq_sam_t out;
 		int n_se = 0, n_pe = 0, mixed = 0;
+		if (dev_ingest) { /* FASTQ text -> device -> records; the batch is cut on the device by bwa's rule */
+			size_t u1 = 0, u2 = 0;
+			int n = 0, more = 0;
+			raw_fill(&R1, raw_target);
+			if (two_files) raw_fill(&R2, raw_target);
+			rc = ssq_aligner_upload_fastq(al, R1.buf ? R1.buf : "", R1.len, R1.eof, two_files ? (R2.buf ? R2.buf : "") : 0, R2.len, R2.eof, smart_pe, keep_comment, chunk_size * n_threads, n_processed,
+			                              &u1, &u2, &n, &more);
+			if (rc == SSQ_EFORMAT) { /* every other legal input: multi-line records, FASTA, unpaired reads among the pairs, ... */
+				if (getenv("SSQ_VERBOSE_INGEST")) fprintf(stderr, "[M::bwa] host tokeniser takes over: %s\n", ssq_last_error());
+				f1 = fq_from_raw(&R1); if (two_files) f2 = fq_from_raw(&R2);
+				dev_ingest = 0;
+				continue;
+			}
+			if (rc) die("ssq_aligner_upload_fastq", rc);
+			if (more) { raw_target += raw_target / 2; continue; }
+			if (n == 0) break;
+			fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)ssq_aligner_counter(al, 109));
+			if (smart_pe) fprintf(stderr, "[M::process] 0 single-end sequences; %d paired-end sequences\n", n);
+			if ((rc = ssq_aligner_compute(al, paired ? pes0 : 0, 1))) die("ssq_aligner_compute", rc);
+			if ((rc = ssq_aligner_fetch(al, &out))) die("ssq_aligner_fetch", rc);
+			if (fused) { put_frame(0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
+			else fwrite(out.text[0], 1, out.len[0], stdout);
+			memmove(R1.buf, R1.buf + u1, R1.len - u1); R1.len -= u1;
+			if (two_files) { memmove(R2.buf, R2.buf + u2, R2.len - u2); R2.len -= u2; }
+			n_processed += n;
+			continue;
+		}
+		size = read_batch(chunk_size * n_threads, f1, f2, &r1, &r2, &v, keep_comment);
 		if (v.n == 0) break;
 		fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", v.n, size);
 		if (smart_pe) { /* interleaved input: adjacent reads with equal names are mates, the others single-end */

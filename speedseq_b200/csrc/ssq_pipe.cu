@@ -253,6 +253,8 @@ struct ssq_aligner {
 	DBuf d_logn, d_lg, d_ctg_names, d_ctg_off, d_sb_off, d_rg;
 	// batch inputs
 	DBuf d_ascii, d_qual, d_names, d_name_off, d_cmt, d_cmt_off;
+	// FASTQ ingest on the device: raw text of the two inputs, newline positions, per-record fields
+	DBuf fq_txt[2], fq_nl[2], fq_rec[2], fq_len, fq_cum, fq_res, fq_nlen, fq_clen, fq_noff, fq_coff;
 	int n_reads, paired, has_qual, has_cmt; i64 n_processed; u64 total_bases; int max_len;
 	// stages
 	DBuf cubtmp, d_cap, d_aoff, d_na, d_areg, d_work, d_pes, d_hist, d_pen, d_slab /* per-thread scratch of whichever slab kernel runs (dedup, rescue, CIGAR tiers: never live together) */, d_rlist, d_tcap, d_tsoff, d_tslots, d_meta, d_pv, d_xcnt,
@@ -370,7 +372,7 @@ extern "C" uint64_t ssq_aligner_counter(const ssq_aligner_t *a, int what)
 {
 	if (!a) return 0;
 	if (what < 100) return ssq_batch_counter(a->b, what);
-	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); case 105: return a->n_rescue_pairs; case 106: return a->n_gapped; case 107: return a->n_sw_local; case 108: return a->sw_local_cells; }
+	switch (what) { case 100: return a->n_tasks_total; case 101: return a->text_len[0]; case 102: return a->text_len[1]; case 103: return a->text_len[2]; case 104: return ssq_dupset_size(a->dups); case 105: return a->n_rescue_pairs; case 106: return a->n_gapped; case 107: return a->n_sw_local; case 108: return a->sw_local_cells; case 109: return a->total_bases; case 110: return (u64)a->n_reads; }
 	return 0;
 }
 
@@ -648,5 +650,199 @@ extern "C" int ssq_sw_local_batch(const ssq_opts_t *opt, int device, uint64_t n,
 	k_sw_local_tasks<<<(unsigned)((n + 3) / 4), 128>>>(*opt, n, dt.as<ssq_swl_task_t>(), dq.as<uint8_t>(), dtb.as<uint8_t>(), dout.as<ssq_swl_result_t>(), dbl.as<u64>(), b_cap);
 	CK(cudaGetLastError());
 	CK(cudaMemcpy(out, dout.p, n * sizeof(ssq_swl_result_t), cudaMemcpyDeviceToHost));
+	return SSQ_OK;
+}
+
+
+// ============================================================== FASTQ ingest on the device ====
+// Upstream bseq_read() -> kseq_read() (`$BWA mem`, /root/reference/bin/speedseq:438,468); tokenisation rules of the reference's
+// in-tree parser /root/reference/src/samtools-1.3.1/htslib-1.3.1/htslib/kseq.h:189-231, restricted to the layout sequencers
+// write: four lines per record ('@name[ comment]', bases, '+...', qualities).  Anything else (multi-line records, FASTA, blank
+// lines, unequal files) is REPORTED (SSQ_EFORMAT) and left to the caller's host tokeniser, which handles every legal input.
+//   k_fq_records   thread per record: field extents from the newline positions, checks, name without /1 /2, comment, lengths
+//   scans          cumulative bases (the batch rule: bases >= chunk and an even number of reads), offsets of the packed fields
+//   k_fq_cut       first record index at which bwa would close the batch
+//   k_fq_gather    thread per read: copies name / bases / qualities / comment into the aligner's concatenated batch buffers
+struct FqRec { u32 name_b, name_l, cmt_b, cmt_l, seq_b, seq_l, qual_b, bad; };
+struct NlPred { const char *t; __device__ bool operator()(const u32 &i) const { return t[i] == '\n'; } };
+
+__global__ void __launch_bounds__(256) k_fq_records(const char *__restrict__ txt, const u32 *__restrict__ nl, u32 n_lines, u32 txt_len, u32 n_rec, FqRec *rec, int *bad)
+{
+	const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_rec) return;
+	u32 b[4], e[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const u32 li = 4 * r + k;
+		b[k] = li ? nl[li - 1] + 1 : 0;
+		e[k] = li < n_lines ? nl[li] : txt_len; // a final line without '\n'
+		if (e[k] > b[k] && txt[e[k] - 1] == '\r') --e[k];
+	}
+	FqRec o; o.bad = 0;
+	if (e[0] == b[0] || txt[b[0]] != '@' || e[2] == b[2] || txt[b[2]] != '+' || e[1] - b[1] != e[3] - b[3] || e[1] - b[1] > SSQ_MAX_READ_LEN) o.bad = 1;
+	u32 p = b[0] + 1;
+	while (p < e[0] && !(txt[p] == ' ' || (txt[p] >= 9 && txt[p] <= 13))) ++p; // isspace
+	o.name_b = b[0] + 1; o.name_l = p - (b[0] + 1);
+	o.cmt_b = p < e[0] ? p + 1 : e[0]; o.cmt_l = e[0] - o.cmt_b;
+	if (o.name_l > 2 && txt[o.name_b + o.name_l - 2] == '/' && txt[o.name_b + o.name_l - 1] >= '0' && txt[o.name_b + o.name_l - 1] <= '9') o.name_l -= 2;
+	if (o.name_l == 0) o.bad = 1;
+	o.seq_b = b[1]; o.seq_l = e[1] - b[1]; o.qual_b = b[3];
+	for (u32 q = b[1]; q < e[1]; ++q) if (txt[q] == ' ' || txt[q] == '\t') o.bad = 1; // kseq would stop the sequence at white space
+	rec[r] = o;
+	if (o.bad) atomicExch(bad, 1);
+}
+// bases per unit (two files: record i of both; one file: record i)
+__global__ void k_fq_unit_len(u32 n, const FqRec *__restrict__ r1, const FqRec *__restrict__ r2, u64 *len)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) len[i] = (u64)r1[i].seq_l + (r2 ? r2[i].seq_l : 0);
+}
+// cum = exclusive scan of len.  res[0] = first unit index closing the batch (two files: cum(i+1) >= chunk; one file: additionally i odd), else n
+__global__ void k_fq_cut(u32 n, const u64 *__restrict__ cum, const u64 *__restrict__ len, u64 chunk, int one_file, unsigned int *res)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (cum[i] + len[i] >= chunk && (!one_file || (i & 1))) atomicMin(res, i);
+}
+__global__ void k_fq_pairnames(u32 n_pairs, const char *__restrict__ t1, const FqRec *__restrict__ r1, const char *__restrict__ t2, const FqRec *__restrict__ r2, int stride, int *bad)
+{
+	const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_pairs) return;
+	const FqRec a = r1[stride == 2 ? 2 * p : p], b = stride == 2 ? r1[2 * p + 1] : r2[p];
+	const char *ta = t1, *tb = stride == 2 ? t1 : t2;
+	bool same = a.name_l == b.name_l;
+	for (u32 k = 0; same && k < a.name_l; ++k) same = ta[a.name_b + k] == tb[b.name_b + k];
+	if (!same) atomicExch(bad, 2);
+}
+// field lengths of read i of the batch (read i = record i of file 1, or records i/2 of files 1/2 alternately)
+__global__ void k_fq_read_lens(u32 n_reads, const FqRec *__restrict__ r1, const FqRec *__restrict__ r2, int keep_comment, u64 *slen, u64 *nlen, u64 *clen, unsigned int *max_len)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_reads) return;
+	const FqRec r = r2 ? ((i & 1) ? r2[i >> 1] : r1[i >> 1]) : r1[i];
+	slen[i] = r.seq_l; nlen[i] = r.name_l; clen[i] = keep_comment ? r.cmt_l : 0;
+	atomicMax(max_len, r.seq_l);
+}
+__global__ void __launch_bounds__(128) k_fq_gather(u32 n_reads, const char *__restrict__ t1, const FqRec *__restrict__ r1, const char *__restrict__ t2, const FqRec *__restrict__ r2, int keep_comment,
+                                                   const u64 *__restrict__ soff, const u64 *__restrict__ noff64, const u64 *__restrict__ coff64, char *seq, char *qual, char *names, char *cmt,
+                                                   u64 *read_off, u32 *name_off, u32 *cmt_off)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n_reads) return;
+	read_off[i] = soff[i]; name_off[i] = (u32)noff64[i]; cmt_off[i] = (u32)coff64[i];
+	if (i == n_reads) return;
+	const bool second = r2 && (i & 1);
+	const FqRec r = r2 ? (second ? r2[i >> 1] : r1[i >> 1]) : r1[i];
+	const char *t = second ? t2 : t1;
+	for (u32 k = 0; k < r.seq_l; ++k) { seq[soff[i] + k] = t[r.seq_b + k]; qual[soff[i] + k] = t[r.qual_b + k]; }
+	for (u32 k = 0; k < r.name_l; ++k) names[noff64[i] + k] = t[r.name_b + k];
+	if (keep_comment) for (u32 k = 0; k < r.cmt_l; ++k) cmt[coff64[i] + k] = t[r.cmt_b + k];
+}
+
+extern "C" void *ssq_host_alloc(size_t bytes) { void *p = 0; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : 0; }
+extern "C" void ssq_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int ssq_aligner_upload_fastq(ssq_aligner_t *a, const char *fq1, size_t len1, int final1, const char *fq2, size_t len2, int final2, int interleaved, int keep_comment,
+                                        int64_t chunk_bases, int64_t n_processed, size_t *used1, size_t *used2, int *n_reads_out, int *need_more)
+{
+	if (!a || !fq1 || !used1 || !n_reads_out || !need_more || (fq2 && !used2) || chunk_bases <= 0) return SSQ_EINVAL;
+	if (len1 >= 0xfffffff0ull || len2 >= 0xfffffff0ull) { ssq_set_error("ssq_aligner_upload_fastq: at most 4 GB of text per call"); return SSQ_EINVAL; }
+	int rc = ssq_use_device(a->device);
+	if (rc) return rc;
+	cudaStream_t st = a->st;
+	*used1 = 0; if (used2) *used2 = 0; *n_reads_out = 0; *need_more = 0;
+	a->computed = 0;
+	CK(cudaEventRecord(a->ev[ST_UPLOAD], st));
+	const int nf = fq2 ? 2 : 1;
+	const char *src[2] = {fq1, fq2}; const size_t len[2] = {len1, len2}; const int fin[2] = {final1, final2};
+	u32 n_lines[2] = {0, 0}, n_rec[2] = {0, 0};
+	if (a->fq_res.need(256)) return SSQ_ENOMEM;
+	CK(cudaMemsetAsync(a->fq_res.p, 0, 256, st));
+	int *d_bad = a->fq_res.as<int>(); unsigned int *d_cut = (unsigned int*)a->fq_res.p + 1, *d_maxlen = (unsigned int*)a->fq_res.p + 2; u64 *d_cnt = (u64*)a->fq_res.p + 2;
+	for (int f = 0; f < nf; ++f) { // text to the device, newline positions, records
+		if (a->fq_txt[f].need(len[f] + 16) || a->fq_nl[f].need((len[f] / 2 + 16) * 4)) return SSQ_ENOMEM; // a record line is at least 1 byte + '\n'
+		if (len[f]) CK(cudaMemcpyAsync(a->fq_txt[f].p, src[f], len[f], cudaMemcpyHostToDevice, st));
+		if (len[f]) {
+			size_t tb = 0;
+			cub::CountingInputIterator<u32> it(0);
+			NlPred pr; pr.t = a->fq_txt[f].as<char>();
+			cub::DeviceSelect::If(0, tb, it, a->fq_nl[f].as<u32>(), d_cnt, (int)len[f], pr, st);
+			if (a->cubtmp.need(tb)) return SSQ_ENOMEM;
+			CK(cub::DeviceSelect::If(a->cubtmp.p, tb, it, a->fq_nl[f].as<u32>(), d_cnt, (int)len[f], pr, st));
+			u64 h = 0;
+			CK(cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			n_lines[f] = (u32)h;
+		}
+		u32 total_lines = n_lines[f];
+		if (fin[f] && len[f] && src[f][len[f] - 1] != '\n') ++total_lines; // the last line has no newline
+		n_rec[f] = total_lines / 4;
+		if (fin[f] && (total_lines & 3)) { ssq_set_error("FASTQ text does not end on a record boundary"); return SSQ_EFORMAT; }
+		if (a->fq_rec[f].need(((size_t)n_rec[f] + 1) * sizeof(FqRec))) return SSQ_ENOMEM;
+		if (n_rec[f]) k_fq_records<<<(n_rec[f] + 255) / 256, 256, 0, st>>>(a->fq_txt[f].as<char>(), a->fq_nl[f].as<u32>(), n_lines[f], (u32)len[f], n_rec[f], a->fq_rec[f].as<FqRec>(), d_bad);
+	}
+	if (nf == 2 && final1 && final2 && n_rec[0] != n_rec[1]) { ssq_set_error("the two FASTQ files hold different numbers of records"); return SSQ_EFORMAT; }
+	const u32 n_units = nf == 2 ? (n_rec[0] < n_rec[1] ? n_rec[0] : n_rec[1]) : n_rec[0];
+	const bool all_final = final1 && (nf == 1 || final2);
+	if (n_units == 0) { if (!all_final) *need_more = 1; a->n_reads = 0; return SSQ_OK; }
+	// the batch rule
+	const FqRec *r1 = a->fq_rec[0].as<FqRec>(), *r2 = nf == 2 ? a->fq_rec[1].as<FqRec>() : 0;
+	if (a->fq_len.need(((size_t)n_units + 2) * 8) || a->fq_cum.need(((size_t)n_units + 2) * 8)) return SSQ_ENOMEM;
+	k_fq_unit_len<<<(n_units + 255) / 256, 256, 0, st>>>(n_units, r1, r2, a->fq_len.as<u64>());
+	if ((rc = scan_u64(a, a->fq_len.as<u64>(), a->fq_cum.as<u64>(), (size_t)n_units + 1))) return rc;
+	const unsigned int none = 0xffffffffu;
+	CK(cudaMemcpyAsync(d_cut, &none, 4, cudaMemcpyHostToDevice, st));
+	k_fq_cut<<<(n_units + 255) / 256, 256, 0, st>>>(n_units, a->fq_cum.as<u64>(), a->fq_len.as<u64>(), (u64)chunk_bases, nf == 1, d_cut);
+	unsigned int h_res[2] = {0, 0};
+	CK(cudaMemcpyAsync(h_res, a->fq_res.p, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (h_res[0] == 1) { ssq_set_error("not plain four-line FASTQ (or a read longer than %d bases)", SSQ_MAX_READ_LEN); return SSQ_EFORMAT; }
+	u32 take; // units in this batch
+	if (h_res[1] != none) take = h_res[1] + 1;
+	else if (all_final) take = n_units;
+	else { *need_more = 1; a->n_reads = 0; return SSQ_OK; }
+	const u32 n_reads = nf == 2 ? 2 * take : take;
+	const int paired = nf == 2 || interleaved;
+	if (paired && (n_reads & 1)) { ssq_set_error("interleaved FASTQ with an odd number of records"); return SSQ_EFORMAT; }
+	if (paired) { // mates must carry the same name (bwa: smart pairing / "paired reads have different names"): anything else goes to the host path
+		k_fq_pairnames<<<(n_reads / 2 + 255) / 256, 256, 0, st>>>(n_reads / 2, a->fq_txt[0].as<char>(), r1, nf == 2 ? a->fq_txt[1].as<char>() : 0, r2, nf == 2 ? 1 : 2, d_bad);
+	}
+	// packed fields
+	if (a->fq_nlen.need(((size_t)n_reads + 2) * 8) || a->fq_clen.need(((size_t)n_reads + 2) * 8) || a->fq_noff.need(((size_t)n_reads + 2) * 8) || a->fq_coff.need(((size_t)n_reads + 2) * 8)) return SSQ_ENOMEM;
+	u64 *slen = a->fq_len.as<u64>(), *soff = a->fq_cum.as<u64>(); // reused: per-read now
+	if (a->fq_len.need(((size_t)n_reads + 2) * 8) || a->fq_cum.need(((size_t)n_reads + 2) * 8)) return SSQ_ENOMEM;
+	slen = a->fq_len.as<u64>(); soff = a->fq_cum.as<u64>();
+	k_fq_read_lens<<<(n_reads + 255) / 256, 256, 0, st>>>(n_reads, r1, r2, keep_comment, slen, a->fq_nlen.as<u64>(), a->fq_clen.as<u64>(), d_maxlen);
+	if ((rc = scan_u64(a, slen, soff, (size_t)n_reads + 1))) return rc;
+	if ((rc = scan_u64(a, a->fq_nlen.as<u64>(), a->fq_noff.as<u64>(), (size_t)n_reads + 1))) return rc;
+	if ((rc = scan_u64(a, a->fq_clen.as<u64>(), a->fq_coff.as<u64>(), (size_t)n_reads + 1))) return rc;
+	u64 tot[3] = {0, 0, 0}; unsigned int h2[3] = {0, 0, 0};
+	CK(cudaMemcpyAsync(&tot[0], soff + n_reads, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&tot[1], a->fq_noff.as<u64>() + n_reads, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&tot[2], a->fq_coff.as<u64>() + n_reads, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h2, a->fq_res.p, 12, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (h2[0]) { ssq_set_error(h2[0] == 2 ? "adjacent records with different names (unpaired reads in an interleaved file)" : "not plain four-line FASTQ"); return SSQ_EFORMAT; }
+	a->n_reads = (int)n_reads; a->paired = paired ? 1 : 0; a->n_processed = n_processed; a->has_qual = 1; a->has_cmt = keep_comment && tot[2] > 0;
+	a->total_bases = tot[0]; a->max_len = (int)h2[2];
+	uint8_t *d_seq; u64 *d_off;
+	if ((rc = ssq_batch_reserve(a->b, (int)n_reads, tot[0], a->max_len, &d_seq, &d_off))) return rc;
+	if (a->d_ascii.need(tot[0] + 16) || a->d_qual.need(tot[0] + 16) || a->d_names.need(tot[1] + 16) || a->d_name_off.need(((size_t)n_reads + 1) * 4) || a->d_cmt.need(tot[2] + 16) ||
+	    a->d_cmt_off.need(((size_t)n_reads + 1) * 4)) return SSQ_ENOMEM;
+	k_fq_gather<<<(n_reads + 1 + 127) / 128, 128, 0, st>>>(n_reads, a->fq_txt[0].as<char>(), r1, nf == 2 ? a->fq_txt[1].as<char>() : 0, r2, keep_comment, soff, a->fq_noff.as<u64>(), a->fq_coff.as<u64>(),
+	                                                         a->d_ascii.as<char>(), a->d_qual.as<char>(), a->d_names.as<char>(), a->d_cmt.as<char>(), d_off, a->d_name_off.as<u32>(), a->d_cmt_off.as<u32>());
+	if (tot[0]) k_encode<<<(unsigned)((tot[0] / 4 + 256) / 256), 256, 0, st>>>(tot[0], a->d_ascii.as<char>(), d_seq);
+	CK(cudaGetLastError());
+	// how much text the batch covers
+	for (int f = 0; f < nf; ++f) {
+		const u32 recs = nf == 2 ? take : n_reads, last_line = 4 * recs - 1;
+		u32 pos = 0;
+		if (last_line < n_lines[f]) { CK(cudaMemcpyAsync(&pos, a->fq_nl[f].as<u32>() + last_line, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); pos += 1; }
+		else pos = (u32)len[f];
+		if (f == 0) *used1 = pos; else *used2 = pos;
+	}
+	CK(cudaEventRecord(a->ev[ST_ALIGN], st));
+	CK(cudaStreamSynchronize(st));
+	*n_reads_out = (int)n_reads;
 	return SSQ_OK;
 }

@@ -195,3 +195,34 @@ def test_cli_fused_samblaster_stage(ssq, cli_ref, tmp_path, monkeypatch):
         assert outs["oracle"][i] == outs["unfused"][i], what
         assert outs["oracle"][i] == outs["fused"][i], what
     assert outs["fused"][0].count(b"\n") > 80000 and outs["fused"][1].count(b"\n") > 100 and outs["fused"][2].count(b"\n") > 500
+
+
+def test_cli_fastq_ingest_on_the_device_and_its_fallbacks(ssq, cli_ref):
+    """the `bwa` shim hands the FASTQ text to the device tokeniser (ssq_aligner_upload_fastq); layouts it does not take — multi-line
+    records, FASTA, blank lines — must silently go through the host tokeniser with identical results; CRLF line ends and a last line
+    without newline are the device tokeniser's business"""
+    d, fa, g, bounds = cli_ref
+    names, seqs, quals = T.simulate_pairs(g, bounds, 1200, 150, 13)
+    quals = ["".join(chr(33 + (7 * i + k) % 40) for k in range(len(s))) for i, s in enumerate(seqs)]  # real-looking qualities incl. '@' and '+' at line starts
+    quals[4] = "@" + quals[4][1:]; quals[7] = "+" + quals[7][1:]
+    rec = lambda i, nl="\n": "@%s/%d cm:Z:%d%s%s%s+%s%s" % (names[i], 1 + (i & 1), i, nl, seqs[i], nl, nl, quals[i])
+    variants = {
+        "plain": "".join(rec(i) + "\n" for i in range(len(names))),
+        "crlf": "".join(rec(i, "\r\n") + "\r\n" for i in range(len(names))),
+        "no_final_newline": "".join(rec(i) + "\n" for i in range(len(names)))[:-1],
+        "multiline": "".join("@%s/%d\n%s\n%s\n+\n%s\n%s\n" % (names[i], 1 + (i & 1), seqs[i][:70], seqs[i][70:], quals[i][:70], quals[i][70:]) for i in range(len(names))),
+        "fasta": "".join(">%s/%d\n%s\n" % (names[i], 1 + (i & 1), seqs[i]) for i in range(len(names))),
+        "blank_lines": "".join(rec(i) + "\n" + ("\n" if i % 50 == 0 else "") for i in range(len(names))),
+    }
+    for tag, text in variants.items():
+        fq = str(d / ("ing_%s.fq" % tag))
+        open(fq, "w", newline="").write(text)
+        for extra in (["-p"], ["-p", "-C"]):
+            a, b = _both(["mem", "-t", "1"] + extra + [fa, fq])
+            assert _records(a) == _records(b), (tag, extra)
+            assert _records(b).count(b"\n") >= 2400
+    # the device path is really taken for the plain layouts (and really left for the others)
+    for tag, want in (("plain", False), ("crlf", False), ("no_final_newline", False), ("multiline", True), ("fasta", True), ("blank_lines", True)):
+        e = dict(os.environ, SSQ_VERBOSE_INGEST="1")
+        err = subprocess.run([BWA, "mem", "-t", "1", "-p", fa, str(d / ("ing_%s.fq" % tag))], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=e, check=True).stderr
+        assert (b"host tokeniser takes over" in err) == want, tag
