@@ -248,6 +248,20 @@ float ssq_aligner_stage_ms(const ssq_aligner_t *al, int stage);
 uint64_t ssq_aligner_counter(const ssq_aligner_t *al, int what);
 void ssq_aligner_free(ssq_aligner_t *al);
 
+/* ----------------------------------------------------------------- BAM records ----
+ * The downstream half of the pipe turns the SAM text straight back into BAM (`sambamba view -S -f bam -l 0 | sambamba sort`,
+ * speedseq:440-441, :444-448).  With ssq_aligner_set_bam(al, 1, ..) the aligner additionally encodes the records of the three
+ * streams as BAM on the device, straight from its structured alignments (layout: htslib sam.c:443-467, bin: hts.h:580-586),
+ * coordinate-sorted within the batch by (reference, position, strand) with equal keys in input order — what sambamba's sort
+ * produces (tests/golden/ex_bam_*: written by the reference's own sambamba, matched byte for byte).  blank_side_streams: the
+ * splitter / discordant records carry no SEQ / QUAL, like after speedseq's gawk step (speedseq:443,446).
+ * ssq_bam_header + ssq_bgzf_compress (host: zlib) make a complete .bam out of header and records of one batch; merging the
+ * sorted runs of several batches is left to the caller. */
+int ssq_aligner_set_bam(ssq_aligner_t *al, int enable, int blank_side_streams);
+int ssq_aligner_fetch_bam(ssq_aligner_t *al, int stream, const void **records, size_t *len); /* after ssq_aligner_compute; owned by the aligner */
+int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_text, int sorted, void **out, size_t *out_len); /* free with ssq_free */
+int ssq_bgzf_compress(const void *in, size_t n, int level, int with_eof, void **out, size_t *out_len);           /* free with ssq_free */
+
 /* ------------------------------------------------------------------ several GPUs ----
  * Batches are dealt to the ranks round-robin with the index replicated (no collective); "first pair seen with a signature is
  * kept" (`$SAMBLASTER`, speedseq:439) stays global through one exchange per round, in C over NCCL: signatures go to the owner rank

@@ -348,6 +348,37 @@ struct SbExtra { i32 or_flag; bool tags; const u32 *mc_cig; i32 mc_n; i32 mq; ch
 // one record.  list[0..n_list): the read's lines (list[which] is written); xa tasks: the read's task slice, outs/cigs addressed
 // through the callbacks below are supplied by the caller as arrays indexed by task
 struct XaSrc { const PTask *tk; int n_tk; const struct AlnOut *outs; const u32 *cigs; int tk_base; };
+// SA:Z — the other non-secondary lines of the read; XA:Z — the alternative hits whose owner is the region a line was built from
+template <class LS> SSQ_HD bool has_sa(const LS &list, int n_list, int which) { for (int i = 0; i < n_list; ++i) if (i != which && !(list(i).flag & 0x100)) return true; return false; }
+template <bool W, class LS>
+SSQ_HD void put_sa(Sink<W> &str, const TextCtx &c, const LS &list, int n_list, int which)
+{
+	for (int i = 0; i < n_list; ++i) {
+		if (i == which) continue;
+		const LineV r = list(i);
+		if (r.flag & 0x100) continue;
+		put_ctg(str, c, r.rid); sput(str, ',');
+		sputn(str, r.pos + 1); sput(str, ',');
+		sput(str, "+-"[r.is_rev]); sput(str, ',');
+		for (int k = 0; k < r.n_cig; ++k) { sputn(str, r.cig[k] >> 4); sput(str, "MIDSH"[r.cig[k] & 0xf]); }
+		sput(str, ','); sputn(str, r.mapq);
+		sput(str, ','); sputn(str, r.NM);
+		sput(str, ';');
+	}
+}
+SSQ_HD bool has_xa(const XaSrc &xa, int reg_idx) { for (int t = 0; t < xa.n_tk; ++t) if (xa.tk[t].kind == 1 && xa.tk[t].xa_owner == reg_idx) return true; return false; }
+template <bool W>
+SSQ_HD void put_xa(Sink<W> &str, const TextCtx &c, const XaSrc &xa, int reg_idx)
+{
+	for (int t = 0; t < xa.n_tk; ++t) {
+		if (xa.tk[t].kind != 1 || xa.tk[t].xa_owner != reg_idx) continue;
+		const AlnOut &ao = xa.outs[xa.tk_base + t];
+		const u32 *cg = xa.cigs + (size_t)(xa.tk_base + t) * CIG_CAP;
+		put_ctg(str, c, ao.rid); sput(str, ','); sput(str, "+-"[ao.is_rev]); sputn(str, ao.pos + 1); sput(str, ',');
+		for (int k = 0; k < ao.n_cigar; ++k) { sputn(str, cg[k] >> 4); sput(str, "MIDSHN"[cg[k] & 0xf]); }
+		sput(str, ','); sputn(str, ao.NM); sput(str, ';');
+	}
+}
 // LS: the read's lines, `LineV operator()(int i) const` (lines are fetched on demand: only SA tags look at the other lines)
 template <bool W, class LS>
 SSQ_HD void sam_line(Sink<W> &str, const TextCtx &c, int read, const LS &list, int n_list, int which, const LineV *m, const XaSrc &xa, const SbExtra *sb)
@@ -409,37 +440,8 @@ SSQ_HD void sam_line(Sink<W> &str, const TextCtx &c, int read, const LS &list, i
 	if (p.score >= 0) { sputs(str, "\tAS:i:", 6); sputn(str, p.score); }
 	if (p.sub >= 0) { sputs(str, "\tXS:i:", 6); sputn(str, p.sub); }
 	if (c.rg_len) { sputs(str, "\tRG:Z:", 6); sputs(str, c.rg_id, c.rg_len); }
-	if (!(v.flag & 0x100)) {
-		int i;
-		for (i = 0; i < n_list; ++i) if (i != which && !(list(i).flag & 0x100)) break;
-		if (i < n_list) {
-			sputs(str, "\tSA:Z:", 6);
-			for (i = 0; i < n_list; ++i) {
-				if (i == which) continue;
-				const LineV r = list(i);
-				if (r.flag & 0x100) continue;
-				put_ctg(str, c, r.rid); sput(str, ',');
-				sputn(str, r.pos + 1); sput(str, ',');
-				sput(str, "+-"[r.is_rev]); sput(str, ',');
-				for (int k = 0; k < r.n_cig; ++k) { sputn(str, r.cig[k] >> 4); sput(str, "MIDSH"[r.cig[k] & 0xf]); }
-				sput(str, ','); sputn(str, r.mapq);
-				sput(str, ','); sputn(str, r.NM);
-				sput(str, ';');
-			}
-		}
-	}
-	{ // XA: the entries whose owner is the region this line was built from, in task order
-		bool first = true;
-		for (int t = 0; t < xa.n_tk; ++t) {
-			if (xa.tk[t].kind != 1 || xa.tk[t].xa_owner != p.reg_idx) continue;
-			if (first) { sputs(str, "\tXA:Z:", 6); first = false; }
-			const AlnOut &ao = xa.outs[xa.tk_base + t];
-			const u32 *cg = xa.cigs + (size_t)(xa.tk_base + t) * CIG_CAP;
-			put_ctg(str, c, ao.rid); sput(str, ','); sput(str, "+-"[ao.is_rev]); sputn(str, ao.pos + 1); sput(str, ',');
-			for (int k = 0; k < ao.n_cigar; ++k) { sputn(str, cg[k] >> 4); sput(str, "MIDSHN"[cg[k] & 0xf]); }
-			sput(str, ','); sputn(str, ao.NM); sput(str, ';');
-		}
-	}
+	if (!(v.flag & 0x100) && has_sa(list, n_list, which)) { sputs(str, "\tSA:Z:", 6); put_sa(str, c, list, n_list, which); }
+	if (has_xa(xa, p.reg_idx)) { sputs(str, "\tXA:Z:", 6); put_xa(str, c, xa, p.reg_idx); }
 	if (c.cmt && c.cmt_off[read + 1] > c.cmt_off[read]) { sput(str, '\t'); sputs(str, c.cmt + c.cmt_off[read], (int)(c.cmt_off[read + 1] - c.cmt_off[read])); }
 	if (sb && sb->tags) {
 		sputs(str, "\tMC:Z:", 6);
@@ -447,6 +449,114 @@ SSQ_HD void sam_line(Sink<W> &str, const TextCtx &c, int read, const LS &list, i
 		sputs(str, "\tMQ:i:", 6); sputn(str, sb->mq);
 	}
 	sput(str, '\n');
+}
+
+
+// =================================================================================== BAM ====
+// The records of the three streams as BAM: what `sambamba view -S -f bam` makes of the SAM text, encoded
+// straight from the structured records.  Layout: /root/reference/src/samtools-1.3.1/htslib-1.3.1/sam.c:443-467 (bam_write1 /
+// the in-memory record), bin: htslib/hts.h:580-586 (hts_reg2bin), integer tags take the smallest type that holds the value.
+// Parity is pinned on the reference's OWN tool: tests/golden/ex_bam_*.gz were produced by /root/reference/src/sambamba (v0.5.9)
+// from the oracle's SAM of the example reads (tests/golden/make_bam_golden.py).
+template <bool W> SSQ_HD void bput32(Sink<W> &s, u32 v) { if (W) { s.p[s.n] = (char)v; s.p[s.n + 1] = (char)(v >> 8); s.p[s.n + 2] = (char)(v >> 16); s.p[s.n + 3] = (char)(v >> 24); } s.n += 4; }
+template <bool W> SSQ_HD void bput16(Sink<W> &s, u32 v) { if (W) { s.p[s.n] = (char)v; s.p[s.n + 1] = (char)(v >> 8); } s.n += 2; }
+template <bool W> SSQ_HD void bput_int_tag(Sink<W> &s, char t0, char t1, long long v)
+{
+	sput(s, t0); sput(s, t1);
+	if (v < 0) { if (v >= -128) { sput(s, 'c'); sput(s, (char)v); } else if (v >= -32768) { sput(s, 's'); bput16(s, (u32)v); } else { sput(s, 'i'); bput32(s, (u32)v); } }
+	else if (v <= 255) { sput(s, 'C'); sput(s, (char)v); } else if (v <= 65535) { sput(s, 'S'); bput16(s, (u32)v); } else { sput(s, 'I'); bput32(s, (u32)v); }
+}
+SSQ_HD int bam_reg2bin(i64 beg, i64 end)
+{
+	--end;
+	if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+	if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+	if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+	if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+	if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+	return 0;
+}
+// coordinate-sort key of a line: (tid, pos, reverse strand), records without a reference last; equal keys keep input order
+SSQ_HD u64 bam_sort_key(const Patched &v) { return v.rid < 0 ? ~0ull : ((u64)(u32)v.rid << 34 | (u64)(v.pos + 1) << 1 | (u64)(v.is_rev ? 1 : 0)); }
+
+// one record (block_size included).  blank: SEQ and QUAL are '*' (what speedseq's gawk step makes of the side streams, speedseq:443,446).
+// *bad is set when a -C comment is not TAG:TYPE:VALUE with TYPE in {Z, i, A}
+template <bool W, class LS>
+SSQ_HD void bam_record(Sink<W> &str, const TextCtx &c, int read, const LS &list, int n_list, int which, const LineV *m, const XaSrc &xa, const SbExtra *sb, bool blank, int *bad)
+{
+	const LineV p = list(which);
+	const Patched v = patch_line(p, m);
+	const int l_read = (int)(c.read_off[read + 1] - c.read_off[read]);
+	const uint8_t *sq = c.seq + c.read_off[read];
+	const int flag = printed_flag(v) | (sb ? sb->or_flag : 0);
+	const size_t at0 = str.n;
+	bput32(str, 0); // block_size, patched below
+	const int n_cig = v.cig_shown ? p.n_cig : 0;
+	const i64 pos = v.rid >= 0 ? v.pos : -1;
+	const int rlen = n_cig ? cig_rlen(p.cig, p.n_cig) : 0;
+	const i64 end = (flag & 4) || rlen == 0 ? pos + 1 : pos + rlen;
+	const int name_l = (int)(c.name_off[read + 1] - c.name_off[read]) + (sb && sb->suffix ? 2 : 0);
+	int qb = 0, qe = l_read;
+	if (v.cig_shown && which) {
+		const int c0 = p.cig[0] & 0xf, c1 = p.cig[p.n_cig - 1] & 0xf;
+		if (!v.is_rev) { if (c0 == 4 || c0 == 3) qb += p.cig[0] >> 4; if (c1 == 4 || c1 == 3) qe -= p.cig[p.n_cig - 1] >> 4; }
+		else { if (c0 == 4 || c0 == 3) qe -= p.cig[0] >> 4; if (c1 == 4 || c1 == 3) qb += p.cig[p.n_cig - 1] >> 4; }
+	}
+	const int l_seq = (blank || (v.flag & 0x100)) ? 0 : qe - qb;
+	bput32(str, (u32)v.rid); bput32(str, (u32)pos);
+	sput(str, (char)(name_l + 1)); sput(str, (char)(v.rid >= 0 ? p.mapq : 0)); bput16(str, (u32)bam_reg2bin(pos, end));
+	bput16(str, (u32)n_cig); bput16(str, (u32)flag); bput32(str, (u32)l_seq);
+	const bool has_mate = m && v.mrid >= 0;
+	bput32(str, (u32)(has_mate ? v.mrid : -1)); bput32(str, (u32)(has_mate ? v.mpos : -1));
+	i64 tlen = 0;
+	if (has_mate && v.rid == v.mrid && v.mcig_shown && v.cig_shown) {
+		const i64 p0 = v.pos + (v.is_rev ? cig_rlen(p.cig, p.n_cig) - 1 : 0), p1 = v.mpos + (v.m_is_rev ? cig_rlen(m->cig, m->n_cig) - 1 : 0);
+		tlen = -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0));
+	}
+	bput32(str, (u32)tlen);
+	sputs(str, c.names + c.name_off[read], (int)(c.name_off[read + 1] - c.name_off[read]));
+	if (sb && sb->suffix) { sput(str, '_'); sput(str, sb->suffix); }
+	sput(str, 0);
+	for (int i = 0; i < n_cig; ++i) {
+		int op = p.cig[i] & 0xf;
+		if (op == 3 || op == 4) op = which ? 4 : 3;
+		bput32(str, (p.cig[i] >> 4) << 4 | (u32)(op == 3 ? 4 : op == 4 ? 5 : op)); // internal 3 = S, 4 = H -> BAM 4, 5
+	}
+	if (l_seq) {
+		const char *ql = c.qual ? c.qual + c.read_off[read] : 0;
+		for (int k = 0; k < l_seq; k += 2) { // 4 bits per base: A 1, C 2, G 4, T 8, N 15
+			int nib[2] = {0, 0};
+			for (int h = 0; h < 2 && k + h < l_seq; ++h) { const int b = !v.is_rev ? sq[qb + k + h] : (sq[qe - 1 - k - h] < 4 ? 3 - sq[qe - 1 - k - h] : 4); nib[h] = b == 0 ? 1 : b == 1 ? 2 : b == 2 ? 4 : b == 3 ? 8 : 15; }
+			sput(str, (char)(nib[0] << 4 | nib[1]));
+		}
+		for (int k = 0; k < l_seq; ++k) sput(str, ql ? (char)((!v.is_rev ? ql[qb + k] : ql[qe - 1 - k]) - 33) : (char)0xff);
+	}
+	if (v.cig_shown) { bput_int_tag(str, 'N', 'M', p.NM); sputs(str, "MDZ", 3); sputs(str, p.md, p.md_len); sput(str, 0); }
+	if (p.score >= 0) bput_int_tag(str, 'A', 'S', p.score);
+	if (p.sub >= 0) bput_int_tag(str, 'X', 'S', p.sub);
+	if (c.rg_len) { sputs(str, "RGZ", 3); sputs(str, c.rg_id, c.rg_len); sput(str, 0); }
+	if (!(v.flag & 0x100) && has_sa(list, n_list, which)) { sputs(str, "SAZ", 3); put_sa(str, c, list, n_list, which); sput(str, 0); }
+	if (has_xa(xa, p.reg_idx)) { sputs(str, "XAZ", 3); put_xa(str, c, xa, p.reg_idx); sput(str, 0); }
+	if (c.cmt && c.cmt_off[read + 1] > c.cmt_off[read]) { // -C: the FASTQ comment holds tab-separated TAG:TYPE:VALUE fields
+		const char *t = c.cmt + c.cmt_off[read]; const int n = (int)(c.cmt_off[read + 1] - c.cmt_off[read]);
+		int i = 0;
+		while (i < n) {
+			int e = i; while (e < n && t[e] != '\t') ++e;
+			if (e - i >= 5 && t[i + 2] == ':' && t[i + 4] == ':' && (t[i + 3] == 'Z' || t[i + 3] == 'A' || t[i + 3] == 'i')) {
+				if (t[i + 3] == 'Z') { sput(str, t[i]); sput(str, t[i + 1]); sput(str, 'Z'); sputs(str, t + i + 5, e - i - 5); sput(str, 0); }
+				else if (t[i + 3] == 'A') { sput(str, t[i]); sput(str, t[i + 1]); sput(str, 'A'); sput(str, e - i > 5 ? t[i + 5] : ' '); }
+				else { long long x = 0; bool neg = false; int k = i + 5; if (k < e && (t[k] == '-' || t[k] == '+')) { neg = t[k] == '-'; ++k; } for (; k < e; ++k) x = x * 10 + (t[k] - '0'); bput_int_tag(str, t[i], t[i + 1], neg ? -x : x); }
+			} else if (bad) *bad = 1;
+			i = e + 1;
+		}
+	}
+	if (sb && sb->tags) {
+		sputs(str, "MCZ", 3);
+		if (sb->mc_n > 0) for (int k = 0; k < sb->mc_n; ++k) { int op = sb->mc_cig[k] & 0xf; if (op == 4) op = 3; sputn(str, sb->mc_cig[k] >> 4); sput(str, "MIDSH"[op]); } else sput(str, '*');
+		sput(str, 0);
+		bput_int_tag(str, 'M', 'Q', sb->mq);
+	}
+	if (W) { const u32 bs = (u32)(str.n - at0 - 4); str.p[at0] = (char)bs; str.p[at0 + 1] = (char)(bs >> 8); str.p[at0 + 2] = (char)(bs >> 16); str.p[at0 + 3] = (char)(bs >> 24); }
 }
 
 // ============================================================================ samblaster ====
@@ -559,6 +669,9 @@ struct PipeView {
 	const i64 *sb_off; u64 *k1, *k2; uint8_t *valid, *dup, *disc; u64 *split_mask;
 	// text: per-read byte counts / offsets of the three streams (0 main, 1 splitters, 2 discordants) and the buffers
 	u64 *len[3]; const u64 *off[3]; char *text[3];
+	// BAM (optional): lines are numbered read by read (line_base), sorted by coordinate (perm: sorted position -> line); per stream the
+	// byte size of every line (0 = not in the stream) and, after the sort, the offset of every sorted position
+	const u64 *line_base; u32 *line_read; u64 *bam_key; u64 *bam_size[3]; const u32 *bam_perm; const u64 *bam_off[3]; char *bam[3]; i32 bam_blank_side;
 	unsigned long long *cnt; // device-measured work: [0] duplicate blocks, [2] local-SW passes of the mate rescue, [3] their cells (rows x query length), [4] banded-DP cells of CIGAR generation
 	i32 *err; // sticky error flags: 1 region-list overflow, 2 task-slot overflow, 4 CIGAR/MD/traceback capacity, 8 rescue window capacity
 };
@@ -767,4 +880,66 @@ SSQ_HD void body_text(const PipeView &V, int r)
 		}
 	}
 	if (!W) for (int k = 0; k < 3; ++k) V.len[k][r] = out[k].n;
+}
+
+// ---- BAM bodies: sizes + sort keys per line (unit = read), then the bytes (unit = sorted position) ----
+struct BamCtx { LineV mh; const LineV *mate; XaSrc xa; SbExtra sb; const SbExtra *sbp; bool dup, disc; u64 smask; };
+SSQ_HD void bam_ctx(const PipeView &V, int r, BamCtx &C)
+{
+	const ReadMeta &m = V.meta[r];
+	C.mate = 0;
+	if (V.paired) { C.mh = mate_header(V, r); C.mate = &C.mh; }
+	C.xa.tk = V.tasks + V.tk_base[r]; C.xa.n_tk = m.n_tasks; C.xa.outs = V.outs; C.xa.cigs = V.cigs; C.xa.tk_base = (int)V.tk_base[r];
+	C.sbp = 0; C.dup = C.disc = false; C.smask = 0;
+	if (V.sb.enabled) {
+		const int u = V.paired ? r >> 1 : r;
+		C.dup = V.dup[u] != 0; C.disc = V.disc[u] != 0; C.smask = V.split_mask[r];
+		C.sb.or_flag = C.dup ? 0x400 : 0; C.sb.tags = false; C.sb.mc_cig = 0; C.sb.mc_n = 0; C.sb.mq = 0; C.sb.suffix = 0;
+		if (V.paired && V.sb.addMateTags) { int mq; const SbLine mp = sb_primary(V, r ^ 1, &mq); C.sb.tags = true; C.sb.mc_cig = mp.cig; C.sb.mc_n = mp.shown ? mp.n_cig : 0; C.sb.mq = mq; }
+		C.sbp = &C.sb;
+	}
+}
+SSQ_HD bool bam_member(const PipeView &V, const BamCtx &C, int k, int i)
+{
+	if (k == 0) return !(V.sb.enabled && V.sb.removeDups && C.dup);
+	if (!V.sb.enabled || (V.sb.excludeDups && C.dup)) return false;
+	return k == 2 ? (V.sb.want_disc && C.disc && i == 0) : (V.sb.want_split && (C.smask >> i & 1));
+}
+template <bool W>
+SSQ_HD void bam_one(const PipeView &V, int r, int i, int k, const BamCtx &C, Sink<W> &out)
+{
+	const ReadLines ls = {&V, r};
+	const int nl = read_n_lines(V, r);
+	int bad = 0;
+	if (k == 1) { SbExtra s2 = C.sb; s2.suffix = V.paired ? ((r & 1) ? '2' : '1') : 0; bam_record(out, V.tc, r, ls, nl, i, C.mate, C.xa, &s2, V.bam_blank_side != 0, &bad); }
+	else bam_record(out, V.tc, r, ls, nl, i, C.mate, C.xa, C.sbp, k == 2 && V.bam_blank_side != 0, &bad);
+	if (bad) PIPE_ERR(V, 32);
+}
+SSQ_HD void body_bam_size(const PipeView &V, int r)
+{
+	BamCtx C; bam_ctx(V, r, C);
+	const int nl = read_n_lines(V, r);
+	const ReadLines ls = {&V, r};
+	for (int i = 0; i < nl; ++i) {
+		const u64 line = V.line_base[r] + i;
+		const LineV p = ls(i);
+		V.bam_key[line] = bam_sort_key(patch_line(p, C.mate));
+		V.line_read[line] = (u32)r;
+		for (int k = 0; k < 3; ++k) {
+			Sink<false> s; s.p = 0; s.n = 0;
+			if (bam_member(V, C, k, i)) bam_one<false>(V, r, i, k, C, s);
+			V.bam_size[k][line] = s.n;
+		}
+	}
+}
+SSQ_HD void body_bam_write(const PipeView &V, u64 sorted_pos)
+{
+	const u64 line = V.bam_perm[sorted_pos];
+	const int r = (int)V.line_read[line], i = (int)(line - V.line_base[r]);
+	BamCtx C; bam_ctx(V, r, C);
+	for (int k = 0; k < 3; ++k) {
+		if (!bam_member(V, C, k, i)) continue;
+		Sink<true> s; s.p = V.bam[k] + V.bam_off[k][sorted_pos]; s.n = 0;
+		bam_one<true>(V, r, i, k, C, s);
+	}
 }

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <zlib.h>
 #include "ssq_host.h"
 
 extern "C" int ssq_mem_batch_sam(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const char *const *names, const char *const *seqs, const char *const *quals,
@@ -50,3 +51,61 @@ extern "C" int ssq_mem_batch_sam(const ssq_index_t *idx, const ssq_opts_t *opt, 
 }
 
 extern "C" void ssq_free(void *p) { free(p); }
+
+// ---- BAM container (host side of f1): BGZF framing and the file header ----
+// BGZF: /root/reference/src/samtools-1.3.1/htslib-1.3.1/bgzf.c:45-63 — a series of gzip members of at most 64 KiB each, every member
+// carrying its compressed size in a "BC" extra field, and a fixed empty member as end-of-file marker.
+extern "C" int ssq_bgzf_compress(const void *in_, size_t n, int level, int with_eof, void **out, size_t *out_len)
+{
+	if ((!in_ && n) || !out || !out_len) return SSQ_EINVAL;
+	static const unsigned char eof_blk[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	const unsigned char *in = (const unsigned char*)in_;
+	const size_t blk = 0xff00, n_blk = (n + blk - 1) / blk;
+	size_t cap = n + n_blk * 64 + 64 + (level == 0 ? n_blk * 8 : 0), at = 0;
+	unsigned char *o = (unsigned char*)malloc(cap);
+	if (!o) return SSQ_ENOMEM;
+	for (size_t b = 0; b < n_blk; ++b) {
+		const size_t len = b + 1 < n_blk ? blk : n - b * blk;
+		z_stream zs; memset(&zs, 0, sizeof zs);
+		if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { free(o); return SSQ_EINVAL; }
+		if (at + 18 + deflateBound(&zs, (uLong)len) + 8 > cap) { cap = cap * 2 + deflateBound(&zs, (uLong)len) + 64; o = (unsigned char*)realloc(o, cap); }
+		unsigned char *h = o + at;
+		const unsigned char hdr[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+		memcpy(h, hdr, 12); h[12] = 'B'; h[13] = 'C'; h[14] = 2; h[15] = 0;
+		zs.next_in = (Bytef*)(in + b * blk); zs.avail_in = (uInt)len; zs.next_out = h + 18; zs.avail_out = (uInt)(cap - at - 18 - 8);
+		if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); free(o); ssq_set_error("deflate failed"); return SSQ_EINVAL; }
+		const size_t clen = zs.total_out;
+		deflateEnd(&zs);
+		const unsigned bsize = (unsigned)(clen + 18 + 8 - 1);
+		h[16] = (unsigned char)bsize; h[17] = (unsigned char)(bsize >> 8);
+		const uLong crc = crc32(crc32(0L, 0, 0), in + b * blk, (uInt)len);
+		unsigned char *t = h + 18 + clen;
+		for (int k = 0; k < 4; ++k) { t[k] = (unsigned char)(crc >> (8 * k)); t[4 + k] = (unsigned char)(len >> (8 * k)); }
+		at += 18 + clen + 8;
+	}
+	if (with_eof) { if (at + 28 > cap) o = (unsigned char*)realloc(o, at + 28); memcpy(o + at, eof_blk, 28); at += 28; }
+	*out = o; *out_len = at;
+	return SSQ_OK;
+}
+
+// "BAM\1", header text, reference table (uncompressed; feed it and the records to ssq_bgzf_compress).  sorted: adds / rewrites
+// @HD ... SO:coordinate the way the pipeline's `sambamba sort` does (speedseq:441)
+extern "C" int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_text, int sorted, void **out, size_t *out_len)
+{
+	if (!idx || !out || !out_len) return SSQ_EINVAL;
+	std::string text;
+	const char *t = sam_header_text ? sam_header_text : "";
+	if (sorted) {
+		text = "@HD\tVN:1.3\tSO:coordinate\n";
+		for (const char *p = t; *p;) { const char *e = strchr(p, '\n'); const size_t l = e ? (size_t)(e - p) + 1 : strlen(p); if (strncmp(p, "@HD", 3) != 0) text.append(p, l); p += l; }
+	} else text = t;
+	std::string o("BAM\1", 4);
+	auto put32 = [&](int32_t v) { char b[4] = {(char)v, (char)(v >> 8), (char)(v >> 16), (char)(v >> 24)}; o.append(b, 4); };
+	put32((int32_t)text.size()); o += text;
+	put32(idx->n_seqs);
+	for (int i = 0; i < idx->n_seqs; ++i) { const size_t l = strlen(idx->names[i]) + 1; put32((int32_t)l); o.append(idx->names[i], l); put32(idx->ann_len[i]); }
+	*out = malloc(o.size());
+	if (!*out) return SSQ_ENOMEM;
+	memcpy(*out, o.data(), o.size()); *out_len = o.size();
+	return SSQ_OK;
+}

@@ -218,6 +218,13 @@ __global__ void __launch_bounds__(128) k_text(PipeView V)
 	if (r >= V.n_reads) return;
 	body_text<W>(V, r);
 }
+// ---- BAM stage (optional): records encoded from the structured alignments, coordinate-sorted per batch ----
+__global__ void k_nlines(int n, PipeView V, u64 *out) { const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r < n) out[r] = (u64)read_n_lines(V, r); }
+__global__ void __launch_bounds__(128) k_bam_size(PipeView V) { const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r < V.n_reads) body_bam_size(V, r); }
+__global__ void k_iota_u32(u64 n, u32 *p) { const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (u32)i; }
+__global__ void k_gather_u64(u64 n, const u32 *__restrict__ perm, const u64 *__restrict__ in, u64 *out) { const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[perm[i]]; }
+__global__ void __launch_bounds__(128) k_bam_write(PipeView V, u64 n_lines) { const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n_lines) body_bam_write(V, i); }
+
 __global__ void k_count_u8(u64 n, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, unsigned long long *out) // out[0] += #a, out[1] += #b
 {
 	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,7 +266,9 @@ struct ssq_aligner {
 	// stages
 	DBuf cubtmp, d_cap, d_aoff, d_na, d_areg, d_work, d_pes, d_hist, d_pen, d_slab /* per-thread scratch of whichever slab kernel runs (dedup, rescue, CIGAR tiers: never live together) */, d_rlist, d_tcap, d_tsoff, d_tslots, d_meta, d_pv, d_xcnt,
 	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
-	PinBuf h_text[3], h_roff, h_hist, h_small;
+	PinBuf h_text[3], h_roff, h_hist, h_small, h_bam[3];
+	int want_bam, bam_blank_side; u64 bam_len[3], n_lines_total;
+	DBuf d_nl, d_lbase, d_lread, d_bkey, d_bkey2, d_bidx, d_bperm, d_bsize[3], d_bsz_s, d_boff[3], d_bam[3];
 	PeStat pes[4];
 	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines, n_rescue_pairs, n_gapped, n_sw_local, sw_local_cells;
 	cudaEvent_t ev[ST_N + 1];
@@ -298,7 +307,7 @@ extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt,
 	int rc = ssq_use_device(idx->device);
 	if (rc) return rc;
 	ssq_aligner *a = new ssq_aligner();
-	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->comm = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->computed = 0; a->n_reads = 0;
+	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->comm = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->want_bam = 0; a->bam_blank_side = 1; a->bam_len[0] = a->bam_len[1] = a->bam_len[2] = 0; a->n_lines_total = 0; a->computed = 0; a->n_reads = 0;
 	memset(a->ev, 0, sizeof a->ev); memset(a->stage_ms, 0, sizeof a->stage_ms); memset(a->pes, 0, sizeof a->pes);
 	memset(&a->sb, 0, sizeof a->sb);
 	if (sb) {
@@ -591,6 +600,42 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 	for (int k = 0; k < 3; ++k) { if (a->d_text[k].need(a->text_len[k] + 64)) return SSQ_ENOMEM; V.text[k] = a->d_text[k].as<char>(); }
 	k_text<true><<<(n + 127) / 128, 128, 0, st>>>(V);
 	CK(cudaGetLastError());
+	if (a->want_bam) { // the same records as BAM, sorted by (reference, position, strand) within the batch (stable: equal keys keep input order)
+		u64 L = 0;
+		if (a->d_nl.need((size_t)(n + 2) * 8) || a->d_lbase.need((size_t)(n + 2) * 8)) return SSQ_ENOMEM;
+		k_nlines<<<(n + 255) / 256, 256, 0, st>>>(n, V, a->d_nl.as<u64>());
+		if ((rc = scan_u64(a, a->d_nl.as<u64>(), a->d_lbase.as<u64>(), (size_t)n + 1))) return rc;
+		CK(cudaMemcpyAsync(&L, a->d_lbase.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		a->n_lines_total = L;
+		if (L >= 0x7fffffffull) { ssq_set_error("more than 2^31-1 records in one batch"); return SSQ_EINVAL; }
+		if (a->d_lread.need((L + 1) * 4) || a->d_bkey.need((L + 1) * 8) || a->d_bkey2.need((L + 1) * 8) || a->d_bidx.need((L + 1) * 4) || a->d_bperm.need((L + 1) * 4) || a->d_bsz_s.need((L + 2) * 8)) return SSQ_ENOMEM;
+		for (int k = 0; k < 3; ++k) { if (a->d_bsize[k].need((L + 1) * 8) || a->d_boff[k].need((L + 2) * 8)) return SSQ_ENOMEM; V.bam_size[k] = a->d_bsize[k].as<u64>(); }
+		V.line_base = a->d_lbase.as<u64>(); V.line_read = a->d_lread.as<u32>(); V.bam_key = a->d_bkey.as<u64>(); V.bam_blank_side = a->bam_blank_side;
+		k_bam_size<<<(n + 127) / 128, 128, 0, st>>>(V);
+		const unsigned gl = (unsigned)((L + 255) / 256);
+		k_iota_u32<<<gl, 256, 0, st>>>(L, a->d_bidx.as<u32>());
+		size_t tb = 0;
+		cub::DeviceRadixSort::SortPairs(0, tb, a->d_bkey.as<u64>(), a->d_bkey2.as<u64>(), a->d_bidx.as<u32>(), a->d_bperm.as<u32>(), (int)L, 0, 64, st);
+		if (a->cubtmp.need(tb)) return SSQ_ENOMEM;
+		CK(cub::DeviceRadixSort::SortPairs(a->cubtmp.p, tb, a->d_bkey.as<u64>(), a->d_bkey2.as<u64>(), a->d_bidx.as<u32>(), a->d_bperm.as<u32>(), (int)L, 0, 64, st));
+		V.bam_perm = a->d_bperm.as<u32>();
+		for (int k = 0; k < n_streams; ++k) {
+			k_gather_u64<<<gl, 256, 0, st>>>(L, a->d_bperm.as<u32>(), a->d_bsize[k].as<u64>(), a->d_bsz_s.as<u64>());
+			if ((rc = scan_u64(a, a->d_bsz_s.as<u64>(), a->d_boff[k].as<u64>(), (size_t)L + 1))) return rc;
+			CK(cudaMemcpyAsync(&a->bam_len[k], a->d_boff[k].as<u64>() + L, 8, cudaMemcpyDeviceToHost, st));
+			V.bam_off[k] = a->d_boff[k].as<u64>();
+		}
+		for (int k = n_streams; k < 3; ++k) { a->bam_len[k] = 0; V.bam_off[k] = a->d_boff[0].as<u64>(); }
+		CK(cudaStreamSynchronize(st));
+		for (int k = 0; k < 3; ++k) { if (a->d_bam[k].need(a->bam_len[k] + 64)) return SSQ_ENOMEM; V.bam[k] = a->d_bam[k].as<char>(); }
+		k_bam_write<<<(unsigned)((L + 127) / 128), 128, 0, st>>>(V, L);
+		CK(cudaGetLastError());
+		int h_err2 = 0;
+		CK(cudaMemcpyAsync(&h_err2, a->d_err.p, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if (h_err2 & 32) { ssq_set_error("a FASTQ comment (-C) is not TAG:TYPE:VALUE with TYPE in {Z, i, A}: it cannot become BAM tags"); return SSQ_EINVAL; }
+	}
 	CK(cudaEventRecord(a->ev[ST_FETCH], st));
 	a->n_ids = (u64)n_units; a->n_dup = h_cnt[0]; a->n_rescue_pairs = h_work[0]; a->n_gapped = h_work[1]; a->n_sw_local = h_cnt[2]; a->sw_local_cells = h_cnt[3];
 	a->computed = 1;
@@ -844,5 +889,23 @@ extern "C" int ssq_aligner_upload_fastq(ssq_aligner_t *a, const char *fq1, size_
 	CK(cudaEventRecord(a->ev[ST_ALIGN], st));
 	CK(cudaStreamSynchronize(st));
 	*n_reads_out = (int)n_reads;
+	return SSQ_OK;
+}
+
+// ---- BAM output (f1) ----
+extern "C" int ssq_aligner_set_bam(ssq_aligner_t *a, int enable, int blank_side_streams)
+{
+	if (!a) return SSQ_EINVAL;
+	a->want_bam = enable ? 1 : 0; a->bam_blank_side = blank_side_streams ? 1 : 0;
+	return SSQ_OK;
+}
+extern "C" int ssq_aligner_fetch_bam(ssq_aligner_t *a, int stream, const void **records, size_t *len)
+{
+	if (!a || !records || !len || stream < 0 || stream > 2 || !a->computed || !a->want_bam) return SSQ_EINVAL;
+	int rc = ssq_use_device(a->device);
+	if (rc) return rc;
+	if (a->h_bam[stream].need(a->bam_len[stream] + 1)) return SSQ_ENOMEM;
+	if (a->bam_len[stream]) { CK(cudaMemcpyAsync(a->h_bam[stream].p, a->d_bam[stream].p, a->bam_len[stream], cudaMemcpyDeviceToHost, a->st)); CK(cudaStreamSynchronize(a->st)); }
+	*records = a->h_bam[stream].p; *len = a->bam_len[stream];
 	return SSQ_OK;
 }

@@ -63,3 +63,13 @@ def syn_index(oracle, tmp_path_factory):
 @pytest.fixture(scope="session")
 def ssq():
     return T.SSQ()
+
+
+@pytest.fixture(scope="session")
+def ssq_lib_cpu():
+    """libssq.so loaded without a GPU: only its pure host helpers (BGZF framing, ABI checks) may be called through this"""
+    import ctypes
+    lib = ctypes.CDLL(T.SSQ_SO)
+    lib.ssq_free.argtypes = [ctypes.c_void_p]
+    lib.ssq_bgzf_compress.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return lib

@@ -262,7 +262,8 @@ static void run_read(const DevIndex &ix, const ssq_opts_t &opt, int len, const u
 // (ssq_dev3.cuh) run in plain loops over host vectors.  Same order of stages, same host-side reductions (ssq_pipe_host.h). ----
 struct HostPipe {
 	std::set<std::pair<u64, u64> > seen; // the streaming dup-set: signatures of every earlier batch
-	std::string text[3];
+	std::string text[3], bam[3]; // bam: coordinate-sorted BAM records of the batch (filled when want_bam)
+	int want_bam = 0, bam_blank_side = 1;
 	std::vector<u64> read_off;
 	PeStat pes[4];
 	int err;
@@ -357,6 +358,20 @@ struct HostPipe {
 		for (int k = 0; k < 3; ++k) { for (int r = 0; r < n; ++r) toff[k][r + 1] = toff[k][r] + len[k][r]; text[k].assign(toff[k][n], '\0'); V.text[k] = &text[k][0]; }
 		for (int r = 0; r < n; ++r) body_text<true>(V, r);
 		read_off = toff[0];
+		if (want_bam) { // BAM records: sizes + keys per line, stable sort by (tid, pos, strand), offsets, bytes — the steps of ssq_pipe.cu
+			std::vector<u64> line_base(n + 1, 0);
+			for (int r = 0; r < n; ++r) line_base[r + 1] = line_base[r] + read_n_lines(V, r);
+			const u64 nl = line_base[n];
+			std::vector<u32> line_read(nl + 1), perm(nl + 1); std::vector<u64> key(nl + 1), bsz[3], boff[3];
+			for (int k = 0; k < 3; ++k) { bsz[k].assign(nl + 1, 0); boff[k].assign(nl + 1, 0); V.bam_size[k] = bsz[k].data(); }
+			V.line_base = line_base.data(); V.line_read = line_read.data(); V.bam_key = key.data(); V.bam_blank_side = bam_blank_side;
+			for (int r = 0; r < n; ++r) body_bam_size(V, r);
+			for (u64 i = 0; i < nl; ++i) perm[i] = (u32)i;
+			std::stable_sort(perm.begin(), perm.begin() + nl, [&](u32 a, u32 b) { return key[a] < key[b]; });
+			V.bam_perm = perm.data();
+			for (int k = 0; k < 3; ++k) { u64 at = 0; for (u64 i = 0; i < nl; ++i) { boff[k][i] = at; at += bsz[k][perm[i]]; } bam[k].assign(at, '\0'); V.bam[k] = &bam[k][0]; V.bam_off[k] = boff[k].data(); }
+			for (u64 i = 0; i < nl; ++i) body_bam_write(V, i);
+		}
 		return err;
 	}
 };
@@ -462,6 +477,14 @@ int hostsim_pipe(const ssqo_idx_t *idx, int n_reads, const char **names, const c
 	char **outs[3] = {out_main, out_split, out_disc};
 	for (int k = 0; k < 3; ++k) { *outs[k] = (char*)malloc(g_pipe.text[k].size() + 1); memcpy(*outs[k], g_pipe.text[k].c_str(), g_pipe.text[k].size() + 1); }
 	return 0;
+}
+// BAM records of the last hostsim_pipe_bam() batch; call with want = 1 before hostsim_pipe to switch the encoder on
+void hostsim_pipe_want_bam(int want, int blank_side) { g_pipe.want_bam = want; g_pipe.bam_blank_side = blank_side; }
+uint64_t hostsim_pipe_bam(int stream, char *out, uint64_t cap)
+{
+	const std::string &b = g_pipe.bam[stream];
+	if (out && cap >= b.size()) memcpy(out, b.data(), b.size());
+	return b.size();
 }
 
 // randomized check of ChainBuilder's tree-ordered chains against a plain ordered-array restatement (look-up = first chain with

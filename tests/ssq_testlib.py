@@ -177,6 +177,22 @@ class HostSim:
             self.o.lib.ssqo_api_free(o)
         return tuple(res)
 
+    def pipe_bam(self, *a, blank_side=1, **kw):
+        """like pipe(), additionally the coordinate-sorted BAM records of the three streams (bytes)"""
+        self.lib.hostsim_pipe_want_bam(C.c_int(1), C.c_int(blank_side))
+        try:
+            txt = self.pipe(*a, **kw)
+        finally:
+            self.lib.hostsim_pipe_want_bam(C.c_int(0), C.c_int(1))
+        self.lib.hostsim_pipe_bam.restype = C.c_uint64
+        bams = []
+        for k in range(3):
+            n = int(self.lib.hostsim_pipe_bam(C.c_int(k), None, C.c_uint64(0)))
+            buf = C.create_string_buffer(max(n, 1))
+            self.lib.hostsim_pipe_bam(C.c_int(k), buf, C.c_uint64(n))
+            bams.append(buf.raw[:n])
+        return txt, tuple(bams)
+
     def align_batch(self, idx, seq, off):
         n = len(off) - 1
         cap = max(1024, 16 * n)

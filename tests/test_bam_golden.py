@@ -1,0 +1,93 @@
+"""f1: the BAM records the pipeline encodes straight from its structured alignment records, coordinate-sorted per batch,
+against what the REFERENCE'S OWN TOOL makes of the oracle's SAM text: tests/golden/ex_bam_*.records.gz were written by
+/root/reference/src/sambamba v0.5.9 (`view -S -f bam -l 0 | sort`, the commands of bin/speedseq:440-448) — see
+tests/golden/make_bam_golden.py.  CPU: the encoder bodies through tests/hostsim.  GPU: the kernels through ssq_aligner_fetch_bam."""
+import gzip
+import os
+
+import pytest
+
+import ssq_testlib as T
+
+SB = dict(exclude_dups=1, add_mate_tags=1, max_split_count=2, min_non_overlap=20)
+
+
+def golden(tag):
+    return gzip.open(os.path.join(T.GOLDEN, "ex_bam_%s.records.gz" % tag)).read()
+
+
+def split_records(b):
+    import struct
+    out, p = [], 0
+    while p < len(b):
+        n = struct.unpack("<i", b[p:p + 4])[0]
+        out.append(b[p:p + 4 + n]); p += 4 + n
+    return out
+
+
+def test_bam_records_match_sambamba_cpu(oracle, hostsim, ex_index, ex_reads):
+    idx = oracle.load(ex_index)
+    names, seqs, quals = ex_reads
+    txt, bams = hostsim.pipe_bam(idx, names, seqs, quals, 0, b"NA12878", 1, (1, 1, 2, 20, 0))
+    for k, tag in enumerate(("main", "spl", "disc")):
+        want, got = golden(tag), bams[k]
+        if got != want:
+            a, b = split_records(want), split_records(got)
+            first = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+            raise AssertionError("%s: %d vs %d records, first difference at record %d:\n%r\n%r" % (tag, len(a), len(b), first, a[first:first + 1], b[first:first + 1]))
+    assert len(split_records(bams[0])) == txt[0].count("\n") > 4000
+
+
+@pytest.mark.gpu
+def test_bam_records_match_sambamba_gpu(ssq, ex_index, ex_reads):
+    import ctypes as C
+    h = ssq.index_load(ex_index)
+    names, seqs, quals = ex_reads
+    al = ssq.aligner_create(h, SB, b"NA12878")
+    ssq.ck(ssq.lib.ssq_aligner_set_bam(al, C.c_int(1), C.c_int(1)), "ssq_aligner_set_bam")
+    rd, keep = T.pack_reads(names, seqs, quals, None, 1, 0)
+    txt, info = ssq.aligner_run(al, rd)
+    for k, tag in enumerate(("main", "spl", "disc")):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        ssq.ck(ssq.lib.ssq_aligner_fetch_bam(al, C.c_int(k), C.byref(p), C.byref(n)), "ssq_aligner_fetch_bam")
+        got = C.string_at(p, n.value)
+        assert got == golden(tag), tag
+    ssq.aligner_free(al)
+    ssq.index_free(h)
+
+
+def test_bgzf_framing_roundtrip_and_sambamba_reads_it(ssq_lib_cpu, oracle, hostsim, ex_index, ex_reads, tmp_path):
+    """ssq_bgzf_compress (host, zlib): members of at most 64 KiB with the BC extra field and the EOF marker; python's gzip and, where the
+    reference checkout is present (this container, not the GPU box), the reference's sambamba read the resulting .bam back"""
+    import ctypes as C
+    import struct
+    import subprocess
+    L = ssq_lib_cpu
+    idx = oracle.load(ex_index)
+    names, seqs, quals = ex_reads
+    txt, bams = hostsim.pipe_bam(idx, names, seqs, quals, 0, b"NA12878", 1, (1, 1, 2, 20, 0))
+    hdr_text = b"@HD\tVN:1.3\tSO:coordinate\n@SQ\tSN:20_slice\tLN:321635\n@RG\tID:NA12878\tSM:NA12878\tLB:lib1\n"
+    raw = b"BAM\x01" + struct.pack("<i", len(hdr_text)) + hdr_text + struct.pack("<i", 1) + struct.pack("<i", 9) + b"20_slice\x00" + struct.pack("<i", 321635) + bams[0]
+    for level in (0, 1, 6):
+        out, n = C.c_void_p(), C.c_size_t(0)
+        assert L.ssq_bgzf_compress(raw, C.c_size_t(len(raw)), C.c_int(level), C.c_int(1), C.byref(out), C.byref(n)) == 0
+        comp = C.string_at(out, n.value)
+        L.ssq_free(out)
+        assert gzip.decompress(comp) == raw
+        p, nb = 0, 0
+        while p < len(comp):  # every member: gzip magic, FEXTRA, "BC", BSIZE
+            assert comp[p:p + 4] == b"\x1f\x8b\x08\x04" and comp[p + 12:p + 14] == b"BC"
+            bsize = struct.unpack("<H", comp[p + 16:p + 18])[0] + 1
+            assert struct.unpack("<I", comp[p + bsize - 4:p + bsize])[0] <= 0xff00
+            p += bsize; nb += 1
+        assert p == len(comp) and nb == (len(raw) + 0xff00 - 1) // 0xff00 + 1
+        assert comp.endswith(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+    sb = "/root/reference/src/sambamba"
+    if os.path.exists(sb):
+        bam = str(tmp_path / "x.bam")
+        open(bam, "wb").write(comp)
+        view = subprocess.run([sb, "view", bam], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+        assert view.count("\n") == txt[0].count("\n")
+        # sambamba's text of our records == the oracle pipeline's SAM records, re-ordered by coordinate (stable)
+        key = lambda l: (1 << 40 if l.split("\t")[2] == "*" else 0, int(l.split("\t")[3]), (int(l.split("\t")[1]) >> 4) & 1)
+        assert view.splitlines() == sorted(txt[0].splitlines(), key=key)

@@ -157,3 +157,72 @@ def test_bench_scale_sample_matches_oracle(ssq, oracle, syn_index, gpu_syn, tmp_
     unflag = lambda l: "\t".join([l.split("\t")[0], str(int(l.split("\t")[1]) & ~0x400)] + l.split("\t")[2:])
     big = [unflag(strip(l)) for l in lines[: ref.count("\n")]]
     assert big == ref.splitlines()
+
+
+def test_invariants_on_200k_reads(ssq, syn_index, gpu_syn):
+    """bwa-free invariants of the GPU's records at a scale the oracle is too slow for (200 k reads, three batches of one run): every
+    alignment re-scored from its CIGAR agrees with AS, NM and MD agree with the reference, the simulated origin is recovered, flags of a
+    pair are consistent, every read appears exactly once as a primary record, in input order, and duplicates planted under new names carry 0x400"""
+    import re
+    fa, g, bounds = syn_index
+    ref = "".join("ACGT"[b] for b in g)
+    names, seqs, quals = T.simulate_pairs(g, bounds, 90000, 150, 77)
+    rng = np.random.default_rng(5)
+    nd = 10000
+    for k in range(nd):  # planted duplicates of earlier pairs
+        j = int(rng.integers(0, 90000))
+        names += ["dup%d" % k] * 2; seqs += [seqs[2 * j], seqs[2 * j + 1]]; quals += [quals[2 * j], quals[2 * j + 1]]
+    al = ssq.aligner_create(gpu_syn, SB_SPEEDSEQ, b"inv")
+    cuts = [0, 70000, 140000, len(names)]
+    lines = []
+    for a, b in zip(cuts, cuts[1:]):
+        rd, keep = T.pack_reads(names[a:b], seqs[a:b], quals[a:b], None, 1, a)
+        txt, info = ssq.aligner_run(al, rd)
+        lines += txt[0].decode().splitlines()
+    ssq.aligner_free(al)
+    ctg = {"ctg%d" % (i + 1): int(bounds[i]) for i in range(len(bounds) - 1)}
+    prim = [l for l in lines if not int(l.split("\t", 2)[1]) & 0x900]
+    assert len(prim) == len(names) and [l.split("\t", 1)[0] for l in prim] == names
+    n_checked = n_hit = n_dupflag = 0
+    for l in lines:
+        f = l.split("\t")
+        flag = int(f[1])
+        if f[0].startswith("dup") and flag & 0x400:
+            n_dupflag += 1
+        if flag & 4 or f[5] == "*" or f[9] == "*":
+            continue
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        pos = ctg[f[2]] + int(f[3]) - 1
+        q = r = sc = nm = run = 0
+        md = []
+        for ln, op in re.findall(r"(\d+)([MIDSH])", f[5]):
+            ln = int(ln)
+            if op == "M":
+                qs, rs = f[9][q:q + ln], ref[pos + r:pos + r + ln]
+                if qs == rs and "N" not in qs:
+                    sc += ln; run += ln
+                else:
+                    for a_, b_ in zip(qs, rs):
+                        if a_ == b_ and a_ != "N":
+                            sc += 1; run += 1
+                        else:
+                            sc -= 1 if "N" in (a_, b_) else 4
+                            nm += 1; md.append(str(run) + b_); run = 0
+                q += ln; r += ln
+            elif op == "I":
+                sc -= 6 + ln; nm += ln; q += ln
+            elif op == "D":
+                sc -= 6 + ln; nm += ln; md.append(str(run) + "^" + ref[pos + r:pos + r + ln]); run = 0; r += ln
+            elif op == "S":
+                q += ln
+        md.append(str(run))
+        assert q == len(f[9]) and nm == int(tags["NM"]) and "".join(md) == tags["MD"], l
+        assert 0 <= int(tags["AS"]) - sc <= 8 and 0 <= int(f[4]) <= 60, l
+        if flag & 1:
+            assert bool(flag & 0x40) != bool(flag & 0x80)
+        n_checked += 1
+        if not flag & 0x900 and f[0].startswith("r"):
+            _, c, p = f[0].split("_")
+            n_hit += abs(pos - (int(bounds[int(c)]) + int(p))) < 700
+    assert n_checked > 195000 and n_hit > 0.97 * 180000
+    assert n_dupflag >= 2 * nd * 0.95  # (a planted copy of a pair that did not align at all cannot be marked)
