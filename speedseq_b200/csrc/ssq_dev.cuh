@@ -24,6 +24,17 @@ typedef int64_t i64;
 typedef uint32_t u32;
 typedef int32_t i32;
 
+// three-input max: one VIMNMX3 (DPX) instruction on sm_90+; plain code on the host (tests/hostsim)
+SSQ_HD int ssq_max2(int a, int b) { return a > b ? a : b; }
+SSQ_HD int ssq_max3(int a, int b, int c)
+{
+#ifdef __CUDA_ARCH__
+	return __vimax3_s32(a, b, c);
+#else
+	return ssq_max2(ssq_max2(a, b), c);
+#endif
+}
+
 // ---------------------------------------------------------------- HBM layout of the index ----
 // bwt  : the occ-interleaved BWT exactly as in PREFIX.bwt after its 40-byte header: one 64-byte block per
 //        128 symbols = u64 occ[4] (A,C,G,T before the block) + u32 w[8] (16 symbols/word, MSB first).
@@ -1038,21 +1049,23 @@ SSQ_HD int sw_extend_impl(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, i
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
 		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+		// the row's substitution scores for query bases 0..4, one byte each (the target base is fixed along a row)
+		u64 sctab = 0;
+		for (int qb = 0; qb < 5; ++qb) sctab |= (u64)(uint8_t)(int8_t)((qb > 3 || tb > 3) ? -1 : (qb == tb ? o.a : -o.b)) << (8 * qb);
+		// row maximum and its column in one word: (h << 16 | column + 1) — equal maxima keep the LATER column, as the reference's
+		// `mj = m > h ? mj : j` does; used in the packed form only (h < 2^13 there)
+		int mpk = 0;
 		// one cell: consumes the packed (H(i-1,j-1), E(i,j)) word of column j, leaves (H(i,j-1), E(i+1,j)) there
 		auto cell = [&](const u32 p, const int qb, const int jj) {
 			int M = (int)(p & 0xffffu), e = (int)((p & VMASK) >> 16), h;
-			const int sc = (qb > 3 || tb > 3) ? -1 : (qb == tb ? o.a : -o.b);
+			const int sc = (int)(int8_t)(sctab >> (8 * qb));
 			M = M ? M + sc : 0;
-			h = M > e ? M : e;
-			h = h > f ? h : f;
-			mj = m > h ? mj : jj;
-			m = m > h ? m : h;
-			t = M - oe_del; t = t > 0 ? t : 0;
-			e -= e_del; e = e > t ? e : t;
+			h = ssq_max3(M, e, f);
+			if (PQ) mpk = ssq_max2(mpk, h << 16 | (jj + 1)); else { mj = m > h ? mj : jj; m = m > h ? m : h; }
+			e = ssq_max3(e - e_del, M - oe_del, 0);
 			eh.set(jj, (u32)h1 | (u32)e << 16 | (p & QMASK));
 			h1 = h;
-			t = M - oe_ins; t = t > 0 ? t : 0;
-			f -= e_ins; f = f > t ? f : t;
+			f = ssq_max3(f - e_ins, M - oe_ins, 0);
 		};
 		// four columns per trip: their row-state words are fetched before the first of them is rewritten (column j's store does
 		// not touch columns j+1..j+3), so the loads overlap the dependent arithmetic of the cells
@@ -1065,6 +1078,8 @@ SSQ_HD int sw_extend_impl(const ssq_opts_t &o, int qlen, QF Q, int tlen, TF T, i
 			}
 		}
 		for (; j < end; ++j) { const u32 p = eh.get(j); cell(p, PQ ? (int)(p >> 29) : Q(j), j); }
+		if (PQ) { m = mpk >> 16; mj = (mpk & 0xffff) - 1; }
+		(void)t;
 		cells += (unsigned long long)(end > beg ? end - beg : 0);
 		eh.set(end, PQ ? ((u32)h1 | (eh.get(end) & QMASK)) : (u32)h1);
 		if (j == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
