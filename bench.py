@@ -459,7 +459,10 @@ def main():
             "k_smem (seeding, all passes)": {"ms": st["k_smem"], "bytes": blk * counters[0] / nb},
             "k_sa (SA look-up)": {"ms": st["k_sa"], "bytes": (blk * counters[1] + float(L.ssq_index_info(idx, 8)) * counters[2]) / nb},
             "k_chain": {"ms": st["k_chain"], "bytes": None},
-            "k_extend (ksw_extend2)": {"ms": st["k_extend"], "bytes": counters[5] / nb, "gcups": counters[4] / nb / (st["k_extend"] * 1e6) if st["k_extend"] else None},
+            "k_extend (ksw_extend2)": {"ms": st["k_extend"], "bytes": counters[5] / nb, "gcups": counters[4] / nb / (st["k_extend"] * 1e6) if st["k_extend"] else None,
+                                       # ALU roofline: ~16 integer lane-operations per DP cell (SASS of k_ext_run's inner loop) against 148 SMs x 128 lanes x clock
+                                       "roofline": {"bound": "alu", "unit": "G lane-ops/s", "ops_per_cell": 16, "achieved": 16 * counters[4] / nb / (st["k_extend"] * 1e6) if st["k_extend"] else None,
+                                                    "peak": 148 * 128 * 1.965, "frac": (16 * counters[4] / nb / (st["k_extend"] * 1e6)) / (148 * 128 * 1.965) if st["k_extend"] else None}},
             "k_select": {"ms": st["k_select"], "bytes": None},
             "k_dedup (sort/dedup/patch)": {"ms": st["sort_dedup_patch"], "bytes": None},
             "k_pestat + host reduction": {"ms": st["insert_size_stats"], "bytes": None},

@@ -140,7 +140,7 @@ typedef struct {
 	int32_t read_id;
 } ssq_alnreg_t;
 
-/* one-shot, HOST buffers in and out (this is what the CLI shim calls per batch; `e2e` in bench.py) */
+/* one-shot, HOST buffers in and out: regions only (parity tests of the seed -> extend half; the CLI shim and bench.py drive ssq_aligner_*) */
 int ssq_align_batch(const ssq_index_t *idx, const ssq_opts_t *opt, int n_reads, const uint8_t *seq, const uint64_t *read_off,
                     int stage, ssq_alnreg_t *out, uint64_t out_cap, uint64_t *out_off, uint64_t *needed);
 

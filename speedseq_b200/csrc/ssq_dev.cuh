@@ -1,7 +1,7 @@
 // ssq_dev.cuh — device-side data layout and the per-read / per-seed routines of the alignment path.
 //
 // Everything that is arithmetic lives here as SSQ_HD templates so that (a) the __global__ wrappers in
-// ssq_fm.cu / ssq_chain.cu / ssq_extend.cu stay thin and (b) tests/hostsim can compile the very same
+// ssq_kernels.cu stay thin and (b) tests/hostsim can compile the very same
 // routines for the host and compare them with the oracle on a box without a GPU (test-only harness,
 // never part of libssq.so: the shipped library has no CPU path).
 //

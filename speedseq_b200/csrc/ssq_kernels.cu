@@ -1,15 +1,18 @@
 // ssq_kernels.cu — sm_100a kernels of the alignment path and their stream-ordered launch sequence.
 //
-// Stage map (reference: inside `$BWA mem`, /root/reference/bin/speedseq:438):
-//   k_smem     a4  warp-per-read SMEM seeding, three passes; the 64-B occ block of each rank query is fetched by one
-//                  half-warp (one coalesced 64-B request), popcounts are done by 8 lanes and merged with shuffles.
-//                  Bound: random 64-B reads (L2 when the BWT fits its 126 MB, else HBM).
-//   k_sa       a5  thread-per-occurrence LF walk to the next sampled SA row. Same bound.
-//   k_chain    a6  thread-per-read chaining + chain filter (small, branchy, integer).
-//   k_extend   a7  thread-per-seed banded affine-gap extension, DP row state in shared memory (int16 H|E pairs,
-//                  bank-conflict-free striding), target bases streamed from the 2-bit reference. Integer-ALU bound.
-//   k_select       thread-per-read replay of the seed-skipping rules over the pre-computed candidates.
-// Scans use CUB (plumbing).  No CPU fallback exists in this library.
+// Stage map (reference: inside `$BWA mem`, /root/reference/bin/speedseq:438; measurements in DESIGN.md §5):
+//   seeding  a4  default: phase-split kernels — forward walks (k_smem_fwd<1|2>, lane = read), backward sweeps (k_smem_bwd, lane = call),
+//                pass-2 selection (k_smem_p2sel), greedy pass (k_smem_p3), one radix sort on (read, qb, qe) to publish the intervals.
+//                Indexes with >= 2^32 rows: the per-lane state machine k_smem_m<u64> + k_smem_p3 on the 64-byte on-disk rank blocks.
+//                One 256-bit load per rank query of the re-blocked 32-byte sectors.  Bound: random sector reads (L2 / HBM).
+//   k_sa     a5  thread per seed occurrence, LF walk to the load-time densified SA sample.  Same bound.
+//   k_chain / k_chain_coop  a6  per-lane ChainBuilder for reads with <= 16 seeds, warp per read (shared-memory chains, three
+//                capacity levels) above.
+//   k_ext_*  a7  seed extension in lazy rounds, jobs radix-sorted by size, one launch per query-length class; thread per
+//                extension, one packed 32-bit word (H | E | query base) per column in shared memory, DPX three-way maxima.
+//   k_select / k_select_heavy   resumable replay of the reference's seed-skipping rules over the candidates.
+//   k_dup_* + CUB radix sort    duplicate marking (batch form, streaming set, device-pointer form used by ssq_pipe.cu / ssq_dist.cu).
+// Scans and radix sorts use CUB (plumbing).  No CPU fallback exists in this library.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <mutex>
