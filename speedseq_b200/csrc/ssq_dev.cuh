@@ -64,7 +64,7 @@ struct DevIndex {
 
 struct Counters { // device-measured work, feeds roofline.achieved (algorithmic bytes)
 	unsigned long long occ_smem, occ_sa, sa_reads, sw_calls, sw_cells, sw_bytes, n_seeds, n_regs;
-	unsigned long long dbg[8]; // kernel-internal cycle counters (diagnostics)
+	unsigned long long dbg[16]; // kernel-internal cycle counters (diagnostics); [8..11]: rank-block counter before/after the two backward-sweep launches
 };
 
 template <class U> struct IntvT { U x0, x1, x2; u32 qb, qe; }; // bi-interval + query span [qb,qe)

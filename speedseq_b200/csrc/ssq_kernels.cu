@@ -15,6 +15,7 @@
 // Scans and radix sorts use CUB (plumbing).  No CPU fallback exists in this library.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <cub/device/device_merge.cuh>
 #include <mutex>
 #include <condition_variable>
 #include <stdio.h>
@@ -519,6 +520,8 @@ __global__ void __launch_bounds__(128, MINB) k_smem_bwd2(DevIndex ix, ssq_opts_t
 }
 
 // range bookkeeping between the kernels; the counters keep counting when a pool is full, the ranges the next kernels walk must not
+// copies the running rank-block counter into a diagnostic slot (brackets one kernel's share of the seeding stage's algorithmic bytes)
+__global__ void k_cnt_mark(Counters *c, int slot) { c->dbg[slot] = c->occ_smem; }
 __global__ void k_smem_snapshot(Split *sp, u64 call_cap, u64 mem_cap, int set1)
 {
 	if (sp->n_calls > sp->need_calls) sp->need_calls = sp->n_calls;
@@ -1345,7 +1348,7 @@ struct ssq_batch {
 	Counters h_cnt;
 	int launches, own_stream, smem_variant;
 	u64 call_cap = 0, fl_cap = 0; // split seeding: capacities of the call and forward-list pools
-	cudaEvent_t ev[6], evc[4], evs[2], evx[2]; // stage boundaries; chaining tiers; k_smem_m alone; selection kernels of one round // stage boundaries; chaining tiers (light start, heavy start, end)
+	cudaEvent_t ev[6], evc[4], evs[2], evx[2], evb[4]; /* evb: around the two backward-sweep launches of the split seeding */ // stage boundaries; chaining tiers; k_smem_m alone; selection kernels of one round // stage boundaries; chaining tiers (light start, heavy start, end)
 	float stage_ms[5];
 	ssq_batch() { memset(&h_cnt, 0, sizeof h_cnt); n_intv = n_seeds = n_tasks = n_regs_total = 0; launches = 0; own_stream = 1; pool_cap = 0; ext_rounds = 0; select_ms = 0.f; { const char *v = getenv("SSQ_SMEM_VARIANT"); smem_variant = v ? atoi(v) : 3; /* phase-split seeding (r02: 48.9 ms vs 59.9 ms for the state machine on the bench workload); indexes without bwt32 use the 64-bit state machine */ } memset(stage_ms, 0, sizeof stage_ms); }
 };
@@ -1405,6 +1408,7 @@ extern "C" int ssq_batch_create(const ssq_index_t *idx, const ssq_opts_t *opt, i
 	for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]));
 	for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&b->evc[i]));
 	for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&b->evs[i])); CK(cudaEventCreate(&b->evx[i])); }
+	for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&b->evb[i]));
 	if (read_off && (rc = ssq_batch_upload(b, n_reads, seq, read_off))) { ssq_batch_free(b); return rc; }
 	*out = b;
 	return SSQ_OK;
@@ -1421,6 +1425,7 @@ extern "C" void ssq_batch_free(ssq_batch_t *b)
 	for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evc[i]);
 	for (int i = 0; i < 2; ++i) { cudaEventDestroy(b->evs[i]); cudaEventDestroy(b->evx[i]); }
+	for (int i = 0; i < 4; ++i) cudaEventDestroy(b->evb[i]);
 	if (b->own_stream) cudaStreamDestroy(b->st);
 	delete b;
 }
@@ -1486,19 +1491,23 @@ static int run_smem_split(ssq_batch *b)
 		kf1<<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 1); // n_calls1 = pass-1 calls (n_mems1 still 0)
+		k_cnt_mark<<<1, 1, 0, b->st>>>(&dm->cnt, 8); CK(cudaEventRecord(b->evb[0], b->st));
 		if (!lean) kb<<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		else kb2<<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 0, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		CK(cudaEventRecord(b->evb[1], b->st)); k_cnt_mark<<<1, 1, 0, b->st>>>(&dm->cnt, 9);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 1); // n_mems1 = pass-1 intervals; n_calls1 unchanged (no calls were added)
 		k_smem_p2sel<<<b->n_sm * 8, 256, 0, b->st>>>(b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->xcalls.as<SeedCall>(), b->call_cap, sp);
 		k_smem_snapshot<<<1, 1, 0, b->st>>>(sp, b->call_cap, b->pool_cap, 0); // clamp the request range
 		kf2<<<fgrid, 256, 0, b->st>>>(b->idx->dev, b->opt, n, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, b->xstage.as<FwdEntry>(), b->xcalls.as<SeedCall>(), b->call_cap,
 		                                       b->xfl.as<FwdEntry>(), b->fl_cap, sp, &dm->cnt);
+		k_cnt_mark<<<1, 1, 0, b->st>>>(&dm->cnt, 10); CK(cudaEventRecord(b->evb[2], b->st));
 		if (!lean) kb<<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), b->read_off.as<u64>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
 		else kb2<<<bgrid, bthreads, lsm, b->st>>>(b->idx->dev, b->opt, b->seq.as<uint8_t>(), lcap, list_cap, b->scratch.as<Intv>(), scratch_cap,
 		                                             b->xcalls.as<SeedCall>(), b->xfl.as<FwdEntry>(), 1, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp, &dm->cnt);
+		CK(cudaEventRecord(b->evb[3], b->st)); k_cnt_mark<<<1, 1, 0, b->st>>>(&dm->cnt, 11);
 		if (with_p3) k_smem_p3_append<<<(n + 255) / 256, 256, 0, b->st>>>(n, b->xp3.as<Intv>(), b->xp3n.as<i32>(), p3_stride, b->xmems.as<Intv>(), b->xmemr.as<u32>(), b->pool_cap, sp);
 		b->launches += 10;
 		CK(cudaGetLastError());
@@ -1884,6 +1893,8 @@ extern "C" uint64_t ssq_batch_counter(const ssq_batch_t *b_, int what)
 	case 9: return b->n_intv; case 10: return b->n_tasks; case 11: return (uint64_t)b->ext_rounds;
 	case 12: case 13: case 14: case 15: case 16: return b->h_cnt.dbg[what - 12];
 	case 23: return b->h_cnt.dbg[6]; // rank blocks dereferenced by k_smem_p3 (part of counter 0)
+	case 25: return (b->h_cnt.dbg[9] - b->h_cnt.dbg[8]) + (b->h_cnt.dbg[11] - b->h_cnt.dbg[10]); // rank blocks dereferenced by the two backward-sweep launches (split seeding)
+	case 26: { float m1 = 0.f, m2 = 0.f; if (cudaEventElapsedTime(&m1, b->evb[0], b->evb[1]) != cudaSuccess || cudaEventElapsedTime(&m2, b->evb[2], b->evb[3]) != cudaSuccess) { cudaGetLastError(); return 0; } return (uint64_t)((m1 + m2) * 1000.f); } // their duration, microseconds
 	case 24: { float ms = 0.f; if (cudaEventElapsedTime(&ms, b->evs[0], b->evs[1]) != cudaSuccess) { cudaGetLastError(); return 0; } return (uint64_t)(ms * 1000.f); } // k_smem_m alone, microseconds
 	case 22: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[3], b->evc[2]); return (uint64_t)(ms * 1000.f); } // the big-shared-memory tier alone
 	case 17: case 18: { float ms = 0.f; cudaEventElapsedTime(&ms, b->evc[what - 17], b->evc[what - 16]); return (uint64_t)(ms * 1000.f); } // chaining tiers, microseconds
@@ -2074,8 +2085,11 @@ extern "C" int ssq_dupmark_batch(int device, uint64_t n, const ssq_dupsig_t *sig
 // signatures seen so far is kept on the device as two parallel arrays sorted by (key1, key2); a batch is (1) marked within
 // itself by the two-pass stable sort above, (2) its survivors are looked up in the set by binary search, (3) the new ones
 // are appended and the set is re-sorted (two stable LSD passes).
+struct __align__(16) P128 { u64 a, b; };
+struct P128Lt { __host__ __device__ bool operator()(const P128 &x, const P128 &y) const { return x.a < y.a || (x.a == y.a && x.b < y.b); } };
 struct ssq_dupset {
-	int device; u64 n, cap; u64 *k1, *k2; DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp, dnew, nk1, nk2, cnt, t1, t2; /* scratch kept across calls */
+	int device; u64 n, cap; P128 *keys, *alt; // every signature seen so far, sorted by (key1, key2); alt: the other half of the double buffer the merge writes into
+	DBuf m1, m2, k1g, ka, idx_a, idx_b, tmp, dnew, cnt, s128, sflag, n128; /* scratch kept across calls */
 	std::mutex mu; std::condition_variable cv; long long turn; // batches of one run mark in batch order even when several host threads drive them
 };
 
@@ -2099,15 +2113,15 @@ extern "C" int ssq_dupset_create(int device, ssq_dupset_t **out)
 	int rc = ssq_use_device(device);
 	if (rc) return rc;
 	ssq_dupset *s = new ssq_dupset();
-	s->device = device; s->n = s->cap = 0; s->k1 = s->k2 = 0; s->turn = 0;
+	s->device = device; s->n = s->cap = 0; s->keys = s->alt = 0; s->turn = 0;
 	*out = s;
 	return SSQ_OK;
 }
-extern "C" void ssq_dupset_free(ssq_dupset_t *s) { if (!s) return; cudaFree(s->k1); cudaFree(s->k2); delete s; }
+extern "C" void ssq_dupset_free(ssq_dupset_t *s) { if (!s) return; cudaFree(s->keys); cudaFree(s->alt); delete s; }
 extern "C" uint64_t ssq_dupset_size(const ssq_dupset_t *s) { return s ? s->n : 0; }
 
 __global__ void k_dupset_lookup_keys(u64 n, const uint8_t *__restrict__ valid, const u64 *__restrict__ key1, const u64 *__restrict__ key2, uint8_t *is_dup,
-                                     const u64 *__restrict__ s1, const u64 *__restrict__ s2, u64 sn, uint8_t *is_new)
+                                     const P128 *__restrict__ set, u64 sn, uint8_t *is_new)
 {
 	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -2115,10 +2129,19 @@ __global__ void k_dupset_lookup_keys(u64 n, const uint8_t *__restrict__ valid, c
 	if (valid[i] && !is_dup[i]) {
 		const u64 a = key1[i], b = key2[i];
 		u64 lo = 0, hi = sn;
-		while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (s1[mid] < a || (s1[mid] == a && s2[mid] < b)) lo = mid + 1; else hi = mid; }
-		if (lo < sn && s1[lo] == a && s2[lo] == b) is_dup[i] = 1; else nw = 1;
+		while (lo < hi) { const u64 mid = (lo + hi) >> 1; const P128 v = set[mid]; if (v.a < a || (v.a == a && v.b < b)) lo = mid + 1; else hi = mid; }
+		if (lo < sn) { const P128 v = set[lo]; if (v.a == a && v.b == b) is_dup[i] = 1; else nw = 1; } else nw = 1;
 	}
 	is_new[i] = nw;
+}
+// the chunk's items in sorted order (idx = the order the two stable sort passes produced): their keys as one 128-bit word and whether they are new
+__global__ void k_dup_sorted_new(u64 n, const u32 *__restrict__ idx, const u64 *__restrict__ key1s, const u64 *__restrict__ key2, const uint8_t *__restrict__ is_new, P128 *out, uint8_t *flag)
+{
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u32 me = idx[i];
+	P128 v; v.a = key1s[i]; v.b = key2[me];
+	out[i] = v; flag[i] = is_new[me];
 }
 __global__ void k_dup_sig_keys(u64 n, const ssq_dupsig_t *__restrict__ sig, u64 *key1, u64 *key2, uint8_t *valid)
 {
@@ -2147,48 +2170,47 @@ extern "C" int ssq_dupset_mark_dev(ssq_dupset_t *set, uint64_t n, const uint64_t
 	if (n == 0) return SSQ_OK;
 	if (n >= 0x7fffffffull) { ssq_set_error("ssq_dupset_mark: more than 2^31-1 pairs in one call"); return SSQ_EINVAL; }
 	cudaStream_t st = (cudaStream_t)stream_;
-	DBuf &m1 = set->m1, &m2 = set->m2, &k1g = set->k1g, &ka = set->ka, &idx_a = set->idx_a, &idx_b = set->idx_b, &tmp = set->tmp, &dnew = set->dnew, &nk1 = set->nk1, &nk2 = set->nk2, &cnt = set->cnt;
-	if (m1.need(n * 8) || m2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dnew.need(n) || nk1.need(n * 8) || nk2.need(n * 8) || cnt.need(16)) return SSQ_ENOMEM;
+	DBuf &m1 = set->m1, &m2 = set->m2, &k1g = set->k1g, &ka = set->ka, &idx_a = set->idx_a, &idx_b = set->idx_b, &tmp = set->tmp, &dnew = set->dnew, &cnt = set->cnt;
+	if (m1.need(n * 8) || m2.need(n * 8) || k1g.need(n * 8) || ka.need(n * 8) || idx_a.need(n * 4) || idx_b.need(n * 4) || dnew.need(n) || cnt.need(16) || set->s128.need(n * 16) || set->sflag.need(n) ||
+	    set->n128.need(n * 16)) return SSQ_ENOMEM;
 	const unsigned g = (unsigned)((n + 255) / 256);
-	size_t tb = 0, tb2 = 0;
-	cub::DeviceRadixSort::SortPairs(0, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st);
-	cub::DeviceSelect::Flagged(0, tb2, m1.as<u64>(), dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n, st);
-	if (tb2 > tb) tb = tb2;
 	const u64 grown = set->n + n;
 	if (grown >= 0x7fffffffull) { ssq_set_error("ssq_dupset: more than 2^31-1 distinct signatures"); return SSQ_ECAP; }
-	cub::DeviceRadixSort::SortPairs(0, tb2, (u64*)0, (u64*)0, (u64*)0, (u64*)0, (int)grown, 0, 64, st);
+	size_t tb = 0, tb2 = 0;
+	cub::DeviceRadixSort::SortPairs(0, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st);
+	cub::DeviceSelect::Flagged(0, tb2, set->s128.as<P128>(), set->sflag.as<uint8_t>(), set->n128.as<P128>(), cnt.as<u64>(), (int)n, st);
+	if (tb2 > tb) tb = tb2;
+	cub::DeviceMerge::MergeKeys(0, tb2, (const P128*)0, (int)set->n, (const P128*)0, (int)n, (P128*)0, P128Lt(), st);
 	if (tb2 > tb) tb = tb2;
 	if (tmp.need(tb)) return SSQ_ENOMEM;
 	k_dup_mask<<<g, 256, 0, st>>>(n, d_valid, d_k1, d_k2, m1.as<u64>(), m2.as<u64>());
 	k_dup_iota<<<g, 256, 0, st>>>(n, idx_a.as<u32>());
 	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, m2.as<u64>(), ka.as<u64>(), idx_a.as<u32>(), idx_b.as<u32>(), (int)n, 0, 64, st)); // stable, by key2
 	k_dup_gather<<<g, 256, 0, st>>>(n, idx_b.as<u32>(), m1.as<u64>(), k1g.as<u64>());
-	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n, 0, 64, st)); // stable, by key1
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1g.as<u64>(), ka.as<u64>(), idx_b.as<u32>(), idx_a.as<u32>(), (int)n, 0, 64, st)); // stable, by key1: now sorted by (key1, key2), input order inside equal keys
 	k_dup_mark_keys<<<g, 256, 0, st>>>(n, idx_a.as<u32>(), ka.as<u64>(), m2.as<u64>(), d_valid, d_is_dup);
-	k_dupset_lookup_keys<<<g, 256, 0, st>>>(n, d_valid, d_k1, d_k2, d_is_dup, set->k1, set->k2, set->n, dnew.as<uint8_t>());
+	k_dupset_lookup_keys<<<g, 256, 0, st>>>(n, d_valid, d_k1, d_k2, d_is_dup, set->keys, set->n, dnew.as<uint8_t>());
+	// absorb the new signatures: they are already in sorted order inside the chunk, so the set grows by ONE merge (16 B/key read +
+	// written), not by a re-sort of everything seen so far
+	k_dup_sorted_new<<<g, 256, 0, st>>>(n, idx_a.as<u32>(), ka.as<u64>(), m2.as<u64>(), dnew.as<uint8_t>(), set->s128.as<P128>(), set->sflag.as<uint8_t>());
 	CK(cudaGetLastError());
-	// absorb the new signatures
 	u64 n_new = 0;
-	CK(cub::DeviceSelect::Flagged(tmp.p, tb, d_k1, dnew.as<uint8_t>(), nk1.as<u64>(), cnt.as<u64>(), (int)n, st));
-	CK(cub::DeviceSelect::Flagged(tmp.p, tb, d_k2, dnew.as<uint8_t>(), nk2.as<u64>(), cnt.as<u64>(), (int)n, st));
+	CK(cub::DeviceSelect::Flagged(tmp.p, tb, set->s128.as<P128>(), set->sflag.as<uint8_t>(), set->n128.as<P128>(), cnt.as<u64>(), (int)n, st));
 	CK(cudaMemcpyAsync(&n_new, cnt.p, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	if (n_new) {
 		const u64 total = set->n + n_new;
-		if (total > set->cap) { // grow, keeping the content
+		if (total > set->cap) { // grow both halves of the double buffer, keeping the content
 			const u64 ncap = total + total / 2 + 1024;
-			u64 *a = 0, *b = 0;
-			CK(cudaMalloc(&a, ncap * 8)); CK(cudaMalloc(&b, ncap * 8));
-			if (set->n) { CK(cudaMemcpyAsync(a, set->k1, set->n * 8, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(b, set->k2, set->n * 8, cudaMemcpyDeviceToDevice, st)); }
+			P128 *a = 0, *b = 0;
+			CK(cudaMalloc(&a, ncap * sizeof(P128))); CK(cudaMalloc(&b, ncap * sizeof(P128)));
+			if (set->n) CK(cudaMemcpyAsync(a, set->keys, set->n * sizeof(P128), cudaMemcpyDeviceToDevice, st));
 			CK(cudaStreamSynchronize(st));
-			cudaFree(set->k1); cudaFree(set->k2);
-			set->k1 = a; set->k2 = b; set->cap = ncap;
+			cudaFree(set->keys); cudaFree(set->alt);
+			set->keys = a; set->alt = b; set->cap = ncap;
 		}
-		CK(cudaMemcpyAsync(set->k1 + set->n, nk1.p, n_new * 8, cudaMemcpyDeviceToDevice, st));
-		CK(cudaMemcpyAsync(set->k2 + set->n, nk2.p, n_new * 8, cudaMemcpyDeviceToDevice, st));
-		if (set->t1.need(total * 8) || set->t2.need(total * 8)) return SSQ_ENOMEM;
-		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, set->k2, set->t2.as<u64>(), set->k1, set->t1.as<u64>(), (int)total, 0, 64, st)); // by key2, key1 rides along
-		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, set->t1.as<u64>(), set->k1, set->t2.as<u64>(), set->k2, (int)total, 0, 64, st)); // stable by key1
+		CK(cub::DeviceMerge::MergeKeys(tmp.p, tb, (const P128*)set->keys, (int)set->n, (const P128*)set->n128.as<P128>(), (int)n_new, set->alt, P128Lt(), st));
+		P128 *t = set->keys; set->keys = set->alt; set->alt = t;
 		set->n = total;
 	}
 	return SSQ_OK;
