@@ -33,7 +33,7 @@ struct TgtBuf { const uint8_t *t; __device__ __forceinline__ int operator()(int 
 template <class T> struct TgtRev { T t; int te; __device__ __forceinline__ int operator()(int i) const { return i <= te ? t(te - i) : t(i); } };
 
 template <class TGT>
-__device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt = 0)
+__device__ LocalRes sw_local_pass_warp_smem(const ssq_opts_t &o, bool bytes, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt = 0)
 {
 	const int P = bytes ? 16 : 8, slen = (qlen + P - 1) / P, n = slen * P;
 	const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
@@ -139,6 +139,148 @@ __device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen
 	}
 	__syncwarp();
 	return r;
+}
+
+
+// Byte mode with the whole striped state of a lane in registers: a segment has at most 16 cells (queries up to 255 bases over 16
+// lanes), so H, E and the query profile of a lane are 16-entry register arrays swept by a fully unrolled loop — no shared-memory
+// traffic and no index arithmetic in the inner loop (the profiler attributed 85 % of k_rescue's instructions to that loop).  The
+// profile of cell k is one word: the scores against target bases A, C, G, T in its four bytes.  Same arithmetic, same order,
+// same results as the shared-memory form above; targets holding N take that form.
+template <int SLEN, class TGT>
+__device__ __noinline__ LocalRes sw_local_pass_warp_reg(const ssq_opts_t &o, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt, bool *has_n)
+{
+	const int P = 16, slen = SLEN;
+	const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
+	const int shift = o.b > 1 ? o.b : 1, maxsc = o.a;
+	const int minsc = (xtra & SSQ_XSUBO) ? xtra & 0xffff : 0x10000;
+	const int endsc = (xtra & SSQ_XSTOP) ? xtra & 0xffff : 0x10000;
+	const bool act = lane < P;
+	LocalRes r;
+	r.score = 0; r.te = r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = r.qb = -1;
+	*has_n = false;
+	if (qlen <= 0) return r;
+	int H[SLEN], E[SLEN], HM[SLEN]; u32 PF[SLEN];
+#pragma unroll
+	for (int k = 0; k < SLEN; ++k) {
+		const int pos = lane * slen + k;
+		const int qc = (act && pos < qlen) ? q[pos] : -1;
+		u32 w = 0;
+#pragma unroll
+		for (int c = 0; c < 4; ++c) w |= (u32)(uint8_t)(int8_t)(qc < 0 ? 0 : score_of(o, qc, c)) << (8 * c);
+		PF[k] = w; H[k] = E[k] = HM[k] = 0;
+	}
+	int gmax = 0, te = -1, n_b = 0, tcache = 0, rows = 0;
+	for (int i = 0; i < tlen; ++i) {
+		if ((i & 31) == 0) tcache = i + lane < tlen ? tgt(i + lane) : 0;
+		const int tb = __shfl_sync(WFULL, tcache, i & 31);
+		if (tb > 3) { *has_n = true; return r; } // (uniform) the caller redoes the pass with the general form
+		++rows;
+		const int sh = 8 * tb;
+		int f = 0, imax = 0;
+		int hd;
+		{ // H of the last cell of the lane below
+			hd = __shfl_up_sync(WFULL, H[SLEN - 1], 1);
+			if (lane == 0) hd = 0;
+		}
+#pragma unroll
+		for (int k = 0; k < SLEN; ++k) {
+			{
+				const int hn = H[k];
+				int h = hd + (int)(int8_t)(PF[k] >> sh), e = E[k], tt;
+				h += shift; if (h > 255) h = 255; h -= shift; if (h < 0) h = 0;
+				h = h > e ? h : e;
+				h = h > f ? h : f;
+				imax = imax > h ? imax : h;
+				H[k] = h;
+				tt = h - oe_del; if (tt < 0) tt = 0;
+				e -= e_del; if (e < 0) e = 0;
+				E[k] = e > tt ? e : tt;
+				tt = h - oe_ins; if (tt < 0) tt = 0;
+				f -= e_ins; if (f < 0) f = 0;
+				f = f > tt ? f : tt;
+				hd = hn;
+			}
+		}
+		if (!act) { imax = 0; f = 0; }
+		{ // lazy F
+			int fl = f;
+			bool done = false;
+			for (int round = 0; round < 16 && !done; ++round) {
+				fl = __shfl_up_sync(WFULL, fl, 1);
+				if (lane == 0) fl = 0;
+#pragma unroll
+				for (int k = 0; k < SLEN; ++k) {
+					if (!done) {
+						bool gt = false;
+						if (act) {
+							int h = H[k], tt;
+							h = h > fl ? h : fl;
+							H[k] = h;
+							tt = h - oe_ins; if (tt < 0) tt = 0;
+							fl -= e_ins; if (fl < 0) fl = 0;
+							gt = fl > tt;
+						}
+						if (!__any_sync(WFULL, gt)) done = true;
+					}
+				}
+			}
+		}
+		imax = __reduce_max_sync(WFULL, imax);
+		if (imax >= minsc && lane == 0) {
+			if (n_b == 0 || (i32)b[n_b - 1] + 1 != i) { if (n_b < b_cap) b[n_b++] = (u64)imax << 32 | (u32)i; }
+			else if ((int)(b[n_b - 1] >> 32) < imax) b[n_b - 1] = (u64)imax << 32 | (u32)i;
+		}
+		if (imax > gmax) {
+			gmax = imax; te = i;
+#pragma unroll
+			for (int k = 0; k < SLEN; ++k) HM[k] = H[k];
+			if (gmax + shift >= 255 || gmax >= endsc) break;
+		}
+	}
+	n_b = __shfl_sync(WFULL, n_b, 0);
+	if (cnt && lane == 0) { atomicAdd(cnt + 2, 1ull); atomicAdd(cnt + 3, (unsigned long long)rows * qlen); }
+	r.score = gmax + shift < 255 ? gmax : 255;
+	r.te = te;
+	if (r.score != 255) {
+		int vmax = -1, qe = 0x7fffffff;
+		if (act) {
+#pragma unroll
+			for (int k = 0; k < SLEN; ++k) { const int v = HM[k], pos = lane * slen + k; if (v > vmax) { vmax = v; qe = pos; } else if (v == vmax && pos < qe) qe = pos; }
+		}
+		const int m = __reduce_max_sync(WFULL, vmax);
+		r.qe = __reduce_min_sync(WFULL, vmax == m ? qe : 0x7fffffff);
+		if (n_b) {
+			int s2 = -1, te2 = -1;
+			if (lane == 0) {
+				const int d = (r.score + maxsc - 1) / maxsc, low = te - d, high = te + d;
+				for (int i = 0; i < n_b; ++i) {
+					const int e = (i32)b[i];
+					if ((e < low || e > high) && (int)(b[i] >> 32) > s2) { s2 = (int)(b[i] >> 32); te2 = e; }
+				}
+			}
+			r.score2 = __shfl_sync(WFULL, s2, 0); r.te2 = __shfl_sync(WFULL, te2, 0);
+		}
+	}
+	return r;
+}
+
+template <class TGT>
+__device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt = 0)
+{
+	if (bytes && qlen > 0 && qlen <= 256) {
+		bool has_n = false;
+		LocalRes r;
+		switch ((qlen + 15) / 16) {
+#define SSQ_SLEN_CASE(n_) case n_: r = sw_local_pass_warp_reg<n_>(o, qlen, q, tlen, tgt, xtra, W, b, b_cap, lane, cnt, &has_n); break;
+		SSQ_SLEN_CASE(1) SSQ_SLEN_CASE(2) SSQ_SLEN_CASE(3) SSQ_SLEN_CASE(4) SSQ_SLEN_CASE(5) SSQ_SLEN_CASE(6) SSQ_SLEN_CASE(7) SSQ_SLEN_CASE(8)
+		SSQ_SLEN_CASE(9) SSQ_SLEN_CASE(10) SSQ_SLEN_CASE(11) SSQ_SLEN_CASE(12) SSQ_SLEN_CASE(13) SSQ_SLEN_CASE(14) SSQ_SLEN_CASE(15) SSQ_SLEN_CASE(16)
+#undef SSQ_SLEN_CASE
+		default: has_n = true;
+		}
+		if (!has_n) return r;
+	}
+	return sw_local_pass_warp_smem(o, bytes, qlen, q, tlen, tgt, xtra, W, b, b_cap, lane, cnt);
 }
 
 // forward pass for score/end, then a pass over the reversed prefixes for the start.  q: the query in shared memory (W.q)
