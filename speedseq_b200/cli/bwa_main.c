@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include <unistd.h>
 #include <zlib.h>
 #include "ssq.h"
@@ -218,6 +219,68 @@ static void put_frame(int stream, const char *p, size_t len)
 	fwrite(&h, sizeof h, 1, stdout); fwrite(p, 1, len, stdout);
 }
 
+/* ------------------------------------------------------------------- stream lanes ----
+ * Device-ingest mode runs SSQ_LANES (default 2) lanes, each a host thread with its own aligner object (own CUDA stream and
+ * buffers): while one lane's batch is on the GPU, the other reads and uploads the next text and writes the previous records —
+ * the read / compute / write overlap of upstream bwa's three-stage pipeline.  Batches are cut one after the other under a lock
+ * (where a batch ends is only known once the device has parsed the text), records are written strictly in batch order (tickets),
+ * and in fused mode the lanes share one dup-set whose turn counter keeps "first seen wins" in input order. */
+typedef struct {
+	raw_t *R1, *R2; int two_files, smart_pe, paired, keep_comment, fused; long chunk; const ssq_pestat_t *pes0;
+	size_t raw_target; long long n_processed, next_ticket, write_turn;
+	int stop, fallback, failed;
+	pthread_mutex_t rd_mu, wr_mu; pthread_cond_t wr_cv;
+} lanes_t;
+typedef struct { lanes_t *S; ssq_aligner_t *al; } lane_arg_t;
+
+static void *lane_main(void *arg_)
+{
+	lane_arg_t *arg = (lane_arg_t*)arg_;
+	lanes_t *S = arg->S;
+	ssq_aligner_t *al = arg->al;
+	for (;;) {
+		size_t u1 = 0, u2 = 0;
+		int n = 0, more = 0, rc;
+		long long ticket;
+		ssq_sam_t out;
+		pthread_mutex_lock(&S->rd_mu);
+		if (S->stop) { pthread_mutex_unlock(&S->rd_mu); break; }
+		raw_fill(S->R1, S->raw_target);
+		if (S->two_files) raw_fill(S->R2, S->raw_target);
+		rc = ssq_aligner_upload_fastq(al, S->R1->buf ? S->R1->buf : "", S->R1->len, S->R1->eof, S->two_files ? (S->R2->buf ? S->R2->buf : "") : 0, S->two_files ? S->R2->len : 0,
+		                              S->two_files ? S->R2->eof : 1, S->smart_pe, S->keep_comment, S->chunk, S->n_processed, &u1, &u2, &n, &more);
+		if (rc == SSQ_EFORMAT) { /* every other legal input: multi-line records, FASTA, unpaired reads among the pairs, ... */
+			if (getenv("SSQ_VERBOSE_INGEST")) fprintf(stderr, "[M::bwa] host tokeniser takes over: %s\n", ssq_last_error());
+			S->fallback = 1; S->stop = 1; pthread_mutex_unlock(&S->rd_mu); break;
+		}
+		if (rc) { fprintf(stderr, "[E::bwa] ssq_aligner_upload_fastq failed (%d): %s\n", rc, ssq_last_error()); S->failed = 1; S->stop = 1; pthread_mutex_unlock(&S->rd_mu); break; }
+		if (more) { S->raw_target += S->raw_target / 2; pthread_mutex_unlock(&S->rd_mu); continue; }
+		if (n == 0) { S->stop = 1; pthread_mutex_unlock(&S->rd_mu); break; }
+		ticket = S->next_ticket++;
+		S->n_processed += n;
+		memmove(S->R1->buf, S->R1->buf + u1, S->R1->len - u1); S->R1->len -= u1;
+		if (S->two_files) { memmove(S->R2->buf, S->R2->buf + u2, S->R2->len - u2); S->R2->len -= u2; }
+		fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)ssq_aligner_counter(al, 109));
+		if (S->smart_pe) fprintf(stderr, "[M::process] 0 single-end sequences; %d paired-end sequences\n", n);
+		pthread_mutex_unlock(&S->rd_mu);
+		ssq_aligner_set_turn(al, ticket);
+		rc = ssq_aligner_compute(al, S->paired ? S->pes0 : 0, 1);
+		if (!rc) rc = ssq_aligner_fetch(al, &out);
+		pthread_mutex_lock(&S->wr_mu);
+		while (S->write_turn != ticket) pthread_cond_wait(&S->wr_cv, &S->wr_mu);
+		if (rc) { fprintf(stderr, "[E::bwa] batch %lld failed (%d): %s\n", ticket, rc, ssq_last_error()); S->failed = 1; }
+		else if (!S->failed) {
+			if (S->fused) { put_frame(0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
+			else fwrite(out.text[0], 1, out.len[0], stdout);
+		}
+		++S->write_turn;
+		pthread_cond_broadcast(&S->wr_cv);
+		pthread_mutex_unlock(&S->wr_mu);
+		if (rc) { pthread_mutex_lock(&S->rd_mu); S->stop = 1; pthread_mutex_unlock(&S->rd_mu); break; }
+	}
+	return 0;
+}
+
 static int main_mem(int argc, char **argv, const char *prog)
 {
 	ssq_opts_t opt;
@@ -306,31 +369,34 @@ static int main_mem(int argc, char **argv, const char *prog)
 		ssq_reads_t rd;
 		ssq_sam_t out;
 		int n_se = 0, n_pe = 0, mixed = 0;
-		if (dev_ingest) { /* FASTQ text -> device -> records; the batch is cut on the device by bwa's rule */
-			size_t u1 = 0, u2 = 0;
-			int n = 0, more = 0;
-			raw_fill(&R1, raw_target);
-			if (two_files) raw_fill(&R2, raw_target);
-			rc = ssq_aligner_upload_fastq(al, R1.buf ? R1.buf : "", R1.len, R1.eof, two_files ? (R2.buf ? R2.buf : "") : 0, R2.len, R2.eof, smart_pe, keep_comment, chunk_size * n_threads, n_processed,
-			                              &u1, &u2, &n, &more);
-			if (rc == SSQ_EFORMAT) { /* every other legal input: multi-line records, FASTA, unpaired reads among the pairs, ... */
-				if (getenv("SSQ_VERBOSE_INGEST")) fprintf(stderr, "[M::bwa] host tokeniser takes over: %s\n", ssq_last_error());
-				f1 = fq_from_raw(&R1); if (two_files) f2 = fq_from_raw(&R2);
-				dev_ingest = 0;
-				continue;
+		if (dev_ingest) { /* FASTQ text -> device -> records, in lanes (see lane_main) */
+			lanes_t S;
+			lane_arg_t la[4];
+			pthread_t th[4];
+			ssq_dupset_t *dset = 0;
+			int n_lanes = getenv("SSQ_LANES") ? atoi(getenv("SSQ_LANES")) : 2, k;
+			if (n_lanes < 1) n_lanes = 1;
+			if (n_lanes > 4) n_lanes = 4;
+			memset(&S, 0, sizeof S);
+			S.R1 = &R1; S.R2 = &R2; S.two_files = two_files; S.smart_pe = smart_pe; S.paired = paired; S.keep_comment = keep_comment; S.fused = fused; S.chunk = chunk_size * n_threads;
+			S.pes0 = pes0; S.raw_target = raw_target; S.n_processed = n_processed;
+			pthread_mutex_init(&S.rd_mu, 0); pthread_mutex_init(&S.wr_mu, 0); pthread_cond_init(&S.wr_cv, 0);
+			if (fused && n_lanes > 1 && (rc = ssq_dupset_create(device, &dset))) die("ssq_dupset_create", rc);
+			for (k = 0; k < n_lanes; ++k) {
+				la[k].S = &S; la[k].al = al;
+				if (k > 0 && (rc = ssq_aligner_create(idx, &opt, fused ? &sb : 0, rg_id, &la[k].al))) die("ssq_aligner_create", rc);
+				if (dset && (rc = ssq_aligner_share_dupset(la[k].al, dset))) die("ssq_aligner_share_dupset", rc);
 			}
-			if (rc) die("ssq_aligner_upload_fastq", rc);
-			if (more) { raw_target += raw_target / 2; continue; }
-			if (n == 0) break;
-			fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)ssq_aligner_counter(al, 109));
-			if (smart_pe) fprintf(stderr, "[M::process] 0 single-end sequences; %d paired-end sequences\n", n);
-			if ((rc = ssq_aligner_compute(al, paired ? pes0 : 0, 1))) die("ssq_aligner_compute", rc);
-			if ((rc = ssq_aligner_fetch(al, &out))) die("ssq_aligner_fetch", rc);
-			if (fused) { put_frame(0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
-			else fwrite(out.text[0], 1, out.len[0], stdout);
-			memmove(R1.buf, R1.buf + u1, R1.len - u1); R1.len -= u1;
-			if (two_files) { memmove(R2.buf, R2.buf + u2, R2.len - u2); R2.len -= u2; }
-			n_processed += n;
+			fflush(stdout);
+			for (k = 0; k < n_lanes; ++k) pthread_create(&th[k], 0, lane_main, &la[k]);
+			for (k = 0; k < n_lanes; ++k) pthread_join(th[k], 0);
+			for (k = 1; k < n_lanes; ++k) ssq_aligner_free(la[k].al);
+			if (S.failed) return 1;
+			n_processed = S.n_processed;
+			dev_ingest = 0;
+			if (!S.fallback) break; /* input exhausted */
+			ssq_aligner_set_turn(al, -1); /* the host tokeniser continues on the first aligner (it keeps the shared dup-set alive until the end) */
+			f1 = fq_from_raw(&R1); if (two_files) f2 = fq_from_raw(&R2);
 			continue;
 		}
 		size = read_batch(chunk_size * n_threads, f1, f2, &r1, &r2, &v, keep_comment);
