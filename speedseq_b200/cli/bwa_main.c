@@ -228,7 +228,7 @@ static void put_frame(int stream, const char *p, size_t len)
 typedef struct {
 	raw_t *R1, *R2; int two_files, smart_pe, paired, keep_comment, fused; long chunk; const ssq_pestat_t *pes0;
 	size_t raw_target; long long n_processed, next_ticket, write_turn;
-	int stop, fallback, failed;
+	int stop, fallback, failed, shared_set;
 	pthread_mutex_t rd_mu, wr_mu; pthread_cond_t wr_cv;
 } lanes_t;
 typedef struct { lanes_t *S; ssq_aligner_t *al; } lane_arg_t;
@@ -263,7 +263,7 @@ static void *lane_main(void *arg_)
 		fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)ssq_aligner_counter(al, 109));
 		if (S->smart_pe) fprintf(stderr, "[M::process] 0 single-end sequences; %d paired-end sequences\n", n);
 		pthread_mutex_unlock(&S->rd_mu);
-		ssq_aligner_set_turn(al, ticket);
+		ssq_aligner_set_turn(al, S->shared_set ? ticket : -1);
 		rc = ssq_aligner_compute(al, S->paired ? S->pes0 : 0, 1);
 		if (!rc) rc = ssq_aligner_fetch(al, &out);
 		pthread_mutex_lock(&S->wr_mu);
@@ -381,7 +381,8 @@ static int main_mem(int argc, char **argv, const char *prog)
 			S.R1 = &R1; S.R2 = &R2; S.two_files = two_files; S.smart_pe = smart_pe; S.paired = paired; S.keep_comment = keep_comment; S.fused = fused; S.chunk = chunk_size * n_threads;
 			S.pes0 = pes0; S.raw_target = raw_target; S.n_processed = n_processed;
 			pthread_mutex_init(&S.rd_mu, 0); pthread_mutex_init(&S.wr_mu, 0); pthread_cond_init(&S.wr_cv, 0);
-			if (fused && n_lanes > 1 && (rc = ssq_dupset_create(device, &dset))) die("ssq_dupset_create", rc);
+			if (n_lanes > 1 && (rc = ssq_dupset_create(device, &dset))) die("ssq_dupset_create", rc); /* shared by the lanes: its turn counter orders their batches (the signatures only matter in fused mode) */
+			S.shared_set = dset != 0;
 			for (k = 0; k < n_lanes; ++k) {
 				la[k].S = &S; la[k].al = al;
 				if (k > 0 && (rc = ssq_aligner_create(idx, &opt, fused ? &sb : 0, rg_id, &la[k].al))) die("ssq_aligner_create", rc);

@@ -128,7 +128,7 @@ def _records(b):
 
 
 def _both(args, stdin=None):
-    return [subprocess.run(exe + args, input=stdin, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout for exe in ([T.ORACLE_BIN], [BWA])]
+    return [subprocess.run(exe + args, input=stdin, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=300).stdout for exe in ([T.ORACLE_BIN], [BWA])]
 
 
 @pytest.fixture(scope="module")
@@ -188,8 +188,8 @@ def test_cli_fused_samblaster_stage(ssq, cli_ref, tmp_path, monkeypatch):
         e = dict(os.environ); e.update(env)
         spl, disc = str(tmp_path / (tag + ".spl")), str(tmp_path / (tag + ".disc"))
         p1 = subprocess.Popen(bwa + ["mem", "-t", "1", "-p", "-R", RG, fa, fq], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e)
-        p2 = subprocess.run(sb + sb_args + ["--splitterFile", spl, "--discordantFile", disc], stdin=p1.stdout, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e, check=True)
-        assert p1.wait() == 0
+        p2 = subprocess.run(sb + sb_args + ["--splitterFile", spl, "--discordantFile", disc], stdin=p1.stdout, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e, check=True, timeout=300)
+        assert p1.wait(timeout=60) == 0
         outs[tag] = (_strip_pg(p2.stdout), _strip_pg(open(spl, "rb").read()), _strip_pg(open(disc, "rb").read()))
     for i, what in enumerate(("main", "splitters", "discordants")):
         assert outs["oracle"][i] == outs["unfused"][i], what

@@ -51,7 +51,7 @@ for tag, env in (("bwa mem, 1 lane", {"SSQ_LANES": "1"}), ("bwa mem, 2 lanes", {
     out = os.path.join(cache, "cli_out.sam")
     t0 = time.time()
     with open(out, "wb") as f:
-        subprocess.run([BWA, "mem", "-t", "30", "-p", "-R", RG, fa, fq], stdout=f, stderr=subprocess.DEVNULL, env=e, check=True)
+        subprocess.run([BWA, "mem", "-t", "30", "-p", "-R", RG, fa, fq], stdout=f, stderr=subprocess.DEVNULL, env=e, check=True, timeout=200)
     dt = time.time() - t0
     res[tag] = md5_of(out)
     print("%-28s %6.2f s  %6.2f M reads/s  (%d MB of SAM)" % (tag, dt, n_reads / dt / 1e6, os.path.getsize(out) >> 20))
@@ -62,8 +62,8 @@ for tag, env in (("unfused bwa | samblaster", {}), ("fused bwa | samblaster", {"
     t0 = time.time()
     p1 = subprocess.Popen([BWA, "mem", "-t", "30", "-p", "-R", RG, fa, fq], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e)
     with open(outs[0], "wb") as f:
-        subprocess.run([SB] + sb_args + ["--splitterFile", outs[1], "--discordantFile", outs[2]], stdin=p1.stdout, stdout=f, stderr=subprocess.DEVNULL, env=e, check=True)
-    assert p1.wait() == 0
+        subprocess.run([SB] + sb_args + ["--splitterFile", outs[1], "--discordantFile", outs[2]], stdin=p1.stdout, stdout=f, stderr=subprocess.DEVNULL, env=e, check=True, timeout=300)
+    assert p1.wait(timeout=60) == 0
     dt = time.time() - t0
     res[tag] = tuple(md5_of(o) for o in outs)
     print("%-28s %6.2f s  %6.2f M reads/s" % (tag, dt, n_reads / dt / 1e6))
