@@ -34,12 +34,7 @@ def records(bam_path):
     return text, d[p:]
 
 
-with tempfile.TemporaryDirectory() as d:
-    fa = os.path.join(d, "ex.fa")
-    open(fa, "wb").write(gzip.open(os.path.join(T.GOLDEN, "ex_ref.fa.gz")).read())
-    o = T.Oracle()
-    o.index_build(fa)
-    fq = os.path.join(T.GOLDEN, "ex_reads_2k.fq.gz")
+def make(prefix, fa, fq, d, o):
     sam = subprocess.run([T.ORACLE_BIN, "mem", "-t", "4", "-p", "-R", RG, fa, fq], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
     spl, disc = os.path.join(d, "spl.sam"), os.path.join(d, "disc.sam")
     main = subprocess.run([T.ORACLE_BIN, "samblaster", "--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20", "--splitterFile", spl, "--discordantFile", disc],
@@ -50,8 +45,26 @@ with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, tag + ".bam")
         subprocess.run([SB, "sort", "-t", "2", "-m", "1G", "--tmpdir=" + d, "-o", out, "/dev/stdin"], input=unsorted, check=True, stderr=subprocess.DEVNULL)
         hdr, recs = records(out)
-        with gzip.GzipFile(os.path.join(HERE, "ex_bam_%s.records.gz" % tag), "wb", mtime=0) as f:
+        with gzip.GzipFile(os.path.join(HERE, "%s_bam_%s.records.gz" % (prefix, tag)), "wb", mtime=0) as f:
             f.write(recs)
-        if tag == "main":
+        if tag == "main" and prefix == "ex":
             open(os.path.join(HERE, "ex_bam_header.txt"), "wb").write(hdr)
-        print(tag, len(recs), "bytes of records")
+        print(prefix, tag, len(recs), "bytes of records")
+
+
+with tempfile.TemporaryDirectory() as d:
+    o = T.Oracle()
+    fa = os.path.join(d, "ex.fa")
+    open(fa, "wb").write(gzip.open(os.path.join(T.GOLDEN, "ex_ref.fa.gz")).read())
+    o.index_build(fa)
+    make("ex", fa, os.path.join(T.GOLDEN, "ex_reads_2k.fq.gz"), d, o)
+    # a seeded synthetic stress set: 3 contigs, duplicates, chimeric reads (SA tags, splitters), junk pairs, orphans, improper pairs, XA hits
+    from test_hostsim_pipe import stress_reads
+    g, bounds = T.synth_genome(400000, 7, n_contigs=3)
+    fa2 = os.path.join(d, "syn.fa")
+    T.write_fasta(fa2, g, bounds)
+    o.index_build(fa2)
+    names, seqs, quals = stress_reads(g, bounds, 700, 150, 5, err=0.01, indel=0.002)
+    fq2 = os.path.join(d, "syn.fq")
+    T.write_fastq(fq2, names, seqs, quals)
+    make("syn", fa2, fq2, d, o)

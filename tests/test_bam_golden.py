@@ -12,8 +12,14 @@ import ssq_testlib as T
 SB = dict(exclude_dups=1, add_mate_tags=1, max_split_count=2, min_non_overlap=20)
 
 
-def golden(tag):
-    return gzip.open(os.path.join(T.GOLDEN, "ex_bam_%s.records.gz" % tag)).read()
+def golden(tag, prefix="ex"):
+    return gzip.open(os.path.join(T.GOLDEN, "%s_bam_%s.records.gz" % (prefix, tag))).read()
+
+
+def syn_reads(syn_index):
+    from test_hostsim_pipe import stress_reads
+    fa, g, bounds = syn_index  # the same seeded genome and reads tests/golden/make_bam_golden.py used
+    return stress_reads(g, bounds, 700, 150, 5, err=0.01, indel=0.002)
 
 
 def split_records(b):
@@ -36,6 +42,33 @@ def test_bam_records_match_sambamba_cpu(oracle, hostsim, ex_index, ex_reads):
             first = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
             raise AssertionError("%s: %d vs %d records, first difference at record %d:\n%r\n%r" % (tag, len(a), len(b), first, a[first:first + 1], b[first:first + 1]))
     assert len(split_records(bams[0])) == txt[0].count("\n") > 4000
+
+
+def test_bam_records_match_sambamba_synthetic_stress_cpu(oracle, hostsim, syn_index):
+    """duplicates, splitters with SA tags, discordants, XA hits, junk pairs and orphans over three contigs"""
+    idx = oracle.load(syn_index[0])
+    names, seqs, quals = syn_reads(syn_index)
+    txt, bams = hostsim.pipe_bam(idx, names, seqs, quals, 0, b"NA12878", 1, (1, 1, 2, 20, 0))
+    for k, tag in enumerate(("main", "spl", "disc")):
+        assert bams[k] == golden(tag, "syn"), tag
+    assert len(split_records(bams[1])) > 20 and len(split_records(bams[2])) > 50
+
+
+@pytest.mark.gpu
+def test_bam_records_match_sambamba_synthetic_stress_gpu(ssq, syn_index):
+    import ctypes as C
+    h = ssq.index_load(syn_index[0])
+    names, seqs, quals = syn_reads(syn_index)
+    al = ssq.aligner_create(h, SB, b"NA12878")
+    ssq.ck(ssq.lib.ssq_aligner_set_bam(al, C.c_int(1), C.c_int(1)), "ssq_aligner_set_bam")
+    rd, keep = T.pack_reads(names, seqs, quals, None, 1, 0)
+    ssq.aligner_run(al, rd)
+    for k, tag in enumerate(("main", "spl", "disc")):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        ssq.ck(ssq.lib.ssq_aligner_fetch_bam(al, C.c_int(k), C.byref(p), C.byref(n)), "ssq_aligner_fetch_bam")
+        assert C.string_at(p, n.value) == golden(tag, "syn"), tag
+    ssq.aligner_free(al)
+    ssq.index_free(h)
 
 
 @pytest.mark.gpu
