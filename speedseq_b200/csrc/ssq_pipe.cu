@@ -398,7 +398,14 @@ extern "C" int ssq_aligner_upload(ssq_aligner_t *a, const ssq_reads_t *rd)
 	a->computed = 0;
 	const u64 total = n ? rd->seq_off[n] : 0;
 	int max_len = 0;
-	for (int i = 0; i < n; ++i) { const int l = (int)(rd->seq_off[i + 1] - rd->seq_off[i]); if (l > max_len) max_len = l; }
+	for (int i = 0; i < n; ++i) {
+		const int l = (int)(rd->seq_off[i + 1] - rd->seq_off[i]);
+		if (l > max_len) max_len = l;
+		if (l > SSQ_MAX_READ_LEN) { // name the read: one long read must not leave the user guessing which of 10^8
+			ssq_set_error("read %d ('%.*s') has %d bases; this build aligns reads of at most %d", i, (int)(rd->name_off[i + 1] - rd->name_off[i]), rd->name + rd->name_off[i], l, SSQ_MAX_READ_LEN);
+			return SSQ_ELEN;
+		}
+	}
 	a->total_bases = total; a->max_len = max_len;
 	uint8_t *d_seq; u64 *d_off;
 	if ((rc = ssq_batch_reserve(a->b, n, total, max_len, &d_seq, &d_off))) return rc;
