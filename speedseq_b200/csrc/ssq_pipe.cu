@@ -72,22 +72,12 @@ __global__ void k_areg_cap(int n, int paired, int max_matesw, const u32 *__restr
 }
 
 struct DedupSlab { i32 h[QMAX + 16], e[QMAX + 16]; uint8_t qbuf[QMAX], rbuf[2048]; };
-// Per-read / per-pair kernels whose cost grows with the number of regions (a read inside a repeat family has hundreds) take their
-// units in the order of a stable radix sort by that number: the lanes of a warp then work on units of similar weight instead of
-// every warp waiting for its one or two heavy lanes (ncu before: 1.4 active lanes per instruction in k_dedup, 2.1 in k_plan).
-__global__ void k_weight_reads(int n, const u32 *__restrict__ n_regs, u32 *key, u32 *id) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) { key[i] = n_regs[i] < 4096 ? n_regs[i] : 4096; id[i] = (u32)i; } }
-__global__ void k_weight_units(int n_units, int paired, const u32 *__restrict__ n_areg, u32 *key, u32 *id)
-{
-	const int u = blockIdx.x * blockDim.x + threadIdx.x;
-	if (u >= n_units) return;
-	const u32 w = paired ? n_areg[2 * u] + n_areg[2 * u + 1] : n_areg[u];
-	key[u] = w < 4096 ? w : 4096; id[u] = (u32)u;
-}
-__global__ void __launch_bounds__(128) k_dedup(PipeView V, DedupSlab *slabs, const u32 *__restrict__ order)
+__global__ void __launch_bounds__(128) k_dedup(PipeView V, DedupSlab *slabs, int *work)
 {
 	DedupSlab &s = slabs[(size_t)blockIdx.x * blockDim.x + threadIdx.x];
 	AlnScratch A; A.qbuf = s.qbuf; A.rbuf = s.rbuf; A.rcap = 2048; A.g.h = s.h; A.g.e = s.e; A.g.z = 0; A.g.zcap = 0;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V.n_reads; i += gridDim.x * blockDim.x) body_dedup(V, (int)order[i], A);
+	(void)work;
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < V.n_reads; r += gridDim.x * blockDim.x) body_dedup(V, r, A); // neighbouring lanes take neighbouring reads: their region lists are adjacent in memory
 }
 
 __global__ void __launch_bounds__(256) k_pestat(PipeView V)
@@ -130,11 +120,11 @@ __global__ void k_tslot_cap(int n, const u32 *__restrict__ n_areg, u64 *cap)
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) cap[i] = 2ull * n_areg[i] + 1;
 }
-__global__ void __launch_bounds__(128) k_plan(PipeView V, const u32 *__restrict__ order)
+__global__ void __launch_bounds__(128) k_plan(PipeView V)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= (V.paired ? V.n_reads >> 1 : V.n_reads)) return;
-	body_plan(V, (int)order[i]);
+	const int u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= (V.paired ? V.n_reads >> 1 : V.n_reads)) return;
+	body_plan(V, u);
 }
 __global__ void k_ntasks(int n, const ReadMeta *__restrict__ meta, u64 *out)
 {
@@ -278,7 +268,6 @@ struct ssq_aligner {
 	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
 	PinBuf h_text[3], h_roff, h_hist, h_small, h_bam[3];
 	int want_bam, bam_blank_side; u64 bam_len[3], n_lines_total;
-	DBuf d_wkey[2], d_wid[2]; // units ordered by weight (see k_weight_reads)
 	DBuf d_nl, d_lbase, d_lread, d_bkey, d_bkey2, d_bidx, d_bperm, d_bsize[3], d_bsz_s, d_boff[3], d_bam[3];
 	PeStat pes[4];
 	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines, n_rescue_pairs, n_gapped, n_sw_local, sw_local_cells;
@@ -462,19 +451,6 @@ static PipeView make_view(ssq_aligner *a)
 }
 
 // ---- stages 1..8: everything on the device; leaves the text of the three streams in HBM ----
-// a->d_wid[1] = unit ids in the order of a stable sort by weight.  mode 0: reads by stage-0 region count; 1 / 2: reads / pairs by region-list length
-static int weight_order(ssq_aligner *a, int n_units, int mode, const u32 *counts)
-{
-	if (n_units <= 0) return 0;
-	for (int k = 0; k < 2; ++k) if (a->d_wkey[k].need((size_t)(n_units + 1) * 4) || a->d_wid[k].need((size_t)(n_units + 1) * 4)) return SSQ_ENOMEM;
-	if (mode == 0) k_weight_reads<<<(n_units + 255) / 256, 256, 0, a->st>>>(n_units, counts, a->d_wkey[0].as<u32>(), a->d_wid[0].as<u32>());
-	else k_weight_units<<<(n_units + 255) / 256, 256, 0, a->st>>>(n_units, mode == 2, counts, a->d_wkey[0].as<u32>(), a->d_wid[0].as<u32>());
-	size_t tb = 0;
-	cub::DeviceRadixSort::SortPairs(0, tb, a->d_wkey[0].as<u32>(), a->d_wkey[1].as<u32>(), a->d_wid[0].as<u32>(), a->d_wid[1].as<u32>(), n_units, 0, 13, a->st);
-	if (a->cubtmp.need(tb)) return SSQ_ENOMEM;
-	CK(cub::DeviceRadixSort::SortPairs(a->cubtmp.p, tb, a->d_wkey[0].as<u32>(), a->d_wkey[1].as<u32>(), a->d_wid[0].as<u32>(), a->d_wid[1].as<u32>(), n_units, 0, 13, a->st));
-	return 0;
-}
 static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose);
 extern "C" int ssq_aligner_compute(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 {
@@ -521,8 +497,7 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 	if (a->d_slab.need((size_t)dedup_blocks * 128 * sizeof(DedupSlab))) return SSQ_ENOMEM;
 	int *work = a->d_work.as<int>();
 	CK(cudaMemsetAsync(work, 0, 256, st));
-	if ((rc = weight_order(a, n, 0, V.n_regs))) return rc;
-	k_dedup<<<dedup_blocks, 128, 0, st>>>(V, a->d_slab.as<DedupSlab>(), a->d_wid[1].as<u32>());
+	k_dedup<<<dedup_blocks, 128, 0, st>>>(V, a->d_slab.as<DedupSlab>(), work);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(a->ev[ST_PESTAT], st));
 	// insert-size statistics and the pairing penalty table
@@ -575,8 +550,7 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 	CK(cudaStreamSynchronize(st));
 	if (a->d_tslots.need((total_slots + 1) * sizeof(PTask))) return SSQ_ENOMEM;
 	V.tslot_off = a->d_tsoff.as<u64>(); V.tslots = a->d_tslots.as<PTask>(); V.meta = a->d_meta.as<ReadMeta>();
-	if ((rc = weight_order(a, n_units, a->paired ? 2 : 1, V.n_areg))) return rc;
-	k_plan<<<(n_units + 127) / 128, 128, 0, st>>>(V, a->d_wid[1].as<u32>());
+	k_plan<<<(n_units + 127) / 128, 128, 0, st>>>(V);
 	k_ntasks<<<(n + 255) / 256, 256, 0, st>>>(n, V.meta, a->d_ntk.as<u64>());
 	if ((rc = scan_u64(a, a->d_ntk.as<u64>(), a->d_tkbase.as<u64>(), (size_t)n + 1))) return rc;
 	CK(cudaMemcpyAsync(&total_tasks, a->d_tkbase.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
