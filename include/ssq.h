@@ -255,12 +255,14 @@ void ssq_aligner_free(ssq_aligner_t *al);
  * coordinate-sorted within the batch by (reference, position, strand) with equal keys in input order — what sambamba's sort
  * produces (tests/golden/ex_bam_*: written by the reference's own sambamba, matched byte for byte).  blank_side_streams: the
  * splitter / discordant records carry no SEQ / QUAL, like after speedseq's gawk step (speedseq:443,446).
- * ssq_bam_header + ssq_bgzf_compress (host: zlib) make a complete .bam out of header and records of one batch; merging the
- * sorted runs of several batches is left to the caller. */
+ * ssq_bam_header + ssq_bgzf_compress (host: zlib) make a complete .bam out of header and records; ssq_bam_merge_runs merges the
+ * sorted runs of the batches of a run into the order `sambamba sort` gives the whole input. */
 int ssq_aligner_set_bam(ssq_aligner_t *al, int enable, int blank_side_streams);
 int ssq_aligner_fetch_bam(ssq_aligner_t *al, int stream, const void **records, size_t *len); /* after ssq_aligner_compute; owned by the aligner */
 int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_text, int sorted, void **out, size_t *out_len); /* free with ssq_free */
 int ssq_bgzf_compress(const void *in, size_t n, int level, int with_eof, void **out, size_t *out_len);           /* free with ssq_free */
+/* the sorted runs of consecutive batches -> one sorted record stream (stable: equal keys keep batch order); free with ssq_free */
+int ssq_bam_merge_runs(int n_runs, const void *const *runs, const size_t *lens, void **out, size_t *out_len);
 
 /* ------------------------------------------------------------------ several GPUs ----
  * Batches are dealt to the ranks round-robin with the index replicated (no collective); "first pair seen with a signature is

@@ -109,3 +109,38 @@ extern "C" int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_tex
 	memcpy(*out, o.data(), o.size()); *out_len = o.size();
 	return SSQ_OK;
 }
+
+// Merge of the coordinate-sorted runs of several batches into one sorted record stream (what `sambamba sort` does with its temporary
+// files, speedseq:441).  Key = (reference id, position, strand) read from the record headers, records without a reference last; equal
+// keys: the earlier run first (earlier batch = earlier input), inside a run the run's own order — i.e. a stable sort of the whole input.
+extern "C" int ssq_bam_merge_runs(int n_runs, const void *const *runs, const size_t *lens, void **out, size_t *out_len)
+{
+	if (n_runs < 0 || (n_runs && (!runs || !lens)) || !out || !out_len) return SSQ_EINVAL;
+	size_t total = 0;
+	for (int r = 0; r < n_runs; ++r) total += lens[r];
+	unsigned char *o = (unsigned char*)malloc(total ? total : 1);
+	if (!o) return SSQ_ENOMEM;
+	std::vector<size_t> at(n_runs, 0);
+	auto key_of = [&](int r) -> uint64_t {
+		const unsigned char *p = (const unsigned char*)runs[r] + at[r];
+		int32_t ref, pos; uint16_t flag;
+		memcpy(&ref, p + 4, 4); memcpy(&pos, p + 8, 4); memcpy(&flag, p + 4 + 14, 2); // block_size | refID pos l_read_name mapq bin n_cigar flag ...
+		return ref < 0 ? ~0ull : ((uint64_t)(uint32_t)ref << 34 | (uint64_t)(pos + 1) << 1 | (uint64_t)((flag >> 4) & 1));
+	};
+	size_t w = 0;
+	for (;;) { // n_runs is small (batches of one run): a linear scan for the minimum keeps the earlier run on ties
+		int best = -1; uint64_t bk = 0;
+		for (int r = 0; r < n_runs; ++r) {
+			if (at[r] + 4 > lens[r]) continue;
+			const uint64_t k = key_of(r);
+			if (best < 0 || k < bk) { best = r; bk = k; }
+		}
+		if (best < 0) break;
+		const unsigned char *p = (const unsigned char*)runs[best] + at[best];
+		int32_t bs; memcpy(&bs, p, 4);
+		if (bs < 32 || at[best] + 4 + (size_t)bs > lens[best]) { free(o); ssq_set_error("ssq_bam_merge_runs: run %d is not a sequence of BAM records", best); return SSQ_EINVAL; }
+		memcpy(o + w, p, 4 + (size_t)bs); w += 4 + (size_t)bs; at[best] += 4 + (size_t)bs;
+	}
+	*out = o; *out_len = w;
+	return SSQ_OK;
+}

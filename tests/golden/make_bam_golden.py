@@ -68,3 +68,17 @@ with tempfile.TemporaryDirectory() as d:
     fq2 = os.path.join(d, "syn.fq")
     T.write_fastq(fq2, names, seqs, quals)
     make("syn", fa2, fq2, d, o)
+    # the same reads as a run of three batches (`bwa mem -t 1` closes a batch at 10 Mbp; here the cuts are made explicitly through the oracle's
+    # library entry so that the fixture stays small): per-batch insert-size statistics, duplicates across batches, one global coordinate sort
+    idx = o.load(fa2)
+    cuts = [0, 1000, 2100, len(names)]
+    body = "".join(o.mem_pe(idx, names[a:b], seqs[a:b], quals[a:b], a, 4, b"NA12878") for a, b in zip(cuts, cuts[1:]))
+    hdr = "@SQ\tSN:ctg1\tLN:%d\n@SQ\tSN:ctg2\tLN:%d\n@SQ\tSN:ctg3\tLN:%d\n" % tuple(int(bounds[i + 1] - bounds[i]) for i in range(3))
+    main = subprocess.run([T.ORACLE_BIN, "samblaster", "--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20"], input=(hdr + body).encode(), check=True,
+                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    unsorted = subprocess.run([SB, "view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], input=main, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    out = os.path.join(d, "syn3.bam")
+    subprocess.run([SB, "sort", "-t", "2", "-m", "1G", "--tmpdir=" + d, "-o", out, "/dev/stdin"], input=unsorted, check=True, stderr=subprocess.DEVNULL)
+    with gzip.GzipFile(os.path.join(HERE, "syn3_bam_main.records.gz"), "wb", mtime=0) as f:
+        f.write(records(out)[1])
+    print("syn3 main (3 batches)", len(records(out)[1]), "bytes of records")

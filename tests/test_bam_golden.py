@@ -54,6 +54,27 @@ def test_bam_records_match_sambamba_synthetic_stress_cpu(oracle, hostsim, syn_in
     assert len(split_records(bams[1])) > 20 and len(split_records(bams[2])) > 50
 
 
+def test_merged_runs_of_three_batches_match_sambamba_sort(ssq_lib_cpu, oracle, hostsim, syn_index):
+    """a run of three batches: every batch's coordinate-sorted records (hostsim bodies) merged by ssq_bam_merge_runs must equal what the
+    reference's sambamba makes of the whole run's SAM (golden syn3: per-batch insert-size statistics, duplicates across batches)"""
+    import ctypes as C
+    idx = oracle.load(syn_index[0])
+    names, seqs, quals = syn_reads(syn_index)
+    cuts = [0, 1000, 2100, len(names)]
+    runs = []
+    for k, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        txt, bams = hostsim.pipe_bam(idx, names[a:b], seqs[a:b], quals[a:b], a, b"NA12878", 1, (1, 1, 2, 20, 0), reset=1 if k == 0 else 0)
+        runs.append(bams[0])
+    L = ssq_lib_cpu
+    arr = (C.c_char_p * 3)(*runs); lens = (C.c_size_t * 3)(*[len(r) for r in runs])
+    out, n = C.c_void_p(), C.c_size_t(0)
+    L.ssq_bam_merge_runs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert L.ssq_bam_merge_runs(3, arr, lens, C.byref(out), C.byref(n)) == 0
+    merged = C.string_at(out, n.value)
+    L.ssq_free(out)
+    assert merged == golden("main", "syn3")
+
+
 @pytest.mark.gpu
 def test_bam_records_match_sambamba_synthetic_stress_gpu(ssq, syn_index):
     import ctypes as C
