@@ -118,3 +118,25 @@ def test_fused_pipeline_batches_share_the_dup_set(oracle, hostsim, syn_index, tm
         for i in range(3):
             got[i] += r[i]
     assert got[0] == rec(out) and got[1] == rec(open(spl).read()) and got[2] == rec(open(disc).read())
+
+
+def test_fused_pipeline_single_end_reads(oracle, hostsim, syn_index, tmp_path):
+    """single-end input through the fused stage: every read is its own block (samblaster's lone-record rule: signature from the one mapped
+    record, duplicates by 5' position and strand, no mate tags, never discordant or splitter)"""
+    import os
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = stress_reads(g, bounds, 400, 150, 17)
+    names = ["s%d" % i for i in range(len(names))]
+    fq = str(tmp_path / "se.fq")
+    with open(fq, "w") as f:
+        for n, s, q in zip(names, seqs, quals):
+            f.write("@%s\n%s\n+\n%s\n" % (n, s, q))
+    sam = subprocess.run([T.ORACLE_BIN, "mem", "-t", "2", fa, fq], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    spl, disc = str(tmp_path / "o.spl"), str(tmp_path / "o.disc")
+    out = subprocess.run([T.ORACLE_BIN, "samblaster", "--excludeDups", "--addMateTags", "--splitterFile", spl, "--discordantFile", disc], input=sam, check=True,
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+    rec = lambda t: "".join(l for l in t.splitlines(True) if not l.startswith("@"))
+    h_main, h_spl, h_disc = hostsim.pipe(idx, names, seqs, quals, 0, b"", 0, (1, 1, 2, 20, 0))
+    assert h_main == rec(out) and h_spl == rec(open(spl).read()) and h_disc == rec(open(disc).read())
+    assert sum(1 for l in h_main.splitlines() if int(l.split("\t")[1]) & 0x400) > 20 and h_disc == ""
