@@ -260,6 +260,9 @@ void ssq_aligner_free(ssq_aligner_t *al);
 int ssq_aligner_set_bam(ssq_aligner_t *al, int enable, int blank_side_streams);
 int ssq_aligner_fetch_bam(ssq_aligner_t *al, int stream, const void **records, size_t *len); /* after ssq_aligner_compute; owned by the aligner */
 int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_text, int sorted, void **out, size_t *out_len); /* free with ssq_free */
+/* the header text alone: sorted != 0 rewrites it the way `sambamba view -S | sambamba sort` does (@HD SO:coordinate first, sambamba's
+ * tag order inside @SQ / @RG / @PG lines); free with ssq_free */
+int ssq_bam_header_text(const char *sam_header_text, int sorted, char **out);
 int ssq_bgzf_compress(const void *in, size_t n, int level, int with_eof, void **out, size_t *out_len);           /* free with ssq_free */
 /* the sorted runs of consecutive batches -> one sorted record stream (stable: equal keys keep batch order); free with ssq_free */
 int ssq_bam_merge_runs(int n_runs, const void *const *runs, const size_t *lens, void **out, size_t *out_len);

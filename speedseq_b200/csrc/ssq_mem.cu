@@ -88,17 +88,52 @@ extern "C" int ssq_bgzf_compress(const void *in_, size_t n, int level, int with_
 	return SSQ_OK;
 }
 
-// "BAM\1", header text, reference table (uncompressed; feed it and the records to ssq_bgzf_compress).  sorted: adds / rewrites
-// @HD ... SO:coordinate the way the pipeline's `sambamba sort` does (speedseq:441)
+// The header text as `sambamba view -S | sambamba sort` leaves it (speedseq:440-441): "@HD VN:1.3 SO:coordinate" first (any @HD of the
+// input replaced), and the tags of @SQ / @RG / @PG lines in sambamba's fixed field order (v0.5.9: SQ: SN LN AS M5 SP UR; RG: ID CN DS DT FO KS
+// LB PG PI PL PU SM; PG: ID PN CL PP VN), tags it does not know after them in input order.  Other lines (@CO) pass through.
+static void reorder_tags(const std::string &line, std::string &out)
+{
+	static const char *SQ[] = {"SN", "LN", "AS", "M5", "SP", "UR", 0}, *RG[] = {"ID", "CN", "DS", "DT", "FO", "KS", "LB", "PG", "PI", "PL", "PU", "SM", 0}, *PG[] = {"ID", "PN", "CL", "PP", "VN", 0};
+	const char **ord = !line.compare(0, 3, "@SQ") ? SQ : !line.compare(0, 3, "@RG") ? RG : !line.compare(0, 3, "@PG") ? PG : 0;
+	if (!ord) { out += line; out += '\n'; return; }
+	std::vector<std::string> f;
+	for (size_t p = 0;;) { const size_t e = line.find('\t', p); f.push_back(line.substr(p, e == std::string::npos ? e : e - p)); if (e == std::string::npos) break; p = e + 1; }
+	std::vector<char> used(f.size(), 0);
+	out += f[0];
+	for (int k = 0; ord[k]; ++k)
+		for (size_t i = 1; i < f.size(); ++i) if (!used[i] && f[i].size() >= 3 && f[i][2] == ':' && !f[i].compare(0, 2, ord[k])) { out += '\t'; out += f[i]; used[i] = 1; }
+	for (size_t i = 1; i < f.size(); ++i) if (!used[i]) { out += '\t'; out += f[i]; }
+	out += '\n';
+}
+extern "C" int ssq_bam_header_text(const char *sam_header_text, int sorted, char **out)
+{
+	if (!out) return SSQ_EINVAL;
+	std::string text;
+	const char *t = sam_header_text ? sam_header_text : "";
+	if (sorted) text = "@HD\tVN:1.3\tSO:coordinate\n";
+	for (const char *p = t; *p;) {
+		const char *e = strchr(p, '\n');
+		const std::string line(p, e ? (size_t)(e - p) : strlen(p));
+		p = e ? e + 1 : p + line.size();
+		if (line.empty()) continue;
+		if (!sorted) { text += line; text += '\n'; }
+		else if (line.compare(0, 3, "@HD") != 0) reorder_tags(line, text);
+	}
+	*out = (char*)malloc(text.size() + 1);
+	if (!*out) return SSQ_ENOMEM;
+	memcpy(*out, text.c_str(), text.size() + 1);
+	return SSQ_OK;
+}
+
+// "BAM\1", header text (ssq_bam_header_text), reference table — uncompressed; feed it and the records to ssq_bgzf_compress
 extern "C" int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_text, int sorted, void **out, size_t *out_len)
 {
 	if (!idx || !out || !out_len) return SSQ_EINVAL;
-	std::string text;
-	const char *t = sam_header_text ? sam_header_text : "";
-	if (sorted) {
-		text = "@HD\tVN:1.3\tSO:coordinate\n";
-		for (const char *p = t; *p;) { const char *e = strchr(p, '\n'); const size_t l = e ? (size_t)(e - p) + 1 : strlen(p); if (strncmp(p, "@HD", 3) != 0) text.append(p, l); p += l; }
-	} else text = t;
+	char *txt = 0;
+	const int rc = ssq_bam_header_text(sam_header_text, sorted, &txt);
+	if (rc) return rc;
+	const std::string text(txt);
+	free(txt);
 	std::string o("BAM\1", 4);
 	auto put32 = [&](int32_t v) { char b[4] = {(char)v, (char)(v >> 8), (char)(v >> 16), (char)(v >> 24)}; o.append(b, 4); };
 	put32((int32_t)text.size()); o += text;

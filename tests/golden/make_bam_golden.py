@@ -48,7 +48,8 @@ def make(prefix, fa, fq, d, o):
         with gzip.GzipFile(os.path.join(HERE, "%s_bam_%s.records.gz" % (prefix, tag)), "wb", mtime=0) as f:
             f.write(recs)
         if tag == "main" and prefix == "ex":
-            open(os.path.join(HERE, "ex_bam_header.txt"), "wb").write(hdr)
+            open(os.path.join(HERE, "ex_bam_header.txt"), "wb").write(hdr)  # sambamba's rewritten header ...
+            open(os.path.join(HERE, "ex_sam_header.txt"), "wb").write(b"".join(l for l in text.splitlines(True) if l.startswith(b"@")))  # ... of this SAM header
         print(prefix, tag, len(recs), "bytes of records")
 
 

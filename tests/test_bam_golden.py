@@ -145,3 +145,17 @@ def test_bgzf_framing_roundtrip_and_sambamba_reads_it(ssq_lib_cpu, oracle, hosts
         # sambamba's text of our records == the oracle pipeline's SAM records, re-ordered by coordinate (stable)
         key = lambda l: (1 << 40 if l.split("\t")[2] == "*" else 0, int(l.split("\t")[3]), (int(l.split("\t")[1]) >> 4) & 1)
         assert view.splitlines() == sorted(txt[0].splitlines(), key=key)
+
+
+def test_header_rewrite_matches_sambamba(ssq_lib_cpu):
+    """@HD SO:coordinate first, @RG / @PG tags in sambamba's field order: the header text of the golden BAM from the SAM header it was made of"""
+    import ctypes as C
+    L = ssq_lib_cpu
+    src = open(os.path.join(T.GOLDEN, "ex_sam_header.txt"), "rb").read()
+    out = C.c_void_p()
+    L.ssq_bam_header_text.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    L.ssq_bam_header_text.restype = C.c_int
+    assert L.ssq_bam_header_text(src, 1, C.byref(out)) == 0
+    got = C.string_at(out)
+    L.ssq_free(out)
+    assert got == open(os.path.join(T.GOLDEN, "ex_bam_header.txt"), "rb").read()
