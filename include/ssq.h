@@ -259,6 +259,9 @@ void ssq_aligner_free(ssq_aligner_t *al);
  * sorted runs of the batches of a run into the order `sambamba sort` gives the whole input. */
 int ssq_aligner_set_bam(ssq_aligner_t *al, int enable, int blank_side_streams);
 int ssq_aligner_fetch_bam(ssq_aligner_t *al, int stream, const void **records, size_t *len); /* after ssq_aligner_compute; owned by the aligner */
+/* the SAM text of one stream alone (0 main, 1 splitters, 2 discordants), for callers that take the main records as BAM and only
+ * want the side streams as text (speedseq:443,446 run them through gawk); after ssq_aligner_compute; owned by the aligner */
+int ssq_aligner_fetch_text(ssq_aligner_t *al, int stream, const char **text, size_t *len);
 int ssq_bam_header(const ssq_index_t *idx, const char *sam_header_text, int sorted, void **out, size_t *out_len); /* free with ssq_free */
 /* the header text alone: sorted != 0 rewrites it the way `sambamba view -S | sambamba sort` does (@HD SO:coordinate first, sambamba's
  * tag order inside @SQ / @RG / @PG lines); free with ssq_free */

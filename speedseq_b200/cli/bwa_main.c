@@ -211,12 +211,25 @@ static char *unescape(char *s)
 	return s;
 }
 
+static int g_bam; /* SSQ_FUSE_BAM: the main records leave as coordinate-sorted BAM runs (ssq_fuse.h) */
+
 static void put_frame(int stream, const char *p, size_t len)
 {
 	ssq_frame_hdr_t h;
 	if (!len) return;
 	memcpy(h.magic, SSQ_FRAME_MAGIC, 8); h.stream = (uint64_t)stream; h.len = (uint64_t)len;
 	fwrite(&h, sizeof h, 1, stdout); fwrite(p, 1, len, stdout);
+}
+
+/* BAM mode: out->text[0] / len[0] = the batch's main records as one sorted BAM run, text[1..2] = the side streams as SAM text */
+static int fetch_bam_mode(ssq_aligner_t *al, ssq_sam_t *out)
+{
+	const void *b = 0; size_t bl = 0; int rc, k;
+	memset(out, 0, sizeof *out);
+	if ((rc = ssq_aligner_fetch_bam(al, 0, &b, &bl))) return rc;
+	out->text[0] = (const char*)b; out->len[0] = bl;
+	for (k = 1; k < 3; ++k) { const char *t = 0; size_t l = 0; if ((rc = ssq_aligner_fetch_text(al, k, &t, &l))) return rc; out->text[k] = t; out->len[k] = l; }
+	return 0;
 }
 
 /* ------------------------------------------------------------------- stream lanes ----
@@ -265,12 +278,13 @@ static void *lane_main(void *arg_)
 		pthread_mutex_unlock(&S->rd_mu);
 		ssq_aligner_set_turn(al, S->shared_set ? ticket : -1);
 		rc = ssq_aligner_compute(al, S->paired ? S->pes0 : 0, 1);
-		if (!rc) rc = ssq_aligner_fetch(al, &out);
+		if (!rc && g_bam) rc = fetch_bam_mode(al, &out);
+		else if (!rc) rc = ssq_aligner_fetch(al, &out);
 		pthread_mutex_lock(&S->wr_mu);
 		while (S->write_turn != ticket) pthread_cond_wait(&S->wr_cv, &S->wr_mu);
 		if (rc) { fprintf(stderr, "[E::bwa] batch %lld failed (%d): %s\n", ticket, rc, ssq_last_error()); S->failed = 1; }
 		else if (!S->failed) {
-			if (S->fused) { put_frame(0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
+			if (S->fused) { put_frame(g_bam ? SSQ_STREAM_BAM_RUN : 0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
 			else fwrite(out.text[0], 1, out.len[0], stdout);
 		}
 		++S->write_turn;
@@ -341,9 +355,11 @@ static int main_mem(int argc, char **argv, const char *prog)
 			else { fprintf(stderr, "[E::bwa] SSQ_FUSE_SAMBLASTER: option '%s' is not one the fused stage implements\n", tok); return 1; }
 		}
 		ssq_fuse_describe(fuse_opts, sizeof fuse_opts, sb.exclude_dups, sb.add_mate_tags, sb.remove_dups, sb.max_split_count, sb.min_non_overlap, sb.min_indel_size, sb.max_unmapped_bases);
-	}
+		g_bam = getenv("SSQ_FUSE_BAM") && atoi(getenv("SSQ_FUSE_BAM"));
+	} else if (getenv("SSQ_FUSE_BAM") && atoi(getenv("SSQ_FUSE_BAM"))) { fprintf(stderr, "[E::bwa] SSQ_FUSE_BAM needs the fused samblaster stage (SSQ_FUSE_SAMBLASTER)\n"); return 1; }
 	if ((rc = ssq_index_load(argv[optind], device, &idx))) die("ssq_index_load", rc);
 	if ((rc = ssq_aligner_create(idx, &opt, fused ? &sb : 0, rg_id, &al))) die("ssq_aligner_create", rc);
+	if (g_bam && (rc = ssq_aligner_set_bam(al, 1, 1))) die("ssq_aligner_set_bam", rc);
 	if (raw_open(&R1, argv[optind + 1])) { fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", argv[optind + 1]); return 1; }
 	if (optind + 2 < argc) {
 		if (smart_pe) fprintf(stderr, "[W::main_mem] when '-p' is in use, the second query file is ignored.\n");
@@ -360,7 +376,7 @@ static int main_mem(int argc, char **argv, const char *prog)
 		printf("@PG\tID:bwa\tPN:bwa\tVN:%s\tCL:%s", SHIM_VERSION, prog);
 		for (i = 0; i < argc; ++i) printf(" %s", argv[i]);
 		printf("\n");
-		if (fused) printf("%s%s\n", SSQ_FUSE_MARKER, fuse_opts);
+		if (fused) printf("%s%s%s\n", SSQ_FUSE_MARKER, fuse_opts, g_bam ? "\tbam" : "");
 	}
 	if (!two_files) memset(&R2, 0, sizeof R2);
 	raw_target = (size_t)((double)chunk_size * n_threads * 2.7 / (two_files ? 2 : 1)) + (1u << 20); /* bytes of text one batch is expected to span */
@@ -386,6 +402,7 @@ static int main_mem(int argc, char **argv, const char *prog)
 			for (k = 0; k < n_lanes; ++k) {
 				la[k].S = &S; la[k].al = al;
 				if (k > 0 && (rc = ssq_aligner_create(idx, &opt, fused ? &sb : 0, rg_id, &la[k].al))) die("ssq_aligner_create", rc);
+				if (k > 0 && g_bam && (rc = ssq_aligner_set_bam(la[k].al, 1, 1))) die("ssq_aligner_set_bam", rc);
 				if (dset && (rc = ssq_aligner_share_dupset(la[k].al, dset))) die("ssq_aligner_share_dupset", rc);
 			}
 			fflush(stdout);
@@ -417,7 +434,8 @@ static int main_mem(int argc, char **argv, const char *prog)
 			if (n_pe) check_pair_names(&v);
 			fill_reads(&rd, &v, n_pe ? 1 : 0, n_processed);
 			if ((rc = ssq_aligner_run(al, &rd, n_pe ? pes0 : 0, 1, &out))) die("ssq_aligner_run", rc);
-			if (fused) { put_frame(0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
+			if (g_bam && (rc = fetch_bam_mode(al, &out))) die("ssq_aligner_fetch_bam", rc);
+			if (fused) { put_frame(g_bam ? SSQ_STREAM_BAM_RUN : 0, out.text[0], out.len[0]); put_frame(1, out.text[1], out.len[1]); put_frame(2, out.text[2], out.len[2]); }
 			else fwrite(out.text[0], 1, out.len[0], stdout);
 		} else { /* single-end reads first, then the pairs (the reference's order of work); records go out in input order */
 			int *id_se = (int*)malloc(sizeof(int) * v.n), *id_pe = (int*)malloc(sizeof(int) * v.n), has_last = 1, k_se = 0, k_pe = 0;

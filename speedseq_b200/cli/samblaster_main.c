@@ -297,19 +297,27 @@ int main(int argc, char **argv)
 			ssq_frame_hdr_t h;
 			char *buf = 0; size_t bcap = 0;
 			unsigned long long n_rec[3] = {0, 0, 0};
+			int bam = 0;
 			ssq_fuse_describe(mine, sizeof mine, o.excludeDups, o.addMateTags, o.removeDups, o.maxSplitCount, o.minNonOverlap, o.minIndelSize, o.maxUnmappedBases);
-			if (len && line[len - 1] == '\n') line[len - 1] = 0;
+			if (len && line[len - 1] == '\n') line[--len] = 0;
+			if (len >= 4 && !strcmp(line + len - 4, "\tbam")) { bam = 1; line[len - 4] = 0; } /* main records arrive as sorted BAM runs (ssq_fuse.h) */
 			if (strcmp(line + strlen(SSQ_FUSE_MARKER), mine) != 0) {
 				fprintf(stderr, "samblaster: the fused stream was produced under other options (SSQ_FUSE_SAMBLASTER: %s; this command line: %s)\n", line + strlen(SSQ_FUSE_MARKER), mine);
 				return 1;
 			}
 			for (i = 0; i < 3; ++i) if (fps[i]) fprintf(fps[i], "@PG\tID:SAMBLASTER\tVN:%s\tCL:%s\n", SB_VERSION, cl);
+			if (bam) fputs(SSQ_BAM_RUNS_MARKER, o.out);
 			hdr_done = 1;
 			while (fread(&h, sizeof h, 1, stdin) == 1) {
 				size_t k;
-				if (memcmp(h.magic, SSQ_FRAME_MAGIC, 8) != 0 || h.stream > 2) { fprintf(stderr, "samblaster: corrupt fused stream\n"); return 1; }
+				if (memcmp(h.magic, SSQ_FRAME_MAGIC, 8) != 0 || h.stream > 3 || (h.stream == SSQ_STREAM_BAM_RUN) != (bam && h.stream != 1 && h.stream != 2)) { fprintf(stderr, "samblaster: corrupt fused stream\n"); return 1; }
 				if (h.len > bcap) { bcap = h.len + h.len / 4; buf = (char*)realloc(buf, bcap); }
 				if (fread(buf, 1, h.len, stdin) != h.len) { fprintf(stderr, "samblaster: truncated fused stream\n"); return 1; }
+				if (h.stream == SSQ_STREAM_BAM_RUN) { /* passed on as it is, frame header included; records counted by their length fields */
+					fwrite(&h, sizeof h, 1, o.out); fwrite(buf, 1, h.len, o.out);
+					for (k = 0; k + 4 <= h.len; ++n_rec[0]) { uint32_t bs; memcpy(&bs, buf + k, 4); k += 4 + (size_t)bs; }
+					continue;
+				}
 				if (fps[h.stream]) fwrite(buf, 1, h.len, fps[h.stream]);
 				for (k = 0; k < h.len; ++k) n_rec[h.stream] += buf[k] == '\n';
 			}

@@ -674,6 +674,20 @@ extern "C" int ssq_aligner_fetch(ssq_aligner_t *a, ssq_sam_t *out)
 	return SSQ_OK;
 }
 
+// one stream's text alone (a caller that takes the main records as BAM still wants the two side streams as text)
+extern "C" int ssq_aligner_fetch_text(ssq_aligner_t *a, int stream, const char **text, size_t *len)
+{
+	if (!a || !text || !len || stream < 0 || stream > 2 || !a->computed) return SSQ_EINVAL;
+	int rc = ssq_use_device(a->device);
+	if (rc) return rc;
+	if (a->h_text[stream].need(a->text_len[stream] + 1)) return SSQ_ENOMEM;
+	if (a->text_len[stream]) CK(cudaMemcpyAsync(a->h_text[stream].p, a->d_text[stream].p, a->text_len[stream], cudaMemcpyDeviceToHost, a->st));
+	CK(cudaStreamSynchronize(a->st));
+	((char*)a->h_text[stream].p)[a->text_len[stream]] = 0;
+	*text = (const char*)a->h_text[stream].p; *len = a->text_len[stream];
+	return SSQ_OK;
+}
+
 extern "C" int ssq_aligner_run(ssq_aligner_t *a, const ssq_reads_t *reads, const ssq_pestat_t *pes0, int verbose, ssq_sam_t *out)
 {
 	int rc;

@@ -159,3 +159,121 @@ def test_header_rewrite_matches_sambamba(ssq_lib_cpu):
     got = C.string_at(out)
     L.ssq_free(out)
     assert got == open(os.path.join(T.GOLDEN, "ex_bam_header.txt"), "rb").read()
+
+
+def contigs_of(syn_index):
+    fa, g, bounds = syn_index
+    return [(b"ctg%d" % (i + 1), int(bounds[i + 1] - bounds[i])) for i in range(len(bounds) - 1)]
+
+
+def _bam_file(path):
+    """(header text, number of references, records) of a BGZF file; every block must be a well-formed BGZF member"""
+    import struct
+    raw = open(path, "rb").read()
+    assert raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")  # the end-of-file block
+    p = 0
+    while p < len(raw):
+        assert raw[p:p + 4] == b"\x1f\x8b\x08\x04" and raw[p + 12:p + 16] == b"BC\x02\x00"
+        p += struct.unpack("<H", raw[p + 16:p + 18])[0] + 1
+    assert p == len(raw)
+    d = gzip.decompress(raw)
+    assert d[:4] == b"BAM\x01"
+    l_text = struct.unpack("<i", d[4:8])[0]
+    text = d[8:8 + l_text]
+    q = 8 + l_text
+    n_ref = struct.unpack("<i", d[q:q + 4])[0]
+    q += 4
+    refs = []
+    for _ in range(n_ref):
+        l = struct.unpack("<i", d[q:q + 4])[0]
+        refs.append((d[q + 4:q + 4 + l - 1], struct.unpack("<i", d[q + 4 + l:q + 8 + l])[0]))
+        q += 8 + l
+    return text, refs, d[q:]
+
+
+def test_sambamba_shim_merges_the_run_stream(ssq_lib_cpu, oracle, hostsim, syn_index, tmp_path):
+    """BAM mode of the shims (ssq_fuse.h): header text + marker + one frame per batch through `sambamba view -S -f bam -l 0 /dev/stdin |
+    sambamba sort ... -o out.bam /dev/stdin` as speedseq:440-441 calls them.  The file's records must be the reference sambamba's
+    (golden syn3), its header the rewritten one, with and without spilling to --tmpdir, for any thread count."""
+    import ctypes as C
+    import struct
+    import subprocess
+    shim = os.path.join(T.ROOT, "speedseq_b200", "bin", "sambamba")
+    idx = oracle.load(syn_index[0])
+    names, seqs, quals = syn_reads(syn_index)
+    cuts = [0, 1000, 2100, len(names)]
+    hdr = b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (n, l) for n, l in contigs_of(syn_index)) + b"@RG\tID:NA12878\tSM:NA12878\tLB:lib1\n@PG\tID:bwa\tPN:bwa\tVN:0.7.12-r1039\tCL:bwa mem x\n" \
+        + b"@PG\tID:SAMBLASTER\tVN:0.1.22\tCL:samblaster -i stdin -o stdout\n"
+    stream = hdr + b"@CO\tssq-bam-runs-v1\n"
+    for k, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        txt, bams = hostsim.pipe_bam(idx, names[a:b], seqs[a:b], quals[a:b], a, b"NA12878", 1, (1, 1, 2, 20, 0), reset=1 if k == 0 else 0)
+        stream += b"SSQFRAME" + struct.pack("<QQ", 3, len(bams[0])) + bams[0]
+    L = ssq_lib_cpu
+    L.ssq_bam_header_text.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    out = C.c_void_p()
+    assert L.ssq_bam_header_text(hdr, 1, C.byref(out)) == 0
+    want_text = C.string_at(out)
+    L.ssq_free(out)
+    files = []
+    for tag, env, t in (("plain", {}, 4), ("spill", {"SSQ_SORT_SPILL_BYTES": "200000"}, 1)):
+        viewed = subprocess.run([shim, "view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], input=stream, stdout=subprocess.PIPE, check=True, timeout=60).stdout
+        assert viewed == stream
+        o = str(tmp_path / (tag + ".bam"))
+        subprocess.run([shim, "sort", "-t", str(t), "-m", "1G", "--tmpdir=" + str(tmp_path), "-o", o, "/dev/stdin"], input=viewed, check=True, timeout=60, env=dict(os.environ, **env))
+        text, refs, recs = _bam_file(o)
+        assert text == want_text and text.startswith(b"@HD\tVN:1.3\tSO:coordinate\n")
+        assert refs == list(contigs_of(syn_index))
+        assert recs == golden("main", "syn3"), tag
+        files.append(open(o, "rb").read())
+    assert files[0] == files[1]  # block boundaries do not depend on threads or spills
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".run")]
+    real = next((p for p in ("/root/reference/src/sambamba", os.path.join(T.ROOT, "oracle", "_ref", "stage", "src", "sambamba")) if os.access(p, os.X_OK)), None)
+    if real:  # the reference's sambamba reads the file, and foreign input goes through the shim to it unchanged
+        n = subprocess.run([real, "view", "-c", str(tmp_path / "plain.bam")], stdout=subprocess.PIPE, check=True).stdout
+        assert int(n) == len(split_records(golden("main", "syn3")))
+        sam = hdr + b"r1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\tIIII\n"
+        a = subprocess.run([real, "view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], input=sam, stdout=subprocess.PIPE, check=True).stdout
+        b = subprocess.run([shim, "view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], input=sam, stdout=subprocess.PIPE, check=True, env=dict(os.environ, SSQ_SAMBAMBA_REAL=real)).stdout
+        assert a == b and a[:2] == b"\x1f\x8b"
+        o2 = str(tmp_path / "foreign.bam")
+        subprocess.run([shim, "sort", "-t", "2", "-m", "1G", "--tmpdir=" + str(tmp_path), "-o", o2, "/dev/stdin"], input=b, check=True, env=dict(os.environ, SSQ_SAMBAMBA_REAL=real))
+        assert int(subprocess.run([real, "view", "-c", o2], stdout=subprocess.PIPE, check=True).stdout) == 1
+
+
+def test_bam_mode_chain_of_the_three_shims_cpu(oracle, hostsim, ex_index, ex_reads, tmp_path):
+    """`bwa mem | samblaster | sambamba view | sambamba sort` in BAM mode with the device stage played by tests/hostsim (same bodies):
+    what `bwa` would write (header, marker, frames: main records as one BAM run, side streams as text) through the real samblaster and
+    sambamba shims.  out.bam must hold the reference sambamba's records of the example reads; the side files the oracle's text."""
+    import struct
+    import subprocess
+    bin_ = os.path.join(T.ROOT, "speedseq_b200", "bin")
+    idx = oracle.load(ex_index)
+    names, seqs, quals = ex_reads
+    txt, bams = hostsim.pipe_bam(idx, names, seqs, quals, 0, b"NA12878", 1, (1, 1, 2, 20, 0))
+    hdr = b"@SQ\tSN:20_slice\tLN:321635\n@RG\tID:NA12878\tSM:NA12878\tLB:lib1\n@PG\tID:bwa\tPN:bwa\tVN:0.7.12-r1039\tCL:bwa mem -p ref reads\n"
+    opts = b"excludeDups=1 addMateTags=1 removeDups=0 maxSplitCount=2 minNonOverlap=20 minIndelSize=50 maxUnmappedBases=50"
+    frame = lambda s, b: b"SSQFRAME" + struct.pack("<QQ", s, len(b)) + b if b else b""
+    side = [t.encode() if isinstance(t, str) else t for t in txt]
+    stream = hdr + b"@CO\tssq-fused-v1\t" + opts + b"\tbam\n" + frame(3, bams[0]) + frame(1, side[1]) + frame(2, side[2])
+    spl, disc, out = str(tmp_path / "spl.sam"), str(tmp_path / "disc.sam"), str(tmp_path / "out.bam")
+    p1 = subprocess.run([os.path.join(bin_, "samblaster"), "--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20", "--splitterFile", spl, "--discordantFile", disc],
+                        input=stream, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert p1.returncode == 0, p1.stderr
+    assert b"routed %d records" % len(split_records(bams[0])) in p1.stderr
+    p2 = subprocess.run([os.path.join(bin_, "sambamba"), "view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], input=p1.stdout, stdout=subprocess.PIPE, check=True, timeout=60)
+    subprocess.run([os.path.join(bin_, "sambamba"), "sort", "-t", "4", "-m", "1G", "--tmpdir=" + str(tmp_path), "-o", out, "/dev/stdin"], input=p2.stdout, check=True, timeout=60)
+    text, refs, recs = _bam_file(out)
+    assert recs == golden("main")
+    assert refs == [(b"20_slice", 321635)]
+    want = open(os.path.join(T.GOLDEN, "ex_bam_header.txt"), "rb").read().split(b"\n")
+    got = text.split(b"\n")
+    assert got[:3] == want[:3]  # @HD, @SQ, @RG (tags re-ordered) as sambamba writes them
+    assert got[3].startswith(b"@PG\tID:bwa\tPN:bwa\tCL:") and got[3].endswith(b"\tVN:0.7.12-r1039") and got[4].startswith(b"@PG\tID:SAMBLASTER\tCL:samblaster ")
+    assert b"ssq-" not in text
+    for fn, k in ((spl, 1), (disc, 2)):  # header + the oracle-identical text of the side stream
+        lines = open(fn, "rb").read().split(b"\n")
+        body = b"\n".join(l for l in lines if not l.startswith(b"@"))
+        assert body == side[k] and lines[0] == b"@SQ\tSN:20_slice\tLN:321635" and any(l.startswith(b"@PG\tID:SAMBLASTER") for l in lines)
+    # a samblaster command line that asks for something else than the stream was made under is refused
+    p3 = subprocess.run([os.path.join(bin_, "samblaster"), "--addMateTags"], input=stream, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert p3.returncode != 0 and b"other options" in p3.stderr

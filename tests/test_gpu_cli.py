@@ -197,6 +197,95 @@ def test_cli_fused_samblaster_stage(ssq, cli_ref, tmp_path, monkeypatch):
     assert outs["fused"][0].count(b"\n") > 80000 and outs["fused"][1].count(b"\n") > 100 and outs["fused"][2].count(b"\n") > 500
 
 
+def _bam_to_sam(d):
+    """records of a decompressed BAM file as SAM lines + their (reference, position, strand) keys (htslib sam.c:443-467 layout)"""
+    import struct
+    assert d[:4] == b"BAM\x01"
+    l_text = struct.unpack("<i", d[4:8])[0]
+    text = d[8:8 + l_text]
+    p = 8 + l_text
+    n_ref = struct.unpack("<i", d[p:p + 4])[0]
+    p += 4
+    refs = []
+    for _ in range(n_ref):
+        l = struct.unpack("<i", d[p:p + 4])[0]
+        refs.append(d[p + 4:p + 4 + l - 1]); p += 8 + l
+    lines, keys = [], []
+    while p < len(d):
+        bs, tid, pos, l_name, mapq, _bin, n_cig, flag, l_seq, mtid, mpos, tlen = struct.unpack("<iiiBBHHHiiii", d[p:p + 36])
+        q = p + 36
+        name = d[q:q + l_name - 1]; q += l_name
+        cig = b"".join(b"%d%c" % (v >> 4, b"MIDNSHP=X"[v & 15]) for v in struct.unpack("<%dI" % n_cig, d[q:q + 4 * n_cig])) or b"*"; q += 4 * n_cig
+        sq = d[q:q + (l_seq + 1) // 2]; q += (l_seq + 1) // 2
+        seq = bytes(b"=ACMGRSVTWYHKDBN"[(sq[i >> 1] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq)) or b"*"
+        ql = d[q:q + l_seq]; q += l_seq
+        qual = b"*" if (l_seq == 0 or ql[0] == 0xff) else bytes(c + 33 for c in ql)
+        tags = []
+        end = p + 4 + bs
+        while q < end:
+            tg, ty = d[q:q + 2], d[q + 2:q + 3]; q += 3
+            if ty == b"Z":
+                e = d.index(b"\0", q); tags.append(tg + b":Z:" + d[q:e]); q = e + 1
+            elif ty == b"A":
+                tags.append(tg + b":A:" + d[q:q + 1]); q += 1
+            else:
+                fmt, n = {b"c": ("<b", 1), b"C": ("<B", 1), b"s": ("<h", 2), b"S": ("<H", 2), b"i": ("<i", 4), b"I": ("<I", 4)}[ty]
+                tags.append(tg + b":i:%d" % struct.unpack(fmt, d[q:q + n])[0]); q += n
+        rn = refs[tid] if tid >= 0 else b"*"
+        mrn = b"*" if mtid < 0 else (b"=" if mtid == tid else refs[mtid])
+        lines.append(b"\t".join([name, b"%d" % flag, rn, b"%d" % (pos + 1), b"%d" % mapq, cig, mrn, b"%d" % (mpos + 1), b"%d" % tlen, seq, qual] + tags))
+        keys.append((tid if tid >= 0 else 1 << 40, pos, (flag >> 4) & 1))
+        p = end
+    return text, lines, keys
+
+
+def test_cli_bam_mode_main_records_leave_as_sorted_runs(ssq, cli_ref, tmp_path):
+    """SSQ_FUSE_BAM: `bwa mem | samblaster | sambamba view -S -f bam -l 0 | sambamba sort` (speedseq:438-441) with the three shims; the
+    main records are encoded and coordinate-sorted on the device per batch and merged by the `sambamba` shim — no SAM text of them
+    exists anywhere.  out.bam decoded must hold exactly the records of the (oracle-identical) fused text pipe, ordered by (reference,
+    position, strand) with ties in input order — the order pinned on the reference's sambamba in tests/test_bam_golden.py; the side
+    streams stay the text they were."""
+    import gzip
+    from test_hostsim_pipe import stress_reads
+    SAMBAMBA = os.path.join(T.ROOT, "speedseq_b200", "bin", "sambamba")
+    d, fa, g, bounds = cli_ref
+    names, seqs, quals = stress_reads(g, bounds, 40000, 150, 8)  # -t 1: two batches = two runs
+    fq = str(d / "bam_mode.fq")
+    T.write_fastq(fq, names, seqs, quals)
+    sb_args = ["--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20"]
+    res = {}
+    for tag, extra in (("text", {}), ("bam", {"SSQ_FUSE_BAM": "1"})):
+        e = dict(os.environ, SSQ_FUSE_SAMBLASTER=" ".join(sb_args), **extra)
+        spl, disc = str(tmp_path / (tag + ".spl")), str(tmp_path / (tag + ".disc"))
+        p1 = subprocess.Popen([BWA, "mem", "-t", "1", "-p", "-R", RG, fa, fq], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e)
+        p2 = subprocess.run([SAMBLASTER] + sb_args + ["--splitterFile", spl, "--discordantFile", disc], stdin=p1.stdout, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=e, check=True, timeout=300)
+        assert p1.wait(timeout=60) == 0
+        res[tag] = (p2.stdout, open(spl, "rb").read(), open(disc, "rb").read())
+    assert _strip_pg(res["bam"][1]) == _strip_pg(res["text"][1]) and _strip_pg(res["bam"][2]) == _strip_pg(res["text"][2])
+    assert b"@CO\tssq-bam-runs-v1\n" in res["bam"][0][:4096] and res["bam"][0].count(b"SSQFRAME") >= 2
+    out = str(tmp_path / "out.bam")
+    v = subprocess.run([SAMBAMBA, "view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], input=res["bam"][0], stdout=subprocess.PIPE, check=True, timeout=120).stdout
+    subprocess.run([SAMBAMBA, "sort", "-t", "4", "-m", "1G", "--tmpdir=" + str(tmp_path), "-o", out, "/dev/stdin"], input=v, check=True, timeout=120)
+    text, lines, keys = _bam_to_sam(gzip.decompress(open(out, "rb").read()))
+    want = _records(res["text"][0]).splitlines()
+    assert len(lines) == len(want) > 80000
+    assert text.startswith(b"@HD\tVN:1.3\tSO:coordinate\n@SQ\t") and b"\n@RG\tID:NA12878\tLB:lib1\tSM:NA12878\n" in text and b"ssq-" not in text
+    assert keys == sorted(keys)
+    order = {}
+    for i, l in enumerate(want):
+        order.setdefault(l, []).append(i)
+    at = {}
+    idx = []
+    for l in lines:  # every BAM record is one text record (identical lines: in their input order)
+        k = at.get(l, 0)
+        assert l in order and k < len(order[l]), l
+        idx.append(order[l][k]); at[l] = k + 1
+    assert sorted(idx) == list(range(len(want)))
+    for a in range(1, len(idx)):
+        if keys[a] == keys[a - 1]:
+            assert idx[a] > idx[a - 1], (a, lines[a])
+
+
 def test_cli_fastq_ingest_on_the_device_and_its_fallbacks(ssq, cli_ref):
     """the `bwa` shim hands the FASTQ text to the device tokeniser (ssq_aligner_upload_fastq); layouts it does not take — multi-line
     records, FASTA, blank lines — must silently go through the host tokeniser with identical results; CRLF line ends and a last line

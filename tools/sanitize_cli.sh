@@ -16,6 +16,6 @@ for tool in ${SSQ_SANITIZE_TOOLS:-memcheck racecheck}; do
 	md5sum < "$W/$tool.out" > "$W/$tool.md5"
 	echo "== $tool: exit $r, output $(cmp -s "$W/plain.md5" "$W/$tool.md5" && echo identical to the uninstrumented run || echo DIFFERS)"
 	grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|Warning:" "$W/$tool.err" | sort | uniq -c | sort -rn | head -8
-	[ $r -ne 0 ] && rc=1
+	[ $r -ne 0 ] && { rc=1; head -c 1500 "$W/$tool.err"; }
 done
 exit $rc
