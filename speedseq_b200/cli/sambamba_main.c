@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
 #include "ssq.h"
@@ -230,6 +231,7 @@ static int sort_runs(head_t *h, size_t body, const char *out_fn, int threads, in
 		if (in_mem > mem_limit) { /* merge what is held and spill it */
 			char fn[4096];
 			FILE *fp;
+			mkdir(tmpdir, 0777); /* sambamba creates its --tmpdir too */
 			snprintf(fn, sizeof fn, "%s/ssq_sort_%ld_%d.run", tmpdir, (long)getpid(), n_spill);
 			if (!(fp = fopen(fn, "wb"))) { fprintf(stderr, "sambamba (B200 shim): cannot create %s: %s\n", fn, strerror(errno)); return 1; }
 			merge_sources(mem, n_mem, file_put, fp);
