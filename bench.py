@@ -491,6 +491,15 @@ def main():
         except Exception:
             pass
         ach = kern[dom]["achieved_GBps"] or 0.0
+        rnd = None
+        try:  # what this device serves when the reads are dependent random 32-byte sectors over a table of the rank structure's size (measured, profiles/)
+            rj = json.load(open(os.path.join(ROOT, "profiles", "r02_random_sector.json")))
+            tab_gb = a.genome_len * 2 * 32 / 64 / 2**30  # 32 bytes per 64 BWT symbols, both strands
+            key = min(rj["table_GB"], key=lambda k: abs(float(k) - tab_gb))
+            if "k_smem" in dom and abs(float(key) - tab_gb) < 0.25 * tab_gb:
+                rnd = {"GBps": rj["table_GB"][key], "table_GB": float(key), "frac_of_ceiling": ach / rj["table_GB"][key], "source": "profiles/r02_random_sector.log (tools/random_sector_bench.cu)"}
+        except Exception:
+            pass
         res = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                "config": {"workload": workload, "batch_reads": a.batch, "batches_per_step": nb, "streams": nstreams, "genome_bp": a.genome_len,
@@ -501,7 +510,8 @@ def main():
                "clocks": clocks, "gpu_launches": int(counters[6]) * a.steps + 14 * nb * a.steps,
                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step[0], "ms_per_step": ms_e2e / a.steps},
                "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                            "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"], "rank_block_bytes": blk},
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"], "rank_block_bytes": blk,
+                            "access_pattern": "dependent random 32-byte sector reads (one or two rank blocks per FM-index extension)", "random_sector_ceiling": rnd},
                "kernels": kern,
                "work_per_step": {"occ_blocks_smem": counters[0], "occ_blocks_sa": counters[1], "sa_samples": counters[2], "sw_calls": counters[3], "sw_cells": counters[4], "seeds": counters[7],
                                  "alignments_written": n_tasks, "sam_bytes": text_bytes, "pairs_through_mate_rescue": n_rescue, "alignments_with_banded_dp": n_gapped, "rescue_sw_passes": n_swl, "rescue_sw_cells": swl_cells},

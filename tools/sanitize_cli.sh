@@ -7,7 +7,7 @@ gzip -dc "$ROOT/tests/golden/ex_ref.fa.gz" > "$W/ref.fa" 2>/dev/null || cp "$ROO
 BWA=$ROOT/speedseq_b200/bin/bwa
 timeout 120 "$BWA" index "$W/ref.fa" > "$W/index.log" 2>&1 || { echo "index failed"; tail -3 "$W/index.log"; exit 1; }
 N=${SSQ_SANITIZE_READS:-600}; gzip -dc "$ROOT/tests/golden/ex_reads_2k.fq.gz" | head -n $((4 * N)) > "$W/reads.fq"
-export SSQ_FUSE_SAMBLASTER=1
+export SSQ_FUSE_SAMBLASTER="--excludeDups --addMateTags --maxSplitCount 2 --minNonOverlap 20"
 timeout 60 "$BWA" mem -p "$W/ref.fa" "$W/reads.fq" 2>/dev/null | md5sum > "$W/plain.md5"
 rc=0
 for tool in ${SSQ_SANITIZE_TOOLS:-memcheck racecheck}; do

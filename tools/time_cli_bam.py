@@ -39,6 +39,15 @@ B = os.path.join(ROOT, "speedseq_b200", "bin")
 RG = r"@RG\tID:x\tSM:x\tLB:l"
 sb_args = ["--excludeDups", "--addMateTags", "--maxSplitCount", "2", "--minNonOverlap", "20"]
 threads = str(min(32, os.cpu_count() or 4))
+for tag, env, with_sb in (("bwa mem (fused, text) > /dev/null", {}, 0), ("bwa mem (BAM runs) > /dev/null", {"SSQ_FUSE_BAM": "1"}, 0), ("bwa mem (BAM runs) | samblaster > /dev/null", {"SSQ_FUSE_BAM": "1"}, 1)):
+    e = dict(os.environ, SSQ_FUSE_SAMBLASTER=" ".join(sb_args), **env)  # where the time of the chain goes: its first stages alone
+    t0 = time.time()
+    with open(os.devnull, "wb") as nul:
+        p1 = subprocess.Popen([os.path.join(B, "bwa"), "mem", "-t", "8", "-p", "-R", RG, fa, fq], stdout=subprocess.PIPE if with_sb else nul, stderr=subprocess.DEVNULL, env=e)
+        if with_sb:
+            subprocess.run([os.path.join(B, "samblaster")] + sb_args + ["--splitterFile", os.devnull, "--discordantFile", os.devnull], stdin=p1.stdout, stdout=nul, stderr=subprocess.DEVNULL, env=e, check=True, timeout=300)
+        assert p1.wait(timeout=300) == 0
+    print("%-46s %6.2f s" % (tag, time.time() - t0), flush=True)
 res = {}
 for tag, env, sambamba in (("text + reference sambamba", {}, REAL), ("BAM runs + sambamba shim", {"SSQ_FUSE_BAM": "1"}, os.path.join(B, "sambamba"))):
     e = dict(os.environ, SSQ_FUSE_SAMBLASTER=" ".join(sb_args), SSQ_SAMBAMBA_REAL=REAL, **env)
