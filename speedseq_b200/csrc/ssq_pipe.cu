@@ -306,6 +306,7 @@ extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt,
 	if (!idx || !opt || !out) return SSQ_EINVAL;
 	int rc = ssq_use_device(idx->device);
 	if (rc) return rc;
+	if (getenv("SSQ_RESCUE_SPLIT")) { const int v = atoi(getenv("SSQ_RESCUE_SPLIT")); CK(cudaMemcpyToSymbol(ssq_rescue_split, &v, sizeof v)); } // 0: the 16-lane form of the local SW (ssq_warp.cuh)
 	ssq_aligner *a = new ssq_aligner();
 	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->comm = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->want_bam = 0; a->bam_blank_side = 1; a->bam_len[0] = a->bam_len[1] = a->bam_len[2] = 0; a->n_lines_total = 0; a->computed = 0; a->n_reads = 0;
 	memset(a->ev, 0, sizeof a->ev); memset(a->stage_ms, 0, sizeof a->stage_ms); memset(a->pes, 0, sizeof a->pes);

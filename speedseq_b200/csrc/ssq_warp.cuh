@@ -265,13 +265,176 @@ __device__ __noinline__ LocalRes sw_local_pass_warp_reg(const ssq_opts_t &o, int
 	return r;
 }
 
+// The same pass with all 32 lanes at work: the striped kernel has 16 byte lanes, so the form above leaves half the warp idle.
+// Here every segment is shared by two lanes — lane s sweeps cells [0, HA) of segment s, lane 16 + s cells [HA, SLEN) — and the
+// values stay those of the 16-lane kernel:
+//   * main pass: within a segment only F runs from cell to cell, F' = max(F - e_ins, H - oe_ins, 0), a max-plus recurrence.  The
+//     second half starts with F = 0; when the first half's F arrives, F_true(j) = max(F_local(j), F_in decayed by j * e_ins), so
+//     its cells are repaired by H = max(H, decayed F_in) (and E, which was derived from H) — a pass that only runs when some
+//     segment hands a positive F across its middle;
+//   * lazy F: the 16-lane loop tests after every cell whether any lane could still raise an H; here the first halves sweep their
+//     cells (exit test over those 16 lanes), then the second halves theirs — the same sequence of cells and tests.
+// tests/hostsim/split_emul.cpp runs this algorithm lane by lane on the host against the scalar restatement (sw_local_pass).
+__device__ int ssq_rescue_split = 1; // SSQ_RESCUE_SPLIT=0 keeps the 16-lane form (A/B measurements)
+template <int SLEN, class TGT>
+__device__ __noinline__ LocalRes sw_local_pass_warp_split(const ssq_opts_t &o, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt, bool *has_n)
+{
+	constexpr int HA = (SLEN + 1) / 2, HB = SLEN / 2;
+	const int slen = SLEN, s = lane & 15, half = lane >> 4, nloc = half ? HB : HA, base = half ? HA : 0;
+	const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
+	const int shift = o.b > 1 ? o.b : 1, maxsc = o.a;
+	const int minsc = (xtra & SSQ_XSUBO) ? xtra & 0xffff : 0x10000;
+	const int endsc = (xtra & SSQ_XSTOP) ? xtra & 0xffff : 0x10000;
+	LocalRes r;
+	r.score = 0; r.te = r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = r.qb = -1;
+	*has_n = false;
+	if (qlen <= 0) return r;
+	int H[HA], E[HA], HM[HA]; u32 PF[HA];
+#pragma unroll
+	for (int j = 0; j < HA; ++j) {
+		const int pos = s * slen + base + j;
+		const int qc = (j < nloc && pos < qlen) ? q[pos] : -1;
+		u32 w = 0;
+#pragma unroll
+		for (int c = 0; c < 4; ++c) w |= (u32)(uint8_t)(int8_t)(qc < 0 ? 0 : score_of(o, qc, c)) << (8 * c);
+		PF[j] = w; H[j] = E[j] = HM[j] = 0;
+	}
+	int gmax = 0, te = -1, n_b = 0, tcache = 0, rows = 0;
+	for (int i = 0; i < tlen; ++i) {
+		if ((i & 31) == 0) tcache = i + lane < tlen ? tgt(i + lane) : 0;
+		const int tb = __shfl_sync(WFULL, tcache, i & 31);
+		if (tb > 3) { *has_n = true; return r; } // (uniform) the caller redoes the pass with the general form
+		++rows;
+		const int sh = 8 * tb;
+		int f = 0, imax = 0, hd;
+		{ // H (previous row) of the cell before this lane's first one: the end of the segment below / of this segment's first half
+			const int last = half ? H[HB - 1] : H[HA - 1];
+			hd = __shfl_sync(WFULL, last, half ? s : (15 + s) & 31);
+			if (lane == 0) hd = 0;
+		}
+#pragma unroll
+		for (int j = 0; j < HA; ++j) {
+			if (j < HB || !half) { // (a second half has one cell less when SLEN is odd)
+				const int hn = H[j];
+				int h = hd + (int)(int8_t)(PF[j] >> sh), e = E[j], tt;
+				h += shift; if (h > 255) h = 255; h -= shift; if (h < 0) h = 0;
+				h = h > e ? h : e;
+				h = h > f ? h : f;
+				imax = imax > h ? imax : h;
+				H[j] = h;
+				tt = h - oe_del; if (tt < 0) tt = 0;
+				e -= e_del; if (e < 0) e = 0;
+				E[j] = e > tt ? e : tt;
+				tt = h - oe_ins; if (tt < 0) tt = 0;
+				f -= e_ins; if (f < 0) f = 0;
+				f = f > tt ? f : tt;
+				hd = hn;
+			}
+		}
+		{ // the first half's F reaches into the second half
+			int g = __shfl_sync(WFULL, f, s);
+			if (!half) g = 0;
+			if (__any_sync(WFULL, g > 0)) {
+#pragma unroll
+				for (int j = 0; j < HB; ++j) { // (first halves: g = 0 never exceeds an H)
+					if (g > H[j]) { H[j] = g; int tt = g - oe_del; if (tt < 0) tt = 0; if (tt > E[j]) E[j] = tt; if (g > imax) imax = g; }
+					g -= e_ins; if (g < 0) g = 0;
+				}
+				if (g > f) f = g;
+			}
+		}
+		{ // lazy F: first halves, then second halves; the exit test after a cell looks at the 16 lanes that own it
+			int fl = f;
+			bool done = false;
+			for (int round = 0; round < 16 && !done; ++round) {
+				const int in = __shfl_sync(WFULL, fl, (15 + s) & 31); // the F the segment below ended its sweep with
+				if (!half) fl = s == 0 ? 0 : in;
+#pragma unroll
+				for (int j = 0; j < HA; ++j) {
+					if (!done) {
+						bool gt = false;
+						if (!half) {
+							int h = H[j], tt;
+							h = h > fl ? h : fl;
+							H[j] = h;
+							tt = h - oe_ins; if (tt < 0) tt = 0;
+							fl -= e_ins; if (fl < 0) fl = 0;
+							gt = fl > tt;
+						}
+						if (!__any_sync(WFULL, gt)) done = true;
+					}
+				}
+				if (done) break;
+				const int fa = __shfl_sync(WFULL, fl, s);
+				if (half) fl = fa;
+#pragma unroll
+				for (int j = 0; j < HB; ++j) {
+					if (!done) {
+						bool gt = false;
+						if (half) {
+							int h = H[j], tt;
+							h = h > fl ? h : fl;
+							H[j] = h;
+							tt = h - oe_ins; if (tt < 0) tt = 0;
+							fl -= e_ins; if (fl < 0) fl = 0;
+							gt = fl > tt;
+						}
+						if (!__any_sync(WFULL, gt)) done = true;
+					}
+				}
+			}
+		}
+		imax = __reduce_max_sync(WFULL, imax);
+		if (imax >= minsc && lane == 0) {
+			if (n_b == 0 || (i32)b[n_b - 1] + 1 != i) { if (n_b < b_cap) b[n_b++] = (u64)imax << 32 | (u32)i; }
+			else if ((int)(b[n_b - 1] >> 32) < imax) b[n_b - 1] = (u64)imax << 32 | (u32)i;
+		}
+		if (imax > gmax) {
+			gmax = imax; te = i;
+#pragma unroll
+			for (int j = 0; j < HA; ++j) HM[j] = H[j];
+			if (gmax + shift >= 255 || gmax >= endsc) break;
+		}
+	}
+	n_b = __shfl_sync(WFULL, n_b, 0);
+	if (cnt && lane == 0) { atomicAdd(cnt + 2, 1ull); atomicAdd(cnt + 3, (unsigned long long)rows * qlen); }
+	r.score = gmax + shift < 255 ? gmax : 255;
+	r.te = te;
+	if (r.score != 255) {
+		int vmax = -1, qe = 0x7fffffff;
+#pragma unroll
+		for (int j = 0; j < HA; ++j) if (j < nloc) { const int v = HM[j], pos = s * slen + base + j; if (v > vmax) { vmax = v; qe = pos; } else if (v == vmax && pos < qe) qe = pos; }
+		const int m = __reduce_max_sync(WFULL, vmax);
+		r.qe = __reduce_min_sync(WFULL, vmax == m ? qe : 0x7fffffff);
+		if (n_b) {
+			int s2 = -1, te2 = -1;
+			if (lane == 0) {
+				const int d = (r.score + maxsc - 1) / maxsc, low = te - d, high = te + d;
+				for (int i = 0; i < n_b; ++i) {
+					const int e = (i32)b[i];
+					if ((e < low || e > high) && (int)(b[i] >> 32) > s2) { s2 = (int)(b[i] >> 32); te2 = e; }
+				}
+			}
+			r.score2 = __shfl_sync(WFULL, s2, 0); r.te2 = __shfl_sync(WFULL, te2, 0);
+		}
+	}
+	return r;
+}
+
 template <class TGT>
 __device__ LocalRes sw_local_pass_warp(const ssq_opts_t &o, bool bytes, int qlen, const uint8_t *q /* shared */, int tlen, TGT tgt, int xtra, WarpSwSmem &W, u64 *b, int b_cap, int lane, unsigned long long *cnt = 0)
 {
 	if (bytes && qlen > 0 && qlen <= 256) {
 		bool has_n = false;
 		LocalRes r;
-		switch ((qlen + 15) / 16) {
+		if (ssq_rescue_split && qlen > 16) switch ((qlen + 15) / 16) {
+#define SSQ_SLEN_CASE(n_) case n_: r = sw_local_pass_warp_split<n_>(o, qlen, q, tlen, tgt, xtra, W, b, b_cap, lane, cnt, &has_n); break;
+		SSQ_SLEN_CASE(2) SSQ_SLEN_CASE(3) SSQ_SLEN_CASE(4) SSQ_SLEN_CASE(5) SSQ_SLEN_CASE(6) SSQ_SLEN_CASE(7) SSQ_SLEN_CASE(8)
+		SSQ_SLEN_CASE(9) SSQ_SLEN_CASE(10) SSQ_SLEN_CASE(11) SSQ_SLEN_CASE(12) SSQ_SLEN_CASE(13) SSQ_SLEN_CASE(14) SSQ_SLEN_CASE(15) SSQ_SLEN_CASE(16)
+#undef SSQ_SLEN_CASE
+		default: has_n = true;
+		}
+		else switch ((qlen + 15) / 16) {
 #define SSQ_SLEN_CASE(n_) case n_: r = sw_local_pass_warp_reg<n_>(o, qlen, q, tlen, tgt, xtra, W, b, b_cap, lane, cnt, &has_n); break;
 		SSQ_SLEN_CASE(1) SSQ_SLEN_CASE(2) SSQ_SLEN_CASE(3) SSQ_SLEN_CASE(4) SSQ_SLEN_CASE(5) SSQ_SLEN_CASE(6) SSQ_SLEN_CASE(7) SSQ_SLEN_CASE(8)
 		SSQ_SLEN_CASE(9) SSQ_SLEN_CASE(10) SSQ_SLEN_CASE(11) SSQ_SLEN_CASE(12) SSQ_SLEN_CASE(13) SSQ_SLEN_CASE(14) SSQ_SLEN_CASE(15) SSQ_SLEN_CASE(16)

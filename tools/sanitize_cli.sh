@@ -11,11 +11,11 @@ export SSQ_FUSE_SAMBLASTER="--excludeDups --addMateTags --maxSplitCount 2 --minN
 timeout 60 "$BWA" mem -p "$W/ref.fa" "$W/reads.fq" 2>/dev/null | md5sum > "$W/plain.md5"
 rc=0
 for tool in ${SSQ_SANITIZE_TOOLS:-memcheck racecheck}; do
-	timeout ${SSQ_SANITIZE_TIMEOUT:-100} compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 "$BWA" mem -p "$W/ref.fa" "$W/reads.fq" > "$W/$tool.out" 2> "$W/$tool.err"
+	timeout ${SSQ_SANITIZE_TIMEOUT:-100} compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 --log-file "$W/$tool.log" "$BWA" mem -p "$W/ref.fa" "$W/reads.fq" > "$W/$tool.out" 2> "$W/$tool.err"
 	r=$?
 	md5sum < "$W/$tool.out" > "$W/$tool.md5"
 	echo "== $tool: exit $r, output $(cmp -s "$W/plain.md5" "$W/$tool.md5" && echo identical to the uninstrumented run || echo DIFFERS)"
-	grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|Warning:" "$W/$tool.err" | sort | uniq -c | sort -rn | head -8
-	[ $r -ne 0 ] && { rc=1; head -c 1500 "$W/$tool.err"; }
+	grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|Warning:" "$W/$tool.log" | sort | uniq -c | sort -rn | head -8
+	[ $r -ne 0 ] && { rc=1; head -c 1500 "$W/$tool.err"; head -c 3000 "$W/$tool.log"; }
 done
 exit $rc
