@@ -382,11 +382,57 @@ SSQ_HD int infer_dir(i64 l_pac, i64 b1, i64 b2, i64 *dist)
 
 struct MateScratch { uint8_t *seq, *ref; int ref_cap; LocalScratch L; AlnScratch A; };
 
+// the window orientation r of one mem_matesw() aligns the mate in: [*rb, *re) on the doubled reference; false when the orientation
+// aligns nothing (window outside the hit's contig, or shorter than a seed)
+SSQ_HD bool rescue_window(const DevIndex &ix, const ssq_opts_t &o, const PeStat *pes, const AlnReg &a, int l_ms, int r, i64 *rb_, i64 *re_)
+{
+	const i64 l_pac = ix.l_pac;
+	const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+	i64 rb, re;
+	int rid = -1;
+	if (!is_rev) {
+		rb = is_larger ? a.rb + pes[r].low : a.rb - pes[r].high;
+		re = (is_larger ? a.rb + pes[r].high : a.rb - pes[r].low) + l_ms;
+	} else {
+		rb = (is_larger ? a.rb + pes[r].low : a.rb - pes[r].high) - l_ms;
+		re = is_larger ? a.rb + pes[r].high : a.rb - pes[r].low;
+	}
+	if (rb < 0) rb = 0;
+	if (re > l_pac << 1) re = l_pac << 1;
+	if (rb < re) { // clamp to the contig/strand holding the window's midpoint
+		int rv;
+		const i64 mid = (rb + re) >> 1;
+		rid = pos2rid(ix, depos(ix, mid, rv));
+		i64 far_beg = ix.ann_off[rid], far_end = far_beg + ix.ann_len[rid];
+		if (rv) { i64 t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+		rb = rb > far_beg ? rb : far_beg;
+		re = re < far_end ? re : far_end;
+	}
+	*rb_ = rb; *re_ = re;
+	return a.rid == rid && re - rb >= o.min_seed_len;
+}
+
+// Speculative mate rescue.  What a rescue alignment computes depends only on the hit it starts from (taken from the snapshot of
+// near-best hits made before any rescue), the orientation and the mate's sequence — not on the mate's region list, which only
+// decides whether the alignment is SKIPPED.  So every alignment the initial lists do not skip can be computed ahead, one task each,
+// spread evenly over the machine; the sequential replay (mate_rescue below, in the reference's order, with the lists evolving as
+// the reference's do) then looks its alignments up instead of computing them.  A replay step whose alignment was not computed
+// ahead (possible when de-duplication removed the hit that had made the initial list skip it) computes it on the spot.
+struct RTask { u32 slot, key; i64 rb; i32 tlen, l_ms; }; // key = end << 16 | snapshot index << 2 | orientation: ascending in replay order
+struct RCache { const RTask *t; const LocalRes *res; int n, cur; unsigned int *miss; };
+SSQ_HD const LocalRes *rcache_find(RCache &c, u32 key, i64 rb, int tlen)
+{
+	while (c.cur < c.n && c.t[c.cur].key < key) ++c.cur;
+	if (c.cur < c.n && c.t[c.cur].key == key && c.t[c.cur].rb == rb && c.t[c.cur].tlen == tlen) return &c.res[c.cur];
+	return 0;
+}
+SSQ_HD int rescue_xtra(const ssq_opts_t &o, int l_ms) { return SSQ_XSUBO | SSQ_XSTART | (l_ms * o.a < 250 ? SSQ_XBYTE : 0) | (o.min_seed_len * o.a); }
+
 // one mem_matesw(): rescue the mate `ms` of hit `a` inside the windows the insert-size bounds allow; ma[0..*n_ma) is the mate's
 // region list (capacity ma_cap), kept sorted by score and de-duplicated.  Returns the number of windows aligned, -1 when a window
 // does not fit S.ref_cap (callers size the scratch from the batch's insert-size bounds and treat -1 as an error)
 SSQ_HD int mate_rescue(const DevIndex &ix, const ssq_opts_t &o, const PeStat pes[4], const AlnReg &a, int l_ms, const uint8_t *ms, AlnReg *ma, int *n_ma, int ma_cap,
-                       const MateScratch &S, i32 *idx = 0)
+                       const MateScratch &S, i32 *idx = 0, RCache *rc = 0, u32 key = 0)
 {
 	const i64 l_pac = ix.l_pac;
 	int i, r, skip[4], n = 0;
@@ -399,34 +445,20 @@ SSQ_HD int mate_rescue(const DevIndex &ix, const ssq_opts_t &o, const PeStat pes
 	if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
 	for (r = 0; r < 4; ++r) {
 		if (skip[r]) continue;
-		const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+		const int is_rev = (r >> 1 != (r & 1));
 		i64 rb, re;
-		int rid = -1;
-		for (i = 0; i < l_ms; ++i) S.seq[is_rev ? l_ms - 1 - i : i] = is_rev ? (ms[i] < 4 ? 3 - ms[i] : 4) : ms[i];
-		if (!is_rev) {
-			rb = is_larger ? a.rb + pes[r].low : a.rb - pes[r].high;
-			re = (is_larger ? a.rb + pes[r].high : a.rb - pes[r].low) + l_ms;
-		} else {
-			rb = (is_larger ? a.rb + pes[r].low : a.rb - pes[r].high) - l_ms;
-			re = is_larger ? a.rb + pes[r].high : a.rb - pes[r].low;
-		}
-		if (rb < 0) rb = 0;
-		if (re > l_pac << 1) re = l_pac << 1;
-		if (rb < re) { // clamp to the contig/strand holding the window's midpoint
-			int rv;
-			const i64 mid = (rb + re) >> 1;
-			rid = pos2rid(ix, depos(ix, mid, rv));
-			i64 far_beg = ix.ann_off[rid], far_end = far_beg + ix.ann_len[rid];
-			if (rv) { i64 t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
-			rb = rb > far_beg ? rb : far_beg;
-			re = re < far_end ? re : far_end;
-		}
-		if (a.rid == rid && re - rb >= o.min_seed_len) {
+		if (rescue_window(ix, o, pes, a, l_ms, r, &rb, &re)) {
 			if (re - rb > S.ref_cap) return -1; // window beyond the caller's scratch: reported, never skipped silently (the reference has no limit)
 			const int tlen = (int)(re - rb);
-			for (i = 0; i < tlen; ++i) S.ref[i] = (uint8_t)ref_base(ix, rb + i);
-			const int xtra = SSQ_XSUBO | SSQ_XSTART | (l_ms * o.a < 250 ? SSQ_XBYTE : 0) | (o.min_seed_len * o.a);
-			const LocalRes aln = sw_local(o, l_ms, S.seq, tlen, S.ref, xtra, S.L);
+			const LocalRes *ahead = rc ? rcache_find(*rc, key | (u32)r, rb, tlen) : 0;
+			LocalRes aln;
+			if (ahead) aln = *ahead;
+			else {
+				if (rc && rc->miss) ++*rc->miss;
+				for (i = 0; i < l_ms; ++i) S.seq[is_rev ? l_ms - 1 - i : i] = is_rev ? (ms[i] < 4 ? 3 - ms[i] : 4) : ms[i];
+				for (i = 0; i < tlen; ++i) S.ref[i] = (uint8_t)ref_base(ix, rb + i);
+				aln = sw_local(o, l_ms, S.seq, tlen, S.ref, rescue_xtra(o, l_ms), S.L);
+			}
 			if (aln.score >= o.min_seed_len && aln.qb >= 0) {
 				AlnReg b;
 				b.rid = a.rid;

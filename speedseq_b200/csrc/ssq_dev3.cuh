@@ -718,9 +718,40 @@ SSQ_HD bool rescue_wanted(const PipeView &V, int p)
 	}
 	return false;
 }
+// the rescue alignments of pair p the lists, as they are before any rescue, do not skip: their count, and with `out` the tasks
+// themselves in replay order (end, snapshot index, orientation).  win_cap: windows beyond it are left to the replay, which reports them
+SSQ_HD int rescue_enum(const PipeView &V, int p, RTask *out, u32 slot, int win_cap)
+{
+	const i64 l_pac = V.ix.l_pac;
+	int n = 0;
+	for (int i = 0; i < 2; ++i) {
+		const AlnReg *a = V.areg + V.areg_off[2 * p + i], *ma = V.areg + V.areg_off[2 * p + !i];
+		const int na = (int)V.n_areg[2 * p + i], nm = (int)V.n_areg[2 * p + !i];
+		const int l_ms = (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]);
+		int nb = 0;
+		for (int j = 0; j < na && nb < V.opt.max_matesw && nb < 64; ++j) {
+			if (!(a[j].score >= a[0].score - V.opt.pen_unpaired)) continue;
+			const int jj = nb++; // index in the snapshot of near-best hits (body_rescue)
+			int skip[4];
+			for (int r = 0; r < 4; ++r) skip[r] = V.pes[r].failed ? 1 : 0;
+			for (int k = 0; k < nm; ++k) {
+				i64 dist;
+				const int r = infer_dir(l_pac, a[j].rb, ma[k].rb, &dist);
+				if (dist >= V.pes[r].low && dist <= V.pes[r].high) skip[r] = 1;
+			}
+			for (int r = 0; r < 4; ++r) {
+				i64 rb, re;
+				if (skip[r] || !rescue_window(V.ix, V.opt, V.pes, a[j], l_ms, r, &rb, &re) || re - rb > win_cap) continue;
+				if (out) { RTask t; t.slot = slot; t.key = (u32)(i << 16 | jj << 2 | r); t.rb = rb; t.tlen = (i32)(re - rb); t.l_ms = l_ms; out[n] = t; }
+				++n;
+			}
+		}
+	}
+	return n;
+}
 // stage 3: mate rescue of one pair (mem_sam_pe's first block).  bbuf: room for 2 x 64 regions (the near-best hits of both ends are
 // copied before any list changes, as the reference does)
-SSQ_HD void body_rescue(const PipeView &V, int p, AlnReg *bbuf, const MateScratch &M)
+SSQ_HD void body_rescue(const PipeView &V, int p, AlnReg *bbuf, const MateScratch &M, RCache *rc = 0)
 {
 	AlnReg *b[2] = {bbuf, bbuf + 64};
 	int nb[2] = {0, 0}, na[2];
@@ -734,7 +765,7 @@ SSQ_HD void body_rescue(const PipeView &V, int p, AlnReg *bbuf, const MateScratc
 		const int cap = (int)(V.areg_off[2 * p + !i + 1] - V.areg_off[2 * p + !i]);
 		for (int j = 0; j < nb[i] && j < V.opt.max_matesw; ++j) {
 			const int before = na[!i];
-			if (mate_rescue(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, M, V.xcnt + V.areg_off[2 * p + !i]) < 0) PIPE_ERR(V, 8);
+			if (mate_rescue(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, M, V.xcnt + V.areg_off[2 * p + !i], rc, (u32)(i << 16 | j << 2)) < 0) PIPE_ERR(V, 8);
 			if (na[!i] >= cap && before < cap) PIPE_ERR(V, 1);
 		}
 	}

@@ -94,11 +94,44 @@ __global__ void __launch_bounds__(256) k_rescue_mark(PipeView V, u32 *list, unsi
 	if (p >= V.n_reads >> 1) return;
 	if (rescue_wanted(V, p)) list[atomicAdd(n_list, 1u)] = (u32)p;
 }
+// speculative form (ssq_dev2.cuh, RTask): the pairs with at least one rescue alignment the initial lists do not skip, each with a
+// contiguous range of tasks
+__global__ void __launch_bounds__(256) k_rescue_count(PipeView V, int win_cap, u32 *list, u32 *t_base, u32 *t_cnt, unsigned int *n_list, unsigned int *n_tasks)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= V.n_reads >> 1) return;
+	const int c = rescue_enum(V, p, 0, 0, win_cap);
+	if (c) { const unsigned int slot = atomicAdd(n_list, 1u); list[slot] = (u32)p; t_cnt[slot] = (u32)c; t_base[slot] = atomicAdd(n_tasks, (unsigned int)c); }
+}
+__global__ void __launch_bounds__(256) k_rescue_fill(PipeView V, int win_cap, const u32 *__restrict__ list, const u32 *__restrict__ t_base, const unsigned int *__restrict__ n_list, RTask *tasks)
+{
+	const unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot < *n_list) rescue_enum(V, (int)list[slot], tasks + t_base[slot], slot, win_cap);
+}
 
 // mate rescue: one warp per marked pair (ssq_warp.cuh).  Per-warp global scratch: the snapshot of the near-best hits of both ends
 // (2 x 64 regions) and the list of sub-optimal rows of the current alignment (win_cap entries); DP state lives in shared memory
 struct RescueCfg { int win_cap; size_t slab_bytes; };
-__global__ void __launch_bounds__(128) k_rescue(PipeView V, const u32 *__restrict__ list, const unsigned int *__restrict__ n_list, uint8_t *slabs, RescueCfg cfg, int *work)
+// the alignments computed ahead: one warp per task, all of about the same size (one window), so the kernel has no tail
+__global__ void __launch_bounds__(128) k_rescue_sw(PipeView V, const u32 *__restrict__ list, const RTask *__restrict__ tasks, const unsigned int *__restrict__ n_tasks, LocalRes *res, uint8_t *slabs, RescueCfg cfg, int *work)
+{
+	__shared__ WarpSwSmem sm[4];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u64 *bl = (u64*)(slabs + ((size_t)blockIdx.x * 4 + wid) * cfg.slab_bytes + 128 * sizeof(AlnReg));
+	const unsigned int n = *n_tasks;
+	for (;;) {
+		unsigned int k = 0;
+		if (lane == 0) k = (unsigned int)atomicAdd(work, 1);
+		k = __shfl_sync(WFULL, k, 0);
+		if (k >= n) break;
+		const RTask t = tasks[k];
+		const LocalRes r = rescue_task_warp(V, t, (int)list[t.slot], sm[wid], bl, cfg.win_cap, lane);
+		if (lane == 0) res[k] = r;
+	}
+}
+// the replay: tasks == 0: every alignment is computed where the replay needs it
+__global__ void __launch_bounds__(128) k_rescue(PipeView V, const u32 *__restrict__ list, const unsigned int *__restrict__ n_list, uint8_t *slabs, RescueCfg cfg, int *work,
+                                                 const RTask *__restrict__ tasks, const LocalRes *__restrict__ res, const u32 *__restrict__ t_base, const u32 *__restrict__ t_cnt, unsigned int *n_miss)
 {
 	__shared__ WarpSwSmem sm[4];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -111,7 +144,10 @@ __global__ void __launch_bounds__(128) k_rescue(PipeView V, const u32 *__restric
 		if (lane == 0) k = (unsigned int)atomicAdd(work, 1);
 		k = __shfl_sync(WFULL, k, 0);
 		if (k >= n) break;
-		body_rescue_warp(V, (int)list[k], bbuf, sm[wid], bl, cfg.win_cap, lane);
+		if (tasks) {
+			RCache rc; rc.t = tasks + t_base[k]; rc.res = res + t_base[k]; rc.n = (int)t_cnt[k]; rc.cur = 0; rc.miss = n_miss;
+			body_rescue_warp(V, (int)list[k], bbuf, sm[wid], bl, cfg.win_cap, lane, &rc);
+		} else body_rescue_warp(V, (int)list[k], bbuf, sm[wid], bl, cfg.win_cap, lane);
 	}
 }
 
@@ -268,6 +304,7 @@ struct ssq_aligner {
 	     d_ntk, d_tkbase, d_tasks, d_outs, d_cigs, d_mds, d_redo, d_k1, d_k2, d_valid, d_dup, d_disc, d_smask, d_len[3], d_off[3], d_text[3], d_err, d_cnt;
 	PinBuf h_text[3], h_roff, h_hist, h_small, h_bam[3];
 	int want_bam, bam_blank_side; u64 bam_len[3], n_lines_total;
+	int rescue_spec; DBuf d_rtbase, d_rtcnt, d_rtasks, d_rres; // speculative mate rescue: task ranges per marked pair, tasks, their results
 	DBuf d_nl, d_lbase, d_lread, d_bkey, d_bkey2, d_bidx, d_bperm, d_bsize[3], d_bsz_s, d_boff[3], d_bam[3];
 	PeStat pes[4];
 	u64 text_len[3]; u64 n_tasks_total, n_ids, n_dup, n_disc_lines, n_split_lines, n_rescue_pairs, n_gapped, n_sw_local, sw_local_cells;
@@ -309,6 +346,7 @@ extern "C" int ssq_aligner_create(const ssq_index_t *idx, const ssq_opts_t *opt,
 	if (getenv("SSQ_RESCUE_SPLIT")) { const int v = atoi(getenv("SSQ_RESCUE_SPLIT")); CK(cudaMemcpyToSymbol(ssq_rescue_split, &v, sizeof v)); } // 0: the 16-lane form of the local SW (ssq_warp.cuh)
 	ssq_aligner *a = new ssq_aligner();
 	a->idx = idx; a->opt = *opt; a->device = idx->device; a->b = 0; a->comm = 0; a->dups = 0; a->own_dups = 1; a->turn = -1; a->want_bam = 0; a->bam_blank_side = 1; a->bam_len[0] = a->bam_len[1] = a->bam_len[2] = 0; a->n_lines_total = 0; a->computed = 0; a->n_reads = 0;
+	a->rescue_spec = !(getenv("SSQ_RESCUE_SPEC") && !atoi(getenv("SSQ_RESCUE_SPEC"))); // 0: every rescue alignment computed inside the sequential replay
 	memset(a->ev, 0, sizeof a->ev); memset(a->stage_ms, 0, sizeof a->stage_ms); memset(a->pes, 0, sizeof a->pes);
 	memset(&a->sb, 0, sizeof a->sb);
 	if (sb) {
@@ -537,8 +575,23 @@ static int compute_impl(ssq_aligner_t *a, const ssq_pestat_t *pes0, int verbose)
 		const int blocks = a->n_sm * 8; // 4 warps per block, 32 warps per SM
 		if (a->d_rlist.need((size_t)(n_pairs + 1) * 4) || a->d_slab.need((size_t)blocks * 4 * cfg.slab_bytes)) return SSQ_ENOMEM;
 		unsigned int *n_list = (unsigned int*)(work + 16);
-		k_rescue_mark<<<(n_pairs + 255) / 256, 256, 0, st>>>(V, a->d_rlist.as<u32>(), n_list);
-		k_rescue<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), n_list, a->d_slab.as<uint8_t>(), cfg, work + 1);
+		if (a->rescue_spec) { // every alignment the initial lists do not skip, computed ahead as evenly sized tasks; then the replay looks them up
+			unsigned int *n_tasks = (unsigned int*)(work + 18), *n_miss = (unsigned int*)(work + 19), h_n[4] = {0, 0, 0, 0};
+			if (a->d_rtbase.need((size_t)(n_pairs + 1) * 4) || a->d_rtcnt.need((size_t)(n_pairs + 1) * 4)) return SSQ_ENOMEM;
+			k_rescue_count<<<(n_pairs + 255) / 256, 256, 0, st>>>(V, cfg.win_cap, a->d_rlist.as<u32>(), a->d_rtbase.as<u32>(), a->d_rtcnt.as<u32>(), n_list, n_tasks);
+			CK(cudaMemcpyAsync(h_n, work + 16, 16, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			const unsigned int nl = h_n[0], nt = h_n[2];
+			if (nl) {
+				if (a->d_rtasks.need(((size_t)nt + 1) * sizeof(RTask)) || a->d_rres.need(((size_t)nt + 1) * sizeof(LocalRes))) return SSQ_ENOMEM;
+				k_rescue_fill<<<(nl + 255) / 256, 256, 0, st>>>(V, cfg.win_cap, a->d_rlist.as<u32>(), a->d_rtbase.as<u32>(), n_list, a->d_rtasks.as<RTask>());
+				k_rescue_sw<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), a->d_rtasks.as<RTask>(), n_tasks, a->d_rres.as<LocalRes>(), a->d_slab.as<uint8_t>(), cfg, work + 3);
+				k_rescue<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), n_list, a->d_slab.as<uint8_t>(), cfg, work + 1, a->d_rtasks.as<RTask>(), a->d_rres.as<LocalRes>(), a->d_rtbase.as<u32>(), a->d_rtcnt.as<u32>(), n_miss);
+			}
+		} else {
+			k_rescue_mark<<<(n_pairs + 255) / 256, 256, 0, st>>>(V, a->d_rlist.as<u32>(), n_list);
+			k_rescue<<<blocks, 128, 0, st>>>(V, a->d_rlist.as<u32>(), n_list, a->d_slab.as<uint8_t>(), cfg, work + 1, 0, 0, 0, 0, 0);
+		}
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(a->ev[ST_PLAN], st));

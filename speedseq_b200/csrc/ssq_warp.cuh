@@ -464,7 +464,7 @@ __device__ LocalRes sw_local_warp(const ssq_opts_t &o, int qlen, int tlen, TGT t
 // one mem_matesw() by a warp: control flow is uniform (every lane evaluates the same scalars), lane 0 owns the writes to the
 // mate's region list.  Same contract as ssq_dev2.cuh::mate_rescue
 __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const PeStat *pes, const AlnReg &a, int l_ms, const uint8_t *ms, AlnReg *ma, int *n_ma, int ma_cap,
-                                WarpSwSmem &W, u64 *bl, int b_cap, int lane, unsigned long long *wcnt = 0, i32 *idx = 0)
+                                WarpSwSmem &W, u64 *bl, int b_cap, int lane, unsigned long long *wcnt = 0, i32 *idx = 0, RCache *rc = 0, u32 key = 0)
 {
 	const i64 l_pac = ix.l_pac;
 	int i, r, skip[4], n = 0, cnt = *n_ma; // cnt: the list length, kept uniform across the lanes (lane 0 changes the list, then broadcasts)
@@ -482,36 +482,22 @@ __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const P
 	AlnScratch noA; noA.qbuf = noA.rbuf = 0; noA.rcap = 0; noA.g.h = noA.g.e = 0; noA.g.z = 0; noA.g.zcap = 0;
 	for (r = 0; r < 4; ++r) {
 		if (skip[r]) continue;
-		const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+		const int is_rev = (r >> 1 != (r & 1));
 		i64 rb, re;
-		int rid = -1;
-		__syncwarp();
-		for (i = lane; i < l_ms; i += 32) W.q[is_rev ? l_ms - 1 - i : i] = is_rev ? (ms[i] < 4 ? 3 - ms[i] : 4) : ms[i];
-		__syncwarp();
-		if (!is_rev) {
-			rb = is_larger ? a.rb + pes[r].low : a.rb - pes[r].high;
-			re = (is_larger ? a.rb + pes[r].high : a.rb - pes[r].low) + l_ms;
-		} else {
-			rb = (is_larger ? a.rb + pes[r].low : a.rb - pes[r].high) - l_ms;
-			re = is_larger ? a.rb + pes[r].high : a.rb - pes[r].low;
-		}
-		if (rb < 0) rb = 0;
-		if (re > l_pac << 1) re = l_pac << 1;
-		if (rb < re) {
-			int rv;
-			const i64 mid = (rb + re) >> 1;
-			rid = pos2rid(ix, depos(ix, mid, rv));
-			i64 far_beg = ix.ann_off[rid], far_end = far_beg + ix.ann_len[rid];
-			if (rv) { i64 t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
-			rb = rb > far_beg ? rb : far_beg;
-			re = re < far_end ? re : far_end;
-		}
-		if (a.rid == rid && re - rb >= o.min_seed_len) {
+		if (rescue_window(ix, o, pes, a, l_ms, r, &rb, &re)) {
 			if (re - rb > b_cap) { *n_ma = cnt; return -1; }
 			const int tlen = (int)(re - rb);
-			const int xtra = SSQ_XSUBO | SSQ_XSTART | (l_ms * o.a < 250 ? SSQ_XBYTE : 0) | (o.min_seed_len * o.a);
-			TgtPac tg; tg.ix = &ix; tg.rb = rb;
-			const LocalRes aln = sw_local_warp(o, l_ms, tlen, tg, xtra, W, bl, b_cap, lane, wcnt);
+			const LocalRes *ahead = rc ? rcache_find(*rc, key | (u32)r, rb, tlen) : 0; // (uniform: every lane walks its own copy of the cursor)
+			LocalRes aln;
+			if (ahead) aln = *ahead;
+			else { // not computed ahead: here and now
+				if (rc && rc->miss && lane == 0) atomicAdd(rc->miss, 1u);
+				__syncwarp();
+				for (i = lane; i < l_ms; i += 32) W.q[is_rev ? l_ms - 1 - i : i] = is_rev ? (ms[i] < 4 ? 3 - ms[i] : 4) : ms[i];
+				__syncwarp();
+				TgtPac tg; tg.ix = &ix; tg.rb = rb;
+				aln = sw_local_warp(o, l_ms, tlen, tg, rescue_xtra(o, l_ms), W, bl, b_cap, lane, wcnt);
+			}
 			if (aln.score >= o.min_seed_len && aln.qb >= 0) {
 				if (lane == 0 && cnt < ma_cap) {
 					AlnReg b;
@@ -542,7 +528,18 @@ __device__ int mate_rescue_warp(const DevIndex &ix, const ssq_opts_t &o, const P
 	*n_ma = cnt;
 	return n;
 }
-
+// one rescue alignment computed ahead of the replay (RTask, ssq_dev2.cuh): the mate's sequence in the orientation's strand against
+// the task's window
+__device__ LocalRes rescue_task_warp(const PipeView &V, const RTask &t, int p, WarpSwSmem &W, u64 *bl, int b_cap, int lane)
+{
+	const int i = (int)(t.key >> 16), r = (int)(t.key & 3), is_rev = (r >> 1 != (r & 1)), l_ms = t.l_ms;
+	const uint8_t *ms = V.tc.seq + V.tc.read_off[2 * p + !i];
+	__syncwarp();
+	for (int x = lane; x < l_ms; x += 32) W.q[is_rev ? l_ms - 1 - x : x] = is_rev ? (ms[x] < 4 ? 3 - ms[x] : 4) : ms[x];
+	__syncwarp();
+	TgtPac tg; tg.ix = &V.ix; tg.rb = t.rb;
+	return sw_local_warp(V.opt, l_ms, t.tlen, tg, rescue_xtra(V.opt, l_ms), W, bl, b_cap, lane, V.cnt);
+}
 // -------------------------------------------------------------------------------- global DP ----
 #define WG_RCAP 2048
 struct WarpGlSmem { i32 H[2][QMAX_W + 16], E[QMAX_W + 16]; uint8_t q[QMAX_W], r[WG_RCAP]; };
@@ -745,7 +742,7 @@ __device__ void reg2aln_warp(const DevIndex &ix, const ssq_opts_t &o, int l_quer
 
 // mem_sam_pe's rescue block for one pair by a warp (the warp form of ssq_dev3.cuh::body_rescue).  bbuf: per-warp global scratch for
 // 2 x 64 regions, bl: per-warp list of b_cap sub-optimal rows
-__device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwSmem &W, u64 *bl, int b_cap, int lane)
+__device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwSmem &W, u64 *bl, int b_cap, int lane, RCache *rc = 0)
 {
 	AlnReg *b[2] = {bbuf, bbuf + 64};
 	int nb[2] = {0, 0}, na[2];
@@ -767,7 +764,7 @@ __device__ void body_rescue_warp(const PipeView &V, int p, AlnReg *bbuf, WarpSwS
 		const int cap = (int)(V.areg_off[2 * p + !i + 1] - V.areg_off[2 * p + !i]);
 		for (int j = 0; j < nb[i] && j < V.opt.max_matesw; ++j) {
 			const int before = na[!i];
-			if (mate_rescue_warp(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, W, bl, b_cap, lane, V.cnt, V.xcnt + V.areg_off[2 * p + !i]) < 0 && lane == 0) PIPE_ERR(V, 8);
+			if (mate_rescue_warp(V.ix, V.opt, V.pes, b[i][j], (int)(V.tc.read_off[2 * p + !i + 1] - V.tc.read_off[2 * p + !i]), V.tc.seq + V.tc.read_off[2 * p + !i], a[!i], &na[!i], cap, W, bl, b_cap, lane, V.cnt, V.xcnt + V.areg_off[2 * p + !i], rc, (u32)(i << 16 | j << 2)) < 0 && lane == 0) PIPE_ERR(V, 8);
 			if (na[!i] >= cap && before < cap && lane == 0) PIPE_ERR(V, 1);
 		}
 	}

@@ -328,7 +328,44 @@ struct HostPipe {
 			std::vector<uint8_t> ref(win_cap); std::vector<u64> bl(win_cap); std::vector<AlnReg> bbuf(128);
 			MateScratch M; M.seq = sq.data(); M.ref = ref.data(); M.ref_cap = win_cap; M.L.H0 = H0.data(); M.L.H1 = H1.data(); M.L.E = E.data(); M.L.Hmax = Hm.data(); M.L.b = bl.data(); M.L.b_cap = win_cap;
 			M.A.qbuf = M.A.rbuf = 0; M.A.rcap = 0; M.A.g.h = M.A.g.e = 0; M.A.g.z = 0; M.A.g.zcap = 0;
-			for (int p = 0; p < n_pairs; ++p) if (rescue_wanted(V, p)) body_rescue(V, p, bbuf.data(), M);
+			// the device's three phases (ssq_pipe.cu): count and list the rescue alignments the initial lists do not skip, compute them
+			// all ahead, then replay every pair in the reference's order with the results looked up.  HOSTSIM_RESCUE_SPEC=0: the plain replay
+			static const bool spec = !(getenv("HOSTSIM_RESCUE_SPEC") && !atoi(getenv("HOSTSIM_RESCUE_SPEC")));
+			std::vector<RTask> tasks; std::vector<LocalRes> res; std::vector<int> t_base(n_pairs + 1, 0);
+			if (spec) {
+				for (int p = 0; p < n_pairs; ++p) t_base[p + 1] = t_base[p] + rescue_enum(V, p, 0, 0, win_cap);
+				tasks.resize(t_base[n_pairs] + 1); res.resize(t_base[n_pairs] + 1);
+				for (int p = 0; p < n_pairs; ++p) if (t_base[p + 1] > t_base[p]) rescue_enum(V, p, tasks.data() + t_base[p], (u32)p, win_cap);
+				std::vector<uint8_t> tq(max_len + 16);
+				for (int k = 0; k < t_base[n_pairs]; ++k) { // one task = what the SW kernel gives a warp
+					const RTask &t = tasks[k];
+					const int p = (int)t.slot, i = (int)(t.key >> 16), r = (int)(t.key & 3), is_rev = (r >> 1 != (r & 1));
+					const uint8_t *ms = V.tc.seq + V.tc.read_off[2 * p + !i];
+					for (int x = 0; x < t.l_ms; ++x) tq[is_rev ? t.l_ms - 1 - x : x] = is_rev ? (ms[x] < 4 ? 3 - ms[x] : 4) : ms[x];
+					for (int x = 0; x < t.tlen; ++x) ref[x] = (uint8_t)ref_base(V.ix, t.rb + x);
+					res[k] = sw_local(opt, t.l_ms, tq.data(), t.tlen, ref.data(), rescue_xtra(opt, t.l_ms), M.L);
+				}
+			}
+			if (spec && getenv("HOSTSIM_RESCUE_DROP") && atoi(getenv("HOSTSIM_RESCUE_DROP")) > 0) { // tests: withhold every N-th result so that the replay's own computation runs
+				const int nth = atoi(getenv("HOSTSIM_RESCUE_DROP"));
+				std::vector<RTask> t2; std::vector<LocalRes> r2; std::vector<int> b2(n_pairs + 1, 0);
+				for (int p = 0; p < n_pairs; ++p) {
+					for (int k = t_base[p]; k < t_base[p + 1]; ++k) if (k % nth != 0) { t2.push_back(tasks[k]); r2.push_back(res[k]); }
+					b2[p + 1] = (int)t2.size();
+					if (b2[p + 1] == b2[p] && t_base[p + 1] > t_base[p]) { t2.push_back(tasks[t_base[p]]); t2.back().key = 0xffffffffu; r2.push_back(res[t_base[p]]); b2[p + 1] = (int)t2.size(); } // keep the pair in the replay
+				}
+				t2.resize(t2.size() + 1); r2.resize(r2.size() + 1);
+				tasks.swap(t2); res.swap(r2); t_base.swap(b2);
+			}
+			static unsigned int n_miss = 0;
+			for (int p = 0; p < n_pairs; ++p) {
+				if (spec) { // (a pair without a task cannot change: every replay step would be skipped or align nothing)
+					if (t_base[p + 1] == t_base[p]) continue;
+					RCache rc; rc.t = tasks.data() + t_base[p]; rc.res = res.data() + t_base[p]; rc.n = t_base[p + 1] - t_base[p]; rc.cur = 0; rc.miss = &n_miss;
+					body_rescue(V, p, bbuf.data(), M, &rc);
+				} else if (rescue_wanted(V, p)) body_rescue(V, p, bbuf.data(), M);
+			}
+			if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "[hostsim] rescue: %d alignments computed ahead, %u computed in the replay\n", t_base[n_pairs], n_miss);
 		}
 		// planning
 		std::vector<u64> tsoff(n + 1, 0);
