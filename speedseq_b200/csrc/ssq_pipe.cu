@@ -14,15 +14,18 @@
 //   k_pestat        insert-size histogram of the batch                                         (thread per pair, atomics)
 //     host:         quartiles / mean / std from the histogram (the reference's double sums replayed in sorted order),
 //                   penalty table .721*log(2*erfc(|z|/sqrt2))*a over the integer insert sizes  -> back to the device
-//   k_rescue_mark   which pairs trigger a mate-rescue alignment at all                         (thread per pair)
-//   k_rescue        mate rescue, striped-order local SW                                        (thread per marked pair)
+//   k_rescue_count  the rescue alignments the lists, as they stand, do not skip: count per pair   (thread per pair)
+//   k_rescue_fill   ... as tasks (hit of the snapshot, orientation, window)                    (thread per marked pair)
+//   k_rescue_sw     those alignments, striped-order local SW on all 32 lanes (ssq_warp.cuh)    (warp per task)
+//   k_rescue        the reference's sequential rescue of a pair with the results looked up     (warp per marked pair)
 //   k_plan          primary marking, pairing, MAPQ, list of alignments to write                (thread per pair / read)
-//   k_cigar         global banded DP + traceback -> position / CIGAR / NM / MD                 (thread per alignment)
+//   k_cigar_fast / k_cigar_warp   position / CIGAR / NM / MD: ungapped per thread, banded DP + traceback per warp
 //   k_sb            samblaster: pair signature, discordant bit, splitter masks                 (thread per pair / read)
 //   dup-set         first-seen-wins over all batches of the run                                (ssq_kernels.cu)
 //   k_text<false>   byte counts of each read's records in the three streams; scans
 //   k_text<true>    the text
-// Host round trips per batch: the size queries inside ssq_batch_run, the histogram, the task count and the text sizes.
+// Host round trips per batch: the size queries inside ssq_batch_run, the histogram, the rescue-task count, the task count and the
+// text sizes.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <math.h>

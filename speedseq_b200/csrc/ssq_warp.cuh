@@ -7,6 +7,8 @@
 //                    striped query, a row is one lock-step sweep over the segment, the cross-segment carries are shuffles and the
 //                    lazy-F exit test is a ballot.  One warp per problem: the latency of one alignment drops by the lane count,
 //                    which is what matters — a batch has few rescue alignments (a few 10^4 per 2 M reads), but each is 10^5 cells.
+//                    The byte kernel has 16 lanes: the register form that runs by default gives every segment to TWO warp lanes
+//                    (sw_local_pass_warp_split), so all 32 lanes work and the values stay those of the 16-lane kernel.
 //   sw_global_warp   upstream ksw_global2 + traceback (CIGAR generation, mem_reg2aln / bwa_gen_cigar2; a14).  Plain banded global
 //                    affine-gap DP: a cell depends on the row above (H diagonal, E) and on the cell to its left only through F,
 //                    and F along a row is a max-plus prefix scan of the gap-open candidates of that row.  Lanes = columns of the

@@ -330,7 +330,7 @@ struct HostPipe {
 			M.A.qbuf = M.A.rbuf = 0; M.A.rcap = 0; M.A.g.h = M.A.g.e = 0; M.A.g.z = 0; M.A.g.zcap = 0;
 			// the device's three phases (ssq_pipe.cu): count and list the rescue alignments the initial lists do not skip, compute them
 			// all ahead, then replay every pair in the reference's order with the results looked up.  HOSTSIM_RESCUE_SPEC=0: the plain replay
-			static const bool spec = !(getenv("HOSTSIM_RESCUE_SPEC") && !atoi(getenv("HOSTSIM_RESCUE_SPEC")));
+			const bool spec = !(getenv("HOSTSIM_RESCUE_SPEC") && !atoi(getenv("HOSTSIM_RESCUE_SPEC")));
 			std::vector<RTask> tasks; std::vector<LocalRes> res; std::vector<int> t_base(n_pairs + 1, 0);
 			if (spec) {
 				for (int p = 0; p < n_pairs; ++p) t_base[p + 1] = t_base[p] + rescue_enum(V, p, 0, 0, win_cap);

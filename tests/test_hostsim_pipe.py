@@ -62,6 +62,19 @@ def test_plain_bwa_mem_synthetic_stress(oracle, hostsim, syn_index, rl, seed, kw
     assert hostsim.mem_pe(idx, names, seqs, quals, 1000, b"rg1") == oracle.mem_pe(idx, names, seqs, quals, 1000, 4, b"rg1")
 
 
+@pytest.mark.parametrize("env", [{"HOSTSIM_RESCUE_SPEC": "0"}, {"HOSTSIM_RESCUE_DROP": "1"}, {"HOSTSIM_RESCUE_DROP": "2"}, {"HOSTSIM_RESCUE_DROP": "5"}])
+def test_mate_rescue_computed_ahead_and_in_the_replay(oracle, hostsim, syn_index, monkeypatch, env):
+    """the rescue alignments are computed ahead as tasks and looked up by the sequential replay (ssq_dev2.cuh: RTask / RCache); a
+    replay step that finds no result computes it itself.  Same records whether everything is computed in the replay (SPEC=0), nothing
+    is found ahead (DROP=1) or every 2nd / 5th result is withheld"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fa, g, bounds = syn_index
+    idx = oracle.load(fa)
+    names, seqs, quals = stress_reads(g, bounds, 500, 150, 2, err=0.02, indel=0.004, n_frac=0.004)
+    assert hostsim.mem_pe(idx, names, seqs, quals, 1000, b"rg1") == oracle.mem_pe(idx, names, seqs, quals, 1000, 4, b"rg1")
+
+
 def test_plain_bwa_mem_single_end(oracle, hostsim, syn_index):
     fa, g, bounds = syn_index
     idx = oracle.load(fa)
