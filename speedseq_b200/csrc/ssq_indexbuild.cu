@@ -11,9 +11,11 @@
 // (CUB DeviceRadixSort — HBM-streaming plumbing), ranks are re-derived with a max-scan, and the loop stops when all ranks
 // are distinct (h doubles from 16, so ~log2(longest repeat/16) rounds).  BWT symbols, the occ checkpoints every 128
 // symbols and the SA samples every 32 rows are then gathered by streaming kernels and written in the reference's layout.
-// Limits: 2*l_pac + 1 < 2^31 symbols in this round (chr20-class genomes; whole GRCh37 needs 64-bit ranks and
-// group-restricted sorting — DESIGN.md §7).  FASTA parsing and the lrand48() replacement of ambiguous bases are
-// inherently sequential (the random stream is consumed in file order) and run on the host.
+// The device sort holds 2*l_pac + 1 < 2^31 suffixes (1.07 Gbp).  Beyond that (whole GRCh37: 6.2 G suffixes) the suffix array is
+// built on the host — induced sorting with 64-bit indices (ssq_sais.h), BWT / occ checkpoints / SA samples by host threads — and
+// written in the same layout; no GPU is touched on that path (SSQ_INDEX_HOST=1 forces it for any size: the CPU tests pin it on
+// the reference's goldens).  FASTA parsing and the lrand48() replacement of ambiguous bases are inherently sequential (the
+// random stream is consumed in file order) and run on the host.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <zlib.h>
@@ -23,7 +25,9 @@
 #include <ctype.h>
 #include <string>
 #include <vector>
+#include <thread>
 #include "ssq_host.h"
+#include "ssq_sais.h"
 
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ssq_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); rc = SSQ_ECUDA; goto done; } } while (0)
 
@@ -208,20 +212,104 @@ __global__ void k_ib_sasample(u32 n_sa, const u32 *__restrict__ sa, u64 *out)
 	if (k >= 1 && k < n_sa) out[k - 1] = (u64)sa[(u64)k * 32];
 }
 
+// ------------------------------------------------------------------------- host path ----
+// PREFIX.bwt / PREFIX.sa from the 2-bit forward strand with everything on the host; I: index type of the suffix array
+template <class I>
+static int build_bwt_sa_host(const char *prefix, const std::vector<uint8_t> &pac, i64 l_pac)
+{
+	const u64 n = 2 * (u64)l_pac, n1 = n + 1;
+	std::vector<uint8_t> s;
+	std::vector<I> SA;
+	std::vector<u32> out, cnt;
+	try { s.resize(n1); SA.resize(n1); } catch (...) { ssq_set_error("not enough host memory for the suffix array of %llu symbols (%llu GB)", (unsigned long long)n, (unsigned long long)((n1 * (sizeof(I) + 1)) >> 30)); return SSQ_ENOMEM; }
+	int n_thr = (int)std::thread::hardware_concurrency();
+	if (n_thr < 1) n_thr = 1;
+	if (n_thr > 64) n_thr = 64;
+	auto par = [&](u64 total, auto fn) { // fn(lo, hi) over [0, total) in n_thr contiguous pieces
+		std::vector<std::thread> th;
+		const u64 per = (total + n_thr - 1) / n_thr;
+		for (int t = 0; t < n_thr; ++t) { const u64 lo = per * t, hi = lo + per < total ? lo + per : total; if (lo < hi) th.emplace_back(fn, lo, hi); }
+		for (auto &x : th) x.join();
+	};
+	// T$ over {0: '$', 1..4: A C G T}: forward strand then its reverse complement (tsym on the device path)
+	par(n, [&](u64 lo, u64 hi) {
+		for (u64 i = lo; i < hi; ++i) {
+			const bool fw = i < (u64)l_pac;
+			const u64 p = fw ? i : n - 1 - i;
+			const int b = pac[p >> 2] >> ((~p & 3) << 1) & 3;
+			s[i] = (uint8_t)(1 + (fw ? b : 3 - b));
+		}
+	});
+	s[n] = 0;
+	ssq_sais<uint8_t, I>(s.data(), SA.data(), (I)n1, (I)5);
+	u64 primary = 0;
+	{
+		std::vector<u64> found(n_thr + 1, ~0ull);
+		std::vector<std::thread> th;
+		const u64 per = (n1 + n_thr - 1) / n_thr;
+		for (int t = 0; t < n_thr; ++t) th.emplace_back([&, t]() { const u64 lo = per * t, hi = lo + per < n1 ? lo + per : n1; for (u64 r = lo; r < hi; ++r) if (SA[r] == 0) found[t] = r; });
+		for (auto &x : th) x.join();
+		for (int t = 0; t < n_thr; ++t) if (found[t] != ~0ull) primary = found[t];
+	}
+	// interleaved occ/BWT: block b at words [16b, 16b+16) = u64 occ[4] then 8 words of 16 symbols (MSB first); totals after the last word
+	const u64 n_blk = (n + 127) / 128, raw_words = (n + 15) / 16, total_words = raw_words + (n_blk + 1) * 8;
+	try { out.assign(total_words, 0); cnt.assign((n_blk + 1) * 4, 0); } catch (...) { ssq_set_error("not enough host memory for the BWT"); return SSQ_ENOMEM; }
+	par(n_blk, [&](u64 lo, u64 hi) {
+		for (u64 b = lo; b < hi; ++b) {
+			u32 c[4] = {0, 0, 0, 0};
+			for (u32 w = 0; w < 8; ++w) {
+				const u64 j0 = b * 128 + (u64)w * 16;
+				if (j0 >= n) break;
+				u32 v = 0;
+				for (u32 k = 0; k < 16; ++k) {
+					const u64 j = j0 + k;
+					u32 sym = 0;
+					if (j < n) { const u64 r = j + (j >= primary); sym = (u32)s[(u64)SA[r] - 1] - 1; ++c[sym]; }
+					v = v << 2 | sym;
+				}
+				out[b * 16 + 8 + w] = v;
+			}
+			for (int k = 0; k < 4; ++k) cnt[b * 4 + k] = c[k];
+		}
+	});
+	u64 run[4] = {0, 0, 0, 0};
+	for (u64 b = 0; b <= n_blk; ++b) { // checkpoints: counts before the block; the last one (totals) sits 8 words before the end
+		u32 *o = b < n_blk ? &out[b * 16] : &out[total_words - 8];
+		for (int k = 0; k < 4; ++k) { o[2 * k] = (u32)run[k]; o[2 * k + 1] = (u32)(run[k] >> 32); if (b < n_blk) run[k] += cnt[b * 4 + k]; }
+	}
+	u64 L2[5] = {0, run[0], run[0] + run[1], run[0] + run[1] + run[2], run[0] + run[1] + run[2] + run[3]};
+	std::string p(prefix);
+	FILE *fp = fopen((p + ".bwt").c_str(), "wb");
+	if (!fp) { ssq_set_error("cannot write %s.bwt", prefix); return SSQ_EIO; }
+	fwrite(&primary, 8, 1, fp); fwrite(L2 + 1, 8, 4, fp); fwrite(out.data(), 4, out.size(), fp);
+	if (fclose(fp)) { ssq_set_error("cannot write %s.bwt", prefix); return SSQ_EIO; }
+	std::vector<u32>().swap(out); std::vector<u32>().swap(cnt);
+	const u64 n_sa = (n + 32) / 32, sa_intv = 32, seq_len = n;
+	std::vector<u64> smp(n_sa ? n_sa - 1 : 0);
+	for (u64 k = 1; k < n_sa; ++k) smp[k - 1] = (u64)SA[k * 32];
+	if (!(fp = fopen((p + ".sa").c_str(), "wb"))) { ssq_set_error("cannot write %s.sa", prefix); return SSQ_EIO; }
+	fwrite(&primary, 8, 1, fp); fwrite(L2 + 1, 8, 4, fp); fwrite(&sa_intv, 8, 1, fp); fwrite(&seq_len, 8, 1, fp); fwrite(smp.data(), 8, smp.size(), fp);
+	if (fclose(fp)) { ssq_set_error("cannot write %s.sa", prefix); return SSQ_EIO; }
+	return SSQ_OK;
+}
+
 // -------------------------------------------------------------------------------- driver ----
 extern "C" int ssq_index_build(const char *fasta, const char *prefix, int device)
 {
 	if (!fasta) return SSQ_EINVAL;
 	if (!prefix) prefix = fasta;
-	int rc = ssq_use_device(device);
-	if (rc) return rc;
+	int rc;
 	std::vector<FaContig> ctg; std::vector<FaHole> holes; std::vector<uint8_t> pac;
 	i64 l_pac = 0;
 	if ((rc = parse_fasta(fasta, ctg, holes, pac, l_pac))) { ssq_set_error("cannot read any sequence from %s", fasta); return rc; }
 	pac.resize((size_t)(l_pac >> 2) + 2, 0);
 	const i64 n64 = 2 * l_pac;
-	// checked BEFORE anything is written: a refused build must not leave a partial index (.ann/.amb/.pac) behind
-	if (n64 + 1 >= 0x7fffffffLL) { ssq_set_error("reference of %lld bases: the GPU suffix sort of this build handles at most 2^31-2 suffixes (1.07 Gbp); build a larger index with upstream `bwa index` — libssq loads its files (on-disk format is the same)", (long long)l_pac); return SSQ_EINVAL; }
+	const char *force = getenv("SSQ_INDEX_HOST"); // 1: host path with the narrowest index type that fits, 64: host path with 64-bit indices
+	if (n64 + 1 >= 0x7fffffffLL || (force && atoi(force))) { // beyond the device sort of this build (or asked for): everything on the host, no GPU needed
+		if ((rc = write_text_files(prefix, ctg, holes, pac, l_pac))) { ssq_set_error("cannot write %s.{ann,amb,pac}", prefix); return rc; }
+		return (n64 + 1 >= 0x7fffffffLL || (force && atoi(force) == 64)) ? build_bwt_sa_host<int64_t>(prefix, pac, l_pac) : build_bwt_sa_host<int32_t>(prefix, pac, l_pac);
+	}
+	if ((rc = ssq_use_device(device))) return rc;
 	if ((rc = write_text_files(prefix, ctg, holes, pac, l_pac))) { ssq_set_error("cannot write %s.{ann,amb,pac}", prefix); return rc; }
 	const u32 n = (u32)n64, n1 = n + 1;
 	const unsigned G1 = (n1 + 255) / 256;
