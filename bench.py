@@ -507,7 +507,7 @@ def main():
                           "index": "replicated per GPU, %.0f MB on the device, loaded in %.1f s" % (L.ssq_index_info(idx, 6) / 1e6, t_load),
                           "parallelism": ("batches dealt round-robin to %d ranks, index replicated; duplicate stage = one NCCL exchange per round (signatures to owner rank hash mod N, 16 B/pair out, 1 B/pair back): rank 0 sent %.1f MB / received back %.1f MB per step" % (world, L.ssq_comm_counter(comm, 0) / 1e6 / max(1, L.ssq_comm_counter(comm, 2) // nb), L.ssq_comm_counter(comm, 1) / 1e6 / max(1, L.ssq_comm_counter(comm, 2) // nb))) if comm is not None else "single GPU: no collective",
                           "samblaster": " ".join(SB_ARGS)},
-               "clocks": clocks, "gpu_launches": int(counters[6]) * a.steps + 14 * nb * a.steps,
+               "clocks": clocks, "gpu_launches": int(counters[6]) * a.steps + 16 * nb * a.steps,  # seed..extend launches counted by the library + the 16 pipeline kernels of a batch (k_dedup .. k_text; CUB scans / sorts not counted)
                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step[0], "ms_per_step": ms_e2e / a.steps},
                "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["bytes"], "launch_ms": kern[dom]["ms"], "rank_block_bytes": blk,
