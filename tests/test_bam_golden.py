@@ -277,3 +277,27 @@ def test_bam_mode_chain_of_the_three_shims_cpu(oracle, hostsim, ex_index, ex_rea
     # a samblaster command line that asks for something else than the stream was made under is refused
     p3 = subprocess.run([os.path.join(bin_, "samblaster"), "--addMateTags"], input=stream, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
     assert p3.returncode != 0 and b"other options" in p3.stderr
+
+
+def test_sambamba_shim_edge_cases(tmp_path):
+    """no runs at all -> a valid BAM without records; a truncated or corrupt run stream -> an error, not a short file that looks
+    complete; anything that is not a run stream needs the real sambamba and says so"""
+    import struct
+    import subprocess
+    shim = os.path.join(T.ROOT, "speedseq_b200", "bin", "sambamba")
+    hdr = b"@SQ\tSN:c1\tLN:1000\n@PG\tID:bwa\tPN:bwa\tVN:x\tCL:y\n"
+    env = {k: v for k, v in os.environ.items() if k != "SSQ_SAMBAMBA_REAL"}
+    out = str(tmp_path / "empty.bam")
+    subprocess.run([shim, "sort", "-t", "2", "-m", "1G", "--tmpdir=" + str(tmp_path), "-o", out, "/dev/stdin"], input=hdr + b"@CO\tssq-bam-runs-v1\n", check=True, timeout=60, env=env)
+    text, refs, recs = _bam_file(out)
+    assert recs == b"" and refs == [(b"c1", 1000)] and text.startswith(b"@HD\tVN:1.3\tSO:coordinate\n@SQ\tSN:c1\tLN:1000\n")
+    rec = struct.pack("<iiiBBHHHiiii", 32 + 2 + 1 + 1, 0, 5, 2, 0, 4680, 0, 4, 1, -1, -1, 0) + b"r\0" + b"\x10" + b"\xff"  # one unmapped-looking record placed at c1:6
+    good = hdr + b"@CO\tssq-bam-runs-v1\n" + b"SSQFRAME" + struct.pack("<QQ", 3, len(rec)) + rec
+    subprocess.run([shim, "sort", "-o", out, "/dev/stdin"], input=good, check=True, timeout=60, env=env)
+    assert _bam_file(out)[2] == rec
+    for bad in (good[:-3], good.replace(b"SSQFRAME", b"SSQFRAMX"), hdr + b"@CO\tssq-bam-runs-v1\n" + b"SSQFRAME" + struct.pack("<QQ", 3, 7) + b"1234567"):
+        p = subprocess.run([shim, "sort", "-o", str(tmp_path / "bad.bam"), "/dev/stdin"], input=bad, stderr=subprocess.PIPE, timeout=60, env=env)
+        assert p.returncode != 0 and b"B200 shim" in p.stderr, bad[-20:]
+    for argv in (["view", "-S", "-f", "bam", "-l", "0", "/dev/stdin"], ["sort", "-o", str(tmp_path / "x.bam"), "/dev/stdin"], ["index", "x.bam"]):
+        p = subprocess.run([shim] + argv, input=hdr + b"r1\t4\t*\t0\t0\t*\t*\t0\t0\tA\tI\n", stderr=subprocess.PIPE, stdout=subprocess.PIPE, timeout=60, env=env)
+        assert p.returncode != 0 and b"needs the real sambamba" in p.stderr

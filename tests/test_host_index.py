@@ -64,3 +64,14 @@ def test_small_reference_still_needs_the_gpu(ssq_lib_cpu, tmp_path, monkeypatch)
     ssq_lib_cpu.ssq_index_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     assert ssq_lib_cpu.ssq_index_build(fa.encode(), None, 0) != 0
     assert not os.path.exists(fa + ".bwt") and not os.path.exists(fa + ".ann")
+
+
+def test_bwa_shim_index_on_the_host_path(tmp_path):
+    """`$BWA index $REF` (speedseq:389) with the shim, host path forced: the five golden files, no GPU in this container"""
+    import subprocess
+    fa = str(tmp_path / "ex.fa")
+    open(fa, "wb").write(gzip.open(os.path.join(T.GOLDEN, "ex_ref.fa.gz")).read())
+    subprocess.run([os.path.join(T.ROOT, "speedseq_b200", "bin", "bwa"), "index", fa], check=True, env=dict(os.environ, SSQ_INDEX_HOST="64"), timeout=120, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+    gold = json.load(open(os.path.join(T.GOLDEN, "ex_index.sha256.json")))
+    for ext, g in gold.items():
+        assert hashlib.sha256(open(fa + "." + ext, "rb").read()).hexdigest() == g["sha256"], ext
