@@ -213,15 +213,25 @@ __global__ void k_ib_sasample(u32 n_sa, const u32 *__restrict__ sa, u64 *out)
 }
 
 // ------------------------------------------------------------------------- host path ----
-// PREFIX.bwt / PREFIX.sa from the 2-bit forward strand with everything on the host; I: index type of the suffix array
-template <class I>
-static int build_bwt_sa_host(const char *prefix, const std::vector<uint8_t> &pac, i64 l_pac)
+// PREFIX.bwt / PREFIX.sa from the 2-bit forward strand with everything on the host; bits: width of a suffix-array entry (32, 40, 64)
+template <class SAP>
+static int build_bwt_sa_host_impl(const char *prefix, const std::vector<uint8_t> &pac, i64 l_pac, std::vector<uint8_t> &s, SAP SA);
+static int build_bwt_sa_host(const char *prefix, const std::vector<uint8_t> &pac, i64 l_pac, int bits)
+{
+	const u64 n1 = 2 * (u64)l_pac + 1;
+	std::vector<uint8_t> s, raw;
+	try { s.resize(n1); raw.resize(n1 * (size_t)(bits / 8) + 8); }
+	catch (...) { ssq_set_error("not enough host memory for the suffix array of %llu symbols (%llu GB)", (unsigned long long)(n1 - 1), (unsigned long long)((n1 * (size_t)(bits / 8 + 1)) >> 30)); return SSQ_ENOMEM; }
+	if (bits == 32) return build_bwt_sa_host_impl(prefix, pac, l_pac, s, (int32_t*)raw.data());
+	if (bits == 64) return build_bwt_sa_host_impl(prefix, pac, l_pac, s, (int64_t*)raw.data());
+	ssq_p40 v; v.p = raw.data();
+	return build_bwt_sa_host_impl(prefix, pac, l_pac, s, v);
+}
+template <class SAP>
+static int build_bwt_sa_host_impl(const char *prefix, const std::vector<uint8_t> &pac, i64 l_pac, std::vector<uint8_t> &s, SAP SA)
 {
 	const u64 n = 2 * (u64)l_pac, n1 = n + 1;
-	std::vector<uint8_t> s;
-	std::vector<I> SA;
 	std::vector<u32> out, cnt;
-	try { s.resize(n1); SA.resize(n1); } catch (...) { ssq_set_error("not enough host memory for the suffix array of %llu symbols (%llu GB)", (unsigned long long)n, (unsigned long long)((n1 * (sizeof(I) + 1)) >> 30)); return SSQ_ENOMEM; }
 	int n_thr = (int)std::thread::hardware_concurrency();
 	if (n_thr < 1) n_thr = 1;
 	if (n_thr > 64) n_thr = 64;
@@ -241,13 +251,13 @@ static int build_bwt_sa_host(const char *prefix, const std::vector<uint8_t> &pac
 		}
 	});
 	s[n] = 0;
-	ssq_sais<uint8_t, I>(s.data(), SA.data(), (I)n1, (I)5);
+	ssq_sais(s.data(), SA, (int64_t)n1, (int64_t)5);
 	u64 primary = 0;
 	{
 		std::vector<u64> found(n_thr + 1, ~0ull);
 		std::vector<std::thread> th;
 		const u64 per = (n1 + n_thr - 1) / n_thr;
-		for (int t = 0; t < n_thr; ++t) th.emplace_back([&, t]() { const u64 lo = per * t, hi = lo + per < n1 ? lo + per : n1; for (u64 r = lo; r < hi; ++r) if (SA[r] == 0) found[t] = r; });
+		for (int t = 0; t < n_thr; ++t) th.emplace_back([&, t]() { const u64 lo = per * t, hi = lo + per < n1 ? lo + per : n1; for (u64 r = lo; r < hi; ++r) if ((i64)SA[(i64)r] == 0) found[t] = r; });
 		for (auto &x : th) x.join();
 		for (int t = 0; t < n_thr; ++t) if (found[t] != ~0ull) primary = found[t];
 	}
@@ -264,7 +274,7 @@ static int build_bwt_sa_host(const char *prefix, const std::vector<uint8_t> &pac
 				for (u32 k = 0; k < 16; ++k) {
 					const u64 j = j0 + k;
 					u32 sym = 0;
-					if (j < n) { const u64 r = j + (j >= primary); sym = (u32)s[(u64)SA[r] - 1] - 1; ++c[sym]; }
+					if (j < n) { const u64 r = j + (j >= primary); sym = (u32)s[(u64)(i64)SA[(i64)r] - 1] - 1; ++c[sym]; }
 					v = v << 2 | sym;
 				}
 				out[b * 16 + 8 + w] = v;
@@ -286,7 +296,7 @@ static int build_bwt_sa_host(const char *prefix, const std::vector<uint8_t> &pac
 	std::vector<u32>().swap(out); std::vector<u32>().swap(cnt);
 	const u64 n_sa = (n + 32) / 32, sa_intv = 32, seq_len = n;
 	std::vector<u64> smp(n_sa ? n_sa - 1 : 0);
-	for (u64 k = 1; k < n_sa; ++k) smp[k - 1] = (u64)SA[k * 32];
+	for (u64 k = 1; k < n_sa; ++k) smp[k - 1] = (u64)(i64)SA[(i64)(k * 32)];
 	if (!(fp = fopen((p + ".sa").c_str(), "wb"))) { ssq_set_error("cannot write %s.sa", prefix); return SSQ_EIO; }
 	fwrite(&primary, 8, 1, fp); fwrite(L2 + 1, 8, 4, fp); fwrite(&sa_intv, 8, 1, fp); fwrite(&seq_len, 8, 1, fp); fwrite(smp.data(), 8, smp.size(), fp);
 	if (fclose(fp)) { ssq_set_error("cannot write %s.sa", prefix); return SSQ_EIO; }
@@ -304,10 +314,11 @@ extern "C" int ssq_index_build(const char *fasta, const char *prefix, int device
 	if ((rc = parse_fasta(fasta, ctg, holes, pac, l_pac))) { ssq_set_error("cannot read any sequence from %s", fasta); return rc; }
 	pac.resize((size_t)(l_pac >> 2) + 2, 0);
 	const i64 n64 = 2 * l_pac;
-	const char *force = getenv("SSQ_INDEX_HOST"); // 1: host path with the narrowest index type that fits, 64: host path with 64-bit indices
+	const char *force = getenv("SSQ_INDEX_HOST"); // 1: host path with the narrowest entry type that fits, 40 / 64: with 40- / 64-bit entries
 	if (n64 + 1 >= 0x7fffffffLL || (force && atoi(force))) { // beyond the device sort of this build (or asked for): everything on the host, no GPU needed
 		if ((rc = write_text_files(prefix, ctg, holes, pac, l_pac))) { ssq_set_error("cannot write %s.{ann,amb,pac}", prefix); return rc; }
-		return (n64 + 1 >= 0x7fffffffLL || (force && atoi(force) == 64)) ? build_bwt_sa_host<int64_t>(prefix, pac, l_pac) : build_bwt_sa_host<int32_t>(prefix, pac, l_pac);
+		const int f = force ? atoi(force) : 0; // entry width: what was asked for, else 32 bits while they suffice, else 40 (5 bytes per suffix)
+		return build_bwt_sa_host(prefix, pac, l_pac, f == 64 ? 64 : (f == 40 || n64 + 1 >= 0x7fffffffLL) ? 40 : 32);
 	}
 	if ((rc = ssq_use_device(device))) return rc;
 	if ((rc = write_text_files(prefix, ctg, holes, pac, l_pac))) { ssq_set_error("cannot write %s.{ann,amb,pac}", prefix); return rc; }

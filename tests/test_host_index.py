@@ -1,6 +1,6 @@
 """`ssq_index_build` beyond the device sort's 2^31 - 2 suffixes builds the suffix array on the host (induced sorting, 64-bit indices,
-csrc/ssq_sais.h) and writes the same five files; no GPU is touched.  SSQ_INDEX_HOST forces that path for any size (1: narrowest index
-type, 64: the 64-bit instantiation a whole genome uses), so it is pinned here, on the CPU, on the reference's own golden index
+csrc/ssq_sais.h) and writes the same five files; no GPU is touched.  SSQ_INDEX_HOST forces that path for any size (1: narrowest entry
+type, 40: the 5-byte entries a whole genome gets, 64: 8-byte entries), so it is pinned here, on the CPU, on the reference's own golden index
 (/root/reference/example/data/*.fasta.{amb,ann,pac,bwt,sa}) and against the oracle's builder on synthetic multi-contig genomes."""
 import ctypes as C
 import gzip
@@ -21,7 +21,7 @@ def _build(lib, fasta, prefix=None):
     assert rc == 0, lib.ssq_last_error()
 
 
-@pytest.mark.parametrize("mode", ["1", "64"])
+@pytest.mark.parametrize("mode", ["1", "40", "64"])
 def test_host_index_matches_reference_goldens(ssq_lib_cpu, tmp_path, monkeypatch, mode):
     monkeypatch.setenv("SSQ_INDEX_HOST", mode)
     fa = str(tmp_path / "ex.fa")
@@ -34,7 +34,7 @@ def test_host_index_matches_reference_goldens(ssq_lib_cpu, tmp_path, monkeypatch
         assert hashlib.sha256(data).hexdigest() == g["sha256"], ext
 
 
-@pytest.mark.parametrize("n,nc,seed,mode", [(1000, 1, 1, "64"), (4097, 3, 2, "1"), (250000, 5, 3, "64"), (1 << 20, 2, 4, "64"), (3, 1, 5, "64")])
+@pytest.mark.parametrize("n,nc,seed,mode", [(1000, 1, 1, "64"), (4097, 3, 2, "1"), (250000, 5, 3, "40"), (1 << 20, 2, 4, "40"), (1 << 20, 2, 4, "64"), (3, 1, 5, "40")])
 def test_host_index_equals_oracle_on_synthetic_genomes(ssq_lib_cpu, oracle, tmp_path, monkeypatch, n, nc, seed, mode):
     """multi-contig genomes with N runs (hole table + lrand48 replacement), long exact repeats and l_pac % 4 in {0,1,2,3}"""
     monkeypatch.setenv("SSQ_INDEX_HOST", mode)
