@@ -63,7 +63,8 @@ typedef struct ssq_index ssq_index_t;
 /* `$BWA index $REF` (/root/reference/bin/speedseq:389): FASTA (plain or gz) -> PREFIX.{amb,ann,pac,bwt,sa}, byte-identical
  * to the reference's goldens for example/data; suffix sorting, BWT, occ checkpoints and SA sampling run on `device`.
  * References beyond the device sort's 2^31 - 2 suffixes (1.07 Gbp; a whole human genome has 6.2 G) are indexed on the host
- * instead — induced sorting with 64-bit indices, same files, no GPU touched (about 21 bytes of host memory per base pair).
+ * instead — induced sorting with 5-byte entries, same files, no GPU touched (about 15 bytes of host memory per base pair:
+ * 45 GB and 51 min for a 3.1 Gbp reference on 8 cores).
  * prefix == NULL means prefix = fasta.  Replaces upstream bwa_idx_build(). */
 int ssq_index_build(const char *fasta, const char *prefix, int device);
 int ssq_index_load(const char *prefix, int device, ssq_index_t **out);

@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """`ssq_index_build` on a reference beyond the device sort's limit (2^31 - 2 suffixes): the host path (64-bit induced sorting,
 csrc/ssq_sais.h).  Builds a seeded synthetic genome (8 contigs, planted repeat family; default 2.2 Gbp = 4.4 G suffixes, more BWT
-rows than 2^32), indexes it without touching a GPU, then checks the result three ways:
+rows than 2^32; 3100000000 = the size of GRCh37), indexes it without touching a GPU, then checks the result three ways:
   * header: primary row, cumulative base counts = the base composition of forward + reverse-complement strand;
   * order: a million random pairs of consecutive SA samples (32 rows apart) are in lexicographic order, compared on the text;
   * function: the CPU oracle loads the index and places simulated read pairs at their origins.
-usage: build_big_index.py [genome_bp] [n_pairs]      (needs ~10 bytes of host memory per reference base pair... 21 x genome_bp)"""
+usage: build_big_index.py [genome_bp] [n_pairs]      (about 15 bytes of host memory per reference base pair)"""
 import ctypes as C
 import os
 import struct
