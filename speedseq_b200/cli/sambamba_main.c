@@ -157,28 +157,42 @@ static void merge_sources(src_t *s, int n_src, sink_fn sink, void *ctx)
 }
 
 /* ---- BGZF output on several threads ---- */
-typedef struct { FILE *fp; uint8_t *buf; size_t n, cap; int threads, level; } bgzf_out_t;
+typedef struct { FILE *fp; const uint8_t *buf; size_t n; int threads, level; } flush_t;
+typedef struct { FILE *fp; uint8_t *buf, *alt; size_t n, cap; int threads, level; pthread_t bg; int bg_live; flush_t job; } bgzf_out_t;
 typedef struct { const uint8_t *in; size_t n; int level; void *out; size_t out_len; int rc; } job_t;
 static void *job_main(void *a) { job_t *j = (job_t*)a; j->rc = ssq_bgzf_compress(j->in, j->n, j->level, 0, &j->out, &j->out_len); return 0; }
-static void bgzf_flush(bgzf_out_t *o)
+static void *flush_main(void *a) /* one buffer: compressed in slices on `threads` threads, written in order */
 {
+	const flush_t *f = (const flush_t*)a;
 	job_t jobs[64];
 	pthread_t th[64];
-	int nj = o->threads, k;
+	int nj = f->threads, k;
 	const size_t blk = 0xff00; /* the payload of one block: slices end on block boundaries, so the file is the same for any thread count */
 	size_t per, at = 0;
-	if (!o->n) return;
-	per = ((o->n / blk + (size_t)nj) / (size_t)nj) * blk;
-	for (k = 0; k < nj && at < o->n; ++k) { jobs[k].in = o->buf + at; jobs[k].n = o->n - at < per ? o->n - at : per; jobs[k].level = o->level; jobs[k].out = 0; jobs[k].out_len = 0; at += jobs[k].n; }
+	per = ((f->n / blk + (size_t)nj) / (size_t)nj) * blk;
+	for (k = 0; k < nj && at < f->n; ++k) { jobs[k].in = f->buf + at; jobs[k].n = f->n - at < per ? f->n - at : per; jobs[k].level = f->level; jobs[k].out = 0; jobs[k].out_len = 0; at += jobs[k].n; }
 	nj = k;
 	for (k = 1; k < nj; ++k) pthread_create(&th[k], 0, job_main, &jobs[k]);
 	job_main(&jobs[0]);
 	for (k = 1; k < nj; ++k) pthread_join(th[k], 0);
 	for (k = 0; k < nj; ++k) {
 		if (jobs[k].rc) { fprintf(stderr, "sambamba (B200 shim): BGZF compression failed: %s\n", ssq_last_error()); exit(1); }
-		if (fwrite(jobs[k].out, 1, jobs[k].out_len, o->fp) != jobs[k].out_len) { perror("sambamba (B200 shim): write"); exit(1); }
+		if (fwrite(jobs[k].out, 1, jobs[k].out_len, f->fp) != jobs[k].out_len) { perror("sambamba (B200 shim): write"); exit(1); }
 		ssq_free(jobs[k].out);
 	}
+	return 0;
+}
+static void bgzf_wait(bgzf_out_t *o) { if (o->bg_live) { pthread_join(o->bg, 0); o->bg_live = 0; } }
+/* the filled buffer goes to a background thread (after the previous one has been written: the file keeps its order) while the
+ * caller goes on merging into the other buffer */
+static void bgzf_flush(bgzf_out_t *o)
+{
+	uint8_t *t;
+	if (!o->n) return;
+	bgzf_wait(o);
+	o->job.fp = o->fp; o->job.buf = o->buf; o->job.n = o->n; o->job.threads = o->threads; o->job.level = o->level;
+	if (pthread_create(&o->bg, 0, flush_main, &o->job)) flush_main(&o->job); else o->bg_live = 1;
+	t = o->buf; o->buf = o->alt; o->alt = t;
 	o->n = 0;
 }
 static void bgzf_put(void *ctx, const uint8_t *p, size_t n)
@@ -249,7 +263,8 @@ static int sort_runs(head_t *h, size_t body, const char *out_fn, int threads, in
 	/* output: header block(s), records, end-of-file block */
 	memset(&o, 0, sizeof o);
 	if (!(o.fp = fopen(out_fn, "wb"))) { fprintf(stderr, "sambamba (B200 shim): cannot create %s: %s\n", out_fn, strerror(errno)); return 1; }
-	o.threads = threads < 1 ? 1 : threads > 64 ? 64 : threads; o.level = level; o.cap = (size_t)0xff00 * 256 * (size_t)o.threads; o.buf = (uint8_t*)malloc(o.cap);
+	o.threads = threads < 1 ? 1 : threads > 64 ? 64 : threads; o.level = level; o.cap = (size_t)0xff00 * 256 * (size_t)o.threads; o.buf = (uint8_t*)malloc(o.cap); o.alt = (uint8_t*)malloc(o.cap);
+	if (!o.buf || !o.alt) { fprintf(stderr, "sambamba (B200 shim): out of memory\n"); return 1; }
 	if (ssq_bam_header_text(hdr_text, 1, &hdr_sorted)) { fprintf(stderr, "sambamba (B200 shim): %s\n", ssq_last_error()); return 1; }
 	{ /* "BAM\1", text, reference table from the @SQ lines */
 		const uint32_t l_text = (uint32_t)strlen(hdr_sorted);
@@ -271,6 +286,7 @@ static int sort_runs(head_t *h, size_t body, const char *out_fn, int threads, in
 	}
 	merge_sources(spill, n_spill + n_mem, bgzf_put, &o);
 	bgzf_flush(&o);
+	bgzf_wait(&o);
 	{ void *eofb = 0; size_t el = 0; if (ssq_bgzf_compress("", 0, level, 1, &eofb, &el)) { fprintf(stderr, "sambamba (B200 shim): %s\n", ssq_last_error()); return 1; } fwrite(eofb, 1, el, o.fp); ssq_free(eofb); }
 	if (fclose(o.fp)) { perror("sambamba (B200 shim): close"); return 1; }
 	for (i = 0; i < n_spill; ++i) { fclose(spill[i].fp); unlink(spill_fn[i]); }
